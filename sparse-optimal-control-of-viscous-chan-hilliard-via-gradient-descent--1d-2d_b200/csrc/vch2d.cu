@@ -1,0 +1,622 @@
+// 2D engine: context, Krylov solver, Newton driver, time loop, adjoint sweep, PGD iteration, C ABI.
+// Host control flow lives here; all arithmetic is in the kernels of vch2d_kernels.cuh / vch_dct.cuh.
+#include "vch2d_kernels.cuh"
+#include <algorithm>
+
+namespace vch {
+
+static thread_local std::string g_last_error;
+void set_last_error(const std::string& m) { g_last_error = m; }
+
+}  // namespace vch
+
+using namespace vch;
+
+struct vch2d_ctx {
+    vch2d_params prm;
+    Geo g;
+    Phys ph;
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    long long launches = 0;
+    double krylov_tol = 1e-11;
+    int krylov_maxit = 200;
+    DctPlan dct;
+    // work vectors (n doubles each)
+    DevBuf phi, mu, phit, mut, w0, w1, cphi, cmu, Rphi, Rmu, a, RphiT, RmuT, aT;
+    DevBuf kb, kx, kr, kr0, kp, kv, ks, kt, ktmp, dmu;
+    DevBuf adj_p[2], adj_q[2], adj_r[2], mu_old;
+    DevBuf red_part;             // partials for grid reductions
+    DevBuf small;                // small device vectors: weights, out4
+    unsigned int* ticket = nullptr;
+    Scal* sc = nullptr;          // device scalars
+    Scal* sc_host = nullptr;     // pinned mirror
+    double* out4 = nullptr;      // device, 8 doubles
+    double* out4_host = nullptr; // pinned
+
+    int eb() const { return (int)((g.n + 255) / 256); }
+    int rb() const { return red_blocks(g.n); }
+};
+
+namespace {
+
+void fetch_scalars(vch2d_ctx* c) {
+    VCH_CUDA(cudaMemcpyAsync(c->sc_host, c->sc, sizeof(Scal), cudaMemcpyDeviceToHost, c->stream));
+    VCH_CUDA(cudaStreamSynchronize(c->stream));
+}
+
+#define LAUNCH(c, kern, grid, block, ...)                       \
+    do {                                                        \
+        kern<<<(grid), (block), 0, (c)->stream>>>(__VA_ARGS__); \
+        ++(c)->launches;                                        \
+    } while (0)
+
+template <bool ADJ>
+void op_apply(vch2d_ctx* c, const double* x, const double* a, double* y, double c0, double c2, const int* done) {
+    dim3 grid((c->g.ni + kTI - 1) / kTI, (c->g.no + kTO - 1) / kTO);
+    op_apply_kernel<ADJ><<<grid, 256, 0, c->stream>>>(x, a, y, c->g, c0, c2, done);
+    ++c->launches;
+}
+
+// Left-preconditioned BiCGStab on  P^-1 A x = P^-1 b  with A = c0 I - {L diag(a) | diag(a) L} + c2 L^2 and
+// P the same operator with a replaced by the device scalar abar.  Scalars stay on the device; every kernel of
+// an iteration is gated on sc->done, so iterations are enqueued in batches and the host only polls.
+// Returns the number of iterations; result in c->kx.
+template <bool ADJ>
+int krylov_solve(vch2d_ctx* c, const double* b, const double* a, double c0, double c2, vch_stats* st) {
+    const long long n = c->g.n;
+    const int rb = c->rb(), eb = c->eb();
+    SymbolArgs sy{c0, c2, &c->sc->abar, 0.0};
+    const int* done = &c->sc->done;
+    c->dct.apply(c->stream, b, c->kr.p, sy, nullptr);
+    LAUNCH(c, bicg_init_kernel, rb, kRedThreads, c->kr.p, c->kr0.p, c->kp.p, c->kv.p, c->kx.p, n, c->sc, c->red_part.p, c->ticket);
+    int launched = 0;
+    int batch = 2;
+    while (true) {
+        for (int k = 0; k < batch; ++k) {
+            LAUNCH(c, bicg_p_kernel, eb, 256, c->kr.p, c->kp.p, c->kv.p, n, c->sc);
+            op_apply<ADJ>(c, c->kp.p, a, c->ktmp.p, c0, c2, done);
+            c->dct.apply(c->stream, c->ktmp.p, c->kv.p, sy, done);
+            LAUNCH(c, bicg_dot1_kernel, rb, kRedThreads, c->kr0.p, c->kv.p, n, c->sc, c->red_part.p, c->ticket);
+            LAUNCH(c, bicg_s_kernel, eb, 256, c->kr.p, c->kv.p, c->ks.p, n, c->sc);
+            op_apply<ADJ>(c, c->ks.p, a, c->ktmp.p, c0, c2, done);
+            c->dct.apply(c->stream, c->ktmp.p, c->kt.p, sy, done);
+            LAUNCH(c, bicg_dot2_kernel, rb, kRedThreads, c->kt.p, c->ks.p, n, c->sc, c->red_part.p, c->ticket);
+            LAUNCH(c, bicg_x_kernel, rb, kRedThreads, c->kx.p, c->kr.p, c->kp.p, c->ks.p, c->kt.p, c->kr0.p, n, c->sc,
+                   c->red_part.p, c->ticket);
+        }
+        launched += batch;
+        fetch_scalars(c);
+        if (c->sc_host->done || launched >= c->krylov_maxit) break;
+        batch = (launched < 8) ? 2 : 4;
+    }
+    VCH_CUDA(cudaGetLastError());
+    const int its = c->sc_host->iters;
+    if (st) {
+        st->krylov_iterations += its;
+        st->krylov_max_iterations = std::max<long long>(st->krylov_max_iterations, its);
+        st->newton_linear_solves += 1;
+        if (!c->sc_host->done) st->krylov_stalls += 1;
+    }
+    if (c->sc_host->nonfinite) throw Error(VCH_E_NONFINITE, "non-finite value in Krylov solve");
+    return its;
+}
+
+void eval_residual(vch2d_ctx* c, const double* phi, const double* mu, double* Rphi, double* Rmu, double* a, double dt) {
+    LAUNCH(c, residual_kernel, c->rb(), kRedThreads, phi, mu, c->cphi.p, c->cmu.p, Rphi, Rmu, a, c->g, c->ph, dt, c->sc,
+           c->red_part.p, c->ticket);
+}
+
+// Solve J [dphi; dmu] = -[Rphi; Rmu] by Schur reduction:  (1/dt I - L(diag(a) - kappa/2 L)) dphi = -Rmu + L Rphi,
+// dmu = 2 (a dphi - kappa/2 L dphi + Rphi).   dphi -> c->kx, dmu -> c->dmu.  phi may be null (no ceiling minima).
+int newton_linear_solve(vch2d_ctx* c, const double* Rphi, const double* Rmu, const double* a, const double* phi,
+                        double dt, vch_stats* st) {
+    LAUNCH(c, schur_rhs_kernel, c->eb(), 256, Rphi, Rmu, c->kb.p, c->g);
+    const int its = krylov_solve<false>(c, c->kb.p, a, 1.0 / dt, 0.5 * c->ph.kappa, st);
+    LAUNCH(c, dmu_ceiling_kernel, c->rb(), kRedThreads, c->kx.p, a, Rphi, phi, c->dmu.p, c->g, c->ph, c->sc, c->red_part.p,
+           c->ticket);
+    return its;
+}
+
+// One Newton solve (Forward2_solver.py:323-427).  Inputs: device phi_old, mu_old, w_old, w_new.
+// Result left in c->phi / c->mu.  hist receives ||R|| per iteration.
+void newton_step(vch2d_ctx* c, const double* phi_old, const double* mu_old, const double* w_old, const double* w_new,
+                 double dt, std::vector<double>* hist, vch_stats* st) {
+    const long long n = c->g.n;
+    const int eb = c->eb();
+    LAUNCH(c, step_setup_kernel, eb, 256, phi_old, mu_old, w_old, w_new, c->cphi.p, c->cmu.p, c->mu.p, c->g, c->ph, dt);
+    VCH_CUDA(cudaMemcpyAsync(c->phi.p, phi_old, n * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+    double *phi = c->phi.p, *mu = c->mu.p, *phit = c->phit.p, *mut = c->mut.p;
+    double *Rp = c->Rphi.p, *Rm = c->Rmu.p, *a = c->a.p, *RpT = c->RphiT.p, *RmT = c->RmuT.p, *aT = c->aT.p;
+    eval_residual(c, phi, mu, Rp, Rm, a, dt);
+    fetch_scalars(c);
+    if (st) st->newton_residual_evals += 1;
+    double normR = std::sqrt(c->sc_host->res2);
+    const double tol = 1e-6, eta = 1e-4;
+    const int max_iter = 500;
+    for (int k = 0; k < max_iter; ++k) {
+        if (hist) hist->push_back(normR);
+        if (st) st->last_newton_residual = normR;
+        if (!std::isfinite(normR)) throw Error(VCH_E_NONFINITE, "non-finite Newton residual");
+        if (normR < tol) break;
+        newton_linear_solve(c, Rp, Rm, a, phi, dt, st);
+        fetch_scalars(c);
+        double amax = 2.0;
+        if (std::isfinite(c->sc_host->ceil_pos)) amax = std::min(amax, 0.9 * c->sc_host->ceil_pos);
+        if (std::isfinite(c->sc_host->ceil_neg)) amax = std::min(amax, 0.9 * c->sc_host->ceil_neg);
+        if (!std::isfinite(amax) || amax <= 0.0) amax = 1.0;
+        double alpha = std::min(1.0, amax);
+        double best = INFINITY, best_alpha = 0.0;
+        bool accepted = false;
+        for (int ls = 0; ls < 12; ++ls) {
+            LAUNCH(c, trial_kernel, eb, 256, phi, mu, c->kx.p, c->dmu.p, phit, mut, n, alpha);
+            eval_residual(c, phit, mut, RpT, RmT, aT, dt);
+            fetch_scalars(c);
+            if (st) st->newton_residual_evals += 1;
+            const double nt = std::sqrt(c->sc_host->res2);
+            if (nt < best) { best = nt; best_alpha = alpha; }
+            if (nt <= (1.0 - eta * alpha) * normR) {
+                accepted = true;
+                normR = nt;
+                break;
+            }
+            alpha *= 0.5;
+        }
+        if (!accepted) {
+            if (best < normR) {   // fall back to the best trial (re-evaluated: same arithmetic, same values)
+                LAUNCH(c, trial_kernel, eb, 256, phi, mu, c->kx.p, c->dmu.p, phit, mut, n, best_alpha);
+                eval_residual(c, phit, mut, RpT, RmT, aT, dt);
+                fetch_scalars(c);
+                normR = std::sqrt(c->sc_host->res2);
+                accepted = true;
+            }
+        }
+        if (accepted) {
+            std::swap(phi, phit); std::swap(mu, mut);
+            std::swap(Rp, RpT); std::swap(Rm, RmT); std::swap(a, aT);
+        }
+        if (k == max_iter - 1 && hist) { /* max iterations reached: the reference returns without a final entry */ }
+    }
+    if (phi != c->phi.p) {   // leave the result in c->phi / c->mu
+        std::swap(c->phi.p, c->phit.p); std::swap(c->mu.p, c->mut.p);
+        std::swap(c->phi.n, c->phit.n); std::swap(c->mu.n, c->mut.n);
+    }
+    if (Rp != c->Rphi.p) {
+        std::swap(c->Rphi.p, c->RphiT.p); std::swap(c->Rmu.p, c->RmuT.p); std::swap(c->a.p, c->aT.p);
+    }
+}
+
+// Post-Newton clip + interior mass correction into `dst` (Forward2_solver.py:562-577).
+void post_step(vch2d_ctx* c, const double* phi_new, double* dst) {
+    const double hxhy = c->prm.hx * c->prm.hy;
+    LAUNCH(c, clip_mass_kernel, c->rb(), kRedThreads, phi_new, dst, c->g, c->ph, hxhy, c->sc, 0, c->red_part.p, c->ticket);
+    LAUNCH(c, mass_shift_kernel, c->eb(), 256, dst, c->g, c->ph, c->prm.Lx * c->prm.Ly, c->sc);
+}
+
+void forward_dev(vch2d_ctx* c, const double* phi0, const double* u, int u_rows, int n_steps, const double* dt_steps,
+                 double* phi_hist, double* mu_hist, double* w_hist, vch_stats* st) {
+    const long long n = c->g.n;
+    const size_t bytes = n * sizeof(double);
+    const int eb = c->eb();
+    VCH_CUDA(cudaMemcpyAsync(phi_hist, phi0, bytes, cudaMemcpyDeviceToDevice, c->stream));
+    VCH_CUDA(cudaMemsetAsync(c->w0.p, 0, bytes, c->stream));
+    c->mu_old.alloc(n);
+    double* mu_old = c->mu_old.p;   // mu_0 = initialize_mu(phi_0, w = 0), Forward2_solver.py:520
+    LAUNCH(c, mu_init_kernel, eb, 256, phi_hist, c->w0.p, mu_old, c->g, c->ph);
+    LAUNCH(c, clip_mass_kernel, c->rb(), kRedThreads, phi_hist, (double*)nullptr, c->g, c->ph, c->prm.hx * c->prm.hy, c->sc, 1,
+           c->red_part.p, c->ticket);
+    for (int s = 0; s < n_steps; ++s) {
+        const double dt = dt_steps[s];
+        const double* un = nullptr; const double* un1 = nullptr;
+        if (u && s < u_rows - 1) { un = u + (size_t)s * n; un1 = u + (size_t)(s + 1) * n; }
+        LAUNCH(c, solve_w_kernel, eb, 256, c->w0.p, un, un1, c->w1.p, n, c->prm.gamma / dt);
+        const double* phi_old = phi_hist + (size_t)s * n;
+        newton_step(c, phi_old, mu_old, c->w0.p, c->w1.p, dt, nullptr, st);
+        post_step(c, c->phi.p, phi_hist + (size_t)(s + 1) * n);
+        VCH_CUDA(cudaMemcpyAsync(mu_old, c->mu.p, bytes, cudaMemcpyDeviceToDevice, c->stream));
+        std::swap(c->w0.p, c->w1.p);
+        if (mu_hist) VCH_CUDA(cudaMemcpyAsync(mu_hist + (size_t)s * n, mu_old, bytes, cudaMemcpyDeviceToDevice, c->stream));
+        if (w_hist) VCH_CUDA(cudaMemcpyAsync(w_hist + (size_t)s * n, c->w0.p, bytes, cudaMemcpyDeviceToDevice, c->stream));
+    }
+    VCH_CUDA(cudaGetLastError());
+}
+
+void adjoint_dev(vch2d_ctx* c, const double* phi_hist, int levels, const double* t_hist, double b1, double b2,
+                 const double* phiQ, const double* phiT, double* p_out, double* q_out, double* r_out, vch_stats* st) {
+    const long long n = c->g.n;
+    const size_t bytes = n * sizeof(double);
+    const int eb = c->eb();
+    for (int k = 0; k < 2; ++k) { c->adj_p[k].alloc(n); c->adj_q[k].alloc(n); c->adj_r[k].alloc(n); }
+    auto slot = [&](double* out, DevBuf (&ring)[2], int lvl) { return out ? out + (size_t)lvl * n : ring[lvl & 1].p; };
+    const int M = levels - 1;
+    double* pM = slot(p_out, c->adj_p, M); double* qM = slot(q_out, c->adj_q, M); double* rM = slot(r_out, c->adj_r, M);
+    LAUNCH(c, adj_terminal_rhs_kernel, eb, 256, phi_hist + (size_t)M * n, phiT, c->kb.p, n, b2);
+    SymbolArgs sy{1.0, 0.0, nullptr, c->ph.tau};
+    c->dct.apply(c->stream, c->kb.p, pM, sy, nullptr);          // (I - tau L) p_M = b2 (phi_M - phi_T): exact in the DCT basis
+    LAUNCH(c, adj_qr_kernel, eb, 256, pM, (const double*)nullptr, (const double*)nullptr, qM, rM, c->g, 0.0, 0.0);
+    for (int k = M - 1; k >= 0; --k) {
+        const double dt = t_hist[k + 1] - t_hist[k];
+        double *p0 = slot(p_out, c->adj_p, k), *q0 = slot(q_out, c->adj_q, k), *r0 = slot(r_out, c->adj_r, k);
+        const double *p1 = slot(p_out, c->adj_p, k + 1), *q1 = slot(q_out, c->adj_q, k + 1), *r1 = slot(r_out, c->adj_r, k + 1);
+        if (dt <= 1e-14) {   // backward2_solver.py:214-216
+            VCH_CUDA(cudaMemcpyAsync(p0, p1, bytes, cudaMemcpyDeviceToDevice, c->stream));
+            VCH_CUDA(cudaMemcpyAsync(q0, q1, bytes, cudaMemcpyDeviceToDevice, c->stream));
+            VCH_CUDA(cudaMemcpyAsync(r0, r1, bytes, cudaMemcpyDeviceToDevice, c->stream));
+            continue;
+        }
+        const double* f1 = phi_hist + (size_t)(k + 1) * n; const double* f0 = phi_hist + (size_t)k * n;
+        LAUNCH(c, adj_rhs_kernel, c->rb(), kRedThreads, p1, q1, f1, f0, phiQ ? phiQ + (size_t)(k + 1) * n : nullptr,
+               phiQ ? phiQ + (size_t)k * n : nullptr, c->kb.p, c->a.p, c->g, c->ph, dt, b1, c->sc, c->red_part.p, c->ticket);
+        krylov_solve<true>(c, c->kb.p, c->a.p, 1.0, 0.5 * dt, st);
+        VCH_CUDA(cudaMemcpyAsync(p0, c->kx.p, bytes, cudaMemcpyDeviceToDevice, c->stream));
+        const double den = c->ph.gamma + 0.5 * dt;
+        LAUNCH(c, adj_qr_kernel, eb, 256, p0, q1, r1, q0, r0, c->g, (c->ph.gamma - 0.5 * dt) / den, 0.5 * dt / den);
+    }
+    VCH_CUDA(cudaGetLastError());
+}
+
+// np.trapz weights for abscissae x: w_i = (x_{i+1}-x_{i-1})/2 with one-sided ends.
+std::vector<double> trapz_weights(const double* x, int n) {
+    std::vector<double> w(n, 0.0);
+    for (int i = 0; i + 1 < n; ++i) { const double h = 0.5 * (x[i + 1] - x[i]); w[i] += h; w[i + 1] += h; }
+    return w;
+}
+
+void cost_dev(vch2d_ctx* c, const double* phi_hist, const double* u, const double* phiQ, const double* phiT, int levels,
+              const double* x, const double* y, const double* t, double b1, double b2, double b3, double ksp, double* J_out) {
+    const int nx1 = c->g.nx1, ny1 = c->g.ny1;
+    std::vector<double> w = trapz_weights(t, levels), wx = trapz_weights(x, nx1), wy = trapz_weights(y, ny1);
+    c->small.alloc((size_t)levels + nx1 + ny1);
+    double *dwt = c->small.p, *dwx = dwt + levels, *dwy = dwx + nx1;
+    VCH_CUDA(cudaMemcpyAsync(dwt, w.data(), levels * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    VCH_CUDA(cudaMemcpyAsync(dwx, wx.data(), nx1 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    VCH_CUDA(cudaMemcpyAsync(dwy, wy.data(), ny1 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    VCH_CUDA(cudaStreamSynchronize(c->stream));   // w/wx/wy are pageable host vectors
+    const long long total = (long long)levels * c->g.n;
+    LAUNCH(c, cost_kernel, red_blocks(total), kRedThreads, phi_hist, u, phiQ, phiT, levels, nx1, ny1, dwt, dwx, dwy, c->out4,
+           c->red_part.p, c->ticket);
+    VCH_CUDA(cudaMemcpyAsync(c->out4_host, c->out4, 4 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    VCH_CUDA(cudaStreamSynchronize(c->stream));
+    const double J1 = 0.5 * b1 * c->out4_host[0], J2 = 0.5 * b2 * c->out4_host[1], J3 = 0.5 * b3 * c->out4_host[2],
+                 J4 = ksp * c->out4_host[3];
+    J_out[0] = J1 + J2 + J3 + J4; J_out[1] = J1; J_out[2] = J2; J_out[3] = J3; J_out[4] = J4;
+}
+
+struct SmallScratch {   // context-free reductions (vch_grad_prox / vch_kkt_counts / vch_solve_w)
+    double* part = nullptr; unsigned int* ticket = nullptr; double* out = nullptr; double* out_host = nullptr;
+    void ensure() {
+        if (part) return;
+        VCH_CUDA(cudaMalloc(&part, 8 * kRedBlocksMax * sizeof(double)));
+        VCH_CUDA(cudaMalloc(&ticket, sizeof(unsigned int)));
+        VCH_CUDA(cudaMemset(ticket, 0, sizeof(unsigned int)));
+        VCH_CUDA(cudaMalloc(&out, 8 * sizeof(double)));
+        VCH_CUDA(cudaMallocHost(&out_host, 8 * sizeof(double)));
+    }
+};
+thread_local SmallScratch g_scratch;
+thread_local long long g_free_launches = 0;
+
+void check_params(const vch2d_params* p) {
+    VCH_REQUIRE(p != nullptr, VCH_E_ARG, "null params");
+    VCH_REQUIRE(p->Nx >= 2 && p->Ny >= 2, VCH_E_SHAPE, "Nx, Ny must be >= 2");
+    VCH_REQUIRE(p->hx > 0 && p->hy > 0, VCH_E_ARG, "hx, hy must be positive");
+}
+
+}  // namespace
+
+// ============================================================================================ C ABI
+extern "C" {
+
+const char* vch_last_error(void) { return g_last_error.c_str(); }
+int vch_version(void) { return 100; }
+int vch_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int vch2d_create(const vch2d_params* p, int device, vch2d_ctx** out) {
+    return guarded([&] {
+        check_params(p);
+        VCH_REQUIRE(out != nullptr, VCH_E_ARG, "null out");
+        VCH_REQUIRE(vch_device_count() > device, VCH_E_CUDA, "no CUDA device: vch_b200 has no CPU fallback");
+        VCH_CUDA(cudaSetDevice(device));
+        auto* c = new vch2d_ctx();
+        c->prm = *p; c->device = device;
+        Geo& g = c->g;
+        g.ni = p->Nx + 1; g.no = p->Ny + 1; g.nx1 = p->Nx + 1; g.ny1 = p->Ny + 1;
+        g.n = (long long)g.ni * g.no;
+        g.ihi2 = 1.0 / (p->hx * p->hx); g.iho2 = 1.0 / (p->hy * p->hy);
+        c->ph = Phys{p->tau, p->gamma, p->c1, p->c2, p->kappa, 1.0 - p->delta_sep, std::max(1e-8, 0.5 * p->delta_sep),
+                     1.0 - p->delta_sep * p->delta_sep};
+        const size_t n = (size_t)g.n;
+        for (DevBuf* b : {&c->phi, &c->mu, &c->phit, &c->mut, &c->w0, &c->w1, &c->cphi, &c->cmu, &c->Rphi, &c->Rmu, &c->a,
+                          &c->RphiT, &c->RmuT, &c->aT, &c->kb, &c->kx, &c->kr, &c->kr0, &c->kp, &c->kv, &c->ks, &c->kt,
+                          &c->ktmp, &c->dmu})
+            b->alloc(n);
+        c->red_part.alloc(8 * kRedBlocksMax);
+        VCH_CUDA(cudaMalloc(&c->ticket, sizeof(unsigned int)));
+        VCH_CUDA(cudaMemset(c->ticket, 0, sizeof(unsigned int)));
+        VCH_CUDA(cudaMalloc(&c->sc, sizeof(Scal)));
+        VCH_CUDA(cudaMemset(c->sc, 0, sizeof(Scal)));
+        VCH_CUDA(cudaMallocHost(&c->sc_host, sizeof(Scal)));
+        VCH_CUDA(cudaMalloc(&c->out4, 8 * sizeof(double)));
+        VCH_CUDA(cudaMallocHost(&c->out4_host, 8 * sizeof(double)));
+        c->dct.init(g.no, g.ni, p->hy, p->hx, &c->launches);
+        Scal init{}; init.tol2 = c->krylov_tol * c->krylov_tol;
+        VCH_CUDA(cudaMemcpy(c->sc, &init, sizeof(Scal), cudaMemcpyHostToDevice));
+        *out = c;
+        return VCH_OK;
+    });
+}
+
+void vch2d_destroy(vch2d_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    c->dct.destroy();
+    cudaFree(c->ticket); cudaFree(c->sc); cudaFreeHost(c->sc_host); cudaFree(c->out4); cudaFreeHost(c->out4_host);
+    delete c;
+}
+
+int vch2d_set_stream(vch2d_ctx* c, void* s) {
+    return guarded([&] { VCH_REQUIRE(c, VCH_E_ARG, "null ctx"); c->stream = (cudaStream_t)s; return VCH_OK; });
+}
+
+int vch2d_set_krylov(vch2d_ctx* c, double rel_tol, int max_iter) {
+    return guarded([&] {
+        VCH_REQUIRE(c && rel_tol > 0 && max_iter > 0, VCH_E_ARG, "bad Krylov settings");
+        c->krylov_tol = rel_tol; c->krylov_maxit = max_iter;
+        const double t2 = rel_tol * rel_tol;
+        VCH_CUDA(cudaMemcpyAsync(&c->sc->tol2, &t2, sizeof(double), cudaMemcpyHostToDevice, c->stream));
+        VCH_CUDA(cudaStreamSynchronize(c->stream));
+        return VCH_OK;
+    });
+}
+
+long long vch2d_launch_count(vch2d_ctx* c) { return c ? c->launches : 0; }
+
+int vch2d_apply_laplacian(vch2d_ctx* c, const double* v, double* out, int mem) {
+    return guarded([&] {
+        VCH_REQUIRE(c && v && out, VCH_E_SHAPE, "apply_laplacian: null array");
+        VCH_CUDA(cudaSetDevice(c->device));
+        Stager st(c->stream, mem);
+        const double* dv = st.in(v, c->g.n); double* dout = st.out(out, c->g.n);
+        LAUNCH(c, lap_kernel, c->eb(), 256, dv, dout, c->g, 1.0);
+        VCH_CUDA(cudaGetLastError());
+        st.finish();
+        return VCH_OK;
+    });
+}
+
+int vch2d_initialize_mu(vch2d_ctx* c, const double* phi, const double* w, double* mu_out, int mem) {
+    return guarded([&] {
+        VCH_REQUIRE(c && phi && w && mu_out, VCH_E_SHAPE, "initialize_mu: null array");
+        VCH_CUDA(cudaSetDevice(c->device));
+        Stager st(c->stream, mem);
+        const double *dp = st.in(phi, c->g.n), *dw = st.in(w, c->g.n); double* dm = st.out(mu_out, c->g.n);
+        LAUNCH(c, mu_init_kernel, c->eb(), 256, dp, dw, dm, c->g, c->ph);
+        VCH_CUDA(cudaGetLastError());
+        st.finish();
+        return VCH_OK;
+    });
+}
+
+int vch_solve_w(void* stream, long long count, const double* w_old, double dt, double gamma, const double* u_n,
+                const double* u_np1, double* w_new_out, int mem) {
+    return guarded([&] {
+        VCH_REQUIRE(count > 0 && w_old && w_new_out, VCH_E_SHAPE, "solve_w: bad arguments");
+        VCH_REQUIRE(vch_device_count() > 0, VCH_E_CUDA, "no CUDA device: vch_b200 has no CPU fallback");
+        cudaStream_t s = (cudaStream_t)stream;
+        Stager st(s, mem);
+        const double *dw = st.in(w_old, count), *da = st.in(u_n, count), *db = st.in(u_np1, count);
+        double* dout = st.out(w_new_out, count);
+        solve_w_kernel<<<(int)std::min<long long>((count + 255) / 256, 1 << 20), 256, 0, s>>>(dw, da, db, dout, count, gamma / dt);
+        ++g_free_launches;
+        VCH_CUDA(cudaGetLastError());
+        st.finish();
+        return VCH_OK;
+    });
+}
+
+int vch2d_residual(vch2d_ctx* c, const double* phi_new, const double* phi_old, const double* mu_new, const double* mu_old,
+                   const double* w_new, const double* w_old, double dt, double* Rphi_out, double* Rmu_out, int mem) {
+    return guarded([&] {
+        VCH_REQUIRE(c && phi_new && phi_old && mu_new && mu_old && w_new && w_old && Rphi_out && Rmu_out, VCH_E_SHAPE,
+                    "residual: null array");
+        VCH_CUDA(cudaSetDevice(c->device));
+        const long long n = c->g.n;
+        Stager st(c->stream, mem);
+        const double *a = st.in(phi_new, n), *b = st.in(phi_old, n), *m1 = st.in(mu_new, n), *m0 = st.in(mu_old, n),
+                     *w1 = st.in(w_new, n), *w0 = st.in(w_old, n);
+        double *rp = st.out(Rphi_out, n), *rm = st.out(Rmu_out, n);
+        LAUNCH(c, residual_full_kernel, c->eb(), 256, a, b, m1, m0, w1, w0, rp, rm, c->g, c->ph, dt);
+        VCH_CUDA(cudaGetLastError());
+        st.finish();
+        return VCH_OK;
+    });
+}
+
+int vch2d_jacobian_solve(vch2d_ctx* c, const double* phi, double dt, const double* Rphi, const double* Rmu,
+                         double* dphi_out, double* dmu_out, int* its_out, int mem) {
+    return guarded([&] {
+        VCH_REQUIRE(c && phi && Rphi && Rmu && dphi_out && dmu_out, VCH_E_SHAPE, "jacobian_solve: null array");
+        VCH_CUDA(cudaSetDevice(c->device));
+        const long long n = c->g.n;
+        Stager st(c->stream, mem);
+        const double *dp = st.in(phi, n), *rp = st.in(Rphi, n), *rm = st.in(Rmu, n);
+        double *o1 = st.out(dphi_out, n), *o2 = st.out(dmu_out, n);
+        LAUNCH(c, jac_diag_kernel, c->rb(), kRedThreads, dp, c->a.p, c->g, c->ph, dt, c->sc, c->red_part.p, c->ticket);
+        vch_stats s{};
+        const int its = newton_linear_solve(c, rp, rm, c->a.p, nullptr, dt, &s);
+        VCH_CUDA(cudaMemcpyAsync(o1, c->kx.p, n * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+        VCH_CUDA(cudaMemcpyAsync(o2, c->dmu.p, n * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+        if (its_out) *its_out = its;
+        st.finish();
+        VCH_REQUIRE(s.krylov_stalls == 0, VCH_E_KRYLOV, "jacobian_solve: BiCGStab stopped above tolerance");
+        return VCH_OK;
+    });
+}
+
+int vch2d_newton(vch2d_ctx* c, const double* phi_old, const double* mu_old, const double* w_old, const double* w_new,
+                 double dt, double* phi_new_out, double* mu_new_out, double* res_hist, int hist_cap, int* n_hist,
+                 vch_stats* stats, int mem) {
+    return guarded([&] {
+        VCH_REQUIRE(c && phi_old && mu_old && w_old && w_new && phi_new_out && mu_new_out, VCH_E_SHAPE, "newton: null array");
+        VCH_CUDA(cudaSetDevice(c->device));
+        const long long n = c->g.n;
+        const long long l0 = c->launches;
+        Stager st(c->stream, mem);
+        const double *p0 = st.in(phi_old, n), *m0 = st.in(mu_old, n), *w0 = st.in(w_old, n), *w1 = st.in(w_new, n);
+        double *po = st.out(phi_new_out, n), *mo = st.out(mu_new_out, n);
+        std::vector<double> hist;
+        vch_stats local{}; vch_stats* s = stats ? stats : &local;
+        newton_step(c, p0, m0, w0, w1, dt, &hist, s);
+        VCH_CUDA(cudaMemcpyAsync(po, c->phi.p, n * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+        VCH_CUDA(cudaMemcpyAsync(mo, c->mu.p, n * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+        st.finish();
+        if (n_hist) *n_hist = (int)hist.size();
+        if (res_hist) for (int i = 0; i < (int)hist.size() && i < hist_cap; ++i) res_hist[i] = hist[i];
+        s->kernel_launches += c->launches - l0;
+        return VCH_OK;
+    });
+}
+
+int vch2d_forward(vch2d_ctx* c, const double* phi0, const double* u, int u_rows, int n_steps, const double* dt_steps,
+                  double* phi_hist_out, double* mu_hist_out, double* w_hist_out, vch_stats* stats, int mem) {
+    return guarded([&] {
+        VCH_REQUIRE(c && phi0 && phi_hist_out && dt_steps && n_steps >= 0, VCH_E_SHAPE, "forward: bad arguments");
+        VCH_REQUIRE(!u || u_rows >= 1, VCH_E_SHAPE, "forward: control needs at least one row");
+        VCH_CUDA(cudaSetDevice(c->device));
+        const long long n = c->g.n, l0 = c->launches;
+        Stager st(c->stream, mem);
+        const double* dphi0 = st.in(phi0, n);
+        const double* du = st.in(u, (size_t)u_rows * n);
+        double* dh = st.out(phi_hist_out, (size_t)(n_steps + 1) * n);
+        double* dm = st.out(mu_hist_out, (size_t)n_steps * n);
+        double* dw = st.out(w_hist_out, (size_t)n_steps * n);
+        vch_stats local{}; vch_stats* s = stats ? stats : &local;
+        forward_dev(c, dphi0, du, u_rows, n_steps, dt_steps, dh, dm, dw, s);
+        st.finish();
+        s->kernel_launches += c->launches - l0;
+        return VCH_OK;
+    });
+}
+
+int vch2d_adjoint(vch2d_ctx* c, const double* phi_hist, int levels, const double* t_hist, double b1, double b2,
+                  const double* phiQ, const double* phiT, double* p_out, double* q_out, double* r_out, vch_stats* stats,
+                  int mem) {
+    return guarded([&] {
+        VCH_REQUIRE(c && phi_hist && t_hist && r_out && levels >= 1, VCH_E_SHAPE, "adjoint: bad arguments");
+        VCH_CUDA(cudaSetDevice(c->device));
+        const long long n = c->g.n, l0 = c->launches;
+        const size_t tot = (size_t)levels * n;
+        Stager st(c->stream, mem);
+        const double *dh = st.in(phi_hist, tot), *dq = st.in(phiQ, tot), *dT = st.in(phiT, n);
+        double *po = st.out(p_out, tot), *qo = st.out(q_out, tot), *ro = st.out(r_out, tot);
+        vch_stats local{}; vch_stats* s = stats ? stats : &local;
+        adjoint_dev(c, dh, levels, t_hist, b1, b2, dq, dT, po, qo, ro, s);
+        st.finish();
+        s->kernel_launches += c->launches - l0;
+        return VCH_OK;
+    });
+}
+
+int vch2d_cost(vch2d_ctx* c, const double* phi_hist, const double* u, const double* phiQ, const double* phiT, int levels,
+               const double* x, const double* y, const double* t_hist, double b1, double b2, double b3, double ksp,
+               double* J_out, int mem) {
+    return guarded([&] {
+        VCH_REQUIRE(c && phi_hist && x && y && t_hist && J_out && levels >= 1, VCH_E_SHAPE, "cost: bad arguments");
+        VCH_CUDA(cudaSetDevice(c->device));
+        const long long n = c->g.n;
+        const size_t tot = (size_t)levels * n;
+        Stager st(c->stream, mem);
+        const double *dh = st.in(phi_hist, tot), *du = st.in(u, tot), *dq = st.in(phiQ, tot), *dT = st.in(phiT, n);
+        cost_dev(c, dh, du, dq, dT, levels, x, y, t_hist, b1, b2, b3, ksp, J_out);
+        st.finish();
+        return VCH_OK;
+    });
+}
+
+int vch_grad_prox(void* stream, long long count, const double* u, const double* r, double b3, double alpha, double ksp,
+                  double umin, double umax, double* grad_out, double* u_new_out, double* red_out, int mem) {
+    return guarded([&] {
+        VCH_REQUIRE(count > 0 && u && r && u_new_out, VCH_E_SHAPE, "grad_prox: bad arguments");
+        VCH_REQUIRE(vch_device_count() > 0, VCH_E_CUDA, "no CUDA device: vch_b200 has no CPU fallback");
+        cudaStream_t s = (cudaStream_t)stream;
+        g_scratch.ensure();
+        Stager st(s, mem);
+        const double *du = st.in(u, count), *dr = st.in(r, count);
+        double *dg = st.out(grad_out, count), *dn = st.out(u_new_out, count);
+        grad_prox_kernel<<<red_blocks(count), kRedThreads, 0, s>>>(du, dr, dg, dn, count, b3, alpha, ksp, umin, umax,
+                                                                    g_scratch.out, g_scratch.part, g_scratch.ticket);
+        ++g_free_launches;
+        VCH_CUDA(cudaGetLastError());
+        VCH_CUDA(cudaMemcpyAsync(g_scratch.out_host, g_scratch.out, 4 * sizeof(double), cudaMemcpyDeviceToHost, s));
+        st.finish();
+        VCH_CUDA(cudaStreamSynchronize(s));
+        if (red_out) for (int k = 0; k < 4; ++k) red_out[k] = g_scratch.out_host[k];
+        return VCH_OK;
+    });
+}
+
+int vch_kkt_counts(void* stream, long long count, const double* u, const double* r, double ksp, double tol,
+                   long long* counts_out, int mem) {
+    return guarded([&] {
+        VCH_REQUIRE(count > 0 && u && r && counts_out, VCH_E_SHAPE, "kkt_counts: bad arguments");
+        VCH_REQUIRE(vch_device_count() > 0, VCH_E_CUDA, "no CUDA device: vch_b200 has no CPU fallback");
+        cudaStream_t s = (cudaStream_t)stream;
+        g_scratch.ensure();
+        Stager st(s, mem);
+        const double *du = st.in(u, count), *dr = st.in(r, count);
+        kkt_kernel<<<red_blocks(count), kRedThreads, 0, s>>>(du, dr, count, ksp, tol, g_scratch.out, g_scratch.part,
+                                                              g_scratch.ticket);
+        ++g_free_launches;
+        VCH_CUDA(cudaGetLastError());
+        VCH_CUDA(cudaMemcpyAsync(g_scratch.out_host, g_scratch.out, 3 * sizeof(double), cudaMemcpyDeviceToHost, s));
+        st.finish();
+        VCH_CUDA(cudaStreamSynchronize(s));
+        for (int k = 0; k < 3; ++k) counts_out[k] = (long long)(g_scratch.out_host[k] + 0.5);
+        return VCH_OK;
+    });
+}
+
+int vch2d_pgd_iteration(vch2d_ctx* c, int levels, const double* t_hist, const double* dt_steps, const double* x,
+                        const double* y, const double* u, const double* phi_hist, const double* phiQ, const double* phiT,
+                        double b1, double b2, double b3, double ksp, double umin, double umax, double alpha,
+                        double* u_new_out, double* phi_hist_out, double* r_out, double* J_out, double* red_out,
+                        vch_stats* stats, int mem) {
+    return guarded([&] {
+        VCH_REQUIRE(c && levels >= 2 && t_hist && dt_steps && x && y && u && phi_hist && u_new_out && phi_hist_out && J_out,
+                    VCH_E_SHAPE, "pgd_iteration: bad arguments");
+        VCH_CUDA(cudaSetDevice(c->device));
+        const long long n = c->g.n, l0 = c->launches;
+        const size_t tot = (size_t)levels * n;
+        Stager st(c->stream, mem);
+        const double *du = st.in(u, tot), *dh = st.in(phi_hist, tot), *dq = st.in(phiQ, tot), *dT = st.in(phiT, n);
+        double *dun = st.out(u_new_out, tot), *dhn = st.out(phi_hist_out, tot);
+        double* dr = st.out(r_out, tot);
+        DevBuf rscratch;
+        if (!dr) { rscratch.alloc(tot); dr = rscratch.p; }
+        vch_stats local{}; vch_stats* s = stats ? stats : &local;
+        // (1) adjoint sweep over the stored trajectory                       GD2_configured.py:299
+        adjoint_dev(c, dh, levels, t_hist, b1, b2, dq, dT, nullptr, nullptr, dr, s);
+        // (2) gradient + soft-threshold prox + box, with the driver's norms  GD2_configured.py:304-305, :375
+        LAUNCH(c, grad_prox_kernel, red_blocks((long long)tot), kRedThreads, du, dr, (double*)nullptr, dun, (long long)tot, b3,
+               alpha, ksp, umin, umax, c->out4 + 4, c->red_part.p, c->ticket);
+        // (3) forward solve under the new control                            GD2_configured.py:309
+        forward_dev(c, dh, dun, levels, levels - 1, dt_steps, dhn, nullptr, nullptr, s);
+        // (4) cost functional                                                GD2_configured.py:312
+        cost_dev(c, dhn, dun, dq, dT, levels, x, y, t_hist, b1, b2, b3, ksp, J_out);
+        if (red_out) {
+            VCH_CUDA(cudaMemcpyAsync(c->out4_host + 4, c->out4 + 4, 4 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+            VCH_CUDA(cudaStreamSynchronize(c->stream));
+            for (int k = 0; k < 4; ++k) red_out[k] = c->out4_host[4 + k];
+        }
+        st.finish();
+        s->kernel_launches += c->launches - l0;
+        return VCH_OK;
+    });
+}
+
+}  // extern "C"

@@ -1,0 +1,470 @@
+// 2D kernels: Neumann stencils, Newton residual, Schur / adjoint operators, BiCGStab vector updates,
+// post-step mass correction, adjoint recurrences.  All fp64, HBM/L2-bound; reductions are deterministic
+// (vch_common.cuh).  Fields are flat arrays of n = no*ni doubles; the Laplacian acts on the (no, ni) view
+// with the contiguous axis ni = Nx+1 (spacing hx) and the strided axis no = Ny+1 (spacing hy) — exactly the
+// operator kron(I_{Ny+1}, L_x) + kron(L_y, I_{Nx+1}) of the reference (Forward2_solver.py:125-137).
+#pragma once
+#include "vch_common.cuh"
+#include "vch_dct.cuh"
+
+namespace vch {
+
+struct Geo {
+    int no, ni;          // Laplacian view
+    int nx1, ny1;        // array view (Nx+1, Ny+1) used by the trapezoid weights
+    long long n;
+    double iho2, ihi2;   // 1/h_outer^2, 1/h_inner^2
+};
+
+struct Phys {
+    double tau, gamma, c1, c2, kappa, lim /* 1-delta_sep */, eps_log /* max(1e-8, delta_sep/2) */, dsq /* 1-delta_sep^2 */;
+};
+
+// Device-resident scalars.  Host reads them through a pinned mirror.
+struct Scal {
+    double rho, rho_new, alpha, omega;
+    double r0v, ts, tt, rr, thr2, bnorm2;
+    double res2, amin, amax, abar;
+    double ceil_pos, ceil_neg;
+    double mass, wint, mass0;
+    double tol2;
+    int done, iters, nonfinite, pad;
+};
+
+__device__ __forceinline__ double lap_g(const double* __restrict__ v, int o, int i, const Geo& g) {
+    const double c = v[(size_t)o * g.ni + i];
+    const int im = (i > 0) ? i - 1 : 1, ip = (i < g.ni - 1) ? i + 1 : g.ni - 2;
+    const int om = (o > 0) ? o - 1 : 1, op = (o < g.no - 1) ? o + 1 : g.no - 2;
+    const double a = (v[(size_t)o * g.ni + ip] - c) + (v[(size_t)o * g.ni + im] - c);
+    const double b = (v[(size_t)op * g.ni + i] - c) + (v[(size_t)om * g.ni + i] - c);
+    return a * g.ihi2 + b * g.iho2;
+}
+
+__device__ __forceinline__ double flory_log(double phi, double eps) {
+    const double s = fmin(fmax(phi, -1.0 + eps), 1.0 - eps);
+    return log((1.0 + s) / (1.0 - s));
+}
+
+// ---------------------------------------------------------------------------------- elementwise / stencil
+__global__ void lap_kernel(const double* __restrict__ v, double* __restrict__ out, Geo g, double scale) {
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < g.n; idx += (long long)gridDim.x * blockDim.x) {
+        const int o = (int)(idx / g.ni), i = (int)(idx - (long long)o * g.ni);
+        out[idx] = scale * lap_g(v, o, i, g);
+    }
+}
+
+__global__ void solve_w_kernel(const double* __restrict__ w0, const double* __restrict__ un, const double* __restrict__ un1,
+                               double* __restrict__ w1, long long n, double gdt) {
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (long long)gridDim.x * blockDim.x) {
+        const double a = un ? un[idx] : 0.0, b = un1 ? un1[idx] : 0.0;
+        // no FMA contraction: bit-identical to the reference's NumPy expression (its tests ask rtol 1e-15)
+        w1[idx] = __ddiv_rn(__dadd_rn(__dmul_rn(gdt - 0.5, w0[idx]), __dmul_rn(0.5, __dadd_rn(b, a))), gdt + 0.5);
+    }
+}
+
+__global__ void mu_init_kernel(const double* __restrict__ phi, const double* __restrict__ w, double* __restrict__ mu, Geo g, Phys p) {
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < g.n; idx += (long long)gridDim.x * blockDim.x) {
+        const int o = (int)(idx / g.ni), i = (int)(idx - (long long)o * g.ni);
+        const double f = phi[idx];
+        mu[idx] = -p.kappa * lap_g(phi, o, i, g) + p.c1 * flory_log(f, p.eps_log) - 2.0 * p.c2 * f - w[idx];
+    }
+}
+
+// Per-step constants of the Newton residual and the reference's initial guess for mu (Forward2_solver.py:351):
+//   cphi = -tau phi0/dt - kappa/2 L phi0 - 2 c2 phi0 - mu0/2 - (w1+w0)/2,   cmu = -phi0/dt - 1/2 L mu0
+__global__ void step_setup_kernel(const double* __restrict__ phi0, const double* __restrict__ mu0,
+                                  const double* __restrict__ w0, const double* __restrict__ w1,
+                                  double* __restrict__ cphi, double* __restrict__ cmu, double* __restrict__ mu_guess,
+                                  Geo g, Phys p, double dt) {
+    const double idt = 1.0 / dt;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < g.n; idx += (long long)gridDim.x * blockDim.x) {
+        const int o = (int)(idx / g.ni), i = (int)(idx - (long long)o * g.ni);
+        const double f = phi0[idx], m = mu0[idx], wa = w0[idx], wb = w1[idx];
+        const double lf = lap_g(phi0, o, i, g), lm = lap_g(mu0, o, i, g);
+        cphi[idx] = -p.tau * f * idt - 0.5 * p.kappa * lf - 2.0 * p.c2 * f - 0.5 * m - 0.5 * (wb + wa);
+        cmu[idx] = -f * idt - 0.5 * lm;
+        if (mu_guess) mu_guess[idx] = -p.kappa * lf + p.c1 * flory_log(f, p.eps_log) - 2.0 * p.c2 * f - wb;
+    }
+}
+
+// [R_phi; R_mu], the Jacobian diagonal a = tau/dt + 2c1/(1 - min(phi^2, 1-delta^2)) and ||R||^2, min a, max a.
+__global__ void residual_kernel(const double* __restrict__ phi, const double* __restrict__ mu,
+                                const double* __restrict__ cphi, const double* __restrict__ cmu,
+                                double* __restrict__ Rphi, double* __restrict__ Rmu, double* __restrict__ a,
+                                Geo g, Phys p, double dt, Scal* sc, double* part, unsigned int* ticket) {
+    const double idt = 1.0 / dt, tdt = p.tau / dt;
+    double v[3] = {0.0, INFINITY, -INFINITY};
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < g.n; idx += (long long)gridDim.x * blockDim.x) {
+        const int o = (int)(idx / g.ni), i = (int)(idx - (long long)o * g.ni);
+        const double f = phi[idx], m = mu[idx];
+        const double rp = tdt * f - 0.5 * p.kappa * lap_g(phi, o, i, g) + p.c1 * flory_log(f, p.eps_log) - 0.5 * m + cphi[idx];
+        const double rm = f * idt - 0.5 * lap_g(mu, o, i, g) + cmu[idx];
+        const double d = tdt + 2.0 * p.c1 / (1.0 - fmin(f * f, p.dsq));
+        Rphi[idx] = rp; Rmu[idx] = rm;
+        if (a) a[idx] = d;
+        v[0] += rp * rp + rm * rm;
+        v[1] = fmin(v[1], d); v[2] = fmax(v[2], d);
+    }
+    const int op[3] = {0, 1, 2};
+    double tot[3];
+    if (grid_reduce<3>(v, op, part, ticket, tot) && threadIdx.x == 0) {
+        sc->res2 = tot[0]; sc->amin = tot[1]; sc->amax = tot[2]; sc->abar = sqrt(tot[1] * tot[2]);
+        if (!isfinite(tot[0])) sc->nonfinite = 1;
+    }
+}
+
+// Reference-form residual for the test-level entry point (all six fields given explicitly).
+__global__ void residual_full_kernel(const double* __restrict__ phi, const double* __restrict__ phi0,
+                                     const double* __restrict__ mu, const double* __restrict__ mu0,
+                                     const double* __restrict__ w1, const double* __restrict__ w0,
+                                     double* __restrict__ Rphi, double* __restrict__ Rmu, Geo g, Phys p, double dt) {
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < g.n; idx += (long long)gridDim.x * blockDim.x) {
+        const int o = (int)(idx / g.ni), i = (int)(idx - (long long)o * g.ni);
+        const double f = phi[idx], f0 = phi0[idx];
+        Rphi[idx] = p.tau * (f - f0) / dt - 0.5 * p.kappa * (lap_g(phi, o, i, g) + lap_g(phi0, o, i, g))
+                    + (p.c1 * flory_log(f, p.eps_log) - 2.0 * p.c2 * f0) - 0.5 * (mu[idx] + mu0[idx]) - 0.5 * (w1[idx] + w0[idx]);
+        Rmu[idx] = (f - f0) / dt - 0.5 * (lap_g(mu, o, i, g) + lap_g(mu0, o, i, g));
+    }
+}
+
+// Jacobian diagonal only (test-level jacobian_solve).
+__global__ void jac_diag_kernel(const double* __restrict__ phi, double* __restrict__ a, Geo g, Phys p, double dt,
+                                Scal* sc, double* part, unsigned int* ticket) {
+    double v[2] = {INFINITY, -INFINITY};
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < g.n; idx += (long long)gridDim.x * blockDim.x) {
+        const double f = phi[idx];
+        const double d = p.tau / dt + 2.0 * p.c1 / (1.0 - fmin(f * f, p.dsq));
+        a[idx] = d; v[0] = fmin(v[0], d); v[1] = fmax(v[1], d);
+    }
+    const int op[2] = {1, 2};
+    double tot[2];
+    if (grid_reduce<2>(v, op, part, ticket, tot) && threadIdx.x == 0) {
+        sc->amin = tot[0]; sc->amax = tot[1]; sc->abar = sqrt(tot[0] * tot[1]);
+    }
+}
+
+// Right-hand side of the Schur-reduced Newton system: b = -R_mu + L R_phi.
+__global__ void schur_rhs_kernel(const double* __restrict__ Rphi, const double* __restrict__ Rmu, double* __restrict__ b, Geo g) {
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < g.n; idx += (long long)gridDim.x * blockDim.x) {
+        const int o = (int)(idx / g.ni), i = (int)(idx - (long long)o * g.ni);
+        b[idx] = lap_g(Rphi, o, i, g) - Rmu[idx];
+    }
+}
+
+// Operator apply with a two-level shared-memory halo tile.
+//   ADJ = false (forward Schur complement):  z = a.x - c2 L x ;  y = c0 x - L z        (= (c0 I - L diag(a) + c2 L^2) x)
+//   ADJ = true  (adjoint CN operator):       z = L x          ;  y = c0 x - a.z + c2 L z (= (c0 I - diag(a) L + c2 L^2) x)
+constexpr int kTO = 16, kTI = 64;
+template <bool ADJ>
+__global__ void __launch_bounds__(256) op_apply_kernel(const double* __restrict__ x, const double* __restrict__ a,
+                                                        double* __restrict__ y, Geo g, double c0, double c2,
+                                                        const int* __restrict__ done) {
+    if (done && *done) return;
+    __shared__ double sx[kTO + 4][kTI + 4];
+    __shared__ double sz[kTO + 2][kTI + 2];
+    const int o0 = blockIdx.y * kTO, i0 = blockIdx.x * kTI;
+    for (int e = threadIdx.x; e < (kTO + 4) * (kTI + 4); e += 256) {
+        const int to = e / (kTI + 4), ti = e - to * (kTI + 4);
+        const int ro = o0 - 2 + to, ri = i0 - 2 + ti;
+        double val = 0.0;
+        if (ro >= -2 && ro <= g.no + 1 && ri >= -2 && ri <= g.ni + 1)
+            val = x[(size_t)mirror(ro, g.no) * g.ni + mirror(ri, g.ni)];
+        sx[to][ti] = val;
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < (kTO + 2) * (kTI + 2); e += 256) {
+        const int to = e / (kTI + 2), ti = e - to * (kTI + 2);
+        const int ro = o0 - 1 + to, ri = i0 - 1 + ti;
+        const double c = sx[to + 1][ti + 1];
+        const double lx = ((sx[to + 1][ti + 2] - c) + (sx[to + 1][ti] - c)) * g.ihi2 + ((sx[to + 2][ti + 1] - c) + (sx[to][ti + 1] - c)) * g.iho2;
+        double z;
+        if (ADJ) z = lx;
+        else {
+            double av = 0.0;
+            if (ro >= -1 && ro <= g.no && ri >= -1 && ri <= g.ni) av = a[(size_t)mirror(ro, g.no) * g.ni + mirror(ri, g.ni)];
+            z = av * c - c2 * lx;
+        }
+        sz[to][ti] = z;
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < kTO * kTI; e += 256) {
+        const int to = e / kTI, ti = e - to * kTI;
+        const int o = o0 + to, i = i0 + ti;
+        if (o < g.no && i < g.ni) {
+            const double c = sz[to + 1][ti + 1];
+            const double lz = ((sz[to + 1][ti + 2] - c) + (sz[to + 1][ti] - c)) * g.ihi2 + ((sz[to + 2][ti + 1] - c) + (sz[to][ti + 1] - c)) * g.iho2;
+            const double xv = sx[to + 2][ti + 2];
+            const size_t idx = (size_t)o * g.ni + i;
+            y[idx] = ADJ ? (c0 * xv - a[idx] * c + c2 * lz) : (c0 * xv - lz);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------- BiCGStab vector kernels
+__global__ void bicg_init_kernel(const double* __restrict__ r, double* __restrict__ r0, double* __restrict__ p,
+                                 double* __restrict__ v, double* __restrict__ x, long long n, Scal* sc, double* part,
+                                 unsigned int* ticket) {
+    double acc[1] = {0.0};
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (long long)gridDim.x * blockDim.x) {
+        const double rv = r[idx];
+        r0[idx] = rv; p[idx] = 0.0; v[idx] = 0.0; x[idx] = 0.0;
+        acc[0] += rv * rv;
+    }
+    const int op[1] = {0};
+    double tot[1];
+    if (grid_reduce<1>(acc, op, part, ticket, tot) && threadIdx.x == 0) {
+        sc->bnorm2 = tot[0]; sc->rr = tot[0]; sc->rho_new = tot[0];
+        sc->rho = 1.0; sc->alpha = 1.0; sc->omega = 1.0;
+        sc->thr2 = sc->tol2 * tot[0];
+        sc->iters = 0;
+        sc->done = (tot[0] == 0.0 || !isfinite(tot[0])) ? 1 : 0;
+        if (!isfinite(tot[0])) sc->nonfinite = 1;
+    }
+}
+
+__global__ void bicg_p_kernel(const double* __restrict__ r, double* __restrict__ p, const double* __restrict__ v,
+                              long long n, const Scal* __restrict__ sc) {
+    if (sc->done) return;
+    const double beta = (sc->rho_new / sc->rho) * (sc->alpha / sc->omega), om = sc->omega;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (long long)gridDim.x * blockDim.x)
+        p[idx] = r[idx] + beta * (p[idx] - om * v[idx]);
+}
+
+__global__ void bicg_dot1_kernel(const double* __restrict__ r0, const double* __restrict__ v, long long n, Scal* sc,
+                                 double* part, unsigned int* ticket) {
+    if (sc->done) return;
+    double acc[1] = {0.0};
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (long long)gridDim.x * blockDim.x)
+        acc[0] += r0[idx] * v[idx];
+    const int op[1] = {0};
+    double tot[1];
+    if (grid_reduce<1>(acc, op, part, ticket, tot) && threadIdx.x == 0) {
+        sc->r0v = tot[0]; sc->alpha = sc->rho_new / tot[0]; sc->rho = sc->rho_new;
+    }
+}
+
+__global__ void bicg_s_kernel(const double* __restrict__ r, const double* __restrict__ v, double* __restrict__ s,
+                              long long n, const Scal* __restrict__ sc) {
+    if (sc->done) return;
+    const double al = sc->alpha;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (long long)gridDim.x * blockDim.x)
+        s[idx] = r[idx] - al * v[idx];
+}
+
+__global__ void bicg_dot2_kernel(const double* __restrict__ t, const double* __restrict__ s, long long n, Scal* sc,
+                                 double* part, unsigned int* ticket) {
+    if (sc->done) return;
+    double acc[2] = {0.0, 0.0};
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (long long)gridDim.x * blockDim.x) {
+        const double tv = t[idx];
+        acc[0] += tv * s[idx]; acc[1] += tv * tv;
+    }
+    const int op[2] = {0, 0};
+    double tot[2];
+    if (grid_reduce<2>(acc, op, part, ticket, tot) && threadIdx.x == 0) {
+        sc->ts = tot[0]; sc->tt = tot[1]; sc->omega = (tot[1] > 0.0) ? tot[0] / tot[1] : 0.0;
+    }
+}
+
+__global__ void bicg_x_kernel(double* __restrict__ x, double* __restrict__ r, const double* __restrict__ p,
+                              const double* __restrict__ s, const double* __restrict__ t, const double* __restrict__ r0,
+                              long long n, Scal* sc, double* part, unsigned int* ticket) {
+    if (sc->done) return;
+    const double al = sc->alpha, om = sc->omega;
+    double acc[2] = {0.0, 0.0};
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (long long)gridDim.x * blockDim.x) {
+        const double sv = s[idx];
+        x[idx] += al * p[idx] + om * sv;
+        const double rv = sv - om * t[idx];
+        r[idx] = rv;
+        acc[0] += rv * rv; acc[1] += r0[idx] * rv;
+    }
+    const int op[2] = {0, 0};
+    double tot[2];
+    if (grid_reduce<2>(acc, op, part, ticket, tot) && threadIdx.x == 0) {
+        sc->rr = tot[0]; sc->rho_new = tot[1]; sc->iters += 1;
+        const bool bad = !isfinite(tot[0]) || !isfinite(tot[1]);
+        if (bad) sc->nonfinite = 1;
+        if (bad || tot[0] <= sc->thr2) sc->done = 1;
+    }
+}
+
+// ---------------------------------------------------------------------------------- Newton step pieces
+// dmu = 2 (a dphi - kappa/2 L dphi + R_phi) and the step ceiling minima (Forward2_solver.py:377-391).
+__global__ void dmu_ceiling_kernel(const double* __restrict__ dphi, const double* __restrict__ a,
+                                   const double* __restrict__ Rphi, const double* __restrict__ phi,
+                                   double* __restrict__ dmu, Geo g, Phys p, Scal* sc, double* part, unsigned int* ticket) {
+    double v[2] = {INFINITY, INFINITY};
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < g.n; idx += (long long)gridDim.x * blockDim.x) {
+        const int o = (int)(idx / g.ni), i = (int)(idx - (long long)o * g.ni);
+        const double d = dphi[idx];
+        dmu[idx] = 2.0 * (a[idx] * d - 0.5 * p.kappa * lap_g(dphi, o, i, g) + Rphi[idx]);
+        if (phi) {
+            const double f = phi[idx];
+            if (d > 0.0) v[0] = fmin(v[0], (p.lim - f) / d);
+            else if (d < 0.0) v[1] = fmin(v[1], (-p.lim - f) / d);
+        }
+    }
+    const int op[2] = {1, 1};
+    double tot[2];
+    if (grid_reduce<2>(v, op, part, ticket, tot) && threadIdx.x == 0) { sc->ceil_pos = tot[0]; sc->ceil_neg = tot[1]; }
+}
+
+__global__ void trial_kernel(const double* __restrict__ phi, const double* __restrict__ mu, const double* __restrict__ dphi,
+                             const double* __restrict__ dmu, double* __restrict__ phit, double* __restrict__ mut,
+                             long long n, double alpha) {
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (long long)gridDim.x * blockDim.x) {
+        phit[idx] = phi[idx] + alpha * dphi[idx];
+        mut[idx] = mu[idx] + alpha * dmu[idx];
+    }
+}
+
+// Weighted mass of clip(phi) and the interior weight (Forward2_solver.py:562-571).  WRITE_CLIP stores the clipped field.
+__global__ void clip_mass_kernel(const double* __restrict__ phin, double* __restrict__ phic, Geo g, Phys p, double hxhy,
+                                 Scal* sc, int set_mass0, double* part, unsigned int* ticket) {
+    double v[2] = {0.0, 0.0};
+    const double thr = p.lim - 5e-3;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < g.n; idx += (long long)gridDim.x * blockDim.x) {
+        const int ix = (int)(idx / g.ny1), iy = (int)(idx - (long long)ix * g.ny1);
+        const double w = hxhy * ((ix == 0 || ix == g.nx1 - 1) ? 0.5 : 1.0) * ((iy == 0 || iy == g.ny1 - 1) ? 0.5 : 1.0);
+        double f = phin[idx];
+        if (!set_mass0) { f = fmin(fmax(f, -p.lim), p.lim); phic[idx] = f; }
+        v[0] += w * f;
+        if (fabs(f) < thr) v[1] += w;
+    }
+    const int op[2] = {0, 0};
+    double tot[2];
+    if (grid_reduce<2>(v, op, part, ticket, tot) && threadIdx.x == 0) {
+        if (set_mass0) sc->mass0 = tot[0];
+        else { sc->mass = tot[0]; sc->wint = tot[1]; }
+    }
+}
+
+// Interior-only mass shift (uniform shift + re-clip when there is no interior), Forward2_solver.py:566-577.
+__global__ void mass_shift_kernel(double* __restrict__ phi, Geo g, Phys p, double area, const Scal* __restrict__ sc) {
+    const double err = sc->mass - sc->mass0;
+    if (!(fabs(err) > 1e-16)) return;
+    const double wint = sc->wint, thr = p.lim - 5e-3;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < g.n; idx += (long long)gridDim.x * blockDim.x) {
+        double f = phi[idx];
+        if (wint > 0.0) { if (fabs(f) < thr) phi[idx] = f - err / wint; }
+        else phi[idx] = fmin(fmax(f - err / area, -p.lim), p.lim);
+    }
+}
+
+// ---------------------------------------------------------------------------------- adjoint sweep pieces
+__device__ __forceinline__ double fpp_dev(double phi, double c1, double c2) {
+    const double s = fmin(fmax(phi, -1.0 + 1e-8), 1.0 - 1e-8);
+    return 2.0 * c1 / (1.0 - s * s) - 2.0 * c2;
+}
+
+__global__ void adj_terminal_rhs_kernel(const double* __restrict__ phiM, const double* __restrict__ phiT,
+                                        double* __restrict__ b, long long n, double b2) {
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (long long)gridDim.x * blockDim.x)
+        b[idx] = b2 * (phiM[idx] - (phiT ? phiT[idx] : 0.0));
+}
+
+// rhs = B(phi_{n+1}) p_{n+1} + src with L p_{n+1} = -q_{n+1} already known (backward2_solver.py:200-203, :222-226):
+//   rhs = p1 + tau q1 + dt/2 L q1 - dt/2 f''(phi1) q1 + dt/2 b1 ((phi0 - Q0) + (phi1 - Q1))
+// and the coefficient a = tau + dt/2 f''(phi0) of the implicit operator A(phi_n) with its min/max.
+__global__ void adj_rhs_kernel(const double* __restrict__ p1, const double* __restrict__ q1,
+                               const double* __restrict__ phi1, const double* __restrict__ phi0,
+                               const double* __restrict__ Q1, const double* __restrict__ Q0,
+                               double* __restrict__ rhs, double* __restrict__ a, Geo g, Phys p, double dt, double b1,
+                               Scal* sc, double* part, unsigned int* ticket) {
+    double v[2] = {INFINITY, -INFINITY};
+    const double hdt = 0.5 * dt;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < g.n; idx += (long long)gridDim.x * blockDim.x) {
+        const int o = (int)(idx / g.ni), i = (int)(idx - (long long)o * g.ni);
+        const double f1 = phi1[idx], f0 = phi0[idx], qv = q1[idx];
+        const double src = hdt * b1 * ((f0 - (Q0 ? Q0[idx] : 0.0)) + (f1 - (Q1 ? Q1[idx] : 0.0)));
+        rhs[idx] = p1[idx] + p.tau * qv + hdt * lap_g(q1, o, i, g) - hdt * fpp_dev(f1, p.c1, p.c2) * qv + src;
+        const double av = p.tau + hdt * fpp_dev(f0, p.c1, p.c2);
+        a[idx] = av; v[0] = fmin(v[0], av); v[1] = fmax(v[1], av);
+    }
+    const int op[2] = {1, 2};
+    double tot[2];
+    if (grid_reduce<2>(v, op, part, ticket, tot) && threadIdx.x == 0) {
+        sc->amin = tot[0]; sc->amax = tot[1];
+        sc->abar = (tot[0] > 0.0) ? sqrt(tot[0] * tot[1]) : 0.5 * (tot[0] + tot[1]);
+    }
+}
+
+// q0 = -L p0 ;  r0 = fb r1 + fs (q0 + q1)      (backward2_solver.py:233-242).  r1 == nullptr: terminal level (r = 0).
+__global__ void adj_qr_kernel(const double* __restrict__ p0, const double* __restrict__ q1, const double* __restrict__ r1,
+                              double* __restrict__ q0, double* __restrict__ r0, Geo g, double fb, double fs) {
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < g.n; idx += (long long)gridDim.x * blockDim.x) {
+        const int o = (int)(idx / g.ni), i = (int)(idx - (long long)o * g.ni);
+        const double qv = -lap_g(p0, o, i, g);
+        q0[idx] = qv;
+        if (r0) r0[idx] = r1 ? fb * r1[idx] + fs * (qv + q1[idx]) : 0.0;
+    }
+}
+
+// ---------------------------------------------------------------------------------- cost / prox / KKT reductions
+// J sums over (levels, Nx+1, Ny+1) with np.trapz weights wt[t] wx[i] wy[j] (cost2_and_function.py:80-108).
+__global__ void cost_kernel(const double* __restrict__ phi, const double* __restrict__ u, const double* __restrict__ Q,
+                            const double* __restrict__ phiT, int levels, int nx1, int ny1,
+                            const double* __restrict__ wt, const double* __restrict__ wx, const double* __restrict__ wy,
+                            double* out4, double* part, unsigned int* ticket) {
+    const long long n = (long long)nx1 * ny1, total = n * levels;
+    double v[4] = {0.0, 0.0, 0.0, 0.0};
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        const int t = (int)(idx / n);
+        const long long node = idx - (long long)t * n;
+        const int ix = (int)(node / ny1), iy = (int)(node - (long long)ix * ny1);
+        const double ws = wx[ix] * wy[iy], w = wt[t] * ws;
+        const double f = phi[idx];
+        const double e = f - (Q ? Q[idx] : 0.0);
+        v[0] += w * e * e;
+        if (t == levels - 1) { const double d = f - (phiT ? phiT[node] : 0.0); v[1] += ws * d * d; }
+        if (u) { const double uv = u[idx]; v[2] += w * uv * uv; v[3] += w * fabs(uv); }
+    }
+    const int op[4] = {0, 0, 0, 0};
+    double tot[4];
+    if (grid_reduce<4>(v, op, part, ticket, tot) && threadIdx.x == 0) {
+        out4[0] = tot[0]; out4[1] = tot[1]; out4[2] = tot[2]; out4[3] = tot[3];
+    }
+}
+
+// g = r + b3 u ; v = u - alpha g ; soft threshold alpha*kappa ; box.  Also ||u_new-u||^2, ||u||^2, support and bound counts.
+__global__ void grad_prox_kernel(const double* __restrict__ u, const double* __restrict__ r, double* __restrict__ grad,
+                                 double* __restrict__ un, long long n, double b3, double alpha, double ksp, double umin,
+                                 double umax, double* out4, double* part, unsigned int* ticket) {
+    double v[4] = {0.0, 0.0, 0.0, 0.0};
+    const double thr = alpha * ksp;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (long long)gridDim.x * blockDim.x) {
+        const double uv = u[idx];
+        // explicit round-to-nearest mul/add (no FMA) so the support pattern matches NumPy's evaluation order bit for bit
+        const double gv = __dadd_rn(r[idx], __dmul_rn(b3, uv));
+        if (grad) grad[idx] = gv;
+        const double y = __dsub_rn(uv, __dmul_rn(alpha, gv));
+        const double m = fmax(__dsub_rn(fabs(y), thr), 0.0);
+        double s = (y > 0.0) ? m : ((y < 0.0) ? -m : 0.0);
+        s = fmin(fmax(s, umin), umax);
+        un[idx] = s;
+        const double d = s - uv;
+        v[0] += d * d; v[1] += uv * uv;
+        v[2] += (s != 0.0) ? 1.0 : 0.0;
+        v[3] += (s == umin || s == umax) ? 1.0 : 0.0;
+    }
+    const int op[4] = {0, 0, 0, 0};
+    double tot[4];
+    if (grid_reduce<4>(v, op, part, ticket, tot) && threadIdx.x == 0) {
+        out4[0] = tot[0]; out4[1] = tot[1]; out4[2] = tot[2]; out4[3] = tot[3];
+    }
+}
+
+__global__ void kkt_kernel(const double* __restrict__ u, const double* __restrict__ r, long long n, double ksp, double tol,
+                           double* out3, double* part, unsigned int* ticket) {
+    double v[3] = {0.0, 0.0, 0.0};
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (long long)gridDim.x * blockDim.x) {
+        const bool a = fabs(u[idx]) < tol, b = fabs(r[idx]) <= ksp;
+        v[0] += a ? 1.0 : 0.0; v[1] += b ? 1.0 : 0.0; v[2] += (a == b) ? 1.0 : 0.0;
+    }
+    const int op[3] = {0, 0, 0};
+    double tot[3];
+    if (grid_reduce<3>(v, op, part, ticket, tot) && threadIdx.x == 0) { out3[0] = tot[0]; out3[1] = tot[1]; out3[2] = tot[2]; }
+}
+
+}  // namespace vch

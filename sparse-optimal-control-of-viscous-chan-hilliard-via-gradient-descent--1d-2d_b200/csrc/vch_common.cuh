@@ -1,0 +1,165 @@
+// Shared device/host helpers for the vch_b200 CUDA library (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <cstdint>
+#include <cstring>
+#include <cmath>
+#include <string>
+#include <vector>
+#include <stdexcept>
+#include "../../include/vch_b200.h"
+
+namespace vch {
+
+// ---------------------------------------------------------------- error plumbing
+struct Error : std::runtime_error {
+    int code;
+    Error(int c, const std::string& m) : std::runtime_error(m), code(c) {}
+};
+void set_last_error(const std::string& m);
+
+#define VCH_CUDA(expr)                                                                          \
+    do {                                                                                        \
+        cudaError_t _e = (expr);                                                                \
+        if (_e != cudaSuccess)                                                                  \
+            throw vch::Error(VCH_E_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));   \
+    } while (0)
+
+#define VCH_REQUIRE(cond, code, msg)                                                            \
+    do { if (!(cond)) throw vch::Error(code, msg); } while (0)
+
+// Wraps the body of every extern "C" entry point.
+template <class F>
+static inline int guarded(F&& f) {
+    try { return f(); }
+    catch (const Error& e) { set_last_error(e.what()); return e.code; }
+    catch (const std::exception& e) { set_last_error(e.what()); return VCH_E_CUDA; }
+}
+
+// ---------------------------------------------------------------- device memory
+struct DevBuf {
+    double* p = nullptr;
+    size_t n = 0;
+    void alloc(size_t count) {
+        if (count <= n && p) return;
+        release();
+        VCH_CUDA(cudaMalloc(&p, count * sizeof(double)));
+        n = count;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+    ~DevBuf() { release(); }
+    DevBuf() = default;
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+};
+
+// Stages caller arrays when mem == VCH_MEM_HOST; passes device pointers through otherwise.
+struct Stager {
+    cudaStream_t s;
+    int mem;
+    std::vector<double*> owned;
+    struct Out { double* host; double* dev; size_t n; };
+    std::vector<Out> outs;
+    Stager(cudaStream_t st, int m) : s(st), mem(m) {}
+    const double* in(const double* a, size_t n) {
+        if (!a || mem == VCH_MEM_DEVICE) return a;
+        double* d; VCH_CUDA(cudaMalloc(&d, n * sizeof(double))); owned.push_back(d);
+        VCH_CUDA(cudaMemcpyAsync(d, a, n * sizeof(double), cudaMemcpyHostToDevice, s));
+        return d;
+    }
+    double* out(double* a, size_t n) {
+        if (!a || mem == VCH_MEM_DEVICE) return a;
+        double* d; VCH_CUDA(cudaMalloc(&d, n * sizeof(double))); owned.push_back(d);
+        outs.push_back({a, d, n});
+        return d;
+    }
+    void finish() {
+        for (auto& o : outs) VCH_CUDA(cudaMemcpyAsync(o.host, o.dev, o.n * sizeof(double), cudaMemcpyDeviceToHost, s));
+        VCH_CUDA(cudaStreamSynchronize(s));
+        outs.clear();
+    }
+    ~Stager() { for (auto d : owned) cudaFree(d); }
+};
+
+// ---------------------------------------------------------------- launch geometry
+constexpr int kSMs = 148;              // B200
+constexpr int kRedThreads = 256;
+constexpr int kRedBlocksMax = kSMs * 4;  // grid-stride reductions: 4 resident CTAs of 256 threads per SM
+
+static inline int red_blocks(long long n) {
+    long long b = (n + kRedThreads - 1) / kRedThreads;
+    if (b < 1) b = 1;
+    return (int)(b > kRedBlocksMax ? kRedBlocksMax : b);
+}
+
+// ---------------------------------------------------------------- deterministic grid reductions
+// Each block reduces K values with warp shuffles + one smem stage, writes its partials to
+// part[k*gridDim.x + blockIdx.x]; the last block to arrive (ticket) re-reduces all partials in a
+// fixed order so the result does not depend on block scheduling.  OP: 0 = sum, 1 = min, 2 = max.
+template <int OP> __device__ __forceinline__ double red_op(double a, double b) {
+    if (OP == 0) return a + b;
+    if (OP == 1) return fmin(a, b);
+    return fmax(a, b);
+}
+template <int OP> __device__ __forceinline__ double red_identity() {
+    if (OP == 0) return 0.0;
+    if (OP == 1) return INFINITY;
+    return -INFINITY;
+}
+template <int OP> __device__ __forceinline__ double warp_red(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = red_op<OP>(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+template <int OP> __device__ __forceinline__ double block_red(double v, double* sh /* >= 32 doubles */) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    v = warp_red<OP>(v);
+    __syncthreads();
+    if (lane == 0) sh[wid] = v;
+    __syncthreads();
+    v = (threadIdx.x < nw) ? sh[threadIdx.x] : red_identity<OP>();
+    if (wid == 0) v = warp_red<OP>(v);
+    return v;   // valid in warp 0 (all lanes)
+}
+
+// Returns true (block-uniform) in the last block; there tot[k] holds the grid-wide result (valid in thread 0).
+template <int K>
+__device__ __forceinline__ bool grid_reduce(double (&v)[K], const int (&op)[K], double* part, unsigned int* ticket,
+                                            double (&tot)[K]) {
+    __shared__ double sh[32];
+    __shared__ bool is_last;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        double r = (op[k] == 0) ? block_red<0>(v[k], sh) : (op[k] == 1) ? block_red<1>(v[k], sh) : block_red<2>(v[k], sh);
+        if (threadIdx.x == 0) part[(size_t)k * gridDim.x + blockIdx.x] = r;
+    }
+    __threadfence();
+    if (threadIdx.x == 0) {
+        unsigned int t = atomicAdd(ticket, 1u);
+        is_last = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!is_last) return false;
+    __threadfence();
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        double a = (op[k] == 0) ? 0.0 : (op[k] == 1 ? INFINITY : -INFINITY);
+        for (unsigned int b = threadIdx.x; b < gridDim.x; b += blockDim.x) {
+            double x = __ldcg(&part[(size_t)k * gridDim.x + b]);
+            a = (op[k] == 0) ? a + x : (op[k] == 1 ? fmin(a, x) : fmax(a, x));
+        }
+        tot[k] = (op[k] == 0) ? block_red<0>(a, sh) : (op[k] == 1) ? block_red<1>(a, sh) : block_red<2>(a, sh);
+    }
+    if (threadIdx.x == 0) *ticket = 0u;   // re-arm for the next launch on this stream
+    return true;
+}
+
+// Mirror (even) reflection of an index into [0, n-1] for ghost offsets up to 2 (Neumann: v[-1] = v[1]).
+__device__ __forceinline__ int mirror(int i, int n) {
+    if (i < 0) i = -i;
+    if (i >= n) i = 2 * (n - 1) - i;
+    return i;
+}
+
+}  // namespace vch

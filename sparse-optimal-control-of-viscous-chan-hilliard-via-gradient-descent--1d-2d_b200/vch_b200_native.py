@@ -1,0 +1,491 @@
+"""ctypes binding of libvch_b200.so (include/vch_b200.h) — the only door between the Python drop-in
+modules and the sm_100a CUDA kernels.
+
+There is no CPU fallback: if the library is missing, or no CUDA device is visible, every compute call raises.
+Arrays may be NumPy (host; the library stages H2D/D2H on its stream) or torch CUDA tensors (device pointers are
+passed through, nothing is copied); one call uses one kind for all of its array arguments.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libvch_b200.so")
+
+MEM_HOST, MEM_DEVICE = 0, 1
+E_CUDA, E_SHAPE, E_NONFINITE, E_KRYLOV, E_ARG = 1, 2, 3, 4, 5
+
+
+class KrylovStall(ArithmeticError):
+    """The matrix-free linear solve stopped above its tolerance (no analogue in the reference's direct solve)."""
+
+
+class Params2D(C.Structure):
+    _fields_ = [("Nx", C.c_int), ("Ny", C.c_int), ("hx", C.c_double), ("hy", C.c_double), ("Lx", C.c_double),
+                ("Ly", C.c_double), ("tau", C.c_double), ("gamma", C.c_double), ("c1", C.c_double), ("c2", C.c_double),
+                ("kappa", C.c_double), ("delta_sep", C.c_double)]
+
+
+class Params1D(C.Structure):
+    _fields_ = [("N", C.c_int), ("h", C.c_double), ("Lx", C.c_double), ("tau", C.c_double), ("gamma", C.c_double),
+                ("c1", C.c_double), ("c2", C.c_double), ("kappa", C.c_double), ("delta_sep", C.c_double)]
+
+
+class Stats(C.Structure):
+    _fields_ = [("newton_residual_evals", C.c_longlong), ("newton_linear_solves", C.c_longlong),
+                ("krylov_iterations", C.c_longlong), ("krylov_max_iterations", C.c_longlong),
+                ("kernel_launches", C.c_longlong), ("krylov_stalls", C.c_longlong), ("last_newton_residual", C.c_double)]
+
+    def as_dict(self):
+        return {f: getattr(self, f) for f, _ in self._fields_}
+
+
+# every symbol include/vch_b200.h declares (tests check the library exports exactly these)
+EXPORTS = [
+    "vch_last_error", "vch_device_count", "vch_version",
+    "vch2d_create", "vch2d_destroy", "vch2d_set_stream", "vch2d_set_krylov", "vch2d_launch_count",
+    "vch2d_apply_laplacian", "vch2d_initialize_mu", "vch_solve_w", "vch2d_residual", "vch2d_jacobian_solve",
+    "vch2d_newton", "vch2d_forward", "vch2d_adjoint", "vch2d_cost", "vch_grad_prox", "vch_kkt_counts",
+    "vch2d_pgd_iteration",
+    "vch1d_create", "vch1d_destroy", "vch1d_set_stream", "vch1d_launch_count", "vch1d_residual", "vch1d_newton",
+    "vch1d_forward", "vch1d_adjoint", "vch1d_cost", "vch1d_grad_prox",
+]
+
+_lib = None
+_lock = threading.Lock()
+
+
+def lib():
+    """Load the shared library (once).  Fails loudly when it has not been built."""
+    global _lib
+    with _lock:
+        if _lib is None:
+            if not os.path.exists(LIB_PATH):
+                raise ImportError(
+                    f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                    "(nvcc, sm_100a).  vch_b200 has no CPU fallback.")
+            L = C.CDLL(LIB_PATH)
+            L.vch_last_error.restype = C.c_char_p
+            L.vch2d_launch_count.restype = C.c_longlong
+            L.vch1d_launch_count.restype = C.c_longlong
+            L.vch2d_launch_count.argtypes = [C.c_void_p]
+            L.vch1d_launch_count.argtypes = [C.c_void_p]
+            L.vch2d_destroy.argtypes = [C.c_void_p]
+            L.vch1d_destroy.argtypes = [C.c_void_p]
+            L.vch2d_destroy.restype = None
+            L.vch1d_destroy.restype = None
+            _lib = L
+    return _lib
+
+
+def device_count() -> int:
+    return int(lib().vch_device_count())
+
+
+def require_device():
+    if device_count() < 1:
+        raise RuntimeError("vch_b200: no CUDA device visible; this build has no CPU fallback")
+
+
+def _check(rc):
+    if rc == 0:
+        return
+    msg = lib().vch_last_error().decode("utf-8", "replace")
+    if rc == E_SHAPE:
+        raise ValueError(msg)
+    if rc == E_NONFINITE:
+        raise RuntimeError(msg)
+    if rc == E_KRYLOV:
+        raise KrylovStall(msg)
+    raise RuntimeError(f"vch_b200 error {rc}: {msg}")
+
+
+def _is_dev(a):
+    return a is not None and hasattr(a, "data_ptr")
+
+
+def _mem_of(*arrays):
+    kinds = {_is_dev(a) for a in arrays if a is not None}
+    if len(kinds) > 1:
+        raise TypeError("mix of NumPy arrays and CUDA tensors in one call")
+    return MEM_DEVICE if (kinds and kinds.pop()) else MEM_HOST
+
+
+class _Args:
+    """Keeps converted arrays alive for the duration of a call."""
+
+    def __init__(self):
+        self.keep = []
+
+    def inp(self, a, shape=None):
+        if a is None:
+            return C.c_void_p(None)
+        if _is_dev(a):
+            import torch
+            assert a.is_cuda and a.dtype == torch.float64 and a.is_contiguous(), "device arrays must be contiguous float64 CUDA tensors"
+            if shape is not None and tuple(a.shape) != tuple(shape):
+                raise ValueError(f"expected shape {tuple(shape)}, got {tuple(a.shape)}")
+            self.keep.append(a)
+            return C.c_void_p(a.data_ptr())
+        b = np.ascontiguousarray(a, dtype=np.float64)
+        if shape is not None and b.shape != tuple(shape):
+            raise ValueError(f"expected shape {tuple(shape)}, got {b.shape}")
+        self.keep.append(b)
+        return b.ctypes.data_as(C.c_void_p)
+
+    def out(self, like, shape):
+        """Allocate an output of the same kind (NumPy / torch) as `like`."""
+        if _is_dev(like):
+            import torch
+            t = torch.empty(tuple(shape), dtype=torch.float64, device=like.device)
+            self.keep.append(t)
+            return t, C.c_void_p(t.data_ptr())
+        o = np.empty(tuple(shape), dtype=np.float64)
+        self.keep.append(o)
+        return o, o.ctypes.data_as(C.c_void_p)
+
+    def host(self, a):
+        b = np.ascontiguousarray(a, dtype=np.float64)
+        self.keep.append(b)
+        return b.ctypes.data_as(C.c_void_p)
+
+
+def _current_stream_ptr():
+    """torch's current CUDA stream when torch is in use (so torch.cuda.Event brackets our kernels), else the default stream."""
+    try:
+        import sys
+        if "torch" in sys.modules:
+            import torch
+            if torch.cuda.is_available():
+                return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    except Exception:
+        pass
+    return C.c_void_p(None)
+
+
+# ------------------------------------------------------------------------------------------------ context-free ops
+def solve_w(w_old, dt, gamma, u_n, u_np1):
+    """Forward2_solver.py:170-181 / Forward_solver.py:88-91."""
+    a = _Args()
+    mem = _mem_of(w_old, u_n, u_np1)
+    shape = tuple(w_old.shape)
+    out, po = a.out(w_old, shape)
+    n = int(np.prod(shape))
+    _check(lib().vch_solve_w(_current_stream_ptr(), C.c_longlong(n), a.inp(w_old), C.c_double(dt), C.c_double(gamma),
+                             a.inp(u_n, shape), a.inp(u_np1, shape), po, mem))
+    return out
+
+
+def grad_prox(u, r, b3, alpha, kappa_sp, u_min, u_max, want_grad=False):
+    """r + b3 u, then soft-threshold + box.  Returns (u_new, grad|None, red[4])."""
+    a = _Args()
+    mem = _mem_of(u, r)
+    shape = tuple(u.shape)
+    un, pun = a.out(u, shape)
+    g, pg = a.out(u, shape) if want_grad else (None, C.c_void_p(None))
+    red = np.zeros(4)
+    _check(lib().vch_grad_prox(_current_stream_ptr(), C.c_longlong(int(np.prod(shape))), a.inp(u), a.inp(r, shape),
+                               C.c_double(b3), C.c_double(alpha), C.c_double(kappa_sp), C.c_double(u_min), C.c_double(u_max),
+                               pg, pun, red.ctypes.data_as(C.c_void_p), mem))
+    return un, g, red
+
+
+def kkt_counts(u, r, kappa_sp, tol=1e-6):
+    a = _Args()
+    mem = _mem_of(u, r)
+    cnt = np.zeros(3, dtype=np.int64)
+    _check(lib().vch_kkt_counts(_current_stream_ptr(), C.c_longlong(int(np.prod(u.shape))), a.inp(u), a.inp(r, tuple(u.shape)),
+                                C.c_double(kappa_sp), C.c_double(tol), cnt.ctypes.data_as(C.c_void_p), mem))
+    return int(cnt[0]), int(cnt[1]), int(cnt[2])
+
+
+# ------------------------------------------------------------------------------------------------ 2D context
+class Ctx2D:
+    def __init__(self, Nx, Ny, hx, hy, Lx, Ly, tau, gamma, c1, c2, kappa, delta_sep=1e-2, device=0):
+        require_device()
+        self.p = Params2D(int(Nx), int(Ny), float(hx), float(hy), float(Lx), float(Ly), float(tau), float(gamma),
+                          float(c1), float(c2), float(kappa), float(delta_sep))
+        self.shape = (int(Nx) + 1, int(Ny) + 1)
+        self.h = C.c_void_p()
+        _check(lib().vch2d_create(C.byref(self.p), int(device), C.byref(self.h)))
+        self.last_stats = {}
+
+    def __del__(self):
+        try:
+            if getattr(self, "h", None) and self.h.value:
+                lib().vch2d_destroy(self.h)
+                self.h = C.c_void_p()
+        except Exception:
+            pass
+
+    def _stream(self):
+        _check(lib().vch2d_set_stream(self.h, _current_stream_ptr()))
+
+    def set_krylov(self, rel_tol=1e-11, max_iter=200):
+        _check(lib().vch2d_set_krylov(self.h, C.c_double(rel_tol), int(max_iter)))
+
+    def launches(self):
+        return int(lib().vch2d_launch_count(self.h))
+
+    def apply_laplacian(self, v):
+        a = _Args(); self._stream()
+        out, po = a.out(v, self.shape)
+        _check(lib().vch2d_apply_laplacian(self.h, a.inp(v, self.shape), po, _mem_of(v)))
+        return out
+
+    def initialize_mu(self, phi, w):
+        a = _Args(); self._stream()
+        out, po = a.out(phi, self.shape)
+        _check(lib().vch2d_initialize_mu(self.h, a.inp(phi, self.shape), a.inp(w, self.shape), po, _mem_of(phi, w)))
+        return out
+
+    def residual(self, phi_new, phi_old, mu_new, mu_old, w_new, w_old, dt):
+        a = _Args(); self._stream()
+        s = self.shape
+        rp, prp = a.out(phi_new, s); rm, prm = a.out(phi_new, s)
+        _check(lib().vch2d_residual(self.h, a.inp(phi_new, s), a.inp(phi_old, s), a.inp(mu_new, s), a.inp(mu_old, s),
+                                    a.inp(w_new, s), a.inp(w_old, s), C.c_double(dt), prp, prm,
+                                    _mem_of(phi_new, phi_old, mu_new, mu_old, w_new, w_old)))
+        return rp, rm
+
+    def jacobian_solve(self, phi, dt, Rphi, Rmu):
+        """Solve J(phi) [dphi; dmu] = -[Rphi; Rmu].  Returns (dphi, dmu, krylov_iterations)."""
+        a = _Args(); self._stream()
+        s = self.shape
+        d1, p1 = a.out(phi, s); d2, p2 = a.out(phi, s)
+        its = C.c_int(0)
+        _check(lib().vch2d_jacobian_solve(self.h, a.inp(phi, s), C.c_double(dt), a.inp(Rphi, s), a.inp(Rmu, s), p1, p2,
+                                          C.byref(its), _mem_of(phi, Rphi, Rmu)))
+        return d1, d2, its.value
+
+    def newton(self, phi_old, mu_old, w_old, w_new, dt, hist_cap=512):
+        a = _Args(); self._stream()
+        s = self.shape
+        pn, ppn = a.out(phi_old, s); mn, pmn = a.out(phi_old, s)
+        hist = np.zeros(hist_cap); nh = C.c_int(0); st = Stats()
+        _check(lib().vch2d_newton(self.h, a.inp(phi_old, s), a.inp(mu_old, s), a.inp(w_old, s), a.inp(w_new, s),
+                                  C.c_double(dt), ppn, pmn, hist.ctypes.data_as(C.c_void_p), hist_cap, C.byref(nh),
+                                  C.byref(st), _mem_of(phi_old, mu_old, w_old, w_new)))
+        self.last_stats = st.as_dict()
+        return pn, mn, [float(v) for v in hist[:min(nh.value, hist_cap)]]
+
+    def forward(self, phi0, u, dt_steps, want_mu=False, want_w=False):
+        """Time loop.  Returns (phi_hist (M+1,..), mu_hist|None, w_hist|None)."""
+        a = _Args(); self._stream()
+        s = self.shape
+        dts = np.ascontiguousarray(dt_steps, dtype=np.float64)
+        M = int(dts.shape[0])
+        if u is not None and (u.ndim != 3 or tuple(u.shape[1:]) != s):
+            raise ValueError(f"control_input must have shape (M, {s[0]}, {s[1]})")
+        hist, ph = a.out(phi0, (M + 1,) + s)
+        mh, pm = a.out(phi0, (M,) + s) if want_mu else (None, C.c_void_p(None))
+        wh, pw = a.out(phi0, (M,) + s) if want_w else (None, C.c_void_p(None))
+        st = Stats()
+        _check(lib().vch2d_forward(self.h, a.inp(phi0, s), a.inp(u), int(u.shape[0]) if u is not None else 0, M,
+                                   a.host(dts), ph, pm, pw, C.byref(st), _mem_of(phi0, u)))
+        self.last_stats = st.as_dict()
+        return hist, mh, wh
+
+    def adjoint(self, phi_hist, t_hist, b1, b2, phiQ=None, phiT=None, want_pq=True):
+        a = _Args(); self._stream()
+        s = self.shape
+        lv = int(phi_hist.shape[0])
+        full = (lv,) + s
+        r, pr = a.out(phi_hist, full)
+        p, pp = a.out(phi_hist, full) if want_pq else (None, C.c_void_p(None))
+        q, pq = a.out(phi_hist, full) if want_pq else (None, C.c_void_p(None))
+        st = Stats()
+        _check(lib().vch2d_adjoint(self.h, a.inp(phi_hist, full), lv, a.host(t_hist), C.c_double(b1), C.c_double(b2),
+                                   a.inp(phiQ, full if phiQ is not None else None), a.inp(phiT, s if phiT is not None else None),
+                                   pp, pq, pr, C.byref(st), _mem_of(phi_hist, phiQ, phiT)))
+        self.last_stats = st.as_dict()
+        return p, q, r
+
+    def cost(self, phi_hist, u, phiQ, phiT, x, y, t_hist, b1, b2, b3, kappa_sp):
+        a = _Args(); self._stream()
+        s = self.shape
+        lv = int(phi_hist.shape[0])
+        full = (lv,) + s
+        J = np.zeros(5)
+        _check(lib().vch2d_cost(self.h, a.inp(phi_hist, full), a.inp(u, full), a.inp(phiQ, full), a.inp(phiT, s), lv,
+                                a.host(x), a.host(y), a.host(t_hist), C.c_double(b1), C.c_double(b2), C.c_double(b3),
+                                C.c_double(kappa_sp), J.ctypes.data_as(C.c_void_p), _mem_of(phi_hist, u, phiQ, phiT)))
+        return J
+
+    def pgd_iteration(self, u, phi_hist, phiQ, phiT, t_hist, dt_steps, x, y, b1, b2, b3, kappa_sp, u_min, u_max, alpha,
+                      u_out=None, phi_out=None, r_out=None):
+        """One optimistic PGD iteration (GD2_configured.py:299-313).  Returns (u_new, phi_hist_new, J[5], red[4], stats)."""
+        a = _Args(); self._stream()
+        s = self.shape
+        lv = int(phi_hist.shape[0])
+        full = (lv,) + s
+        if u_out is None:
+            u_out, pun = a.out(u, full)
+        else:
+            pun = a.inp(u_out, full)
+        if phi_out is None:
+            phi_out, phn = a.out(u, full)
+        else:
+            phn = a.inp(phi_out, full)
+        pr = a.inp(r_out, full) if r_out is not None else C.c_void_p(None)
+        J = np.zeros(5); red = np.zeros(4); st = Stats()
+        _check(lib().vch2d_pgd_iteration(self.h, lv, a.host(t_hist), a.host(dt_steps), a.host(x), a.host(y),
+                                         a.inp(u, full), a.inp(phi_hist, full), a.inp(phiQ, full), a.inp(phiT, s),
+                                         C.c_double(b1), C.c_double(b2), C.c_double(b3), C.c_double(kappa_sp),
+                                         C.c_double(u_min), C.c_double(u_max), C.c_double(alpha), pun, phn, pr,
+                                         J.ctypes.data_as(C.c_void_p), red.ctypes.data_as(C.c_void_p), C.byref(st),
+                                         _mem_of(u, phi_hist, phiQ, phiT)))
+        self.last_stats = st.as_dict()
+        return u_out, phi_out, J, red, self.last_stats
+
+
+# ------------------------------------------------------------------------------------------------ 1D context
+class Ctx1D:
+    def __init__(self, N, h, Lx, tau, gamma, c1, c2, kappa, delta_sep=1e-2, device=0):
+        require_device()
+        self.p = Params1D(int(N), float(h), float(Lx), float(tau), float(gamma), float(c1), float(c2), float(kappa),
+                          float(delta_sep))
+        self.n = int(N) + 1
+        self.h = C.c_void_p()
+        _check(lib().vch1d_create(C.byref(self.p), int(device), C.byref(self.h)))
+
+    def __del__(self):
+        try:
+            if getattr(self, "h", None) and self.h.value:
+                lib().vch1d_destroy(self.h)
+                self.h = C.c_void_p()
+        except Exception:
+            pass
+
+    def _stream(self):
+        _check(lib().vch1d_set_stream(self.h, _current_stream_ptr()))
+
+    def launches(self):
+        return int(lib().vch1d_launch_count(self.h))
+
+    @staticmethod
+    def _batched(a, tail):
+        """View `a` with a leading batch axis; returns (array, batch, had_batch)."""
+        if a.ndim == len(tail):
+            return a.reshape((1,) + tuple(a.shape)), 1, False
+        return a, int(a.shape[0]), True
+
+    def residual(self, phi_new, phi_old, mu_new, mu_old, w_new, w_old, dt):
+        a = _Args(); self._stream()
+        x, B, had = self._batched(phi_new, (self.n,))
+        sh = (B, self.n)
+        rs = lambda v: v.reshape(sh)
+        rp, prp = a.out(phi_new, sh); rm, prm = a.out(phi_new, sh)
+        _check(lib().vch1d_residual(self.h, B, a.inp(rs(phi_new)), a.inp(rs(phi_old)), a.inp(rs(mu_new)), a.inp(rs(mu_old)),
+                                    a.inp(rs(w_new)), a.inp(rs(w_old)), C.c_double(dt), prp, prm,
+                                    _mem_of(phi_new, phi_old, mu_new, mu_old, w_new, w_old)))
+        return (rp, rm) if had else (rp[0], rm[0])
+
+    def newton(self, phi_old, mu_old, w_old, w_new, dt, hist_cap=64):
+        a = _Args(); self._stream()
+        x, B, had = self._batched(phi_old, (self.n,))
+        sh = (B, self.n)
+        rs = lambda v: v.reshape(sh)
+        pn, ppn = a.out(phi_old, sh); mn, pmn = a.out(phi_old, sh)
+        hist = np.zeros((B, hist_cap)); nh = np.zeros(B, dtype=np.int32); status = np.zeros(B, dtype=np.int32)
+        _check(lib().vch1d_newton(self.h, B, a.inp(rs(phi_old)), a.inp(rs(mu_old)), a.inp(rs(w_old)), a.inp(rs(w_new)),
+                                  C.c_double(dt), ppn, pmn, hist.ctypes.data_as(C.c_void_p), hist_cap,
+                                  nh.ctypes.data_as(C.c_void_p), status.ctypes.data_as(C.c_void_p),
+                                  _mem_of(phi_old, mu_old, w_old, w_new)))
+        hists = [[float(v) for v in hist[b, :min(int(nh[b]), hist_cap)]] for b in range(B)]
+        return (pn, mn, hists) if had else (pn[0], mn[0], hists[0])
+
+    def forward(self, phi0, u, dt_steps, want_mu=False, want_w=False):
+        """phi0 (N+1,) or (B, N+1); u (rows, N+1) / (B, rows, N+1) / None.  Returns (phi_hist, mu_hist|None, w_hist|None)
+        with phi_hist (M+2, N+1) or (B, M+2, N+1) — level 0 stored twice like the reference."""
+        a = _Args(); self._stream()
+        p0, B, had = self._batched(phi0, (self.n,))
+        dts = np.ascontiguousarray(dt_steps, dtype=np.float64)
+        M = int(dts.shape[0])
+        rows = 0
+        if u is not None:
+            ub = u if had else u.reshape((1,) + tuple(u.shape))
+            if ub.ndim != 3 or ub.shape[0] != B or ub.shape[2] != self.n:
+                raise ValueError(f"control_input must have shape (rows, {self.n})")
+            rows = int(ub.shape[1])
+        else:
+            ub = None
+        hist, ph = a.out(phi0, (B, M + 2, self.n))
+        mh, pm = a.out(phi0, (B, M, self.n)) if want_mu else (None, C.c_void_p(None))
+        wh, pw = a.out(phi0, (B, M, self.n)) if want_w else (None, C.c_void_p(None))
+        status = np.zeros(B, dtype=np.int32); st = Stats()
+        _check(lib().vch1d_forward(self.h, B, a.inp(p0), a.inp(ub), rows, M, a.host(dts), ph, pm, pw,
+                                   status.ctypes.data_as(C.c_void_p), C.byref(st), _mem_of(phi0, u)))
+        if had:
+            return hist, mh, wh
+        return hist[0], (mh[0] if mh is not None else None), (wh[0] if wh is not None else None)
+
+    def adjoint(self, phi_hist, t_hist, b1, b2, phiQ=None, phiT=None):
+        a = _Args(); self._stream()
+        F, B, had = self._batched(phi_hist, (0, self.n))
+        lv = int(F.shape[1])
+        full = (B, lv, self.n)
+        b1v = np.ascontiguousarray(np.broadcast_to(np.asarray(b1, dtype=np.float64), (B,)))
+        b2v = np.ascontiguousarray(np.broadcast_to(np.asarray(b2, dtype=np.float64), (B,)))
+        Q = None if phiQ is None else phiQ.reshape(full)
+        T = None if phiT is None else phiT.reshape((B, self.n))
+        p, pp = a.out(phi_hist, full); q, pq = a.out(phi_hist, full); r, pr = a.out(phi_hist, full)
+        _check(lib().vch1d_adjoint(self.h, B, a.inp(F), lv, a.host(t_hist), a.host(b1v), a.host(b2v), a.inp(Q), a.inp(T),
+                                   pp, pq, pr, _mem_of(phi_hist, phiQ, phiT)))
+        return (p, q, r) if had else (p[0], q[0], r[0])
+
+    def cost(self, phi_hist, u, phiQ, phiT, x, t_hist, b1, b2, b3, kappa_sp):
+        a = _Args(); self._stream()
+        F, B, had = self._batched(phi_hist, (0, self.n))
+        lv = int(F.shape[1])
+        full = (B, lv, self.n)
+        wts = np.ascontiguousarray(np.stack([np.broadcast_to(np.asarray(v, dtype=np.float64), (B,)) for v in (b1, b2, b3, kappa_sp)], axis=1))
+        J = np.zeros((B, 5))
+        _check(lib().vch1d_cost(self.h, B, a.inp(F), a.inp(None if u is None else u.reshape(full)),
+                                a.inp(None if phiQ is None else phiQ.reshape(full)),
+                                a.inp(None if phiT is None else phiT.reshape((B, self.n))), lv, a.host(x), a.host(t_hist),
+                                a.host(wts), J.ctypes.data_as(C.c_void_p), _mem_of(phi_hist, u, phiQ, phiT)))
+        return J if had else J[0]
+
+    def grad_prox(self, u, r, b3, alpha, kappa_sp, u_min, u_max):
+        """Per-problem parameters (scalars broadcast).  u, r: (B, levels, N+1).  Returns (u_new, red (B,4))."""
+        a = _Args(); self._stream()
+        B = int(u.shape[0])
+        per = int(np.prod(u.shape[1:]))
+        par = np.ascontiguousarray(np.stack([np.broadcast_to(np.asarray(v, dtype=np.float64), (B,))
+                                             for v in (b3, alpha, kappa_sp, u_min, u_max, 0.0)], axis=1))
+        un, pun = a.out(u, tuple(u.shape))
+        red = np.zeros((B, 4))
+        _check(lib().vch1d_grad_prox(self.h, B, C.c_longlong(per), a.inp(u), a.inp(r, tuple(u.shape)), a.host(par), pun,
+                                     red.ctypes.data_as(C.c_void_p), _mem_of(u, r)))
+        return un, red
+
+
+# ------------------------------------------------------------------------------------------------ context cache
+_ctx_cache: dict = {}
+
+
+def ctx2d(Nx, Ny, hx, hy, Lx, Ly, tau, gamma, c1, c2, kappa, delta_sep=1e-2, device=0) -> Ctx2D:
+    key = ("2d", int(Nx), int(Ny), float(hx), float(hy), float(Lx), float(Ly), float(tau), float(gamma), float(c1),
+           float(c2), float(kappa), float(delta_sep), int(device))
+    c = _ctx_cache.get(key)
+    if c is None:
+        if len(_ctx_cache) > 16:
+            _ctx_cache.clear()
+        c = _ctx_cache[key] = Ctx2D(*key[1:])
+    return c
+
+
+def ctx1d(N, h, Lx, tau, gamma, c1, c2, kappa, delta_sep=1e-2, device=0) -> Ctx1D:
+    key = ("1d", int(N), float(h), float(Lx), float(tau), float(gamma), float(c1), float(c2), float(kappa),
+           float(delta_sep), int(device))
+    c = _ctx_cache.get(key)
+    if c is None:
+        if len(_ctx_cache) > 16:
+            _ctx_cache.clear()
+        c = _ctx_cache[key] = Ctx1D(*key[1:])
+    return c
