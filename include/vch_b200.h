@@ -76,7 +76,16 @@ int  vch2d_create(const vch2d_params* p, int device, vch2d_ctx** out);
 void vch2d_destroy(vch2d_ctx* c);
 int  vch2d_set_stream(vch2d_ctx* c, void* cuda_stream);          /* cudaStream_t; NULL = legacy default stream */
 int  vch2d_set_krylov(vch2d_ctx* c, double rel_tol, int max_iter);/* defaults 1e-11, 200 */
+/* Newton stop rule.  floor_aware = 1 (default): besides the reference's ||R||_2 < 1e-6 (Forward2_solver.py:353-365) the
+ * iteration also stops when it stalls within 50x the fp64 resolution of the residual, eps*(1/hx^2+1/hy^2)*||mu||_2 — only
+ * reachable on grids >= 1024^2, where the reference's absolute tolerance lies below that resolution and its loop would spin
+ * to max_iter = 500 on rounding noise.  floor_aware = 0: the reference's rule verbatim. */
+int  vch2d_set_newton(vch2d_ctx* c, int floor_aware);
 long long vch2d_launch_count(vch2d_ctx* c);                        /* kernels launched since creation */
+/* Per-kernel device timing (bench.py's roofline leg).  While enabled every launch is bracketed by CUDA events on the
+ * launching stream; the report returns ';'-joined kernel names with total milliseconds and launch counts. */
+int  vch2d_profile(vch2d_ctx* c, int enable);
+int  vch2d_profile_report(vch2d_ctx* c, char* names, int names_cap, double* ms, long long* counts, int cap, int* n_out);
 
 /* ------------------------------------------------------------------ 2D building blocks (test-level surface) */
 /* apply_laplacian(L, v, Nx, Ny)                       2D/Vch_control_2D/Forward2_solver.py:140-152 (operator :105-137) */

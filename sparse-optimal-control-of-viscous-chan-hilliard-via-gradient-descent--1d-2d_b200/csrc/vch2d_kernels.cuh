@@ -24,7 +24,7 @@ struct Phys {
 struct Scal {
     double rho, rho_new, alpha, omega;
     double r0v, ts, tt, rr, thr2, bnorm2;
-    double res2, amin, amax, abar;
+    double res2, amin, amax, abar, mu2;
     double ceil_pos, ceil_neg;
     double mass, wint, mass0;
     double tol2;
@@ -93,7 +93,7 @@ __global__ void residual_kernel(const double* __restrict__ phi, const double* __
                                 double* __restrict__ Rphi, double* __restrict__ Rmu, double* __restrict__ a,
                                 Geo g, Phys p, double dt, Scal* sc, double* part, unsigned int* ticket) {
     const double idt = 1.0 / dt, tdt = p.tau / dt;
-    double v[3] = {0.0, INFINITY, -INFINITY};
+    double v[4] = {0.0, INFINITY, -INFINITY, 0.0};
     for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < g.n; idx += (long long)gridDim.x * blockDim.x) {
         const int o = (int)(idx / g.ni), i = (int)(idx - (long long)o * g.ni);
         const double f = phi[idx], m = mu[idx];
@@ -104,11 +104,12 @@ __global__ void residual_kernel(const double* __restrict__ phi, const double* __
         if (a) a[idx] = d;
         v[0] += rp * rp + rm * rm;
         v[1] = fmin(v[1], d); v[2] = fmax(v[2], d);
+        v[3] += m * m;
     }
-    const int op[3] = {0, 1, 2};
-    double tot[3];
-    if (grid_reduce<3>(v, op, part, ticket, tot) && threadIdx.x == 0) {
-        sc->res2 = tot[0]; sc->amin = tot[1]; sc->amax = tot[2]; sc->abar = sqrt(tot[1] * tot[2]);
+    const int op[4] = {0, 1, 2, 0};
+    double tot[4];
+    if (grid_reduce<4>(v, op, part, ticket, tot) && threadIdx.x == 0) {
+        sc->res2 = tot[0]; sc->amin = tot[1]; sc->amax = tot[2]; sc->abar = sqrt(tot[1] * tot[2]); sc->mu2 = tot[3];
         if (!isfinite(tot[0])) sc->nonfinite = 1;
     }
 }

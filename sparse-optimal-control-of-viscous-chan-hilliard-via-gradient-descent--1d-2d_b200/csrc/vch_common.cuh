@@ -82,6 +82,48 @@ struct Stager {
     ~Stager() { for (auto d : owned) cudaFree(d); }
 };
 
+// ---------------------------------------------------------------- launch accounting / per-kernel event timing
+// Every kernel launch of the library goes through a LaunchLog.  With profiling on, each launch is bracketed by a
+// pair of CUDA events on the launching stream; report() folds them into per-kernel totals (bench.py's roofline leg).
+struct LaunchLog {
+    long long count = 0;
+    bool profiling = false;
+    struct Rec { const char* name; cudaEvent_t a, b; };
+    std::vector<Rec> recs;
+    std::vector<cudaEvent_t> pool;
+    cudaEvent_t get() {
+        if (!pool.empty()) { cudaEvent_t e = pool.back(); pool.pop_back(); return e; }
+        cudaEvent_t e; VCH_CUDA(cudaEventCreate(&e)); return e;
+    }
+    void begin(const char* name, cudaStream_t s) {
+        ++count;
+        if (!profiling) return;
+        Rec r{name, get(), get()};
+        VCH_CUDA(cudaEventRecord(r.a, s));
+        recs.push_back(r);
+    }
+    void end(cudaStream_t s) {
+        if (!profiling) return;
+        VCH_CUDA(cudaEventRecord(recs.back().b, s));
+    }
+    struct Row { std::string name; double ms = 0; long long n = 0; };
+    std::vector<Row> report() {
+        std::vector<Row> rows;
+        for (auto& r : recs) {
+            VCH_CUDA(cudaEventSynchronize(r.b));
+            float ms = 0.f; VCH_CUDA(cudaEventElapsedTime(&ms, r.a, r.b));
+            Row* row = nullptr;
+            for (auto& x : rows) if (x.name == r.name) { row = &x; break; }
+            if (!row) { rows.push_back(Row{r.name, 0.0, 0}); row = &rows.back(); }
+            row->ms += ms; row->n += 1;
+            pool.push_back(r.a); pool.push_back(r.b);
+        }
+        recs.clear();
+        return rows;
+    }
+    ~LaunchLog() { for (auto& r : recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); } for (auto e : pool) cudaEventDestroy(e); }
+};
+
 // ---------------------------------------------------------------- launch geometry
 constexpr int kSMs = 148;              // B200
 constexpr int kRedThreads = 256;

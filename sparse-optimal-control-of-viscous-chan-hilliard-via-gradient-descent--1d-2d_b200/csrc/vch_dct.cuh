@@ -31,8 +31,8 @@ struct DctPlan {
     DctAxis inner, outer;     // inner = contiguous axis (length ni), outer = strided axis (length no)
     int ni = 0, no = 0;
     DevBuf tmp1, tmp2;
-    long long* launches = nullptr;
-    void init(int no_, int ni_, double h_outer, double h_inner, long long* launch_counter);
+    LaunchLog* log = nullptr;
+    void init(int no_, int ni_, double h_outer, double h_inner, LaunchLog* launch_log);
     void destroy();
     // out = P^-1 in   (in may equal out)
     void apply(cudaStream_t s, const double* in, double* out, const SymbolArgs& sym, const int* done_flag);
@@ -264,8 +264,8 @@ static inline int dct_cols_ppb(const DctAxis& ax, int ncols) {
     return ppb;
 }
 
-inline void DctPlan::init(int no_, int ni_, double h_outer, double h_inner, long long* launch_counter) {
-    no = no_; ni = ni_; launches = launch_counter;
+inline void DctPlan::init(int no_, int ni_, double h_outer, double h_inner, LaunchLog* launch_log) {
+    no = no_; ni = ni_; log = launch_log;
     dct_axis_init(inner, ni, h_inner);
     dct_axis_init(outer, no, h_outer);
     tmp1.alloc((size_t)no * ni);
@@ -283,11 +283,13 @@ inline void DctPlan::apply(cudaStream_t s, const double* in, double* out, const 
             const int ppb = dct_rows_ppb(inner, no), tpf = inner.Lf >> 3;
             const int grid = ((no + 1) / 2 + ppb - 1) / ppb;
             const size_t smem = sizeof(double2) * (size_t)ppb * (inner.Lf + 1);
+            log->begin("dct_rows_fft", s);
             dct_rows_fft_kernel<<<grid, ppb * tpf, smem, s>>>(a, b, no, ni, inner.Lf, inner.log2L, ppb, inner.tw, done);
         } else {
+            log->begin("dct_rows_dense", s);
             dct_rows_dense_kernel<<<eb, 256, 0, s>>>(a, b, no, ni, inner.denseT, done);
         }
-        ++*launches;
+        log->end(s);
     };
     if (outer.fft) {
         // rows (in -> tmp1), fused column solve in place on tmp1, rows (tmp1 -> out)
@@ -296,16 +298,17 @@ inline void DctPlan::apply(cudaStream_t s, const double* in, double* out, const 
         const int ppb = dct_cols_ppb(outer, ni), tpf = outer.Lf >> 3;
         const int grid = ((ni + 1) / 2 + ppb - 1) / ppb;
         const size_t smem = sizeof(double2) * (size_t)ppb * (outer.Lf + 1);
+        log->begin("dct_cols_fft_solve", s);
         dct_cols_fft_solve_kernel<<<grid, ppb * tpf, smem, s>>>(t1, no, ni, outer.Lf, outer.log2L, ppb, outer.tw,
                                                                outer.lam, inner.lam, sym, norm, done);
-        ++*launches;
+        log->end(s);
         if (inner.fft) rows(t1, out); else { rows(t1, tmp2.p); VCH_CUDA(cudaMemcpyAsync(out, tmp2.p, n * sizeof(double), cudaMemcpyDeviceToDevice, s)); }
     } else {
         double *t1 = tmp1.p, *t2 = tmp2.p;
         rows(in, t1);
-        dct_cols_dense_kernel<<<eb, 256, 0, s>>>(t1, t2, no, ni, outer.denseT, done); ++*launches;
-        dct_scale_kernel<<<eb, 256, 0, s>>>(t2, no, ni, outer.lam, inner.lam, sym, norm, done); ++*launches;
-        dct_cols_dense_kernel<<<eb, 256, 0, s>>>(t2, t1, no, ni, outer.denseT, done); ++*launches;
+        log->begin("dct_cols_dense", s); dct_cols_dense_kernel<<<eb, 256, 0, s>>>(t1, t2, no, ni, outer.denseT, done); log->end(s);
+        log->begin("dct_scale", s); dct_scale_kernel<<<eb, 256, 0, s>>>(t2, no, ni, outer.lam, inner.lam, sym, norm, done); log->end(s);
+        log->begin("dct_cols_dense", s); dct_cols_dense_kernel<<<eb, 256, 0, s>>>(t2, t1, no, ni, outer.denseT, done); log->end(s);
         if (inner.fft) rows(t1, out);
         else { rows(t1, t2); VCH_CUDA(cudaMemcpyAsync(out, t2, n * sizeof(double), cudaMemcpyDeviceToDevice, s)); }
     }
