@@ -158,6 +158,8 @@ long long vch1d_launch_count(vch1d_ctx* c);
 int vch1d_residual(vch1d_ctx* c, int batch, const double* phi_new, const double* phi_old, const double* mu_new,
                    const double* mu_old, const double* w_new, const double* w_old, double dt,
                    double* Rphi_out, double* Rmu_out, int mem);
+/* initialize_mu(phi, w, c1, c2, L, kappa)              Forward_solver.py:82-86 */
+int vch1d_initialize_mu(vch1d_ctx* c, int batch, const double* phi, const double* w, double* mu_out, int mem);
 /* newton_raphson                                      Forward_solver.py:139-235.  res_hist (host, batch*hist_cap), n_hist (host, batch) */
 int vch1d_newton(vch1d_ctx* c, int batch, const double* phi_old, const double* mu_old, const double* w_old,
                  const double* w_new, double dt, double* phi_new_out, double* mu_new_out,

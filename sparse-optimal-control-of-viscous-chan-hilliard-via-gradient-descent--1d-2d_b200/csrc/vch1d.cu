@@ -271,6 +271,15 @@ __global__ void residual1d_kernel(P1 p, const double* __restrict__ phi, const do
     }
 }
 
+__global__ void mu_init1d_kernel(P1 p, const double* __restrict__ phi, const double* __restrict__ w, double* __restrict__ mu,
+                                 long long total) {
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        const long long prob = idx / p.n; const int i = (int)(idx - prob * p.n);
+        const double* f = phi + prob * p.n;
+        mu[idx] = -p.kappa * lap1(f, i, p.n, p.a) + p.c1 * flog1(f[i], p.eps_log) - 2.0 * p.c2 * f[i] - w[idx];
+    }
+}
+
 // Whole adjoint sweep of one problem per CTA (backward_solver.py:72-125).
 __global__ void adjoint1d_kernel(P1 p, const double* __restrict__ phi_hist, int levels, const double* __restrict__ t,
                                  const double* __restrict__ b1v, const double* __restrict__ b2v,
@@ -461,6 +470,23 @@ int vch1d_residual(vch1d_ctx* c, int batch, const double* phi_new, const double*
                      *w1 = st.in(w_new, tot), *w0 = st.in(w_old, tot);
         double *rp = st.out(Rphi_out, tot), *rm = st.out(Rmu_out, tot);
         residual1d_kernel<<<red_blocks(tot), 256, 0, c->stream>>>(p, a, b, m1, m0, w1, w0, dt, rp, rm, tot);
+        ++c->launches;
+        VCH_CUDA(cudaGetLastError());
+        st.finish();
+        return VCH_OK;
+    });
+}
+
+int vch1d_initialize_mu(vch1d_ctx* c, int batch, const double* phi, const double* w, double* mu_out, int mem) {
+    return guarded([&] {
+        VCH_REQUIRE(c && batch >= 1 && phi && w && mu_out, VCH_E_SHAPE, "initialize_mu: bad arguments");
+        VCH_CUDA(cudaSetDevice(c->device));
+        const P1 p = make_p1(c->prm);
+        const long long tot = (long long)batch * p.n;
+        Stager st(c->stream, mem);
+        const double *a = st.in(phi, tot), *b = st.in(w, tot);
+        double* o = st.out(mu_out, tot);
+        mu_init1d_kernel<<<red_blocks(tot), 256, 0, c->stream>>>(p, a, b, o, tot);
         ++c->launches;
         VCH_CUDA(cudaGetLastError());
         st.finish();

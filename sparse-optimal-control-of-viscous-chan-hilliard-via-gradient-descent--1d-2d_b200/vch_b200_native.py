@@ -51,7 +51,7 @@ EXPORTS = [
     "vch2d_apply_laplacian", "vch2d_initialize_mu", "vch_solve_w", "vch2d_residual", "vch2d_jacobian_solve",
     "vch2d_newton", "vch2d_forward", "vch2d_adjoint", "vch2d_cost", "vch_grad_prox", "vch_kkt_counts",
     "vch2d_pgd_iteration",
-    "vch1d_create", "vch1d_destroy", "vch1d_set_stream", "vch1d_launch_count", "vch1d_residual", "vch1d_newton",
+    "vch1d_create", "vch1d_destroy", "vch1d_set_stream", "vch1d_launch_count", "vch1d_residual", "vch1d_initialize_mu", "vch1d_newton",
     "vch1d_forward", "vch1d_adjoint", "vch1d_cost", "vch1d_grad_prox",
 ]
 
@@ -397,6 +397,13 @@ class Ctx1D:
                                     a.inp(rs(w_new)), a.inp(rs(w_old)), C.c_double(dt), prp, prm,
                                     _mem_of(phi_new, phi_old, mu_new, mu_old, w_new, w_old)))
         return (rp, rm) if had else (rp[0], rm[0])
+
+    def initialize_mu(self, phi, w):
+        a = _Args(); self._stream()
+        x, B, had = self._batched(phi, (self.n,))
+        out, po = a.out(phi, (B, self.n))
+        _check(lib().vch1d_initialize_mu(self.h, B, a.inp(phi.reshape(B, self.n)), a.inp(w.reshape(B, self.n)), po, _mem_of(phi, w)))
+        return out if had else out[0]
 
     def newton(self, phi_old, mu_old, w_old, w_new, dt, hist_cap=64):
         a = _Args(); self._stream()

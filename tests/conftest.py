@@ -18,7 +18,7 @@ def pytest_configure(config):
 
 def rel(a, b):
     a, b = np.asarray(a, dtype=float), np.asarray(b, dtype=float)
-    return float(np.linalg.norm((a - b).ravel()) / max(np.linalg.norm(b.ravel()), 1e-300))
+    return float(np.linalg.norm(a.ravel() - b.ravel()) / max(np.linalg.norm(b.ravel()), 1e-300))
 
 
 @pytest.fixture(scope="session")
@@ -34,3 +34,22 @@ def native():
     if nat.device_count() < 1:
         pytest.skip("no CUDA device")
     return nat
+
+
+DROPIN_NAMES = ("config", "Forward_solver", "backward_solver", "cost_and_function", "GD_1D", "second_order_conditions",
+                "Forward2_solver", "backward2_solver", "cost2_and_function", "GD2_configured", "second_order_conditions_2d")
+
+
+def load_dropin(dim):
+    """Put <package>/Vch_control_<dim> first on sys.path (the reference's modules import each other by bare name,
+    SURVEY §1) and drop bare-named modules of the other dimension from sys.modules."""
+    import importlib
+    for m in DROPIN_NAMES:
+        sys.modules.pop(m, None)
+    for d in ("1D", "2D"):
+        p = os.path.join(PKG, f"Vch_control_{d}")
+        while p in sys.path:
+            sys.path.remove(p)
+    sys.path.insert(0, os.path.join(PKG, f"Vch_control_{dim}"))
+    names = [n for n in DROPIN_NAMES if ("2" in n) == (dim == "2D") or n == "config"]
+    return {n: importlib.import_module(n) for n in names}
