@@ -81,12 +81,10 @@ int krylov_solve(vch2d_ctx* c, const double* b, const double* a, double c0, doub
         for (int k = 0; k < batch; ++k) {
             LAUNCH(c, bicg_p_kernel, eb, 256, c->kr.p, c->kp.p, c->kv.p, n, c->sc);
             op_apply<ADJ>(c, c->kp.p, a, c->ktmp.p, c0, c2, done);
-            c->dct.apply(c->stream, c->ktmp.p, c->kv.p, sy, done);
-            LAUNCH(c, bicg_dot1_kernel, rb, kRedThreads, c->kr0.p, c->kv.p, n, c->sc, c->red_part.p, c->ticket);
+            c->dct.apply(c->stream, c->ktmp.p, c->kv.p, sy, done, DotEpilogue{1, c->kr0.p, c->sc, c->red_part.p, c->ticket});   // + (r0, v) -> alpha
             LAUNCH(c, bicg_s_kernel, eb, 256, c->kr.p, c->kv.p, c->ks.p, n, c->sc);
             op_apply<ADJ>(c, c->ks.p, a, c->ktmp.p, c0, c2, done);
-            c->dct.apply(c->stream, c->ktmp.p, c->kt.p, sy, done);
-            LAUNCH(c, bicg_dot2_kernel, rb, kRedThreads, c->kt.p, c->ks.p, n, c->sc, c->red_part.p, c->ticket);
+            c->dct.apply(c->stream, c->ktmp.p, c->kt.p, sy, done, DotEpilogue{2, c->ks.p, c->sc, c->red_part.p, c->ticket});    // + (t, s), (t, t) -> omega
             LAUNCH(c, bicg_x_kernel, rb, kRedThreads, c->kx.p, c->kr.p, c->kp.p, c->ks.p, c->kt.p, c->kr0.p, n, c->sc,
                    c->red_part.p, c->ticket);
         }
@@ -356,7 +354,7 @@ int vch2d_create(const vch2d_params* p, int device, vch2d_ctx** out) {
                           &c->RphiT, &c->RmuT, &c->aT, &c->kb, &c->kx, &c->kr, &c->kr0, &c->kp, &c->kv, &c->ks, &c->kt,
                           &c->ktmp, &c->dmu})
             b->alloc(n);
-        c->red_part.alloc(8 * kRedBlocksMax);
+
         VCH_CUDA(cudaMalloc(&c->ticket, sizeof(unsigned int)));
         VCH_CUDA(cudaMemset(c->ticket, 0, sizeof(unsigned int)));
         VCH_CUDA(cudaMalloc(&c->sc, sizeof(Scal)));
@@ -365,6 +363,7 @@ int vch2d_create(const vch2d_params* p, int device, vch2d_ctx** out) {
         VCH_CUDA(cudaMalloc(&c->out4, 8 * sizeof(double)));
         VCH_CUDA(cudaMallocHost(&c->out4_host, 8 * sizeof(double)));
         c->dct.init(g.no, g.ni, p->hy, p->hx, &c->log);
+        c->red_part.alloc(8 * (size_t)c->dct.max_grid());
         Scal init{}; init.tol2 = c->krylov_tol * c->krylov_tol;
         VCH_CUDA(cudaMemcpy(c->sc, &init, sizeof(Scal), cudaMemcpyHostToDevice));
         *out = c;

@@ -20,17 +20,6 @@ struct Phys {
     double tau, gamma, c1, c2, kappa, lim /* 1-delta_sep */, eps_log /* max(1e-8, delta_sep/2) */, dsq /* 1-delta_sep^2 */;
 };
 
-// Device-resident scalars.  Host reads them through a pinned mirror.
-struct Scal {
-    double rho, rho_new, alpha, omega;
-    double r0v, ts, tt, rr, thr2, bnorm2;
-    double res2, amin, amax, abar, mu2;
-    double ceil_pos, ceil_neg;
-    double mass, wint, mass0;
-    double tol2;
-    int done, iters, nonfinite, pad;
-};
-
 __device__ __forceinline__ double lap_g(const double* __restrict__ v, int o, int i, const Geo& g) {
     const double c = v[(size_t)o * g.ni + i];
     const int im = (i > 0) ? i - 1 : 1, ip = (i < g.ni - 1) ? i + 1 : g.ni - 2;

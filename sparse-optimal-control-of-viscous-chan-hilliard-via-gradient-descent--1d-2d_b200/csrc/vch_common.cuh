@@ -124,6 +124,17 @@ struct LaunchLog {
     ~LaunchLog() { for (auto& r : recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); } for (auto e : pool) cudaEventDestroy(e); }
 };
 
+// Device-resident scalars.  Host reads them through a pinned mirror.
+struct Scal {
+    double rho, rho_new, alpha, omega;
+    double r0v, ts, tt, rr, thr2, bnorm2;
+    double res2, amin, amax, abar, mu2;
+    double ceil_pos, ceil_neg;
+    double mass, wint, mass0;
+    double tol2;
+    int done, iters, nonfinite, pad;
+};
+
 // ---------------------------------------------------------------- launch geometry
 constexpr int kSMs = 148;              // B200
 constexpr int kRedThreads = 256;

@@ -2,19 +2,30 @@
 // (eigenvectors cos(pi j k / N), eigenvalues -(4/h^2) sin^2(pi k / 2N)) and
 // f(lambda) = c0 + abar*lambda + c2*lambda^2 is the constant-coefficient symbol of the Schur / adjoint operator.
 //
-// A line of N+1 reals is transformed through the FFT of its even extension (length 2N).  Two lines share one
-// complex FFT (line a -> real part, line b -> imaginary part): the transform of a real-even sequence is real,
-// so Re/Im of the result are the two DCT-I outputs and no post-twiddle pass is needed.  The FFT itself is an
-// in-place shared-memory Stockham transform, radix 8 with one radix-4/2 tail pass, 8 points per thread in
-// registers, twiddles from a precomputed table.  Power-of-two N only; other N use the dense-table kernels below.
+// A line of N+1 reals is transformed through the FFT of its even extension (length Lf = 2N).  Two lines share one
+// complex FFT (line a -> real part, line b -> imaginary part): the transform of a real-even sequence is real, so
+// Re/Im of the result are the two DCT-I outputs and no post-twiddle pass is needed.
+//
+// The FFT is a Stockham autosort transform, radix 8 with one radix-8/4/2 last pass, 8 points per thread in registers:
+//   * the FIRST pass reads its 8 points straight from global memory (the even extension is formed by index
+//     reflection in the load), so the input is never staged;
+//   * middle passes go through a padded shared-memory array (index i -> i + i/8: the stride-8 stores of pass 1
+//     become conflict-free for 16-byte accesses);
+//   * the LAST pass hands its natural-order outputs to an epilogue: global store (rows), symbol division + mirrored
+//     store for the inverse transform (fused column solve), optionally dot products for BiCGStab;
+//   * twiddles w^r are built from 3 table loads (w, w^2, w^4) and 4 complex multiplies.
+// Rows (contiguous lines) and columns (stride-ni lines, 2*ppb adjacent columns per CTA so every 32-byte sector that
+// is fetched is fully used) share one kernel template.  N must be a power of two >= 32 for this path; other N use the
+// dense-table kernels at the bottom (small validation grids).
 #pragma once
 #include "vch_common.cuh"
+#include <algorithm>
 
 namespace vch {
 
 struct DctAxis {
     int n = 0;            // nodes = N+1
-    bool fft = false;     // N is a power of two >= 4
+    bool fft = false;     // N is a power of two, 32 <= N <= 4096
     int Lf = 0, log2L = 0;
     double2* tw = nullptr;    // Lf twiddles exp(-2 pi i m / Lf)
     double* denseT = nullptr; // n*n, denseT[j*n + k] = 2 c_j cos(pi j k / N)   (transposed for coalescing)
@@ -27,6 +38,15 @@ struct SymbolArgs {
     double abar_const;
 };
 
+// Optional epilogue of the last row transform: BiCGStab dot products over the freshly produced vector.
+struct DotEpilogue {
+    int mode = 0;                 // 0 none, 1: (other, out) -> alpha = rho_new / dot, rho = rho_new ; 2: (out, other), (out, out) -> omega
+    const double* other = nullptr;
+    Scal* sc = nullptr;
+    double* part = nullptr;
+    unsigned int* ticket = nullptr;
+};
+
 struct DctPlan {
     DctAxis inner, outer;     // inner = contiguous axis (length ni), outer = strided axis (length no)
     int ni = 0, no = 0;
@@ -34,8 +54,10 @@ struct DctPlan {
     LaunchLog* log = nullptr;
     void init(int no_, int ni_, double h_outer, double h_inner, LaunchLog* launch_log);
     void destroy();
-    // out = P^-1 in   (in may equal out)
-    void apply(cudaStream_t s, const double* in, double* out, const SymbolArgs& sym, const int* done_flag);
+    int max_grid() const;
+    // out = P^-1 in   (in may equal out); epi = optional fused dots on `out`
+    void apply(cudaStream_t s, const double* in, double* out, const SymbolArgs& sym, const int* done_flag,
+               const DotEpilogue& epi = DotEpilogue());
 };
 
 // ------------------------------------------------------------------------------------------------ device side
@@ -45,6 +67,7 @@ __device__ __forceinline__ double2 cmul(double2 a, double2 b) {
 __device__ __forceinline__ double2 cadd(double2 a, double2 b) { return make_double2(a.x + b.x, a.y + b.y); }
 __device__ __forceinline__ double2 csub(double2 a, double2 b) { return make_double2(a.x - b.x, a.y - b.y); }
 __device__ __forceinline__ double2 mul_mi(double2 a) { return make_double2(a.y, -a.x); }   // a * (-i)
+__device__ __forceinline__ int padi(int i) { return i + (i >> 3); }
 
 template <int R> __device__ __forceinline__ void dft(double2 (&v)[R]);
 template <> __device__ __forceinline__ void dft<2>(double2 (&v)[2]) {
@@ -69,114 +92,188 @@ template <> __device__ __forceinline__ void dft<8>(double2 (&v)[8]) {
     v[3] = cadd(e[3], o3);   v[7] = csub(e[3], o3);
 }
 
-// One Stockham pass of radix R over the FFT stored in `data` (length Lf), executed by tpf = Lf/8 threads.
+// Multiply v[r] by w^r, w = exp(-2 pi i k twstep / Lf); powers from 3 table loads.
 template <int R>
-__device__ __forceinline__ void fft_pass(double2* data, int Lf, int Ns, int t, int tpf, const double2* __restrict__ tw) {
+__device__ __forceinline__ void twiddle(double2 (&v)[R], int k, int twstep, const double2* __restrict__ tw) {
+    if (k == 0) return;
+    const double2 w1 = __ldg(&tw[k * twstep]);
+    v[1] = cmul(v[1], w1);
+    if (R >= 4) {
+        const double2 w2 = __ldg(&tw[2 * k * twstep]);
+        const double2 w3 = cmul(w1, w2);
+        v[2] = cmul(v[2], w2); v[3] = cmul(v[3], w3);
+        if (R == 8) {
+            const double2 w4 = __ldg(&tw[4 * k * twstep]);
+            v[4] = cmul(v[4], w4); v[5] = cmul(v[5], cmul(w1, w4));
+            v[6] = cmul(v[6], cmul(w2, w4)); v[7] = cmul(v[7], cmul(w3, w4));
+        }
+    }
+}
+
+// Middle radix-8 pass through padded shared memory: load, twiddle, DFT, barrier, store, barrier.
+__device__ __forceinline__ void fft_mid_pass(double2* data, int Lf, int Ns, int t, int tpf, const double2* __restrict__ tw) {
+    double2 v[8];
+    const int k = t & (Ns - 1);
+#pragma unroll
+    for (int r = 0; r < 8; ++r) v[r] = data[padi(t + r * tpf)];
+    twiddle<8>(v, k, Lf / (Ns * 8), tw);
+    dft<8>(v);
+    __syncthreads();
+    const int j0 = (t - k) * 8 + k;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) data[padi(j0 + r * Ns)] = v[r];
+    __syncthreads();
+}
+
+// First pass on 8 register values (Ns = 1: no twiddles): DFT and autosort store, then a barrier.
+__device__ __forceinline__ void fft_first_pass_store(double2* data, double2 (&v)[8], int t) {
+    dft<8>(v);
+#pragma unroll
+    for (int r = 0; r < 8; ++r) data[padi(8 * t + r)] = v[r];
+    __syncthreads();
+}
+
+// Last pass of radix R (8 / 4 / 2): loads, twiddles, DFT; outputs stay in registers: v[m][r] has natural index
+// j0[m] + r * Ns.
+template <int R>
+__device__ __forceinline__ void fft_last_pass_load(const double2* data, int Lf, int Ns, int t, int tpf,
+                                                   const double2* __restrict__ tw, double2 (&v)[8 / R][R], int (&j0)[8 / R]) {
     constexpr int NB = 8 / R;
     const int stride = Lf / R;
-    const int twstep = Lf / (Ns * R);
-    double2 v[NB][R];
-    int kk[NB], jj[NB];
 #pragma unroll
     for (int m = 0; m < NB; ++m) {
-        const int j = t + m * tpf;
-        const int k = j & (Ns - 1);
-        jj[m] = j; kk[m] = k;
+        const int j = t + m * tpf, k = j & (Ns - 1);
 #pragma unroll
-        for (int r = 0; r < R; ++r) {
-            double2 x = data[j + r * stride];
-            if (r > 0 && k > 0) x = cmul(x, __ldg(&tw[r * k * twstep]));
-            v[m][r] = x;
-        }
+        for (int r = 0; r < R; ++r) v[m][r] = data[padi(j + r * stride)];
+        twiddle<R>(v[m], k, Lf / (Ns * R), tw);
         dft<R>(v[m]);
+        j0[m] = (j - k) * R + k;
     }
-    __syncthreads();
-#pragma unroll
-    for (int m = 0; m < NB; ++m) {
-        const int j0 = (jj[m] - kk[m]) * R + kk[m];
-#pragma unroll
-        for (int r = 0; r < R; ++r) data[j0 + r * Ns] = v[m][r];
-    }
-    __syncthreads();
 }
 
-__device__ __forceinline__ void fft_inplace(double2* data, int Lf, int log2L, int t, int tpf, const double2* __restrict__ tw) {
-    int Ns = 1;
+// Runs the middle passes between the first-pass store and the last pass.  Returns Ns of the last pass.
+__device__ __forceinline__ int fft_middle(double2* data, int Lf, int log2L, int t, int tpf, const double2* __restrict__ tw) {
     const int n8 = log2L / 3, rem = log2L - 3 * n8;
-    for (int p = 0; p < n8; ++p) { fft_pass<8>(data, Lf, Ns, t, tpf, tw); Ns *= 8; }
-    if (rem == 2) fft_pass<4>(data, Lf, Ns, t, tpf, tw);
-    else if (rem == 1) fft_pass<2>(data, Lf, Ns, t, tpf, tw);
+    const int mids = (rem == 0) ? n8 - 2 : n8 - 1;     // radix-8 passes strictly between first and last
+    int Ns = 8;
+    for (int p = 0; p < mids; ++p) { fft_mid_pass(data, Lf, Ns, t, tpf, tw); Ns *= 8; }
+    return Ns;
 }
 
-// Lines along the contiguous axis.  Each CTA owns ppb line pairs; blockDim = ppb * Lf/8.
-__global__ void dct_rows_fft_kernel(const double* __restrict__ in, double* __restrict__ out, int lines, int n,
-                                    int Lf, int log2L, int ppb, const double2* __restrict__ tw,
-                                    const int* __restrict__ done) {
-    if (done && *done) return;
-    extern __shared__ double2 sm[];
-    const int N = n - 1, ld = Lf + 1;
-    const int pair0 = blockIdx.x * ppb;
-    for (int e = threadIdx.x; e < ppb * n; e += blockDim.x) {
-        const int f = e / n, j = e - f * n;
-        const int a = 2 * (pair0 + f), b = a + 1;
-        double2 z;
-        z.x = (a < lines) ? in[(size_t)a * n + j] : 0.0;
-        z.y = (b < lines) ? in[(size_t)b * n + j] : 0.0;
-        sm[f * ld + j] = z;
-        if (j > 0 && j < N) sm[f * ld + 2 * N - j] = z;
-    }
-    __syncthreads();
-    const int tpf = Lf >> 3;
-    const int f = threadIdx.x / tpf, t = threadIdx.x - f * tpf;
-    fft_inplace(sm + f * ld, Lf, log2L, t, tpf, tw);
-    for (int e = threadIdx.x; e < ppb * n; e += blockDim.x) {
-        const int ff = e / n, k = e - ff * n;
-        const int a = 2 * (pair0 + ff), b = a + 1;
-        const double2 z = sm[ff * ld + k];
-        if (a < lines) out[(size_t)a * n + k] = z.x;
-        if (b < lines) out[(size_t)b * n + k] = z.y;
+// Last pass into an 8-entry register list (index + value), any tail radix.
+__device__ __forceinline__ void fft_last_pass(const double2* data, int Lf, int log2L, int Ns, int t, int tpf,
+                                              const double2* __restrict__ tw, double2 (&z)[8], int (&kk)[8]) {
+    const int rem = log2L % 3;
+    if (rem == 0) {
+        double2 o[1][8]; int j0[1];
+        fft_last_pass_load<8>(data, Lf, Ns, t, tpf, tw, o, j0);
+#pragma unroll
+        for (int r = 0; r < 8; ++r) { z[r] = o[0][r]; kk[r] = j0[0] + r * Ns; }
+    } else if (rem == 2) {
+        double2 o[2][4]; int j0[2];
+        fft_last_pass_load<4>(data, Lf, Ns, t, tpf, tw, o, j0);
+#pragma unroll
+        for (int m = 0; m < 2; ++m)
+#pragma unroll
+            for (int r = 0; r < 4; ++r) { z[m * 4 + r] = o[m][r]; kk[m * 4 + r] = j0[m] + r * Ns; }
+    } else {
+        double2 o[4][2]; int j0[4];
+        fft_last_pass_load<2>(data, Lf, Ns, t, tpf, tw, o, j0);
+#pragma unroll
+        for (int m = 0; m < 4; ++m)
+#pragma unroll
+            for (int r = 0; r < 2; ++r) { z[m * 2 + r] = o[m][r]; kk[m * 2 + r] = j0[m] + r * Ns; }
     }
 }
 
-// Lines along the strided axis, fused forward transform -> divide by the symbol -> inverse transform.
-// Each CTA owns 2*ppb adjacent columns so global accesses are 16*ppb-byte segments.
-__global__ void dct_cols_fft_solve_kernel(double* d, int no, int ni,
-                                          int Lf, int log2L, int ppb, const double2* __restrict__ tw,
-                                          const double* __restrict__ lam_o, const double* __restrict__ lam_i,
-                                          SymbolArgs sy, double norm, const int* __restrict__ done) {
+// One CTA = ppb complex FFTs (2*ppb lines).  Line l, element e lives at base[l*line_stride + e*elem_stride].
+//   SOLVE = false: out = DCT-I(in) per line (unnormalised "FFT of the even extension").
+//   SOLVE = true : fused  forward transform -> divide by symbol -> inverse transform  (column solve, in place).
+template <bool SOLVE, int MAXT>
+__global__ void __launch_bounds__(MAXT, 1024 / MAXT)
+dct_fft_kernel(const double* in, double* out, int nlines, int n, int line_stride, int elem_stride, int Lf,
+               int log2L, int ppb, const double2* __restrict__ tw, const double* __restrict__ lam_line,
+               const double* __restrict__ lam_elem, SymbolArgs sy, double norm, DotEpilogue epi,
+               const int* __restrict__ done) {
     if (done && *done) return;
     extern __shared__ double2 sm[];
-    const int N = no - 1, ld = Lf + 1, cw = 2 * ppb;
-    const int c0 = blockIdx.x * cw;
-    double* smd = reinterpret_cast<double*>(sm);
-    for (int e = threadIdx.x; e < no * cw; e += blockDim.x) {
-        const int o = e / cw, cc = e - o * cw, c = c0 + cc;
-        const double x = (c < ni) ? d[(size_t)o * ni + c] : 0.0;
-        const int f = cc >> 1, part = cc & 1;
-        smd[2 * (f * ld + o) + part] = x;
-        if (o > 0 && o < N) smd[2 * (f * ld + 2 * N - o) + part] = x;
-    }
-    __syncthreads();
-    const int tpf = Lf >> 3;
+    const int N = n - 1, tpf = Lf >> 3, ld = Lf + (Lf >> 3) + 1;
     const int f = threadIdx.x / tpf, t = threadIdx.x - f * tpf;
-    fft_inplace(sm + f * ld, Lf, log2L, t, tpf, tw);
-    const double abar = sy.abar_ptr ? *sy.abar_ptr : sy.abar_const;
-    for (int e = threadIdx.x; e < ppb * no; e += blockDim.x) {
-        const int ff = e / no, k = e - ff * no;
-        const int ca = c0 + 2 * ff, cb = ca + 1;
-        double2 z = sm[ff * ld + k];
-        const double lo = lam_o[k];
-        const double la = lo + ((ca < ni) ? lam_i[ca] : 0.0), lb = lo + ((cb < ni) ? lam_i[cb] : 0.0);
-        z.x *= norm / (sy.c0 + la * (abar + sy.c2 * la));
-        z.y *= norm / (sy.c0 + lb * (abar + sy.c2 * lb));
-        sm[ff * ld + k] = z;
-        if (k > 0 && k < N) sm[ff * ld + 2 * N - k] = z;
+    double2* data = sm + (size_t)f * ld;
+    const int la = 2 * (blockIdx.x * ppb + f), lb = la + 1;
+    const bool va = la < nlines, vb = lb < nlines;
+    const double* pa = in + (size_t)la * line_stride;
+    const double* pb = in + (size_t)lb * line_stride;
+
+    // ---- first pass straight from global memory (even extension by index reflection)
+    double2 v[8];
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+        const int e = t + r * tpf;
+        const int off = (e <= N ? e : Lf - e) * elem_stride;
+        v[r].x = va ? pa[off] : 0.0;
+        v[r].y = vb ? pb[off] : 0.0;
     }
-    __syncthreads();
-    fft_inplace(sm + f * ld, Lf, log2L, t, tpf, tw);
-    for (int e = threadIdx.x; e < no * cw; e += blockDim.x) {
-        const int o = e / cw, cc = e - o * cw, c = c0 + cc;
-        if (c < ni) d[(size_t)o * ni + c] = smd[2 * ((cc >> 1) * ld + o) + (cc & 1)];
+    fft_first_pass_store(data, v, t);
+    int Ns = fft_middle(data, Lf, log2L, t, tpf, tw);
+    double2 z[8]; int kk[8];
+    fft_last_pass(data, Lf, log2L, Ns, t, tpf, tw, z, kk);
+
+    if (SOLVE) {
+        // forward outputs -> divide by the symbol -> mirrored store = input of the inverse transform
+        const double abar = sy.abar_ptr ? *sy.abar_ptr : sy.abar_const;
+        const double lla = va ? lam_line[la] : 0.0, llb = vb ? lam_line[lb] : 0.0;
+        __syncthreads();                         // every thread has finished reading the forward data
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            if (kk[q] <= N) {
+                const double le = lam_elem[kk[q]];
+                const double s1 = le + lla, s2 = le + llb;
+                double2 w = z[q];
+                w.x *= norm / (sy.c0 + s1 * (abar + sy.c2 * s1));
+                w.y *= norm / (sy.c0 + s2 * (abar + sy.c2 * s2));
+                data[padi(kk[q])] = w;
+                if (kk[q] > 0 && kk[q] < N) data[padi(Lf - kk[q])] = w;
+            }
+        }
+        __syncthreads();
+        // inverse = the same transform applied to the (real-even) scaled spectrum; its first pass reads shared memory
+#pragma unroll
+        for (int r = 0; r < 8; ++r) v[r] = data[padi(t + r * tpf)];
+        __syncthreads();
+        fft_first_pass_store(data, v, t);
+        Ns = fft_middle(data, Lf, log2L, t, tpf, tw);
+        fft_last_pass(data, Lf, log2L, Ns, t, tpf, tw, z, kk);
+    }
+
+    double acc1 = 0.0, acc2 = 0.0;
+    double* qa = out + (size_t)la * line_stride;
+    double* qb = out + (size_t)lb * line_stride;
+    const double* oa = epi.other + (size_t)la * line_stride;
+    const double* ob = epi.other + (size_t)lb * line_stride;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        if (kk[q] <= N) {
+            const int off = kk[q] * elem_stride;
+            if (va) {
+                qa[off] = z[q].x;
+                if (epi.mode) { acc1 += oa[off] * z[q].x; acc2 += z[q].x * z[q].x; }
+            }
+            if (vb) {
+                qb[off] = z[q].y;
+                if (epi.mode) { acc1 += ob[off] * z[q].y; acc2 += z[q].y * z[q].y; }
+            }
+        }
+    }
+    if (epi.mode) {     // block-uniform: every thread of every CTA takes part in the reduction
+        double vals[2] = {acc1, acc2};
+        const int op[2] = {0, 0};
+        double tot[2];
+        if (grid_reduce<2>(vals, op, epi.part, epi.ticket, tot) && threadIdx.x == 0) {
+            Scal* sc = epi.sc;
+            if (epi.mode == 1) { sc->r0v = tot[0]; sc->alpha = sc->rho_new / tot[0]; sc->rho = sc->rho_new; }
+            else { sc->ts = tot[0]; sc->tt = tot[1]; sc->omega = (tot[1] > 0.0) ? tot[0] / tot[1] : 0.0; }
+        }
     }
 }
 
@@ -213,12 +310,28 @@ __global__ void dct_scale_kernel(double* __restrict__ d, int no, int ni, const d
     const double l = lam_o[k] + lam_i[c];
     d[idx] *= norm / (sy.c0 + l * (abar + sy.c2 * l));
 }
+// Stand-alone BiCGStab dots for the paths without the fused epilogue.
+__global__ void dct_dots_kernel(const double* __restrict__ outv, DotEpilogue epi, long long n, const int* __restrict__ done) {
+    if (done && *done) return;
+    double vals[2] = {0.0, 0.0};
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (long long)gridDim.x * blockDim.x) {
+        const double zz = outv[idx];
+        vals[0] += epi.other[idx] * zz; vals[1] += zz * zz;
+    }
+    const int op[2] = {0, 0};
+    double tot[2];
+    if (grid_reduce<2>(vals, op, epi.part, epi.ticket, tot) && threadIdx.x == 0) {
+        Scal* sc = epi.sc;
+        if (epi.mode == 1) { sc->r0v = tot[0]; sc->alpha = sc->rho_new / tot[0]; sc->rho = sc->rho_new; }
+        else { sc->ts = tot[0]; sc->tt = tot[1]; sc->omega = (tot[1] > 0.0) ? tot[0] / tot[1] : 0.0; }
+    }
+}
 
 // ------------------------------------------------------------------------------------------------ host side
 static inline void dct_axis_init(DctAxis& ax, int n, double h) {
     const int N = n - 1;
     ax.n = n;
-    ax.fft = (N >= 4) && ((N & (N - 1)) == 0) && (2 * N <= 8192);
+    ax.fft = (N >= 32) && ((N & (N - 1)) == 0) && (N <= 4096);
     std::vector<double> lam(n);
     for (int k = 0; k < n; ++k) {
         const long double s = sinl(3.14159265358979323846264338327950288L * k / (2.0L * N));
@@ -258,10 +371,16 @@ static inline int dct_rows_ppb(const DctAxis& ax, int lines) {
 }
 static inline int dct_cols_ppb(const DctAxis& ax, int ncols) {
     const int tpf = ax.Lf >> 3;
-    int ppb = 512 / tpf; if (ppb < 1) ppb = 1; if (ppb > 8) ppb = 8;
+    int ppb = 512 / tpf;
+    if (ppb < 2 && tpf <= 512) ppb = 2;       // >= 4 adjacent columns so fetched 32-byte sectors are fully used
+    if (ppb < 1) ppb = 1;
+    if (ppb > 8) ppb = 8;
     const int pairs = (ncols + 1) / 2;
     if (ppb > pairs) ppb = pairs;
     return ppb;
+}
+static inline size_t dct_smem(const DctAxis& ax, int ppb) {
+    return sizeof(double2) * (size_t)ppb * (ax.Lf + (ax.Lf >> 3) + 1);
 }
 
 inline void DctPlan::init(int no_, int ni_, double h_outer, double h_inner, LaunchLog* launch_log) {
@@ -270,47 +389,77 @@ inline void DctPlan::init(int no_, int ni_, double h_outer, double h_inner, Laun
     dct_axis_init(outer, no, h_outer);
     tmp1.alloc((size_t)no * ni);
     tmp2.alloc((size_t)no * ni);
-    VCH_CUDA(cudaFuncSetAttribute(dct_rows_fft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    VCH_CUDA(cudaFuncSetAttribute(dct_cols_fft_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    const int big = 200 * 1024;
+    VCH_CUDA(cudaFuncSetAttribute(dct_fft_kernel<false, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    VCH_CUDA(cudaFuncSetAttribute(dct_fft_kernel<true, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    VCH_CUDA(cudaFuncSetAttribute(dct_fft_kernel<false, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    VCH_CUDA(cudaFuncSetAttribute(dct_fft_kernel<true, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
 }
 
-inline void DctPlan::apply(cudaStream_t s, const double* in, double* out, const SymbolArgs& sym, const int* done) {
+inline int DctPlan::max_grid() const {
+    int g = kRedBlocksMax;
+    if (inner.fft) { const int ppb = dct_rows_ppb(inner, no); g = std::max(g, ((no + 1) / 2 + ppb - 1) / ppb); }
+    return g;
+}
+
+inline void DctPlan::apply(cudaStream_t s, const double* in, double* out, const SymbolArgs& sym, const int* done,
+                           const DotEpilogue& epi) {
     const long long n = (long long)no * ni;
     const int eb = (int)((n + 255) / 256);
     const double norm = 1.0 / (4.0 * (double)(ni - 1) * (double)(no - 1));
-    auto rows = [&](const double* a, double* b) {
+    const SymbolArgs nosym{1.0, 0.0, nullptr, 0.0};
+    bool epi_done = (epi.mode == 0);
+    auto rows = [&](const double* a, double* b, bool last) {
         if (inner.fft) {
-            const int ppb = dct_rows_ppb(inner, no), tpf = inner.Lf >> 3;
+            const int ppb = dct_rows_ppb(inner, no), tpf = inner.Lf >> 3, threads = ppb * tpf;
             const int grid = ((no + 1) / 2 + ppb - 1) / ppb;
-            const size_t smem = sizeof(double2) * (size_t)ppb * (inner.Lf + 1);
+            const size_t smem = dct_smem(inner, ppb);
+            const DotEpilogue e = last ? epi : DotEpilogue();
+            if (last) epi_done = true;
             log->begin("dct_rows_fft", s);
-            dct_rows_fft_kernel<<<grid, ppb * tpf, smem, s>>>(a, b, no, ni, inner.Lf, inner.log2L, ppb, inner.tw, done);
+            if (threads <= 512)
+                dct_fft_kernel<false, 512><<<grid, threads, smem, s>>>(a, b, no, ni, ni, 1, inner.Lf, inner.log2L, ppb, inner.tw,
+                                                                       nullptr, nullptr, nosym, 1.0, e, done);
+            else
+                dct_fft_kernel<false, 1024><<<grid, threads, smem, s>>>(a, b, no, ni, ni, 1, inner.Lf, inner.log2L, ppb, inner.tw,
+                                                                        nullptr, nullptr, nosym, 1.0, e, done);
         } else {
             log->begin("dct_rows_dense", s);
             dct_rows_dense_kernel<<<eb, 256, 0, s>>>(a, b, no, ni, inner.denseT, done);
         }
         log->end(s);
     };
+    double* t1 = tmp1.p;
+    double* t2 = tmp2.p;
+    rows(in, t1, false);
     if (outer.fft) {
-        // rows (in -> tmp1), fused column solve in place on tmp1, rows (tmp1 -> out)
-        double* t1 = tmp1.p;
-        rows(in, t1);
-        const int ppb = dct_cols_ppb(outer, ni), tpf = outer.Lf >> 3;
+        // fused column solve, in place on t1: lines = columns (stride 1), elements stride ni
+        const int ppb = dct_cols_ppb(outer, ni), tpf = outer.Lf >> 3, threads = ppb * tpf;
         const int grid = ((ni + 1) / 2 + ppb - 1) / ppb;
-        const size_t smem = sizeof(double2) * (size_t)ppb * (outer.Lf + 1);
+        const size_t smem = dct_smem(outer, ppb);
         log->begin("dct_cols_fft_solve", s);
-        dct_cols_fft_solve_kernel<<<grid, ppb * tpf, smem, s>>>(t1, no, ni, outer.Lf, outer.log2L, ppb, outer.tw,
-                                                               outer.lam, inner.lam, sym, norm, done);
+        if (threads <= 512)
+            dct_fft_kernel<true, 512><<<grid, threads, smem, s>>>(t1, t1, ni, no, 1, ni, outer.Lf, outer.log2L, ppb, outer.tw,
+                                                                  inner.lam, outer.lam, sym, norm, DotEpilogue(), done);
+        else
+            dct_fft_kernel<true, 1024><<<grid, threads, smem, s>>>(t1, t1, ni, no, 1, ni, outer.Lf, outer.log2L, ppb, outer.tw,
+                                                                   inner.lam, outer.lam, sym, norm, DotEpilogue(), done);
         log->end(s);
-        if (inner.fft) rows(t1, out); else { rows(t1, tmp2.p); VCH_CUDA(cudaMemcpyAsync(out, tmp2.p, n * sizeof(double), cudaMemcpyDeviceToDevice, s)); }
     } else {
-        double *t1 = tmp1.p, *t2 = tmp2.p;
-        rows(in, t1);
         log->begin("dct_cols_dense", s); dct_cols_dense_kernel<<<eb, 256, 0, s>>>(t1, t2, no, ni, outer.denseT, done); log->end(s);
         log->begin("dct_scale", s); dct_scale_kernel<<<eb, 256, 0, s>>>(t2, no, ni, outer.lam, inner.lam, sym, norm, done); log->end(s);
         log->begin("dct_cols_dense", s); dct_cols_dense_kernel<<<eb, 256, 0, s>>>(t2, t1, no, ni, outer.denseT, done); log->end(s);
-        if (inner.fft) rows(t1, out);
-        else { rows(t1, t2); VCH_CUDA(cudaMemcpyAsync(out, t2, n * sizeof(double), cudaMemcpyDeviceToDevice, s)); }
+    }
+    if (inner.fft) {
+        rows(t1, out, true);
+    } else {                                   // the dense row kernel is not in-place safe and `in` may alias `out`
+        rows(t1, t2, true);
+        VCH_CUDA(cudaMemcpyAsync(out, t2, n * sizeof(double), cudaMemcpyDeviceToDevice, s));
+    }
+    if (!epi_done) {
+        log->begin("dct_dots", s);
+        dct_dots_kernel<<<red_blocks(n), kRedThreads, 0, s>>>(out, epi, n, done);
+        log->end(s);
     }
     VCH_CUDA(cudaGetLastError());
 }

@@ -206,3 +206,30 @@ def test_adjoint_step_identity_small_rect(native):
         rhs = B @ p[n + 1].ravel() + 0.5 * dt * b1 * (hist[n].ravel() + hist[n + 1].ravel())
         res = np.linalg.norm(A @ p[n].ravel() - rhs) / np.linalg.norm(rhs)
         assert res < 2e3 * np.finfo(float).eps * np.linalg.cond(A)
+
+
+@pytest.mark.parametrize("N", [32, 64, 128, 256, 512, 1024, 2048])
+def test_dct_fast_solve_is_exact_for_constant_coefficients(native, N):
+    """With phi = const the Schur operator has constant coefficients, so ONE application of the DCT-I preconditioner is
+    the exact solve.  Checked against SciPy's dctn at every power-of-two FFT length the kernels support up to 2048
+    (this is the size-independent property that covers the 1024^2 benchmark grid)."""
+    from scipy.fft import dctn
+    P = O.Phys2D(Nx=N, Ny=N)
+    c = make_ctx(native, P)
+    n1 = N + 1
+    rng = np.random.default_rng(N)
+    phi = np.full((n1, n1), 0.3)
+    Rp, Rm = rng.standard_normal((n1, n1)), rng.standard_normal((n1, n1))
+    dt = 1e-2
+    dphi, dmu, its = c.jacobian_solve(phi, dt, Rp, Rm)
+    assert its <= 2
+    h = 1.0 / N
+    lam1 = (4 / h ** 2) * np.sin(np.pi * np.arange(n1) / (2 * N)) ** 2
+    lam = lam1[:, None] + lam1[None, :]
+    a = P.tau / dt + 2 * P.c1 / (1 - 0.09)
+    sym = 1 / dt + a * lam + 0.5 * P.kappa * lam ** 2
+    apply_L = lambda v: dctn(-lam * dctn(v, type=1), type=1) / (4 * N * N)
+    b = -Rm + apply_L(Rp)
+    ref = dctn(dctn(b, type=1) / sym, type=1) / (4 * N * N)
+    assert rel(dphi, ref) < 1e-10
+    assert rel(dmu, 2 * (a * ref - 0.5 * P.kappa * apply_L(ref) + Rp)) < 1e-8     # L amplifies rounding by 1/h^2
