@@ -49,7 +49,7 @@ struct DotEpilogue {
 
 struct DctPlan {
     DctAxis inner, outer;     // inner = contiguous axis (length ni), outer = strided axis (length no)
-    int ni = 0, no = 0;
+    int ni = 0, no = 0, pitch = 0;   // pitch of tmp1 (even, so column pairs are 16-byte aligned)
     DevBuf tmp1, tmp2;
     LaunchLog* log = nullptr;
     void init(int no_, int ni_, double h_outer, double h_inner, LaunchLog* launch_log);
@@ -92,18 +92,32 @@ template <> __device__ __forceinline__ void dft<8>(double2 (&v)[8]) {
     v[3] = cadd(e[3], o3);   v[7] = csub(e[3], o3);
 }
 
-// Multiply v[r] by w^r, w = exp(-2 pi i k twstep / Lf); powers from 3 table loads.
+// Twiddle tables in shared memory: w(m) = exp(-2 pi i m / Lf) = hi[m >> 5] * lo[m & 31]  (32 + Lf/32 entries instead of a
+// global table of Lf entries: no global loads inside the passes).  lo is stored padded (i -> i + i/8) so that the
+// stride-4 reads of the third pass are conflict-free.
+struct TwTab { const double2* lo; const double2* hi; };
+constexpr int kTwLo = 32 + 4;   // padded length of the low table
+
+__device__ __forceinline__ double2 tw_get(const TwTab& T, int m) {
+    const int l = m & 31;
+    return cmul(T.hi[m >> 5], T.lo[l + (l >> 3)]);
+}
+
+// Multiply v[r] by w^r, w = exp(-2 pi i k twstep / Lf); w from the tables, powers by squaring / multiplying.
 template <int R>
-__device__ __forceinline__ void twiddle(double2 (&v)[R], int k, int twstep, const double2* __restrict__ tw) {
+__device__ __forceinline__ void twiddle(double2 (&v)[R], int k, int twstep, const TwTab& T) {
+#ifdef VCH_FFT_NOTW
+    return;
+#endif
     if (k == 0) return;
-    const double2 w1 = __ldg(&tw[k * twstep]);
+    const double2 w1 = tw_get(T, k * twstep);
     v[1] = cmul(v[1], w1);
     if (R >= 4) {
-        const double2 w2 = __ldg(&tw[2 * k * twstep]);
+        const double2 w2 = cmul(w1, w1);
         const double2 w3 = cmul(w1, w2);
         v[2] = cmul(v[2], w2); v[3] = cmul(v[3], w3);
         if (R == 8) {
-            const double2 w4 = __ldg(&tw[4 * k * twstep]);
+            const double2 w4 = cmul(w2, w2);
             v[4] = cmul(v[4], w4); v[5] = cmul(v[5], cmul(w1, w4));
             v[6] = cmul(v[6], cmul(w2, w4)); v[7] = cmul(v[7], cmul(w3, w4));
         }
@@ -111,7 +125,7 @@ __device__ __forceinline__ void twiddle(double2 (&v)[R], int k, int twstep, cons
 }
 
 // Middle radix-8 pass through padded shared memory: load, twiddle, DFT, barrier, store, barrier.
-__device__ __forceinline__ void fft_mid_pass(double2* data, int Lf, int Ns, int t, int tpf, const double2* __restrict__ tw) {
+__device__ __forceinline__ void fft_mid_pass(double2* data, int Lf, int Ns, int t, int tpf, const TwTab& tw) {
     double2 v[8];
     const int k = t & (Ns - 1);
 #pragma unroll
@@ -137,7 +151,7 @@ __device__ __forceinline__ void fft_first_pass_store(double2* data, double2 (&v)
 // j0[m] + r * Ns.
 template <int R>
 __device__ __forceinline__ void fft_last_pass_load(const double2* data, int Lf, int Ns, int t, int tpf,
-                                                   const double2* __restrict__ tw, double2 (&v)[8 / R][R], int (&j0)[8 / R]) {
+                                                   const TwTab& tw, double2 (&v)[8 / R][R], int (&j0)[8 / R]) {
     constexpr int NB = 8 / R;
     const int stride = Lf / R;
 #pragma unroll
@@ -152,17 +166,21 @@ __device__ __forceinline__ void fft_last_pass_load(const double2* data, int Lf, 
 }
 
 // Runs the middle passes between the first-pass store and the last pass.  Returns Ns of the last pass.
-__device__ __forceinline__ int fft_middle(double2* data, int Lf, int log2L, int t, int tpf, const double2* __restrict__ tw) {
+__device__ __forceinline__ int fft_middle(double2* data, int Lf, int log2L, int t, int tpf, const TwTab& tw) {
     const int n8 = log2L / 3, rem = log2L - 3 * n8;
     const int mids = (rem == 0) ? n8 - 2 : n8 - 1;     // radix-8 passes strictly between first and last
     int Ns = 8;
+#ifndef VCH_FFT_NOMID
     for (int p = 0; p < mids; ++p) { fft_mid_pass(data, Lf, Ns, t, tpf, tw); Ns *= 8; }
+#else
+    for (int p = 0; p < mids; ++p) Ns *= 8;
+#endif
     return Ns;
 }
 
 // Last pass into an 8-entry register list (index + value), any tail radix.
 __device__ __forceinline__ void fft_last_pass(const double2* data, int Lf, int log2L, int Ns, int t, int tpf,
-                                              const double2* __restrict__ tw, double2 (&z)[8], int (&kk)[8]) {
+                                              const TwTab& tw, double2 (&z)[8], int (&kk)[8]) {
     const int rem = log2L % 3;
     if (rem == 0) {
         double2 o[1][8]; int j0[1];
@@ -189,30 +207,47 @@ __device__ __forceinline__ void fft_last_pass(const double2* data, int Lf, int l
 // One CTA = ppb complex FFTs (2*ppb lines).  Line l, element e lives at base[l*line_stride + e*elem_stride].
 //   SOLVE = false: out = DCT-I(in) per line (unnormalised "FFT of the even extension").
 //   SOLVE = true : fused  forward transform -> divide by symbol -> inverse transform  (column solve, in place).
+#ifndef VCH_FFT_MINB
+#define VCH_FFT_MINB (1024 / MAXT)
+#endif
 template <bool SOLVE, int MAXT>
-__global__ void __launch_bounds__(MAXT, 1024 / MAXT)
-dct_fft_kernel(const double* in, double* out, int nlines, int n, int line_stride, int elem_stride, int Lf,
-               int log2L, int ppb, const double2* __restrict__ tw, const double* __restrict__ lam_line,
+__global__ void __launch_bounds__(MAXT, VCH_FFT_MINB)
+dct_fft_kernel(const double* in, double* out, int nlines, int n, int in_ls, int in_es, int out_ls, int out_es, int Lf,
+               int log2L, int ppb, const double2* __restrict__ twg, const double* __restrict__ lam_line,
                const double* __restrict__ lam_elem, SymbolArgs sy, double norm, DotEpilogue epi,
                const int* __restrict__ done) {
     if (done && *done) return;
     extern __shared__ double2 sm[];
     const int N = n - 1, tpf = Lf >> 3, ld = Lf + (Lf >> 3) + 1;
     const int f = threadIdx.x / tpf, t = threadIdx.x - f * tpf;
-    double2* data = sm + (size_t)f * ld;
+    // twiddle tables first (visible after the first-pass barrier), FFT buffers behind them
+    double2* tlo = sm;
+    double2* thi = sm + kTwLo;
+    for (int i = threadIdx.x; i < 32 + (Lf >> 5); i += blockDim.x) {
+        if (i < 32) tlo[i + (i >> 3)] = twg[i];
+        else thi[i - 32] = twg[(i - 32) << 5];
+    }
+    const TwTab tw{tlo, thi};
+    double2* data = sm + kTwLo + (Lf >> 5) + (size_t)f * ld;
     const int la = 2 * (blockIdx.x * ppb + f), lb = la + 1;
     const bool va = la < nlines, vb = lb < nlines;
-    const double* pa = in + (size_t)la * line_stride;
-    const double* pb = in + (size_t)lb * line_stride;
+    const double* pa = in + (size_t)la * in_ls;
+    const double* pb = in + (size_t)lb * in_ls;
 
-    // ---- first pass straight from global memory (even extension by index reflection)
+    // ---- first pass straight from global memory (even extension by index reflection).
+    // SOLVE (columns): the two lines of a pair are adjacent doubles of a pitched buffer whose pitch is even, so one
+    // 16-byte access moves both.
     double2 v[8];
 #pragma unroll
     for (int r = 0; r < 8; ++r) {
         const int e = t + r * tpf;
-        const int off = (e <= N ? e : Lf - e) * elem_stride;
-        v[r].x = va ? pa[off] : 0.0;
-        v[r].y = vb ? pb[off] : 0.0;
+        const int off = (e <= N ? e : Lf - e) * in_es;
+        if (SOLVE) {
+            v[r] = va ? *reinterpret_cast<const double2*>(pa + off) : make_double2(0.0, 0.0);
+        } else {
+            v[r].x = va ? pa[off] : 0.0;
+            v[r].y = vb ? pb[off] : 0.0;
+        }
     }
     fft_first_pass_store(data, v, t);
     int Ns = fft_middle(data, Lf, log2L, t, tpf, tw);
@@ -247,21 +282,25 @@ dct_fft_kernel(const double* in, double* out, int nlines, int n, int line_stride
     }
 
     double acc1 = 0.0, acc2 = 0.0;
-    double* qa = out + (size_t)la * line_stride;
-    double* qb = out + (size_t)lb * line_stride;
-    const double* oa = epi.other + (size_t)la * line_stride;
-    const double* ob = epi.other + (size_t)lb * line_stride;
+    double* qa = out + (size_t)la * out_ls;
+    double* qb = out + (size_t)lb * out_ls;
+    const double* oa = epi.other + (size_t)la * out_ls;
+    const double* ob = epi.other + (size_t)lb * out_ls;
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
         if (kk[q] <= N) {
-            const int off = kk[q] * elem_stride;
-            if (va) {
-                qa[off] = z[q].x;
-                if (epi.mode) { acc1 += oa[off] * z[q].x; acc2 += z[q].x * z[q].x; }
-            }
-            if (vb) {
-                qb[off] = z[q].y;
-                if (epi.mode) { acc1 += ob[off] * z[q].y; acc2 += z[q].y * z[q].y; }
+            const int off = kk[q] * out_es;
+            if (SOLVE) {
+                if (va) *reinterpret_cast<double2*>(qa + off) = make_double2(z[q].x, vb ? z[q].y : 0.0);
+            } else {
+                if (va) {
+                    qa[off] = z[q].x;
+                    if (epi.mode) { acc1 += oa[off] * z[q].x; acc2 += z[q].x * z[q].x; }
+                }
+                if (vb) {
+                    qb[off] = z[q].y;
+                    if (epi.mode) { acc1 += ob[off] * z[q].y; acc2 += z[q].y * z[q].y; }
+                }
             }
         }
     }
@@ -371,8 +410,12 @@ static inline int dct_rows_ppb(const DctAxis& ax, int lines) {
 }
 static inline int dct_cols_ppb(const DctAxis& ax, int ncols) {
     const int tpf = ax.Lf >> 3;
+#ifdef VCH_FFT_COLS_PPB1
+    int ppb = 256 / tpf;
+#else
     int ppb = 512 / tpf;
     if (ppb < 2 && tpf <= 512) ppb = 2;       // >= 4 adjacent columns so fetched 32-byte sectors are fully used
+#endif
     if (ppb < 1) ppb = 1;
     if (ppb > 8) ppb = 8;
     const int pairs = (ncols + 1) / 2;
@@ -380,14 +423,16 @@ static inline int dct_cols_ppb(const DctAxis& ax, int ncols) {
     return ppb;
 }
 static inline size_t dct_smem(const DctAxis& ax, int ppb) {
-    return sizeof(double2) * (size_t)ppb * (ax.Lf + (ax.Lf >> 3) + 1);
+    return sizeof(double2) * ((size_t)ppb * (ax.Lf + (ax.Lf >> 3) + 1) + kTwLo + (ax.Lf >> 5));
 }
 
 inline void DctPlan::init(int no_, int ni_, double h_outer, double h_inner, LaunchLog* launch_log) {
     no = no_; ni = ni_; log = launch_log;
     dct_axis_init(inner, ni, h_inner);
     dct_axis_init(outer, no, h_outer);
-    tmp1.alloc((size_t)no * ni);
+    pitch = (ni + 3) & ~3;
+    tmp1.alloc((size_t)no * pitch);
+    VCH_CUDA(cudaMemset(tmp1.p, 0, (size_t)no * pitch * sizeof(double)));
     tmp2.alloc((size_t)no * ni);
     const int big = 200 * 1024;
     VCH_CUDA(cudaFuncSetAttribute(dct_fft_kernel<false, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
@@ -409,7 +454,9 @@ inline void DctPlan::apply(cudaStream_t s, const double* in, double* out, const 
     const double norm = 1.0 / (4.0 * (double)(ni - 1) * (double)(no - 1));
     const SymbolArgs nosym{1.0, 0.0, nullptr, 0.0};
     bool epi_done = (epi.mode == 0);
-    auto rows = [&](const double* a, double* b, bool last) {
+    // tmp1 is pitched only when both axes use the FFT kernels (the dense kernels address dense arrays)
+    const int P = (inner.fft && outer.fft) ? pitch : ni;
+    auto rows = [&](const double* a, int a_ls, double* b, int b_ls, bool last) {
         if (inner.fft) {
             const int ppb = dct_rows_ppb(inner, no), tpf = inner.Lf >> 3, threads = ppb * tpf;
             const int grid = ((no + 1) / 2 + ppb - 1) / ppb;
@@ -418,11 +465,11 @@ inline void DctPlan::apply(cudaStream_t s, const double* in, double* out, const 
             if (last) epi_done = true;
             log->begin("dct_rows_fft", s);
             if (threads <= 512)
-                dct_fft_kernel<false, 512><<<grid, threads, smem, s>>>(a, b, no, ni, ni, 1, inner.Lf, inner.log2L, ppb, inner.tw,
-                                                                       nullptr, nullptr, nosym, 1.0, e, done);
+                dct_fft_kernel<false, 512><<<grid, threads, smem, s>>>(a, b, no, ni, a_ls, 1, b_ls, 1, inner.Lf, inner.log2L, ppb,
+                                                                       inner.tw, nullptr, nullptr, nosym, 1.0, e, done);
             else
-                dct_fft_kernel<false, 1024><<<grid, threads, smem, s>>>(a, b, no, ni, ni, 1, inner.Lf, inner.log2L, ppb, inner.tw,
-                                                                        nullptr, nullptr, nosym, 1.0, e, done);
+                dct_fft_kernel<false, 1024><<<grid, threads, smem, s>>>(a, b, no, ni, a_ls, 1, b_ls, 1, inner.Lf, inner.log2L, ppb,
+                                                                        inner.tw, nullptr, nullptr, nosym, 1.0, e, done);
         } else {
             log->begin("dct_rows_dense", s);
             dct_rows_dense_kernel<<<eb, 256, 0, s>>>(a, b, no, ni, inner.denseT, done);
@@ -431,19 +478,38 @@ inline void DctPlan::apply(cudaStream_t s, const double* in, double* out, const 
     };
     double* t1 = tmp1.p;
     double* t2 = tmp2.p;
-    rows(in, t1, false);
+    rows(in, ni, t1, P, false);
     if (outer.fft) {
-        // fused column solve, in place on t1: lines = columns (stride 1), elements stride ni
+        // fused column solve, in place on t1: lines = columns (stride 1), elements stride P
         const int ppb = dct_cols_ppb(outer, ni), tpf = outer.Lf >> 3, threads = ppb * tpf;
         const int grid = ((ni + 1) / 2 + ppb - 1) / ppb;
         const size_t smem = dct_smem(outer, ppb);
         log->begin("dct_cols_fft_solve", s);
-        if (threads <= 512)
-            dct_fft_kernel<true, 512><<<grid, threads, smem, s>>>(t1, t1, ni, no, 1, ni, outer.Lf, outer.log2L, ppb, outer.tw,
-                                                                  inner.lam, outer.lam, sym, norm, DotEpilogue(), done);
-        else
-            dct_fft_kernel<true, 1024><<<grid, threads, smem, s>>>(t1, t1, ni, no, 1, ni, outer.Lf, outer.log2L, ppb, outer.tw,
-                                                                   inner.lam, outer.lam, sym, norm, DotEpilogue(), done);
+        if (inner.fft) {
+            if (threads <= 512)
+                dct_fft_kernel<true, 512><<<grid, threads, smem, s>>>(t1, t1, ni, no, 1, P, 1, P, outer.Lf, outer.log2L, ppb, outer.tw,
+                                                                      inner.lam, outer.lam, sym, norm, DotEpilogue(), done);
+            else
+                dct_fft_kernel<true, 1024><<<grid, threads, smem, s>>>(t1, t1, ni, no, 1, P, 1, P, outer.Lf, outer.log2L, ppb, outer.tw,
+                                                                       inner.lam, outer.lam, sym, norm, DotEpilogue(), done);
+        } else {
+            // dense rows + FFT columns: unpitched buffer, scalar accesses
+            if (threads <= 512)
+                dct_fft_kernel<false, 512><<<grid, threads, smem, s>>>(t1, t2, ni, no, 1, ni, 1, ni, outer.Lf, outer.log2L, ppb, outer.tw,
+                                                                       nullptr, nullptr, nosym, 1.0, DotEpilogue(), done);
+            else
+                dct_fft_kernel<false, 1024><<<grid, threads, smem, s>>>(t1, t2, ni, no, 1, ni, 1, ni, outer.Lf, outer.log2L, ppb, outer.tw,
+                                                                        nullptr, nullptr, nosym, 1.0, DotEpilogue(), done);
+            log->end(s);
+            log->begin("dct_scale", s); dct_scale_kernel<<<eb, 256, 0, s>>>(t2, no, ni, outer.lam, inner.lam, sym, norm, done); log->end(s);
+            log->begin("dct_cols_fft", s);
+            if (threads <= 512)
+                dct_fft_kernel<false, 512><<<grid, threads, smem, s>>>(t2, t1, ni, no, 1, ni, 1, ni, outer.Lf, outer.log2L, ppb, outer.tw,
+                                                                       nullptr, nullptr, nosym, 1.0, DotEpilogue(), done);
+            else
+                dct_fft_kernel<false, 1024><<<grid, threads, smem, s>>>(t2, t1, ni, no, 1, ni, 1, ni, outer.Lf, outer.log2L, ppb, outer.tw,
+                                                                        nullptr, nullptr, nosym, 1.0, DotEpilogue(), done);
+        }
         log->end(s);
     } else {
         log->begin("dct_cols_dense", s); dct_cols_dense_kernel<<<eb, 256, 0, s>>>(t1, t2, no, ni, outer.denseT, done); log->end(s);
@@ -451,9 +517,9 @@ inline void DctPlan::apply(cudaStream_t s, const double* in, double* out, const 
         log->begin("dct_cols_dense", s); dct_cols_dense_kernel<<<eb, 256, 0, s>>>(t2, t1, no, ni, outer.denseT, done); log->end(s);
     }
     if (inner.fft) {
-        rows(t1, out, true);
+        rows(t1, P, out, ni, true);
     } else {                                   // the dense row kernel is not in-place safe and `in` may alias `out`
-        rows(t1, t2, true);
+        rows(t1, ni, t2, ni, true);
         VCH_CUDA(cudaMemcpyAsync(out, t2, n * sizeof(double), cudaMemcpyDeviceToDevice, s));
     }
     if (!epi_done) {
