@@ -10,7 +10,7 @@ int main(int argc, char** argv) {
     double *a, *b; cudaMalloc(&a, n * 8); cudaMalloc(&b, n * 8);
     std::vector<double> h(n); for (size_t i = 0; i < n; ++i) h[i] = sin(0.001 * i) + 0.3 * cos(0.37 * i);
     cudaMemcpy(a, h.data(), n * 8, cudaMemcpyHostToDevice);
-    SymbolArgs sy{100.0, 5e-5, nullptr, 7.0};
+    SymbolArgs sy{100.0, 5e-5, nullptr, 7.0, nullptr};
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
     for (int w = 0; w < 5; ++w) plan.apply(0, a, b, sy, nullptr);
     cudaEventRecord(e0);

@@ -18,7 +18,12 @@ struct vch2d_ctx {
     Geo g;
     Phys ph;
     int device = 0;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr;   // private work stream: every kernel of the library runs here (capturable)
+    cudaStream_t user = nullptr;     // caller's stream (vch2d_set_stream); ordered with `stream` by events per call
+    cudaEvent_t ev_in = nullptr, ev_out = nullptr;
+    int use_graphs = 1;
+    struct SolveGraph { bool adj; const double* a; cudaGraph_t g; cudaGraphExec_t exec; };
+    std::vector<SolveGraph> graphs;
     LaunchLog log;
     double krylov_tol = 1e-11;
     int krylov_maxit = 200;
@@ -56,10 +61,10 @@ void fetch_scalars(vch2d_ctx* c) {
     } while (0)
 
 template <bool ADJ>
-void op_apply(vch2d_ctx* c, const double* x, const double* a, double* y, double c0, double c2, const int* done) {
+void op_apply(vch2d_ctx* c, const double* x, const double* a, double* y, const int* done) {
     dim3 grid((c->g.ni + kTI - 1) / kTI, (c->g.no + kTO - 1) / kTO);
     c->log.begin(ADJ ? "op_apply_adj" : "op_apply_fwd", c->stream);
-    op_apply_kernel<ADJ><<<grid, 256, 0, c->stream>>>(x, a, y, c->g, c0, c2, done);
+    op_apply_kernel<ADJ><<<grid, 256, 0, c->stream>>>(x, a, y, c->g, &c->sc->c0, done);
     c->log.end(c->stream);
 }
 
@@ -67,42 +72,137 @@ void op_apply(vch2d_ctx* c, const double* x, const double* a, double* y, double 
 // P the same operator with a replaced by the device scalar abar.  Scalars stay on the device; every kernel of
 // an iteration is gated on sc->done, so iterations are enqueued in batches and the host only polls.
 // Returns the number of iterations; result in c->kx.
+// Orders the library's private stream after the caller's stream on entry and the caller's stream after ours on exit,
+// so callers see ordinary stream semantics (torch.cuda.Event on their stream brackets our kernels).
+struct StreamScope {
+    vch2d_ctx* c;
+    explicit StreamScope(vch2d_ctx* ctx) : c(ctx) {
+        VCH_CUDA(cudaSetDevice(c->device));
+        VCH_CUDA(cudaEventRecord(c->ev_in, c->user));
+        VCH_CUDA(cudaStreamWaitEvent(c->stream, c->ev_in, 0));
+    }
+    ~StreamScope() {
+        cudaEventRecord(c->ev_out, c->stream);
+        cudaStreamWaitEvent(c->user, c->ev_out, 0);
+    }
+};
+
+// One BiCGStab iteration: 2 x (operator apply + DCT solve with fused dots) + 3 vector kernels = 11 launches.
 template <bool ADJ>
-int krylov_solve(vch2d_ctx* c, const double* b, const double* a, double c0, double c2, vch_stats* st) {
+void enqueue_bicg_iteration(vch2d_ctx* c, const double* a, const SymbolArgs& sy, cudaGraphConditionalHandle cond, int use_cond) {
     const long long n = c->g.n;
     const int rb = c->rb(), eb = c->eb();
-    SymbolArgs sy{c0, c2, &c->sc->abar, 0.0};
     const int* done = &c->sc->done;
-    c->dct.apply(c->stream, b, c->kr.p, sy, nullptr);
-    LAUNCH(c, bicg_init_kernel, rb, kRedThreads, c->kr.p, c->kr0.p, c->kp.p, c->kv.p, c->kx.p, n, c->sc, c->red_part.p, c->ticket);
-    int launched = 0;
-    int batch = 2;
+    LAUNCH(c, bicg_p_kernel, eb, 256, c->kr.p, c->kp.p, c->kv.p, n, c->sc);
+    op_apply<ADJ>(c, c->kp.p, a, c->ktmp.p, done);
+    c->dct.apply(c->stream, c->ktmp.p, c->kv.p, sy, done, DotEpilogue{1, c->kr0.p, c->sc, c->red_part.p, c->ticket});   // + (r0, v) -> alpha
+    LAUNCH(c, bicg_s_kernel, eb, 256, c->kr.p, c->kv.p, c->ks.p, n, c->sc);
+    op_apply<ADJ>(c, c->ks.p, a, c->ktmp.p, done);
+    c->dct.apply(c->stream, c->ktmp.p, c->kt.p, sy, done, DotEpilogue{2, c->ks.p, c->sc, c->red_part.p, c->ticket});    // + (t, s), (t, t) -> omega
+    LAUNCH(c, bicg_x_kernel, rb, kRedThreads, c->kx.p, c->kr.p, c->kp.p, c->ks.p, c->kt.p, c->kr0.p, n, c->sc, c->red_part.p,
+           c->ticket, cond, use_cond);
+}
+
+// Whole linear solve as ONE CUDA graph: [P^-1 b, init] -> WHILE(not converged){ BiCGStab iteration } — the loop condition
+// is set on the device by the last kernel of each iteration (cudaGraphSetConditional), so the host never polls.
+template <bool ADJ>
+cudaGraphExec_t solve_graph(vch2d_ctx* c, const double* a) {
+    for (auto& g : c->graphs)
+        if (g.adj == ADJ && g.a == a) return g.exec;
+    if (c->graphs.size() >= 12) {
+        for (auto& g : c->graphs) { cudaGraphExecDestroy(g.exec); cudaGraphDestroy(g.g); }
+        c->graphs.clear();
+    }
+    const long long n = c->g.n;
+    SymbolArgs sy{0.0, 0.0, &c->sc->abar, 0.0, &c->sc->c0};
+    const long long count0 = c->log.count;
+    cudaGraph_t graph;
+    VCH_CUDA(cudaGraphCreate(&graph, 0));
+    cudaGraphConditionalHandle cond;
+    VCH_CUDA(cudaGraphConditionalHandleCreate(&cond, graph, 1, cudaGraphCondAssignDefault));
+    // prologue nodes
+    VCH_CUDA(cudaStreamBeginCaptureToGraph(c->stream, graph, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal));
+    c->dct.apply(c->stream, c->kb.p, c->kr.p, sy, nullptr);
+    LAUNCH(c, bicg_init_kernel, c->rb(), kRedThreads, c->kr.p, c->kr0.p, c->kp.p, c->kv.p, c->kx.p, n, c->sc, c->red_part.p,
+           c->ticket, cond, 1);
+    cudaStreamCaptureStatus st; const cudaGraphNode_t* deps = nullptr; size_t ndeps = 0;
+    VCH_CUDA(cudaStreamGetCaptureInfo(c->stream, &st, nullptr, nullptr, &deps, &ndeps));
+    std::vector<cudaGraphNode_t> leaf(deps, deps + ndeps);
+    cudaGraph_t tmp;
+    VCH_CUDA(cudaStreamEndCapture(c->stream, &tmp));
+    // WHILE node
+    cudaGraphNodeParams np = {};
+    np.type = cudaGraphNodeTypeConditional;
+    np.conditional.handle = cond;
+    np.conditional.type = cudaGraphCondTypeWhile;
+    np.conditional.size = 1;
+    cudaGraphNode_t wnode;
+    VCH_CUDA(cudaGraphAddNode(&wnode, graph, leaf.data(), leaf.size(), &np));
+    cudaGraph_t body = np.conditional.phGraph_out[0];
+    VCH_CUDA(cudaStreamBeginCaptureToGraph(c->stream, body, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal));
+    enqueue_bicg_iteration<ADJ>(c, a, sy, cond, 1);
+    VCH_CUDA(cudaStreamEndCapture(c->stream, &tmp));
+    cudaGraphExec_t exec;
+    VCH_CUDA(cudaGraphInstantiate(&exec, graph, 0));
+    c->log.count = count0;            // capture launches nothing
+    c->graphs.push_back({ADJ, a, graph, exec});
+    return exec;
+}
+
+// Left-preconditioned BiCGStab on  P^-1 A x = P^-1 b  with A = c0 I - {L diag(a) | diag(a) L} + c2 L^2 and
+// P the same operator with a replaced by the device scalar abar.  Scalars stay on the device.
+//   graph path (default): one graph launch, no host polling; iteration statistics accumulate in Scal.
+//   polled path (profiling, VCH_NO_GRAPHS=1): kernels gated on sc->done, enqueued in batches, host polls per batch.
+// Result in c->kx.  Returns the iteration count, or -1 when it is not known yet (graph path, read later from Scal).
+template <bool ADJ>
+int krylov_solve(vch2d_ctx* c, const double* b, const double* a, vch_stats* st) {   // coefficients: sc->c0 / sc->c2, set by the rhs kernel
+    const long long n = c->g.n;
+    if (b != c->kb.p) VCH_CUDA(cudaMemcpyAsync(c->kb.p, b, n * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+    if (c->use_graphs && !c->log.profiling) {
+        cudaGraphExec_t exec = solve_graph<ADJ>(c, a);
+        VCH_CUDA(cudaGraphLaunch(exec, c->stream));
+        return -1;
+    }
+    SymbolArgs sy{0.0, 0.0, &c->sc->abar, 0.0, &c->sc->c0};
+    c->dct.apply(c->stream, c->kb.p, c->kr.p, sy, nullptr);
+    LAUNCH(c, bicg_init_kernel, c->rb(), kRedThreads, c->kr.p, c->kr0.p, c->kp.p, c->kv.p, c->kx.p, n, c->sc, c->red_part.p,
+           c->ticket, (cudaGraphConditionalHandle)0, 0);
+    int launched = 0, batch = 2;
     while (true) {
-        for (int k = 0; k < batch; ++k) {
-            LAUNCH(c, bicg_p_kernel, eb, 256, c->kr.p, c->kp.p, c->kv.p, n, c->sc);
-            op_apply<ADJ>(c, c->kp.p, a, c->ktmp.p, c0, c2, done);
-            c->dct.apply(c->stream, c->ktmp.p, c->kv.p, sy, done, DotEpilogue{1, c->kr0.p, c->sc, c->red_part.p, c->ticket});   // + (r0, v) -> alpha
-            LAUNCH(c, bicg_s_kernel, eb, 256, c->kr.p, c->kv.p, c->ks.p, n, c->sc);
-            op_apply<ADJ>(c, c->ks.p, a, c->ktmp.p, c0, c2, done);
-            c->dct.apply(c->stream, c->ktmp.p, c->kt.p, sy, done, DotEpilogue{2, c->ks.p, c->sc, c->red_part.p, c->ticket});    // + (t, s), (t, t) -> omega
-            LAUNCH(c, bicg_x_kernel, rb, kRedThreads, c->kx.p, c->kr.p, c->kp.p, c->ks.p, c->kt.p, c->kr0.p, n, c->sc,
-                   c->red_part.p, c->ticket);
-        }
+        for (int k = 0; k < batch; ++k) enqueue_bicg_iteration<ADJ>(c, a, sy, (cudaGraphConditionalHandle)0, 0);
         launched += batch;
         fetch_scalars(c);
         if (c->sc_host->done || launched >= c->krylov_maxit) break;
         batch = (launched < 8) ? 2 : 4;
     }
     VCH_CUDA(cudaGetLastError());
-    const int its = c->sc_host->iters;
-    if (st) {
-        st->krylov_iterations += its;
-        st->krylov_max_iterations = std::max<long long>(st->krylov_max_iterations, its);
-        st->newton_linear_solves += 1;
-        if (!c->sc_host->done) st->krylov_stalls += 1;
+    if (!c->sc_host->done) {   // mirror the device-side accounting of the graph path
+        long long one = c->sc_host->stalls + 1;
+        VCH_CUDA(cudaMemcpyAsync(&c->sc->stalls, &one, sizeof(one), cudaMemcpyHostToDevice, c->stream));
+        VCH_CUDA(cudaStreamSynchronize(c->stream));
     }
     if (c->sc_host->nonfinite) throw Error(VCH_E_NONFINITE, "non-finite value in Krylov solve");
-    return its;
+    (void)st;
+    return c->sc_host->iters;
+}
+
+// Device-side solver counters -> vch_stats (call after a fetch_scalars).
+struct StatMark { long long its, solves, stalls, launches, gits, gsolves; };
+StatMark stat_mark(vch2d_ctx* c) {
+    fetch_scalars(c);
+    return {c->sc_host->iters_total, c->sc_host->solves, c->sc_host->stalls, c->log.count, c->sc_host->g_iters, c->sc_host->g_solves};
+}
+void stat_collect(vch2d_ctx* c, const StatMark& m0, vch_stats* st) {
+    fetch_scalars(c);
+    if (c->sc_host->nonfinite) throw Error(VCH_E_NONFINITE, "non-finite value in Krylov solve");
+    if (!st) return;
+    const long long its = c->sc_host->iters_total - m0.its, solves = c->sc_host->solves - m0.solves;
+    st->krylov_iterations += its;
+    st->newton_linear_solves += solves;
+    st->krylov_stalls += c->sc_host->stalls - m0.stalls;
+    st->krylov_max_iterations = std::max<long long>(st->krylov_max_iterations, c->sc_host->iters_max);
+    // kernels inside solve graphs are not seen by the launch log: 4 prologue kernels per solve + 11 per iteration
+    st->kernel_launches += (c->log.count - m0.launches) + 4 * (c->sc_host->g_solves - m0.gsolves) + 11 * (c->sc_host->g_iters - m0.gits);
 }
 
 void eval_residual(vch2d_ctx* c, const double* phi, const double* mu, double* Rphi, double* Rmu, double* a, double dt) {
@@ -112,13 +212,12 @@ void eval_residual(vch2d_ctx* c, const double* phi, const double* mu, double* Rp
 
 // Solve J [dphi; dmu] = -[Rphi; Rmu] by Schur reduction:  (1/dt I - L(diag(a) - kappa/2 L)) dphi = -Rmu + L Rphi,
 // dmu = 2 (a dphi - kappa/2 L dphi + Rphi).   dphi -> c->kx, dmu -> c->dmu.  phi may be null (no ceiling minima).
-int newton_linear_solve(vch2d_ctx* c, const double* Rphi, const double* Rmu, const double* a, const double* phi,
-                        double dt, vch_stats* st) {
-    LAUNCH(c, schur_rhs_kernel, c->eb(), 256, Rphi, Rmu, c->kb.p, c->g);
-    const int its = krylov_solve<false>(c, c->kb.p, a, 1.0 / dt, 0.5 * c->ph.kappa, st);
+void newton_linear_solve(vch2d_ctx* c, const double* Rphi, const double* Rmu, const double* a, const double* phi,
+                         double dt, vch_stats* st) {
+    LAUNCH(c, schur_rhs_kernel, c->eb(), 256, Rphi, Rmu, c->kb.p, c->g, c->sc, 1.0 / dt, 0.5 * c->ph.kappa);
+    krylov_solve<false>(c, c->kb.p, a, st);
     LAUNCH(c, dmu_ceiling_kernel, c->rb(), kRedThreads, c->kx.p, a, Rphi, phi, c->dmu.p, c->g, c->ph, c->sc, c->red_part.p,
            c->ticket);
-    return its;
 }
 
 // One Newton solve (Forward2_solver.py:323-427).  Inputs: device phi_old, mu_old, w_old, w_new.
@@ -152,7 +251,13 @@ void newton_step(vch2d_ctx* c, const double* phi_old, const double* mu_old, cons
         if (normR < tol) break;
         const double normR_prev = normR;
         newton_linear_solve(c, Rp, Rm, a, phi, dt, st);
+        // speculative full step: almost always alpha = 1 is both allowed by the ceiling and accepted by Armijo, so the
+        // trial iterate and its residual are enqueued before the host has seen the ceiling -> ONE sync per Newton iteration
+        LAUNCH(c, trial_kernel, eb, 256, phi, mu, c->kx.p, c->dmu.p, phit, mut, n, 1.0);
+        eval_residual(c, phit, mut, RpT, RmT, aT, dt);
         fetch_scalars(c);
+        if (c->sc_host->nonfinite) throw Error(VCH_E_NONFINITE, "non-finite value in Krylov solve");
+        if (st) st->newton_residual_evals += 1;
         double amax = 2.0;
         if (std::isfinite(c->sc_host->ceil_pos)) amax = std::min(amax, 0.9 * c->sc_host->ceil_pos);
         if (std::isfinite(c->sc_host->ceil_neg)) amax = std::min(amax, 0.9 * c->sc_host->ceil_neg);
@@ -160,11 +265,15 @@ void newton_step(vch2d_ctx* c, const double* phi_old, const double* mu_old, cons
         double alpha = std::min(1.0, amax);
         double best = INFINITY, best_alpha = 0.0;
         bool accepted = false;
+        bool have_trial = (alpha == 1.0);      // the speculative evaluation is the first trial
         for (int ls = 0; ls < 12; ++ls) {
-            LAUNCH(c, trial_kernel, eb, 256, phi, mu, c->kx.p, c->dmu.p, phit, mut, n, alpha);
-            eval_residual(c, phit, mut, RpT, RmT, aT, dt);
-            fetch_scalars(c);
-            if (st) st->newton_residual_evals += 1;
+            if (!have_trial) {
+                LAUNCH(c, trial_kernel, eb, 256, phi, mu, c->kx.p, c->dmu.p, phit, mut, n, alpha);
+                eval_residual(c, phit, mut, RpT, RmT, aT, dt);
+                fetch_scalars(c);
+                if (st) st->newton_residual_evals += 1;
+            }
+            have_trial = false;
             const double nt = std::sqrt(c->sc_host->res2);
             if (nt < best) { best = nt; best_alpha = alpha; }
             if (nt <= (1.0 - eta * alpha) * normR) {
@@ -249,7 +358,7 @@ void adjoint_dev(vch2d_ctx* c, const double* phi_hist, int levels, const double*
     const int M = levels - 1;
     double* pM = slot(p_out, c->adj_p, M); double* qM = slot(q_out, c->adj_q, M); double* rM = slot(r_out, c->adj_r, M);
     LAUNCH(c, adj_terminal_rhs_kernel, eb, 256, phi_hist + (size_t)M * n, phiT, c->kb.p, n, b2);
-    SymbolArgs sy{1.0, 0.0, nullptr, c->ph.tau};
+    SymbolArgs sy{1.0, 0.0, nullptr, c->ph.tau, nullptr};
     c->dct.apply(c->stream, c->kb.p, pM, sy, nullptr);          // (I - tau L) p_M = b2 (phi_M - phi_T): exact in the DCT basis
     LAUNCH(c, adj_qr_kernel, eb, 256, pM, (const double*)nullptr, (const double*)nullptr, qM, rM, c->g, 0.0, 0.0);
     for (int k = M - 1; k >= 0; --k) {
@@ -265,7 +374,7 @@ void adjoint_dev(vch2d_ctx* c, const double* phi_hist, int levels, const double*
         const double* f1 = phi_hist + (size_t)(k + 1) * n; const double* f0 = phi_hist + (size_t)k * n;
         LAUNCH(c, adj_rhs_kernel, c->rb(), kRedThreads, p1, q1, f1, f0, phiQ ? phiQ + (size_t)(k + 1) * n : nullptr,
                phiQ ? phiQ + (size_t)k * n : nullptr, c->kb.p, c->a.p, c->g, c->ph, dt, b1, c->sc, c->red_part.p, c->ticket);
-        krylov_solve<true>(c, c->kb.p, c->a.p, 1.0, 0.5 * dt, st);
+        krylov_solve<true>(c, c->kb.p, c->a.p, st);
         VCH_CUDA(cudaMemcpyAsync(p0, c->kx.p, bytes, cudaMemcpyDeviceToDevice, c->stream));
         const double den = c->ph.gamma + 0.5 * dt;
         LAUNCH(c, adj_qr_kernel, eb, 256, p0, q1, r1, q0, r0, c->g, (c->ph.gamma - 0.5 * dt) / den, 0.5 * dt / den);
@@ -364,8 +473,12 @@ int vch2d_create(const vch2d_params* p, int device, vch2d_ctx** out) {
         VCH_CUDA(cudaMallocHost(&c->out4_host, 8 * sizeof(double)));
         c->dct.init(g.no, g.ni, p->hy, p->hx, &c->log);
         c->red_part.alloc(8 * (size_t)c->dct.max_grid());
-        Scal init{}; init.tol2 = c->krylov_tol * c->krylov_tol;
+        Scal init{}; init.tol2 = c->krylov_tol * c->krylov_tol; init.maxit = c->krylov_maxit;
         VCH_CUDA(cudaMemcpy(c->sc, &init, sizeof(Scal), cudaMemcpyHostToDevice));
+        VCH_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+        VCH_CUDA(cudaEventCreateWithFlags(&c->ev_in, cudaEventDisableTiming));
+        VCH_CUDA(cudaEventCreateWithFlags(&c->ev_out, cudaEventDisableTiming));
+        if (getenv("VCH_NO_GRAPHS")) c->use_graphs = 0;
         *out = c;
         return VCH_OK;
     });
@@ -375,13 +488,15 @@ void vch2d_destroy(vch2d_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
+    for (auto& g : c->graphs) { cudaGraphExecDestroy(g.exec); cudaGraphDestroy(g.g); }
+    cudaEventDestroy(c->ev_in); cudaEventDestroy(c->ev_out); cudaStreamDestroy(c->stream);
     c->dct.destroy();
     cudaFree(c->ticket); cudaFree(c->sc); cudaFreeHost(c->sc_host); cudaFree(c->out4); cudaFreeHost(c->out4_host);
     delete c;
 }
 
 int vch2d_set_stream(vch2d_ctx* c, void* s) {
-    return guarded([&] { VCH_REQUIRE(c, VCH_E_ARG, "null ctx"); c->stream = (cudaStream_t)s; return VCH_OK; });
+    return guarded([&] { VCH_REQUIRE(c, VCH_E_ARG, "null ctx"); c->user = (cudaStream_t)s; return VCH_OK; });
 }
 
 int vch2d_set_krylov(vch2d_ctx* c, double rel_tol, int max_iter) {
@@ -389,8 +504,10 @@ int vch2d_set_krylov(vch2d_ctx* c, double rel_tol, int max_iter) {
         VCH_REQUIRE(c && rel_tol > 0 && max_iter > 0, VCH_E_ARG, "bad Krylov settings");
         c->krylov_tol = rel_tol; c->krylov_maxit = max_iter;
         const double t2 = rel_tol * rel_tol;
-        VCH_CUDA(cudaMemcpyAsync(&c->sc->tol2, &t2, sizeof(double), cudaMemcpyHostToDevice, c->stream));
+        VCH_CUDA(cudaSetDevice(c->device));
         VCH_CUDA(cudaStreamSynchronize(c->stream));
+        VCH_CUDA(cudaMemcpy(&c->sc->tol2, &t2, sizeof(double), cudaMemcpyHostToDevice));
+        VCH_CUDA(cudaMemcpy(&c->sc->maxit, &max_iter, sizeof(int), cudaMemcpyHostToDevice));
         return VCH_OK;
     });
 }
@@ -399,7 +516,13 @@ int vch2d_set_newton(vch2d_ctx* c, int floor_aware) {
     return guarded([&] { VCH_REQUIRE(c, VCH_E_ARG, "null ctx"); c->floor_aware = floor_aware ? 1 : 0; return VCH_OK; });
 }
 
-long long vch2d_launch_count(vch2d_ctx* c) { return c ? c->log.count : 0; }
+long long vch2d_launch_count(vch2d_ctx* c) {
+    if (!c) return 0;
+    cudaSetDevice(c->device);
+    if (cudaMemcpyAsync(c->sc_host, c->sc, sizeof(Scal), cudaMemcpyDeviceToHost, c->stream) != cudaSuccess) return c->log.count;
+    cudaStreamSynchronize(c->stream);
+    return c->log.count + 4 * c->sc_host->g_solves + 11 * c->sc_host->g_iters;   // + kernels that ran inside solve graphs
+}
 
 int vch2d_profile(vch2d_ctx* c, int enable) {
     return guarded([&] {
@@ -434,7 +557,7 @@ int vch2d_profile_report(vch2d_ctx* c, char* names, int names_cap, double* ms, l
 int vch2d_apply_laplacian(vch2d_ctx* c, const double* v, double* out, int mem) {
     return guarded([&] {
         VCH_REQUIRE(c && v && out, VCH_E_SHAPE, "apply_laplacian: null array");
-        VCH_CUDA(cudaSetDevice(c->device));
+        StreamScope scope(c);
         Stager st(c->stream, mem);
         const double* dv = st.in(v, c->g.n); double* dout = st.out(out, c->g.n);
         LAUNCH(c, lap_kernel, c->eb(), 256, dv, dout, c->g, 1.0);
@@ -447,7 +570,7 @@ int vch2d_apply_laplacian(vch2d_ctx* c, const double* v, double* out, int mem) {
 int vch2d_initialize_mu(vch2d_ctx* c, const double* phi, const double* w, double* mu_out, int mem) {
     return guarded([&] {
         VCH_REQUIRE(c && phi && w && mu_out, VCH_E_SHAPE, "initialize_mu: null array");
-        VCH_CUDA(cudaSetDevice(c->device));
+        StreamScope scope(c);
         Stager st(c->stream, mem);
         const double *dp = st.in(phi, c->g.n), *dw = st.in(w, c->g.n); double* dm = st.out(mu_out, c->g.n);
         LAUNCH(c, mu_init_kernel, c->eb(), 256, dp, dw, dm, c->g, c->ph);
@@ -479,7 +602,7 @@ int vch2d_residual(vch2d_ctx* c, const double* phi_new, const double* phi_old, c
     return guarded([&] {
         VCH_REQUIRE(c && phi_new && phi_old && mu_new && mu_old && w_new && w_old && Rphi_out && Rmu_out, VCH_E_SHAPE,
                     "residual: null array");
-        VCH_CUDA(cudaSetDevice(c->device));
+        StreamScope scope(c);
         const long long n = c->g.n;
         Stager st(c->stream, mem);
         const double *a = st.in(phi_new, n), *b = st.in(phi_old, n), *m1 = st.in(mu_new, n), *m0 = st.in(mu_old, n),
@@ -496,17 +619,19 @@ int vch2d_jacobian_solve(vch2d_ctx* c, const double* phi, double dt, const doubl
                          double* dphi_out, double* dmu_out, int* its_out, int mem) {
     return guarded([&] {
         VCH_REQUIRE(c && phi && Rphi && Rmu && dphi_out && dmu_out, VCH_E_SHAPE, "jacobian_solve: null array");
-        VCH_CUDA(cudaSetDevice(c->device));
+        StreamScope scope(c);
         const long long n = c->g.n;
         Stager st(c->stream, mem);
         const double *dp = st.in(phi, n), *rp = st.in(Rphi, n), *rm = st.in(Rmu, n);
         double *o1 = st.out(dphi_out, n), *o2 = st.out(dmu_out, n);
         LAUNCH(c, jac_diag_kernel, c->rb(), kRedThreads, dp, c->a.p, c->g, c->ph, dt, c->sc, c->red_part.p, c->ticket);
         vch_stats s{};
-        const int its = newton_linear_solve(c, rp, rm, c->a.p, nullptr, dt, &s);
+        const StatMark mark0 = stat_mark(c);
+        newton_linear_solve(c, rp, rm, c->a.p, nullptr, dt, &s);
         VCH_CUDA(cudaMemcpyAsync(o1, c->kx.p, n * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
         VCH_CUDA(cudaMemcpyAsync(o2, c->dmu.p, n * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
-        if (its_out) *its_out = its;
+        stat_collect(c, mark0, &s);
+        if (its_out) *its_out = (int)s.krylov_iterations;
         st.finish();
         VCH_REQUIRE(s.krylov_stalls == 0, VCH_E_KRYLOV, "jacobian_solve: BiCGStab stopped above tolerance");
         return VCH_OK;
@@ -518,9 +643,9 @@ int vch2d_newton(vch2d_ctx* c, const double* phi_old, const double* mu_old, cons
                  vch_stats* stats, int mem) {
     return guarded([&] {
         VCH_REQUIRE(c && phi_old && mu_old && w_old && w_new && phi_new_out && mu_new_out, VCH_E_SHAPE, "newton: null array");
-        VCH_CUDA(cudaSetDevice(c->device));
+        StreamScope scope(c);
         const long long n = c->g.n;
-        const long long l0 = c->log.count;
+        const StatMark mark0 = stat_mark(c);
         Stager st(c->stream, mem);
         const double *p0 = st.in(phi_old, n), *m0 = st.in(mu_old, n), *w0 = st.in(w_old, n), *w1 = st.in(w_new, n);
         double *po = st.out(phi_new_out, n), *mo = st.out(mu_new_out, n);
@@ -532,7 +657,7 @@ int vch2d_newton(vch2d_ctx* c, const double* phi_old, const double* mu_old, cons
         st.finish();
         if (n_hist) *n_hist = (int)hist.size();
         if (res_hist) for (int i = 0; i < (int)hist.size() && i < hist_cap; ++i) res_hist[i] = hist[i];
-        s->kernel_launches += c->log.count - l0;
+        stat_collect(c, mark0, s);
         return VCH_OK;
     });
 }
@@ -542,8 +667,9 @@ int vch2d_forward(vch2d_ctx* c, const double* phi0, const double* u, int u_rows,
     return guarded([&] {
         VCH_REQUIRE(c && phi0 && phi_hist_out && dt_steps && n_steps >= 0, VCH_E_SHAPE, "forward: bad arguments");
         VCH_REQUIRE(!u || u_rows >= 1, VCH_E_SHAPE, "forward: control needs at least one row");
-        VCH_CUDA(cudaSetDevice(c->device));
-        const long long n = c->g.n, l0 = c->log.count;
+        StreamScope scope(c);
+        const long long n = c->g.n;
+        const StatMark mark0 = stat_mark(c);
         Stager st(c->stream, mem);
         const double* dphi0 = st.in(phi0, n);
         const double* du = st.in(u, (size_t)u_rows * n);
@@ -553,7 +679,7 @@ int vch2d_forward(vch2d_ctx* c, const double* phi0, const double* u, int u_rows,
         vch_stats local{}; vch_stats* s = stats ? stats : &local;
         forward_dev(c, dphi0, du, u_rows, n_steps, dt_steps, dh, dm, dw, s);
         st.finish();
-        s->kernel_launches += c->log.count - l0;
+        stat_collect(c, mark0, s);
         return VCH_OK;
     });
 }
@@ -563,8 +689,9 @@ int vch2d_adjoint(vch2d_ctx* c, const double* phi_hist, int levels, const double
                   int mem) {
     return guarded([&] {
         VCH_REQUIRE(c && phi_hist && t_hist && r_out && levels >= 1, VCH_E_SHAPE, "adjoint: bad arguments");
-        VCH_CUDA(cudaSetDevice(c->device));
-        const long long n = c->g.n, l0 = c->log.count;
+        StreamScope scope(c);
+        const long long n = c->g.n;
+        const StatMark mark0 = stat_mark(c);
         const size_t tot = (size_t)levels * n;
         Stager st(c->stream, mem);
         const double *dh = st.in(phi_hist, tot), *dq = st.in(phiQ, tot), *dT = st.in(phiT, n);
@@ -572,7 +699,7 @@ int vch2d_adjoint(vch2d_ctx* c, const double* phi_hist, int levels, const double
         vch_stats local{}; vch_stats* s = stats ? stats : &local;
         adjoint_dev(c, dh, levels, t_hist, b1, b2, dq, dT, po, qo, ro, s);
         st.finish();
-        s->kernel_launches += c->log.count - l0;
+        stat_collect(c, mark0, s);
         return VCH_OK;
     });
 }
@@ -582,7 +709,7 @@ int vch2d_cost(vch2d_ctx* c, const double* phi_hist, const double* u, const doub
                double* J_out, int mem) {
     return guarded([&] {
         VCH_REQUIRE(c && phi_hist && x && y && t_hist && J_out && levels >= 1, VCH_E_SHAPE, "cost: bad arguments");
-        VCH_CUDA(cudaSetDevice(c->device));
+        StreamScope scope(c);
         const long long n = c->g.n;
         const size_t tot = (size_t)levels * n;
         Stager st(c->stream, mem);
@@ -644,8 +771,9 @@ int vch2d_pgd_iteration(vch2d_ctx* c, int levels, const double* t_hist, const do
     return guarded([&] {
         VCH_REQUIRE(c && levels >= 2 && t_hist && dt_steps && x && y && u && phi_hist && u_new_out && phi_hist_out && J_out,
                     VCH_E_SHAPE, "pgd_iteration: bad arguments");
-        VCH_CUDA(cudaSetDevice(c->device));
-        const long long n = c->g.n, l0 = c->log.count;
+        StreamScope scope(c);
+        const long long n = c->g.n;
+        const StatMark mark0 = stat_mark(c);
         const size_t tot = (size_t)levels * n;
         Stager st(c->stream, mem);
         const double *du = st.in(u, tot), *dh = st.in(phi_hist, tot), *dq = st.in(phiQ, tot), *dT = st.in(phiT, n);
@@ -669,7 +797,7 @@ int vch2d_pgd_iteration(vch2d_ctx* c, int levels, const double* t_hist, const do
             for (int k = 0; k < 4; ++k) red_out[k] = c->out4_host[4 + k];
         }
         st.finish();
-        s->kernel_launches += c->log.count - l0;
+        stat_collect(c, mark0, s);
         return VCH_OK;
     });
 }

@@ -134,7 +134,9 @@ __global__ void jac_diag_kernel(const double* __restrict__ phi, double* __restri
 }
 
 // Right-hand side of the Schur-reduced Newton system: b = -R_mu + L R_phi.
-__global__ void schur_rhs_kernel(const double* __restrict__ Rphi, const double* __restrict__ Rmu, double* __restrict__ b, Geo g) {
+__global__ void schur_rhs_kernel(const double* __restrict__ Rphi, const double* __restrict__ Rmu, double* __restrict__ b, Geo g,
+                                 Scal* sc, double c0, double c2) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) { sc->c0 = c0; sc->c2 = c2; }   // coefficients of the solve that follows
     for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < g.n; idx += (long long)gridDim.x * blockDim.x) {
         const int o = (int)(idx / g.ni), i = (int)(idx - (long long)o * g.ni);
         b[idx] = lap_g(Rphi, o, i, g) - Rmu[idx];
@@ -147,9 +149,10 @@ __global__ void schur_rhs_kernel(const double* __restrict__ Rphi, const double* 
 constexpr int kTO = 16, kTI = 64;
 template <bool ADJ>
 __global__ void __launch_bounds__(256) op_apply_kernel(const double* __restrict__ x, const double* __restrict__ a,
-                                                        double* __restrict__ y, Geo g, double c0, double c2,
+                                                        double* __restrict__ y, Geo g, const double* __restrict__ coef,
                                                         const int* __restrict__ done) {
     if (done && *done) return;
+    const double c0 = coef[0], c2 = coef[1];
     __shared__ double sx[kTO + 4][kTI + 4];
     __shared__ double sz[kTO + 2][kTI + 2];
     const int o0 = blockIdx.y * kTO, i0 = blockIdx.x * kTI;
@@ -191,9 +194,10 @@ __global__ void __launch_bounds__(256) op_apply_kernel(const double* __restrict_
 }
 
 // ---------------------------------------------------------------------------------- BiCGStab vector kernels
+// cond/use_cond: CUDA-graph WHILE handle of the enclosing solve graph (device-driven Krylov loop); ignored when use_cond = 0.
 __global__ void bicg_init_kernel(const double* __restrict__ r, double* __restrict__ r0, double* __restrict__ p,
                                  double* __restrict__ v, double* __restrict__ x, long long n, Scal* sc, double* part,
-                                 unsigned int* ticket) {
+                                 unsigned int* ticket, cudaGraphConditionalHandle cond, int use_cond) {
     double acc[1] = {0.0};
     for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (long long)gridDim.x * blockDim.x) {
         const double rv = r[idx];
@@ -209,6 +213,8 @@ __global__ void bicg_init_kernel(const double* __restrict__ r, double* __restric
         sc->iters = 0;
         sc->done = (tot[0] == 0.0 || !isfinite(tot[0])) ? 1 : 0;
         if (!isfinite(tot[0])) sc->nonfinite = 1;
+        sc->solves += 1;
+        if (use_cond) { sc->g_solves += 1; cudaGraphSetConditional(cond, sc->done ? 0u : 1u); }
     }
 }
 
@@ -258,7 +264,8 @@ __global__ void bicg_dot2_kernel(const double* __restrict__ t, const double* __r
 
 __global__ void bicg_x_kernel(double* __restrict__ x, double* __restrict__ r, const double* __restrict__ p,
                               const double* __restrict__ s, const double* __restrict__ t, const double* __restrict__ r0,
-                              long long n, Scal* sc, double* part, unsigned int* ticket) {
+                              long long n, Scal* sc, double* part, unsigned int* ticket, cudaGraphConditionalHandle cond,
+                              int use_cond) {
     if (sc->done) return;
     const double al = sc->alpha, om = sc->omega;
     double acc[2] = {0.0, 0.0};
@@ -272,10 +279,17 @@ __global__ void bicg_x_kernel(double* __restrict__ x, double* __restrict__ r, co
     const int op[2] = {0, 0};
     double tot[2];
     if (grid_reduce<2>(acc, op, part, ticket, tot) && threadIdx.x == 0) {
-        sc->rr = tot[0]; sc->rho_new = tot[1]; sc->iters += 1;
+        sc->rr = tot[0]; sc->rho_new = tot[1]; sc->iters += 1; sc->iters_total += 1;
         const bool bad = !isfinite(tot[0]) || !isfinite(tot[1]);
         if (bad) sc->nonfinite = 1;
         if (bad || tot[0] <= sc->thr2) sc->done = 1;
+        if (sc->iters > sc->iters_max) sc->iters_max = sc->iters;
+        if (use_cond) {
+            sc->g_iters += 1;
+            const bool stop = sc->done || sc->iters >= sc->maxit;
+            if (stop && !sc->done) sc->stalls += 1;
+            cudaGraphSetConditional(cond, stop ? 0u : 1u);
+        }
     }
 }
 
@@ -377,6 +391,7 @@ __global__ void adj_rhs_kernel(const double* __restrict__ p1, const double* __re
     if (grid_reduce<2>(v, op, part, ticket, tot) && threadIdx.x == 0) {
         sc->amin = tot[0]; sc->amax = tot[1];
         sc->abar = (tot[0] > 0.0) ? sqrt(tot[0] * tot[1]) : 0.5 * (tot[0] + tot[1]);
+        sc->c0 = 1.0; sc->c2 = hdt;                                            // coefficients of the solve that follows
     }
 }
 

@@ -132,7 +132,11 @@ struct Scal {
     double ceil_pos, ceil_neg;
     double mass, wint, mass0;
     double tol2;
-    int done, iters, nonfinite, pad;
+    double c0, c2;            // operator coefficients of the current solve (read by the graph's kernels: one graph serves every dt)
+    int done, iters, nonfinite, maxit;
+    long long iters_total, solves, stalls;   // accumulated on the device (graph-driven solves are never polled)
+    long long g_iters, g_solves;             // the part of the above that ran inside solve graphs
+    int iters_max, pad;
 };
 
 // ---------------------------------------------------------------- launch geometry

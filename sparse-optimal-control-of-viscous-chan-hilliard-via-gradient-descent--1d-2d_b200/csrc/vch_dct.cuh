@@ -36,6 +36,7 @@ struct SymbolArgs {
     double c0, c2;
     const double* abar_ptr;   // device scalar (may be null -> abar_const)
     double abar_const;
+    const double* coef_ptr;   // device {c0, c2} (may be null -> the immediate values above)
 };
 
 // Optional epilogue of the last row transform: BiCGStab dot products over the freshly produced vector.
@@ -257,6 +258,7 @@ dct_fft_kernel(const double* in, double* out, int nlines, int n, int in_ls, int 
     if (SOLVE) {
         // forward outputs -> divide by the symbol -> mirrored store = input of the inverse transform
         const double abar = sy.abar_ptr ? *sy.abar_ptr : sy.abar_const;
+        const double sc0 = sy.coef_ptr ? sy.coef_ptr[0] : sy.c0, sc2 = sy.coef_ptr ? sy.coef_ptr[1] : sy.c2;
         const double lla = va ? lam_line[la] : 0.0, llb = vb ? lam_line[lb] : 0.0;
         __syncthreads();                         // every thread has finished reading the forward data
 #pragma unroll
@@ -265,8 +267,8 @@ dct_fft_kernel(const double* in, double* out, int nlines, int n, int in_ls, int 
                 const double le = lam_elem[kk[q]];
                 const double s1 = le + lla, s2 = le + llb;
                 double2 w = z[q];
-                w.x *= norm / (sy.c0 + s1 * (abar + sy.c2 * s1));
-                w.y *= norm / (sy.c0 + s2 * (abar + sy.c2 * s2));
+                w.x *= norm / (sc0 + s1 * (abar + sc2 * s1));
+                w.y *= norm / (sc0 + s2 * (abar + sc2 * s2));
                 data[padi(kk[q])] = w;
                 if (kk[q] > 0 && kk[q] < N) data[padi(Lf - kk[q])] = w;
             }
@@ -346,8 +348,9 @@ __global__ void dct_scale_kernel(double* __restrict__ d, int no, int ni, const d
     if (idx >= (long long)no * ni) return;
     const int k = (int)(idx / ni), c = (int)(idx - (long long)k * ni);
     const double abar = sy.abar_ptr ? *sy.abar_ptr : sy.abar_const;
+    const double sc0 = sy.coef_ptr ? sy.coef_ptr[0] : sy.c0, sc2 = sy.coef_ptr ? sy.coef_ptr[1] : sy.c2;
     const double l = lam_o[k] + lam_i[c];
-    d[idx] *= norm / (sy.c0 + l * (abar + sy.c2 * l));
+    d[idx] *= norm / (sc0 + l * (abar + sc2 * l));
 }
 // Stand-alone BiCGStab dots for the paths without the fused epilogue.
 __global__ void dct_dots_kernel(const double* __restrict__ outv, DotEpilogue epi, long long n, const int* __restrict__ done) {
@@ -452,7 +455,7 @@ inline void DctPlan::apply(cudaStream_t s, const double* in, double* out, const 
     const long long n = (long long)no * ni;
     const int eb = (int)((n + 255) / 256);
     const double norm = 1.0 / (4.0 * (double)(ni - 1) * (double)(no - 1));
-    const SymbolArgs nosym{1.0, 0.0, nullptr, 0.0};
+    const SymbolArgs nosym{1.0, 0.0, nullptr, 0.0, nullptr};
     bool epi_done = (epi.mode == 0);
     // tmp1 is pitched only when both axes use the FFT kernels (the dense kernels address dense arrays)
     const int P = (inner.fft && outer.fft) ? pitch : ni;
