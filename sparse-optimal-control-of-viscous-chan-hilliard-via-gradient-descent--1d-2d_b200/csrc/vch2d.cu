@@ -32,7 +32,7 @@ struct vch2d_ctx {
     DctPlan dct;
     // work vectors (n doubles each)
     DevBuf phi, mu, phit, mut, w0, w1, cphi, cmu, Rphi, Rmu, a, RphiT, RmuT, aT;
-    DevBuf kb, kx, kr, kr0, kp, kv, ks, kt, ktmp, dmu;
+    DevBuf kb, kx, kr, kr0, kp, kv, ks, kt, ktmp, kq, dmu;
     DevBuf adj_p[2], adj_q[2], adj_r[2], mu_old;
     DevBuf red_part;             // partials for grid reductions
     DevBuf small;                // small device vectors: weights, out4
@@ -87,20 +87,34 @@ struct StreamScope {
     }
 };
 
-// One BiCGStab iteration: 2 x (operator apply + DCT solve with fused dots) + 3 vector kernels = 11 launches.
+// One BiCGStab iteration.
+//   Forward Schur operator (ADJ = false): A = P - L diag(a - abar), so P^-1 A x = x + DCT^-1[(lambda/sym) DCT((a - abar) x)]:
+//     no stencil kernel at all.  7 launches: rows[p = r + beta q; (a-abar)p] -> cols[lambda/sym] -> rows[+p, (r0,v)] ->
+//     rows[s = r - alpha v; (a-abar)s] -> cols -> rows[+s, (t,s),(t,t)] -> x/r/q update with (r,r),(r0,r).
+//   Adjoint operator (ADJ = true): A = P - diag(a - abar) L has the multiply on the other side, so it keeps the explicit
+//     two-level stencil: p-update, stencil, 3-kernel DCT solve (+dots), s-update, stencil, DCT solve, x/r update = 11 launches.
 template <bool ADJ>
 void enqueue_bicg_iteration(vch2d_ctx* c, const double* a, const SymbolArgs& sy, cudaGraphConditionalHandle cond, int use_cond) {
     const long long n = c->g.n;
     const int rb = c->rb(), eb = c->eb();
     const int* done = &c->sc->done;
-    LAUNCH(c, bicg_p_kernel, eb, 256, c->kr.p, c->kp.p, c->kv.p, n, c->sc);
-    op_apply<ADJ>(c, c->kp.p, a, c->ktmp.p, done);
-    c->dct.apply(c->stream, c->ktmp.p, c->kv.p, sy, done, DotEpilogue{1, c->kr0.p, c->sc, c->red_part.p, c->ticket});   // + (r0, v) -> alpha
-    LAUNCH(c, bicg_s_kernel, eb, 256, c->kr.p, c->kv.p, c->ks.p, n, c->sc);
-    op_apply<ADJ>(c, c->ks.p, a, c->ktmp.p, done);
-    c->dct.apply(c->stream, c->ktmp.p, c->kt.p, sy, done, DotEpilogue{2, c->ks.p, c->sc, c->red_part.p, c->ticket});    // + (t, s), (t, t) -> omega
-    LAUNCH(c, bicg_x_kernel, rb, kRedThreads, c->kx.p, c->kr.p, c->kp.p, c->ks.p, c->kt.p, c->kr0.p, n, c->sc, c->red_part.p,
-           c->ticket, cond, use_cond);
+    if (ADJ) {
+        LAUNCH(c, bicg_p_kernel, eb, 256, c->kr.p, c->kp.p, c->kv.p, n, c->sc);
+        op_apply<true>(c, c->kp.p, a, c->ktmp.p, done);
+        c->dct.apply(c->stream, c->ktmp.p, c->kv.p, sy, done, DotEpilogue{1, c->kr0.p, c->sc, c->red_part.p, c->ticket, nullptr});
+        LAUNCH(c, bicg_s_kernel, eb, 256, c->kr.p, c->kv.p, c->ks.p, n, c->sc);
+        op_apply<true>(c, c->ks.p, a, c->ktmp.p, done);
+        c->dct.apply(c->stream, c->ktmp.p, c->kt.p, sy, done, DotEpilogue{2, c->ks.p, c->sc, c->red_part.p, c->ticket, nullptr});
+        LAUNCH(c, bicg_x_kernel, rb, kRedThreads, c->kx.p, c->kr.p, c->kp.p, c->ks.p, c->kt.p, c->kr0.p, (const double*)nullptr,
+               (double*)nullptr, n, c->sc, c->red_part.p, c->ticket, cond, use_cond);
+    } else {
+        c->dct.apply(c->stream, c->kr.p, c->kv.p, sy, done, DotEpilogue{1, c->kr0.p, c->sc, c->red_part.p, c->ticket, c->kp.p},
+                     RowPrologue{1, c->kr.p, c->kq.p, a, c->kp.p, c->sc}, 1);
+        c->dct.apply(c->stream, c->kr.p, c->kt.p, sy, done, DotEpilogue{2, c->ks.p, c->sc, c->red_part.p, c->ticket, c->ks.p},
+                     RowPrologue{2, c->kr.p, c->kv.p, a, c->ks.p, c->sc}, 1);
+        LAUNCH(c, bicg_x_kernel, rb, kRedThreads, c->kx.p, c->kr.p, c->kp.p, c->ks.p, c->kt.p, c->kr0.p, c->kv.p, c->kq.p, n, c->sc,
+               c->red_part.p, c->ticket, cond, use_cond);
+    }
 }
 
 // Whole linear solve as ONE CUDA graph: [P^-1 b, init] -> WHILE(not converged){ BiCGStab iteration } — the loop condition
@@ -123,8 +137,8 @@ cudaGraphExec_t solve_graph(vch2d_ctx* c, const double* a) {
     // prologue nodes
     VCH_CUDA(cudaStreamBeginCaptureToGraph(c->stream, graph, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal));
     c->dct.apply(c->stream, c->kb.p, c->kr.p, sy, nullptr);
-    LAUNCH(c, bicg_init_kernel, c->rb(), kRedThreads, c->kr.p, c->kr0.p, c->kp.p, c->kv.p, c->kx.p, n, c->sc, c->red_part.p,
-           c->ticket, cond, 1);
+    LAUNCH(c, bicg_init_kernel, c->rb(), kRedThreads, c->kr.p, c->kr0.p, c->kp.p, c->kv.p, c->kx.p, c->kq.p, n, c->sc,
+           c->red_part.p, c->ticket, cond, 4);
     cudaStreamCaptureStatus st; const cudaGraphNode_t* deps = nullptr; size_t ndeps = 0;
     VCH_CUDA(cudaStreamGetCaptureInfo(c->stream, &st, nullptr, nullptr, &deps, &ndeps));
     std::vector<cudaGraphNode_t> leaf(deps, deps + ndeps);
@@ -140,7 +154,7 @@ cudaGraphExec_t solve_graph(vch2d_ctx* c, const double* a) {
     VCH_CUDA(cudaGraphAddNode(&wnode, graph, leaf.data(), leaf.size(), &np));
     cudaGraph_t body = np.conditional.phGraph_out[0];
     VCH_CUDA(cudaStreamBeginCaptureToGraph(c->stream, body, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal));
-    enqueue_bicg_iteration<ADJ>(c, a, sy, cond, 1);
+    enqueue_bicg_iteration<ADJ>(c, a, sy, cond, ADJ ? 11 : 7);
     VCH_CUDA(cudaStreamEndCapture(c->stream, &tmp));
     cudaGraphExec_t exec;
     VCH_CUDA(cudaGraphInstantiate(&exec, graph, 0));
@@ -165,8 +179,8 @@ int krylov_solve(vch2d_ctx* c, const double* b, const double* a, vch_stats* st) 
     }
     SymbolArgs sy{0.0, 0.0, &c->sc->abar, 0.0, &c->sc->c0};
     c->dct.apply(c->stream, c->kb.p, c->kr.p, sy, nullptr);
-    LAUNCH(c, bicg_init_kernel, c->rb(), kRedThreads, c->kr.p, c->kr0.p, c->kp.p, c->kv.p, c->kx.p, n, c->sc, c->red_part.p,
-           c->ticket, (cudaGraphConditionalHandle)0, 0);
+    LAUNCH(c, bicg_init_kernel, c->rb(), kRedThreads, c->kr.p, c->kr0.p, c->kp.p, c->kv.p, c->kx.p, c->kq.p, n, c->sc,
+           c->red_part.p, c->ticket, (cudaGraphConditionalHandle)0, 0);
     int launched = 0, batch = 2;
     while (true) {
         for (int k = 0; k < batch; ++k) enqueue_bicg_iteration<ADJ>(c, a, sy, (cudaGraphConditionalHandle)0, 0);
@@ -187,10 +201,10 @@ int krylov_solve(vch2d_ctx* c, const double* b, const double* a, vch_stats* st) 
 }
 
 // Device-side solver counters -> vch_stats (call after a fetch_scalars).
-struct StatMark { long long its, solves, stalls, launches, gits, gsolves; };
+struct StatMark { long long its, solves, stalls, launches, glaunches; };
 StatMark stat_mark(vch2d_ctx* c) {
     fetch_scalars(c);
-    return {c->sc_host->iters_total, c->sc_host->solves, c->sc_host->stalls, c->log.count, c->sc_host->g_iters, c->sc_host->g_solves};
+    return {c->sc_host->iters_total, c->sc_host->solves, c->sc_host->stalls, c->log.count, c->sc_host->g_launches};
 }
 void stat_collect(vch2d_ctx* c, const StatMark& m0, vch_stats* st) {
     fetch_scalars(c);
@@ -202,7 +216,7 @@ void stat_collect(vch2d_ctx* c, const StatMark& m0, vch_stats* st) {
     st->krylov_stalls += c->sc_host->stalls - m0.stalls;
     st->krylov_max_iterations = std::max<long long>(st->krylov_max_iterations, c->sc_host->iters_max);
     // kernels inside solve graphs are not seen by the launch log: 4 prologue kernels per solve + 11 per iteration
-    st->kernel_launches += (c->log.count - m0.launches) + 4 * (c->sc_host->g_solves - m0.gsolves) + 11 * (c->sc_host->g_iters - m0.gits);
+    st->kernel_launches += (c->log.count - m0.launches) + (c->sc_host->g_launches - m0.glaunches);
 }
 
 void eval_residual(vch2d_ctx* c, const double* phi, const double* mu, double* Rphi, double* Rmu, double* a, double dt) {
@@ -461,7 +475,7 @@ int vch2d_create(const vch2d_params* p, int device, vch2d_ctx** out) {
         const size_t n = (size_t)g.n;
         for (DevBuf* b : {&c->phi, &c->mu, &c->phit, &c->mut, &c->w0, &c->w1, &c->cphi, &c->cmu, &c->Rphi, &c->Rmu, &c->a,
                           &c->RphiT, &c->RmuT, &c->aT, &c->kb, &c->kx, &c->kr, &c->kr0, &c->kp, &c->kv, &c->ks, &c->kt,
-                          &c->ktmp, &c->dmu})
+                          &c->ktmp, &c->kq, &c->dmu})
             b->alloc(n);
 
         VCH_CUDA(cudaMalloc(&c->ticket, sizeof(unsigned int)));
@@ -521,7 +535,7 @@ long long vch2d_launch_count(vch2d_ctx* c) {
     cudaSetDevice(c->device);
     if (cudaMemcpyAsync(c->sc_host, c->sc, sizeof(Scal), cudaMemcpyDeviceToHost, c->stream) != cudaSuccess) return c->log.count;
     cudaStreamSynchronize(c->stream);
-    return c->log.count + 4 * c->sc_host->g_solves + 11 * c->sc_host->g_iters;   // + kernels that ran inside solve graphs
+    return c->log.count + c->sc_host->g_launches;   // + kernels that ran inside solve graphs
 }
 
 int vch2d_profile(vch2d_ctx* c, int enable) {

@@ -196,12 +196,13 @@ __global__ void __launch_bounds__(256) op_apply_kernel(const double* __restrict_
 // ---------------------------------------------------------------------------------- BiCGStab vector kernels
 // cond/use_cond: CUDA-graph WHILE handle of the enclosing solve graph (device-driven Krylov loop); ignored when use_cond = 0.
 __global__ void bicg_init_kernel(const double* __restrict__ r, double* __restrict__ r0, double* __restrict__ p,
-                                 double* __restrict__ v, double* __restrict__ x, long long n, Scal* sc, double* part,
-                                 unsigned int* ticket, cudaGraphConditionalHandle cond, int use_cond) {
+                                 double* __restrict__ v, double* __restrict__ x, double* __restrict__ q, long long n, Scal* sc,
+                                 double* part, unsigned int* ticket, cudaGraphConditionalHandle cond, int use_cond) {
     double acc[1] = {0.0};
     for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (long long)gridDim.x * blockDim.x) {
         const double rv = r[idx];
         r0[idx] = rv; p[idx] = 0.0; v[idx] = 0.0; x[idx] = 0.0;
+        if (q) q[idx] = 0.0;
         acc[0] += rv * rv;
     }
     const int op[1] = {0};
@@ -214,7 +215,7 @@ __global__ void bicg_init_kernel(const double* __restrict__ r, double* __restric
         sc->done = (tot[0] == 0.0 || !isfinite(tot[0])) ? 1 : 0;
         if (!isfinite(tot[0])) sc->nonfinite = 1;
         sc->solves += 1;
-        if (use_cond) { sc->g_solves += 1; cudaGraphSetConditional(cond, sc->done ? 0u : 1u); }
+        if (use_cond) { sc->g_launches += use_cond; cudaGraphSetConditional(cond, sc->done ? 0u : 1u); }
     }
 }
 
@@ -262,16 +263,18 @@ __global__ void bicg_dot2_kernel(const double* __restrict__ t, const double* __r
     }
 }
 
+// q (optional) = p - omega v: the next iteration's fused prologue forms p = r + beta q without an in-place hazard.
 __global__ void bicg_x_kernel(double* __restrict__ x, double* __restrict__ r, const double* __restrict__ p,
                               const double* __restrict__ s, const double* __restrict__ t, const double* __restrict__ r0,
-                              long long n, Scal* sc, double* part, unsigned int* ticket, cudaGraphConditionalHandle cond,
-                              int use_cond) {
+                              const double* __restrict__ v, double* __restrict__ q, long long n, Scal* sc, double* part,
+                              unsigned int* ticket, cudaGraphConditionalHandle cond, int use_cond) {
     if (sc->done) return;
     const double al = sc->alpha, om = sc->omega;
     double acc[2] = {0.0, 0.0};
     for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (long long)gridDim.x * blockDim.x) {
-        const double sv = s[idx];
-        x[idx] += al * p[idx] + om * sv;
+        const double sv = s[idx], pv = p[idx];
+        if (q) q[idx] = pv - om * v[idx];
+        x[idx] += al * pv + om * sv;
         const double rv = sv - om * t[idx];
         r[idx] = rv;
         acc[0] += rv * rv; acc[1] += r0[idx] * rv;
@@ -285,7 +288,7 @@ __global__ void bicg_x_kernel(double* __restrict__ x, double* __restrict__ r, co
         if (bad || tot[0] <= sc->thr2) sc->done = 1;
         if (sc->iters > sc->iters_max) sc->iters_max = sc->iters;
         if (use_cond) {
-            sc->g_iters += 1;
+            sc->g_launches += use_cond;
             const bool stop = sc->done || sc->iters >= sc->maxit;
             if (stop && !sc->done) sc->stalls += 1;
             cudaGraphSetConditional(cond, stop ? 0u : 1u);

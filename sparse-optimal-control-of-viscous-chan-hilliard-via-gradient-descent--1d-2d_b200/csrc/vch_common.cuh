@@ -135,7 +135,7 @@ struct Scal {
     double c0, c2;            // operator coefficients of the current solve (read by the graph's kernels: one graph serves every dt)
     int done, iters, nonfinite, maxit;
     long long iters_total, solves, stalls;   // accumulated on the device (graph-driven solves are never polled)
-    long long g_iters, g_solves;             // the part of the above that ran inside solve graphs
+    long long g_launches;                    // kernels that ran inside solve graphs (not seen by the host launch log)
     int iters_max, pad;
 };
 

@@ -39,13 +39,27 @@ struct SymbolArgs {
     const double* coef_ptr;   // device {c0, c2} (may be null -> the immediate values above)
 };
 
-// Optional epilogue of the last row transform: BiCGStab dot products over the freshly produced vector.
+// Optional epilogue of the last row transform: add a vector (out = z + addend) and BiCGStab dot products over `out`.
 struct DotEpilogue {
     int mode = 0;                 // 0 none, 1: (other, out) -> alpha = rho_new / dot, rho = rho_new ; 2: (out, other), (out, out) -> omega
     const double* other = nullptr;
     Scal* sc = nullptr;
     double* part = nullptr;
     unsigned int* ticket = nullptr;
+    const double* addend = nullptr;
+};
+
+// Optional prologue of the first row transform (fused BiCGStab vector update + coefficient multiply):
+//   mode 0: x = in
+//   mode 1: p = r + beta*q   (written to w), x = (a - abar) * p        beta = (rho_new/rho)(alpha/omega)
+//   mode 2: s = r - alpha*v  (written to w), x = (a - abar) * s
+struct RowPrologue {
+    int mode = 0;
+    const double* r = nullptr;
+    const double* qv = nullptr;
+    const double* a = nullptr;
+    double* w = nullptr;
+    const Scal* sc = nullptr;
 };
 
 struct DctPlan {
@@ -57,8 +71,10 @@ struct DctPlan {
     void destroy();
     int max_grid() const;
     // out = P^-1 in   (in may equal out); epi = optional fused dots on `out`
+    // scale_mode 0: divide by the symbol (P^-1);  1: multiply by lambda/symbol (-P^-1 L, the identity-plus-correction
+    // form of P^-1 A for the forward Schur operator: P^-1 A x = x + DCT^-1[(lambda/sym) DCT((a - abar) x)])
     void apply(cudaStream_t s, const double* in, double* out, const SymbolArgs& sym, const int* done_flag,
-               const DotEpilogue& epi = DotEpilogue());
+               const DotEpilogue& epi = DotEpilogue(), const RowPrologue& pro = RowPrologue(), int scale_mode = 0);
 };
 
 // ------------------------------------------------------------------------------------------------ device side
@@ -215,8 +231,8 @@ template <bool SOLVE, int MAXT>
 __global__ void __launch_bounds__(MAXT, VCH_FFT_MINB)
 dct_fft_kernel(const double* in, double* out, int nlines, int n, int in_ls, int in_es, int out_ls, int out_es, int Lf,
                int log2L, int ppb, const double2* __restrict__ twg, const double* __restrict__ lam_line,
-               const double* __restrict__ lam_elem, SymbolArgs sy, double norm, DotEpilogue epi,
-               const int* __restrict__ done) {
+               const double* __restrict__ lam_elem, SymbolArgs sy, double norm, int scale_mode, RowPrologue pro,
+               DotEpilogue epi, const int* __restrict__ done) {
     if (done && *done) return;
     extern __shared__ double2 sm[];
     const int N = n - 1, tpf = Lf >> 3, ld = Lf + (Lf >> 3) + 1;
@@ -245,9 +261,19 @@ dct_fft_kernel(const double* in, double* out, int nlines, int n, int in_ls, int 
         const int off = (e <= N ? e : Lf - e) * in_es;
         if (SOLVE) {
             v[r] = va ? *reinterpret_cast<const double2*>(pa + off) : make_double2(0.0, 0.0);
-        } else {
+        } else if (pro.mode == 0) {
             v[r].x = va ? pa[off] : 0.0;
             v[r].y = vb ? pb[off] : 0.0;
+        } else {
+            // fused vector update: every element is recomputed where its mirror image is needed; it is written once
+            const Scal* sc = pro.sc;
+            const double coef = (pro.mode == 1) ? (sc->rho_new / sc->rho) * (sc->alpha / sc->omega) : -sc->alpha;
+            const double abar = sc->abar;
+            const size_t ia = (size_t)la * in_ls + off, ib = (size_t)lb * in_ls + off;
+            double xa = 0.0, xb = 0.0;
+            if (va) { const double w = pro.r[ia] + coef * pro.qv[ia]; if (e <= N) pro.w[ia] = w; xa = (pro.a[ia] - abar) * w; }
+            if (vb) { const double w = pro.r[ib] + coef * pro.qv[ib]; if (e <= N) pro.w[ib] = w; xb = (pro.a[ib] - abar) * w; }
+            v[r] = make_double2(xa, xb);
         }
     }
     fft_first_pass_store(data, v, t);
@@ -256,28 +282,39 @@ dct_fft_kernel(const double* in, double* out, int nlines, int n, int in_ls, int 
     fft_last_pass(data, Lf, log2L, Ns, t, tpf, tw, z, kk);
 
     if (SOLVE) {
-        // forward outputs -> divide by the symbol -> mirrored store = input of the inverse transform
+        // Forward outputs -> multiply by the spectral factor -> inverse transform.  The last pass leaves every thread
+        // with exactly the 8 spectrum entries {t + q*tpf} that the first pass of the next transform consumes, so the
+        // hand-over stays in registers (entries beyond N are the thread's own copy of the mirror image; the spectrum of
+        // a real-even line is even up to rounding).
         const double abar = sy.abar_ptr ? *sy.abar_ptr : sy.abar_const;
         const double sc0 = sy.coef_ptr ? sy.coef_ptr[0] : sy.c0, sc2 = sy.coef_ptr ? sy.coef_ptr[1] : sy.c2;
         const double lla = va ? lam_line[la] : 0.0, llb = vb ? lam_line[lb] : 0.0;
-        __syncthreads();                         // every thread has finished reading the forward data
+        const int rem = log2L % 3;
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-            if (kk[q] <= N) {
-                const double le = lam_elem[kk[q]];
-                const double s1 = le + lla, s2 = le + llb;
-                double2 w = z[q];
-                w.x *= norm / (sc0 + s1 * (abar + sc2 * s1));
-                w.y *= norm / (sc0 + s2 * (abar + sc2 * s2));
-                data[padi(kk[q])] = w;
-                if (kk[q] > 0 && kk[q] < N) data[padi(Lf - kk[q])] = w;
-            }
+        for (int i = 0; i < 8; ++i) {
+            const int kf = (kk[i] <= N) ? kk[i] : Lf - kk[i];
+            const double le = lam_elem[kf];
+            const double s1 = le + lla, s2 = le + llb;
+            double f1 = norm / (sc0 + s1 * (abar + sc2 * s1)), f2 = norm / (sc0 + s2 * (abar + sc2 * s2));
+            if (scale_mode == 1) { f1 *= s1; f2 *= s2; }
+            z[i].x *= f1; z[i].y *= f2;
         }
-        __syncthreads();
-        // inverse = the same transform applied to the (real-even) scaled spectrum; its first pass reads shared memory
+        // static permutation z[] (last-pass order) -> v[q], q = (kk - t) / tpf
+        if (rem == 0) {
 #pragma unroll
-        for (int r = 0; r < 8; ++r) v[r] = data[padi(t + r * tpf)];
-        __syncthreads();
+            for (int r = 0; r < 8; ++r) v[r] = z[r];
+        } else if (rem == 2) {
+#pragma unroll
+            for (int m = 0; m < 2; ++m)
+#pragma unroll
+                for (int r = 0; r < 4; ++r) v[m + 2 * r] = z[m * 4 + r];
+        } else {
+#pragma unroll
+            for (int m = 0; m < 4; ++m)
+#pragma unroll
+                for (int r = 0; r < 2; ++r) v[m + 4 * r] = z[m * 2 + r];
+        }
+        __syncthreads();                         // every thread has finished reading the forward data
         fft_first_pass_store(data, v, t);
         Ns = fft_middle(data, Lf, log2L, t, tpf, tw);
         fft_last_pass(data, Lf, log2L, Ns, t, tpf, tw, z, kk);
@@ -288,6 +325,8 @@ dct_fft_kernel(const double* in, double* out, int nlines, int n, int in_ls, int 
     double* qb = out + (size_t)lb * out_ls;
     const double* oa = epi.other + (size_t)la * out_ls;
     const double* ob = epi.other + (size_t)lb * out_ls;
+    const double* da = epi.addend + (size_t)la * out_ls;
+    const double* db = epi.addend + (size_t)lb * out_ls;
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
         if (kk[q] <= N) {
@@ -296,12 +335,14 @@ dct_fft_kernel(const double* in, double* out, int nlines, int n, int in_ls, int 
                 if (va) *reinterpret_cast<double2*>(qa + off) = make_double2(z[q].x, vb ? z[q].y : 0.0);
             } else {
                 if (va) {
-                    qa[off] = z[q].x;
-                    if (epi.mode) { acc1 += oa[off] * z[q].x; acc2 += z[q].x * z[q].x; }
+                    const double o = epi.addend ? z[q].x + da[off] : z[q].x;
+                    qa[off] = o;
+                    if (epi.mode) { acc1 += oa[off] * o; acc2 += o * o; }
                 }
                 if (vb) {
-                    qb[off] = z[q].y;
-                    if (epi.mode) { acc1 += ob[off] * z[q].y; acc2 += z[q].y * z[q].y; }
+                    const double o = epi.addend ? z[q].y + db[off] : z[q].y;
+                    qb[off] = o;
+                    if (epi.mode) { acc1 += ob[off] * o; acc2 += o * o; }
                 }
             }
         }
@@ -351,6 +392,31 @@ __global__ void dct_scale_kernel(double* __restrict__ d, int no, int ni, const d
     const double sc0 = sy.coef_ptr ? sy.coef_ptr[0] : sy.c0, sc2 = sy.coef_ptr ? sy.coef_ptr[1] : sy.c2;
     const double l = lam_o[k] + lam_i[c];
     d[idx] *= norm / (sc0 + l * (abar + sc2 * l));
+}
+// Dense-path stand-ins for the fused prologue / epilogue / spectral factor.
+__global__ void dct_prologue_kernel(RowPrologue pro, double* __restrict__ x, long long n, const int* __restrict__ done) {
+    if (done && *done) return;
+    const Scal* sc = pro.sc;
+    const double coef = (pro.mode == 1) ? (sc->rho_new / sc->rho) * (sc->alpha / sc->omega) : -sc->alpha;
+    const double abar = sc->abar;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (long long)gridDim.x * blockDim.x) {
+        const double w = pro.r[idx] + coef * pro.qv[idx];
+        pro.w[idx] = w;
+        x[idx] = (pro.a[idx] - abar) * w;
+    }
+}
+__global__ void dct_addend_kernel(double* __restrict__ outv, const double* __restrict__ addend, long long n, const int* __restrict__ done) {
+    if (done && *done) return;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (long long)gridDim.x * blockDim.x)
+        outv[idx] += addend[idx];
+}
+__global__ void dct_lambda_kernel(double* __restrict__ d, int no, int ni, const double* __restrict__ lam_o,
+                                  const double* __restrict__ lam_i, const int* __restrict__ done) {
+    if (done && *done) return;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)no * ni) return;
+    const int k = (int)(idx / ni), c = (int)(idx - (long long)k * ni);
+    d[idx] *= lam_o[k] + lam_i[c];
 }
 // Stand-alone BiCGStab dots for the paths without the fused epilogue.
 __global__ void dct_dots_kernel(const double* __restrict__ outv, DotEpilogue epi, long long n, const int* __restrict__ done) {
@@ -451,85 +517,71 @@ inline int DctPlan::max_grid() const {
 }
 
 inline void DctPlan::apply(cudaStream_t s, const double* in, double* out, const SymbolArgs& sym, const int* done,
-                           const DotEpilogue& epi) {
+                           const DotEpilogue& epi, const RowPrologue& pro, int scale_mode) {
     const long long n = (long long)no * ni;
     const int eb = (int)((n + 255) / 256);
     const double norm = 1.0 / (4.0 * (double)(ni - 1) * (double)(no - 1));
     const SymbolArgs nosym{1.0, 0.0, nullptr, 0.0, nullptr};
-    bool epi_done = (epi.mode == 0);
+    const bool all_fft = inner.fft && outer.fft;
     // tmp1 is pitched only when both axes use the FFT kernels (the dense kernels address dense arrays)
-    const int P = (inner.fft && outer.fft) ? pitch : ni;
-    auto rows = [&](const double* a, int a_ls, double* b, int b_ls, bool last) {
-        if (inner.fft) {
-            const int ppb = dct_rows_ppb(inner, no), tpf = inner.Lf >> 3, threads = ppb * tpf;
-            const int grid = ((no + 1) / 2 + ppb - 1) / ppb;
-            const size_t smem = dct_smem(inner, ppb);
-            const DotEpilogue e = last ? epi : DotEpilogue();
-            if (last) epi_done = true;
-            log->begin("dct_rows_fft", s);
-            if (threads <= 512)
-                dct_fft_kernel<false, 512><<<grid, threads, smem, s>>>(a, b, no, ni, a_ls, 1, b_ls, 1, inner.Lf, inner.log2L, ppb,
-                                                                       inner.tw, nullptr, nullptr, nosym, 1.0, e, done);
-            else
-                dct_fft_kernel<false, 1024><<<grid, threads, smem, s>>>(a, b, no, ni, a_ls, 1, b_ls, 1, inner.Lf, inner.log2L, ppb,
-                                                                        inner.tw, nullptr, nullptr, nosym, 1.0, e, done);
-        } else {
-            log->begin("dct_rows_dense", s);
-            dct_rows_dense_kernel<<<eb, 256, 0, s>>>(a, b, no, ni, inner.denseT, done);
-        }
-        log->end(s);
-    };
+    const int P = all_fft ? pitch : ni;
     double* t1 = tmp1.p;
     double* t2 = tmp2.p;
-    rows(in, ni, t1, P, false);
-    if (outer.fft) {
-        // fused column solve, in place on t1: lines = columns (stride 1), elements stride P
-        const int ppb = dct_cols_ppb(outer, ni), tpf = outer.Lf >> 3, threads = ppb * tpf;
-        const int grid = ((ni + 1) / 2 + ppb - 1) / ppb;
-        const size_t smem = dct_smem(outer, ppb);
-        log->begin("dct_cols_fft_solve", s);
-        if (inner.fft) {
-            if (threads <= 512)
-                dct_fft_kernel<true, 512><<<grid, threads, smem, s>>>(t1, t1, ni, no, 1, P, 1, P, outer.Lf, outer.log2L, ppb, outer.tw,
-                                                                      inner.lam, outer.lam, sym, norm, DotEpilogue(), done);
-            else
-                dct_fft_kernel<true, 1024><<<grid, threads, smem, s>>>(t1, t1, ni, no, 1, P, 1, P, outer.Lf, outer.log2L, ppb, outer.tw,
-                                                                       inner.lam, outer.lam, sym, norm, DotEpilogue(), done);
+    auto fft_launch = [&](bool solve, const DctAxis& ax, int grid, int threads, size_t smem, const double* a, double* b, int nl,
+                          int nn, int ils, int ies, int ols, int oes, const double* ll, const double* le, const SymbolArgs& sy,
+                          double nrm, int smode, const RowPrologue& pr, const DotEpilogue& ep) {
+        if (solve) {
+            if (threads <= 512) dct_fft_kernel<true, 512><<<grid, threads, smem, s>>>(a, b, nl, nn, ils, ies, ols, oes, ax.Lf, ax.log2L, threads / (ax.Lf >> 3), ax.tw, ll, le, sy, nrm, smode, pr, ep, done);
+            else dct_fft_kernel<true, 1024><<<grid, threads, smem, s>>>(a, b, nl, nn, ils, ies, ols, oes, ax.Lf, ax.log2L, threads / (ax.Lf >> 3), ax.tw, ll, le, sy, nrm, smode, pr, ep, done);
         } else {
-            // dense rows + FFT columns: unpitched buffer, scalar accesses
-            if (threads <= 512)
-                dct_fft_kernel<false, 512><<<grid, threads, smem, s>>>(t1, t2, ni, no, 1, ni, 1, ni, outer.Lf, outer.log2L, ppb, outer.tw,
-                                                                       nullptr, nullptr, nosym, 1.0, DotEpilogue(), done);
-            else
-                dct_fft_kernel<false, 1024><<<grid, threads, smem, s>>>(t1, t2, ni, no, 1, ni, 1, ni, outer.Lf, outer.log2L, ppb, outer.tw,
-                                                                        nullptr, nullptr, nosym, 1.0, DotEpilogue(), done);
-            log->end(s);
-            log->begin("dct_scale", s); dct_scale_kernel<<<eb, 256, 0, s>>>(t2, no, ni, outer.lam, inner.lam, sym, norm, done); log->end(s);
-            log->begin("dct_cols_fft", s);
-            if (threads <= 512)
-                dct_fft_kernel<false, 512><<<grid, threads, smem, s>>>(t2, t1, ni, no, 1, ni, 1, ni, outer.Lf, outer.log2L, ppb, outer.tw,
-                                                                       nullptr, nullptr, nosym, 1.0, DotEpilogue(), done);
-            else
-                dct_fft_kernel<false, 1024><<<grid, threads, smem, s>>>(t2, t1, ni, no, 1, ni, 1, ni, outer.Lf, outer.log2L, ppb, outer.tw,
-                                                                        nullptr, nullptr, nosym, 1.0, DotEpilogue(), done);
+            if (threads <= 512) dct_fft_kernel<false, 512><<<grid, threads, smem, s>>>(a, b, nl, nn, ils, ies, ols, oes, ax.Lf, ax.log2L, threads / (ax.Lf >> 3), ax.tw, ll, le, sy, nrm, smode, pr, ep, done);
+            else dct_fft_kernel<false, 1024><<<grid, threads, smem, s>>>(a, b, nl, nn, ils, ies, ols, oes, ax.Lf, ax.log2L, threads / (ax.Lf >> 3), ax.tw, ll, le, sy, nrm, smode, pr, ep, done);
         }
+    };
+    const int rppb = inner.fft ? dct_rows_ppb(inner, no) : 0, rthreads = inner.fft ? rppb * (inner.Lf >> 3) : 0;
+    const int rgrid = inner.fft ? ((no + 1) / 2 + rppb - 1) / rppb : 0;
+    const int cppb = outer.fft ? dct_cols_ppb(outer, ni) : 0, cthreads = outer.fft ? cppb * (outer.Lf >> 3) : 0;
+    const int cgrid = outer.fft ? ((ni + 1) / 2 + cppb - 1) / cppb : 0;
+
+    if (all_fft) {
+        // rows (prologue fused) -> fused column solve in place on the pitched buffer -> rows (addend + dots fused)
+        log->begin("dct_rows_fft", s);
+        fft_launch(false, inner, rgrid, rthreads, dct_smem(inner, rppb), in, t1, no, ni, ni, 1, P, 1, nullptr, nullptr, nosym, 1.0, 0, pro, DotEpilogue());
         log->end(s);
-    } else {
-        log->begin("dct_cols_dense", s); dct_cols_dense_kernel<<<eb, 256, 0, s>>>(t1, t2, no, ni, outer.denseT, done); log->end(s);
-        log->begin("dct_scale", s); dct_scale_kernel<<<eb, 256, 0, s>>>(t2, no, ni, outer.lam, inner.lam, sym, norm, done); log->end(s);
-        log->begin("dct_cols_dense", s); dct_cols_dense_kernel<<<eb, 256, 0, s>>>(t2, t1, no, ni, outer.denseT, done); log->end(s);
-    }
-    if (inner.fft) {
-        rows(t1, P, out, ni, true);
-    } else {                                   // the dense row kernel is not in-place safe and `in` may alias `out`
-        rows(t1, ni, t2, ni, true);
-        VCH_CUDA(cudaMemcpyAsync(out, t2, n * sizeof(double), cudaMemcpyDeviceToDevice, s));
-    }
-    if (!epi_done) {
-        log->begin("dct_dots", s);
-        dct_dots_kernel<<<red_blocks(n), kRedThreads, 0, s>>>(out, epi, n, done);
+        log->begin("dct_cols_fft_solve", s);
+        fft_launch(true, outer, cgrid, cthreads, dct_smem(outer, cppb), t1, t1, ni, no, 1, P, 1, P, inner.lam, outer.lam, sym, norm, scale_mode, RowPrologue(), DotEpilogue());
         log->end(s);
+        log->begin("dct_rows_fft", s);
+        fft_launch(false, inner, rgrid, rthreads, dct_smem(inner, rppb), t1, out, no, ni, P, 1, ni, 1, nullptr, nullptr, nosym, 1.0, 0, RowPrologue(), epi);
+        log->end(s);
+        VCH_CUDA(cudaGetLastError());
+        return;
     }
+    // ---- mixed / dense path (validation grids): prologue, transforms, spectral factor and epilogue as separate kernels
+    const double* src = in;
+    if (pro.mode) {
+        log->begin("dct_prologue", s); dct_prologue_kernel<<<red_blocks(n), 256, 0, s>>>(pro, t2, n, done); log->end(s);
+        src = t2;
+    }
+    auto rows = [&](const double* a, double* b) {     // a != b
+        if (inner.fft) { log->begin("dct_rows_fft", s); fft_launch(false, inner, rgrid, rthreads, dct_smem(inner, rppb), a, b, no, ni, ni, 1, ni, 1, nullptr, nullptr, nosym, 1.0, 0, RowPrologue(), DotEpilogue()); }
+        else { log->begin("dct_rows_dense", s); dct_rows_dense_kernel<<<eb, 256, 0, s>>>(a, b, no, ni, inner.denseT, done); }
+        log->end(s);
+    };
+    auto cols = [&](const double* a, double* b) {     // a != b
+        if (outer.fft) { log->begin("dct_cols_fft", s); fft_launch(false, outer, cgrid, cthreads, dct_smem(outer, cppb), a, b, ni, no, 1, ni, 1, ni, nullptr, nullptr, nosym, 1.0, 0, RowPrologue(), DotEpilogue()); }
+        else { log->begin("dct_cols_dense", s); dct_cols_dense_kernel<<<eb, 256, 0, s>>>(a, b, no, ni, outer.denseT, done); }
+        log->end(s);
+    };
+    rows(src, t1);
+    cols(t1, t2);
+    log->begin("dct_scale", s); dct_scale_kernel<<<eb, 256, 0, s>>>(t2, no, ni, outer.lam, inner.lam, sym, norm, done); log->end(s);
+    if (scale_mode == 1) { log->begin("dct_lambda", s); dct_lambda_kernel<<<eb, 256, 0, s>>>(t2, no, ni, outer.lam, inner.lam, done); log->end(s); }
+    cols(t2, t1);
+    rows(t1, t2);
+    VCH_CUDA(cudaMemcpyAsync(out, t2, n * sizeof(double), cudaMemcpyDeviceToDevice, s));
+    if (epi.addend) { log->begin("dct_addend", s); dct_addend_kernel<<<red_blocks(n), 256, 0, s>>>(out, epi.addend, n, done); log->end(s); }
+    if (epi.mode) { log->begin("dct_dots", s); dct_dots_kernel<<<red_blocks(n), kRedThreads, 0, s>>>(out, epi, n, done); log->end(s); }
     VCH_CUDA(cudaGetLastError());
 }
 

@@ -232,4 +232,4 @@ def test_dct_fast_solve_is_exact_for_constant_coefficients(native, N):
     b = -Rm + apply_L(Rp)
     ref = dctn(dctn(b, type=1) / sym, type=1) / (4 * N * N)
     assert rel(dphi, ref) < 1e-10
-    assert rel(dmu, 2 * (a * ref - 0.5 * P.kappa * apply_L(ref) + Rp)) < 1e-8     # L amplifies rounding by 1/h^2
+    assert rel(dmu, 2 * (a * ref - 0.5 * P.kappa * apply_L(ref) + Rp)) < 1e-7     # L amplifies rounding by 1/h^2 (4e6 at N = 2048)
