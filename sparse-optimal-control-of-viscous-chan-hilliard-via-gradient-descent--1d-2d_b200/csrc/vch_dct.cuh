@@ -141,83 +141,78 @@ __device__ __forceinline__ void twiddle(double2 (&v)[R], int k, int twstep, cons
     }
 }
 
+// All FFT geometry is a compile-time function of LOG2L (Lf = 2^LOG2L = 2N), so shared-memory offsets fold into
+// immediates: with Lf/8 and Ns multiples of 8,  padi(x + r*S) = padi(x) + r*(S + S/8).
+template <int LOG2L> struct FftGeom {
+    static constexpr int Lf = 1 << LOG2L, tpf = Lf / 8;
+    static constexpr int n8 = LOG2L / 3, rem = LOG2L % 3;
+    static constexpr int mids = (rem == 0) ? n8 - 2 : n8 - 1;     // radix-8 passes strictly between first and last
+    static constexpr int lastR = (rem == 0) ? 8 : (rem == 2 ? 4 : 2);
+    static constexpr int lastNs = Lf / lastR;
+    static constexpr int ld = Lf + Lf / 8 + 1;
+};
+
 // Middle radix-8 pass through padded shared memory: load, twiddle, DFT, barrier, store, barrier.
-__device__ __forceinline__ void fft_mid_pass(double2* data, int Lf, int Ns, int t, int tpf, const TwTab& tw) {
+template <int LOG2L, int NS>
+__device__ __forceinline__ void fft_mid_pass(double2* data, int t, const TwTab& tw) {
+    using G = FftGeom<LOG2L>;
     double2 v[8];
-    const int k = t & (Ns - 1);
+    const int k = t & (NS - 1);
+    const double2* src = data + padi(t);
 #pragma unroll
-    for (int r = 0; r < 8; ++r) v[r] = data[padi(t + r * tpf)];
-    twiddle<8>(v, k, Lf / (Ns * 8), tw);
+    for (int r = 0; r < 8; ++r) v[r] = src[r * (G::tpf + G::tpf / 8)];
+    twiddle<8>(v, k, G::Lf / (NS * 8), tw);
     dft<8>(v);
     __syncthreads();
-    const int j0 = (t - k) * 8 + k;
+    double2* dst = data + padi((t - k) * 8 + k);
 #pragma unroll
-    for (int r = 0; r < 8; ++r) data[padi(j0 + r * Ns)] = v[r];
+    for (int r = 0; r < 8; ++r) dst[r * (NS + NS / 8)] = v[r];
     __syncthreads();
 }
 
 // First pass on 8 register values (Ns = 1: no twiddles): DFT and autosort store, then a barrier.
 __device__ __forceinline__ void fft_first_pass_store(double2* data, double2 (&v)[8], int t) {
     dft<8>(v);
+    double2* dst = data + 9 * t;            // padi(8t + r) = 9t + r
 #pragma unroll
-    for (int r = 0; r < 8; ++r) data[padi(8 * t + r)] = v[r];
+    for (int r = 0; r < 8; ++r) dst[r] = v[r];
     __syncthreads();
 }
 
-// Last pass of radix R (8 / 4 / 2): loads, twiddles, DFT; outputs stay in registers: v[m][r] has natural index
-// j0[m] + r * Ns.
-template <int R>
-__device__ __forceinline__ void fft_last_pass_load(const double2* data, int Lf, int Ns, int t, int tpf,
-                                                   const TwTab& tw, double2 (&v)[8 / R][R], int (&j0)[8 / R]) {
-    constexpr int NB = 8 / R;
-    const int stride = Lf / R;
+template <int LOG2L>
+__device__ __forceinline__ void fft_middle(double2* data, int t, const TwTab& tw) {
+    using G = FftGeom<LOG2L>;
+#ifndef VCH_FFT_NOMID
+    if constexpr (G::mids >= 1) fft_mid_pass<LOG2L, 8>(data, t, tw);
+    if constexpr (G::mids >= 2) fft_mid_pass<LOG2L, 64>(data, t, tw);
+    if constexpr (G::mids >= 3) fft_mid_pass<LOG2L, 512>(data, t, tw);
+#endif
+}
+
+// Last pass (radix 8 / 4 / 2): outputs stay in registers; z[i] has natural index t + FftOut<LOG2L>::off(i).
+template <int LOG2L> struct FftOut {
+    using G = FftGeom<LOG2L>;
+    // i = m*R + r  ->  offset m*tpf + r*Ns  (j0 = j because j < Ns in the last pass)
+    __host__ __device__ static constexpr int off(int i) { return (i / G::lastR) * G::tpf + (i % G::lastR) * G::lastNs; }
+    // position of z[i] among the inputs {t + q*tpf} of a following first pass: q = off / tpf
+    __host__ __device__ static constexpr int q(int i) { return off(i) / G::tpf; }
+};
+
+template <int LOG2L>
+__device__ __forceinline__ void fft_last_pass(const double2* data, int t, const TwTab& tw, double2 (&z)[8]) {
+    using G = FftGeom<LOG2L>;
+    constexpr int R = G::lastR, NB = 8 / R, stride = G::Lf / R;
 #pragma unroll
     for (int m = 0; m < NB; ++m) {
-        const int j = t + m * tpf, k = j & (Ns - 1);
+        const int j = t + m * G::tpf;
+        double2 v[R];
+        const double2* src = data + padi(j);
 #pragma unroll
-        for (int r = 0; r < R; ++r) v[m][r] = data[padi(j + r * stride)];
-        twiddle<R>(v[m], k, Lf / (Ns * R), tw);
-        dft<R>(v[m]);
-        j0[m] = (j - k) * R + k;
-    }
-}
-
-// Runs the middle passes between the first-pass store and the last pass.  Returns Ns of the last pass.
-__device__ __forceinline__ int fft_middle(double2* data, int Lf, int log2L, int t, int tpf, const TwTab& tw) {
-    const int n8 = log2L / 3, rem = log2L - 3 * n8;
-    const int mids = (rem == 0) ? n8 - 2 : n8 - 1;     // radix-8 passes strictly between first and last
-    int Ns = 8;
-#ifndef VCH_FFT_NOMID
-    for (int p = 0; p < mids; ++p) { fft_mid_pass(data, Lf, Ns, t, tpf, tw); Ns *= 8; }
-#else
-    for (int p = 0; p < mids; ++p) Ns *= 8;
-#endif
-    return Ns;
-}
-
-// Last pass into an 8-entry register list (index + value), any tail radix.
-__device__ __forceinline__ void fft_last_pass(const double2* data, int Lf, int log2L, int Ns, int t, int tpf,
-                                              const TwTab& tw, double2 (&z)[8], int (&kk)[8]) {
-    const int rem = log2L % 3;
-    if (rem == 0) {
-        double2 o[1][8]; int j0[1];
-        fft_last_pass_load<8>(data, Lf, Ns, t, tpf, tw, o, j0);
+        for (int r = 0; r < R; ++r) v[r] = src[r * (stride + stride / 8)];
+        twiddle<R>(v, j, 1, tw);             // k = j, twstep = Lf / (Ns R) = 1
+        dft<R>(v);
 #pragma unroll
-        for (int r = 0; r < 8; ++r) { z[r] = o[0][r]; kk[r] = j0[0] + r * Ns; }
-    } else if (rem == 2) {
-        double2 o[2][4]; int j0[2];
-        fft_last_pass_load<4>(data, Lf, Ns, t, tpf, tw, o, j0);
-#pragma unroll
-        for (int m = 0; m < 2; ++m)
-#pragma unroll
-            for (int r = 0; r < 4; ++r) { z[m * 4 + r] = o[m][r]; kk[m * 4 + r] = j0[m] + r * Ns; }
-    } else {
-        double2 o[4][2]; int j0[4];
-        fft_last_pass_load<2>(data, Lf, Ns, t, tpf, tw, o, j0);
-#pragma unroll
-        for (int m = 0; m < 4; ++m)
-#pragma unroll
-            for (int r = 0; r < 2; ++r) { z[m * 2 + r] = o[m][r]; kk[m * 2 + r] = j0[m] + r * Ns; }
+        for (int r = 0; r < R; ++r) z[m * R + r] = v[r];
     }
 }
 
@@ -227,15 +222,16 @@ __device__ __forceinline__ void fft_last_pass(const double2* data, int Lf, int l
 #ifndef VCH_FFT_MINB
 #define VCH_FFT_MINB (1024 / MAXT)
 #endif
-template <bool SOLVE, int MAXT>
+template <int LOG2L, bool SOLVE, int MAXT>
 __global__ void __launch_bounds__(MAXT, VCH_FFT_MINB)
-dct_fft_kernel(const double* in, double* out, int nlines, int n, int in_ls, int in_es, int out_ls, int out_es, int Lf,
-               int log2L, int ppb, const double2* __restrict__ twg, const double* __restrict__ lam_line,
-               const double* __restrict__ lam_elem, SymbolArgs sy, double norm, int scale_mode, RowPrologue pro,
-               DotEpilogue epi, const int* __restrict__ done) {
+dct_fft_kernel(const double* in, double* out, int nlines, int n, int in_ls, int in_es, int out_ls, int out_es, int ppb,
+               const double2* __restrict__ twg, const double* __restrict__ lam_line, const double* __restrict__ lam_elem,
+               SymbolArgs sy, double norm, int scale_mode, RowPrologue pro, DotEpilogue epi, const int* __restrict__ done) {
+    using G = FftGeom<LOG2L>;
+    constexpr int Lf = G::Lf, tpf = G::tpf, ld = G::ld;
     if (done && *done) return;
     extern __shared__ double2 sm[];
-    const int N = n - 1, tpf = Lf >> 3, ld = Lf + (Lf >> 3) + 1;
+    const int N = n - 1;
     const int f = threadIdx.x / tpf, t = threadIdx.x - f * tpf;
     // twiddle tables first (visible after the first-pass barrier), FFT buffers behind them
     double2* tlo = sm;
@@ -277,9 +273,9 @@ dct_fft_kernel(const double* in, double* out, int nlines, int n, int in_ls, int 
         }
     }
     fft_first_pass_store(data, v, t);
-    int Ns = fft_middle(data, Lf, log2L, t, tpf, tw);
-    double2 z[8]; int kk[8];
-    fft_last_pass(data, Lf, log2L, Ns, t, tpf, tw, z, kk);
+    fft_middle<LOG2L>(data, t, tw);
+    double2 z[8];
+    fft_last_pass<LOG2L>(data, t, tw, z);
 
     if (SOLVE) {
         // Forward outputs -> multiply by the spectral factor -> inverse transform.  The last pass leaves every thread
@@ -289,35 +285,20 @@ dct_fft_kernel(const double* in, double* out, int nlines, int n, int in_ls, int 
         const double abar = sy.abar_ptr ? *sy.abar_ptr : sy.abar_const;
         const double sc0 = sy.coef_ptr ? sy.coef_ptr[0] : sy.c0, sc2 = sy.coef_ptr ? sy.coef_ptr[1] : sy.c2;
         const double lla = va ? lam_line[la] : 0.0, llb = vb ? lam_line[lb] : 0.0;
-        const int rem = log2L % 3;
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-            const int kf = (kk[i] <= N) ? kk[i] : Lf - kk[i];
+            const int kk = t + FftOut<LOG2L>::off(i);
+            const int kf = (kk <= N) ? kk : Lf - kk;
             const double le = lam_elem[kf];
             const double s1 = le + lla, s2 = le + llb;
             double f1 = norm / (sc0 + s1 * (abar + sc2 * s1)), f2 = norm / (sc0 + s2 * (abar + sc2 * s2));
             if (scale_mode == 1) { f1 *= s1; f2 *= s2; }
-            z[i].x *= f1; z[i].y *= f2;
-        }
-        // static permutation z[] (last-pass order) -> v[q], q = (kk - t) / tpf
-        if (rem == 0) {
-#pragma unroll
-            for (int r = 0; r < 8; ++r) v[r] = z[r];
-        } else if (rem == 2) {
-#pragma unroll
-            for (int m = 0; m < 2; ++m)
-#pragma unroll
-                for (int r = 0; r < 4; ++r) v[m + 2 * r] = z[m * 4 + r];
-        } else {
-#pragma unroll
-            for (int m = 0; m < 4; ++m)
-#pragma unroll
-                for (int r = 0; r < 2; ++r) v[m + 4 * r] = z[m * 2 + r];
+            v[FftOut<LOG2L>::q(i)] = make_double2(z[i].x * f1, z[i].y * f2);   // static permutation into first-pass order
         }
         __syncthreads();                         // every thread has finished reading the forward data
         fft_first_pass_store(data, v, t);
-        Ns = fft_middle(data, Lf, log2L, t, tpf, tw);
-        fft_last_pass(data, Lf, log2L, Ns, t, tpf, tw, z, kk);
+        fft_middle<LOG2L>(data, t, tw);
+        fft_last_pass<LOG2L>(data, t, tw, z);
     }
 
     double acc1 = 0.0, acc2 = 0.0;
@@ -329,8 +310,9 @@ dct_fft_kernel(const double* in, double* out, int nlines, int n, int in_ls, int 
     const double* db = epi.addend + (size_t)lb * out_ls;
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
-        if (kk[q] <= N) {
-            const int off = kk[q] * out_es;
+        const int kk = t + FftOut<LOG2L>::off(q);
+        if (kk <= N) {
+            const int off = kk * out_es;
             if (SOLVE) {
                 if (va) *reinterpret_cast<double2*>(qa + off) = make_double2(z[q].x, vb ? z[q].y : 0.0);
             } else {
@@ -483,7 +465,7 @@ static inline int dct_cols_ppb(const DctAxis& ax, int ncols) {
     int ppb = 256 / tpf;
 #else
     int ppb = 512 / tpf;
-    if (ppb < 2 && tpf <= 512) ppb = 2;       // >= 4 adjacent columns so fetched 32-byte sectors are fully used
+    if (ppb < 2 && tpf <= 256) ppb = 2;       // >= 4 adjacent columns so fetched 32-byte sectors are fully used (CTA <= 512 threads)
 #endif
     if (ppb < 1) ppb = 1;
     if (ppb > 8) ppb = 8;
@@ -504,10 +486,18 @@ inline void DctPlan::init(int no_, int ni_, double h_outer, double h_inner, Laun
     VCH_CUDA(cudaMemset(tmp1.p, 0, (size_t)no * pitch * sizeof(double)));
     tmp2.alloc((size_t)no * ni);
     const int big = 200 * 1024;
-    VCH_CUDA(cudaFuncSetAttribute(dct_fft_kernel<false, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
-    VCH_CUDA(cudaFuncSetAttribute(dct_fft_kernel<true, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
-    VCH_CUDA(cudaFuncSetAttribute(dct_fft_kernel<false, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
-    VCH_CUDA(cudaFuncSetAttribute(dct_fft_kernel<true, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+#define VCH_FFT_ATTR(LG)                                                                                                                        \
+    VCH_CUDA(cudaFuncSetAttribute(dct_fft_kernel<LG, false, ((1 << LG) / 8 <= 512 ? 512 : 1024)>, cudaFuncAttributeMaxDynamicSharedMemorySize, big)); \
+    VCH_CUDA(cudaFuncSetAttribute(dct_fft_kernel<LG, true, ((1 << LG) / 8 <= 512 ? 512 : 1024)>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    for (const DctAxis* ax : {&inner, &outer}) {
+        if (!ax->fft) continue;
+        switch (ax->log2L) {
+            case 6: VCH_FFT_ATTR(6) break; case 7: VCH_FFT_ATTR(7) break; case 8: VCH_FFT_ATTR(8) break; case 9: VCH_FFT_ATTR(9) break;
+            case 10: VCH_FFT_ATTR(10) break; case 11: VCH_FFT_ATTR(11) break; case 12: VCH_FFT_ATTR(12) break; case 13: VCH_FFT_ATTR(13) break;
+            default: break;
+        }
+    }
+#undef VCH_FFT_ATTR
 }
 
 inline int DctPlan::max_grid() const {
@@ -530,13 +520,20 @@ inline void DctPlan::apply(cudaStream_t s, const double* in, double* out, const 
     auto fft_launch = [&](bool solve, const DctAxis& ax, int grid, int threads, size_t smem, const double* a, double* b, int nl,
                           int nn, int ils, int ies, int ols, int oes, const double* ll, const double* le, const SymbolArgs& sy,
                           double nrm, int smode, const RowPrologue& pr, const DotEpilogue& ep) {
-        if (solve) {
-            if (threads <= 512) dct_fft_kernel<true, 512><<<grid, threads, smem, s>>>(a, b, nl, nn, ils, ies, ols, oes, ax.Lf, ax.log2L, threads / (ax.Lf >> 3), ax.tw, ll, le, sy, nrm, smode, pr, ep, done);
-            else dct_fft_kernel<true, 1024><<<grid, threads, smem, s>>>(a, b, nl, nn, ils, ies, ols, oes, ax.Lf, ax.log2L, threads / (ax.Lf >> 3), ax.tw, ll, le, sy, nrm, smode, pr, ep, done);
-        } else {
-            if (threads <= 512) dct_fft_kernel<false, 512><<<grid, threads, smem, s>>>(a, b, nl, nn, ils, ies, ols, oes, ax.Lf, ax.log2L, threads / (ax.Lf >> 3), ax.tw, ll, le, sy, nrm, smode, pr, ep, done);
-            else dct_fft_kernel<false, 1024><<<grid, threads, smem, s>>>(a, b, nl, nn, ils, ies, ols, oes, ax.Lf, ax.log2L, threads / (ax.Lf >> 3), ax.tw, ll, le, sy, nrm, smode, pr, ep, done);
+        const int ppb_ = threads / (ax.Lf >> 3);
+#define VCH_FFT_CASE(LG)                                                                                                      \
+        case LG:                                                                                                              \
+            if (solve) dct_fft_kernel<LG, true, ((1 << LG) / 8 <= 512 ? 512 : 1024)><<<grid, threads, smem, s>>>(              \
+                a, b, nl, nn, ils, ies, ols, oes, ppb_, ax.tw, ll, le, sy, nrm, smode, pr, ep, done);                          \
+            else dct_fft_kernel<LG, false, ((1 << LG) / 8 <= 512 ? 512 : 1024)><<<grid, threads, smem, s>>>(                   \
+                a, b, nl, nn, ils, ies, ols, oes, ppb_, ax.tw, ll, le, sy, nrm, smode, pr, ep, done);                          \
+            break;
+        switch (ax.log2L) {
+            VCH_FFT_CASE(6) VCH_FFT_CASE(7) VCH_FFT_CASE(8) VCH_FFT_CASE(9) VCH_FFT_CASE(10) VCH_FFT_CASE(11) VCH_FFT_CASE(12)
+            VCH_FFT_CASE(13)
+            default: throw Error(VCH_E_ARG, "unsupported FFT length");
         }
+#undef VCH_FFT_CASE
     };
     const int rppb = inner.fft ? dct_rows_ppb(inner, no) : 0, rthreads = inner.fft ? rppb * (inner.Lf >> 3) : 0;
     const int rgrid = inner.fft ? ((no + 1) / 2 + rppb - 1) / rppb : 0;
