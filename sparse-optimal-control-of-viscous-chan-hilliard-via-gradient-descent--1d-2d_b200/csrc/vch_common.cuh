@@ -142,7 +142,7 @@ struct Scal {
 // ---------------------------------------------------------------- launch geometry
 constexpr int kSMs = 148;              // B200
 constexpr int kRedThreads = 256;
-constexpr int kRedBlocksMax = kSMs * 4;  // grid-stride reductions: 4 resident CTAs of 256 threads per SM
+constexpr int kRedBlocksMax = kSMs * 4;  // grid-stride reductions: 4 resident CTAs of 256 threads per SM (8/SM measured slower)
 
 static inline int red_blocks(long long n) {
     long long b = (n + kRedThreads - 1) / kRedThreads;
