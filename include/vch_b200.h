@@ -77,7 +77,7 @@ void vch2d_destroy(vch2d_ctx* c);
 int  vch2d_set_stream(vch2d_ctx* c, void* cuda_stream);          /* cudaStream_t; NULL = legacy default stream */
 int  vch2d_set_krylov(vch2d_ctx* c, double rel_tol, int max_iter);/* defaults 1e-11, 200 */
 /* Newton stop rule.  floor_aware = 1 (default): besides the reference's ||R||_2 < 1e-6 (Forward2_solver.py:353-365) the
- * iteration also stops when it stalls within 50x the fp64 resolution of the residual, eps*(1/hx^2+1/hy^2)*||mu||_2 — only
+ * iteration also stops when ||R||_2 reaches the fp64 resolution of the residual, eps*(1/hx^2+1/hy^2)*||mu||_2, or stalls within 50x of it — only
  * reachable on grids >= 1024^2, where the reference's absolute tolerance lies below that resolution and its loop would spin
  * to max_iter = 500 on rounding noise.  floor_aware = 0: the reference's rule verbatim. */
 int  vch2d_set_newton(vch2d_ctx* c, int floor_aware);

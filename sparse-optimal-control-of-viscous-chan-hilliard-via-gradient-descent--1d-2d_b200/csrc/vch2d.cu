@@ -253,7 +253,8 @@ void newton_step(vch2d_ctx* c, const double* phi_old, const double* mu_old, cons
     // Resolution of R_mu in fp64: mu is stored to eps|mu| and L amplifies that by ~(1/hx^2 + 1/hy^2), so ||R||_2 cannot
     // be driven below ~eps (1/hx^2+1/hy^2) ||mu||_2.  On the reference's grids (<= 512^2) this is < 1e-7 and the rule
     // below never fires; at >= 1024^2 it is ABOVE the reference's absolute tolerance 1e-6, where the reference's loop
-    // would spin to max_iter on rounding noise.  floor_aware stops once Newton stalls inside 50x that resolution.
+    // would spin to max_iter on rounding noise.  floor_aware stops as soon as ||R|| is at that resolution, or once Newton
+    // stalls (fails to halve ||R||) inside 50x of it.
     auto floor_est = [&] { return 2.220446049250313e-16 * (c->g.ihi2 + c->g.iho2) * std::sqrt(c->sc_host->mu2); };
     double floor_now = floor_est();
     int k_done = 0;
@@ -263,6 +264,8 @@ void newton_step(vch2d_ctx* c, const double* phi_old, const double* mu_old, cons
         if (st) st->last_newton_residual = normR;
         if (!std::isfinite(normR)) throw Error(VCH_E_NONFINITE, "non-finite Newton residual");
         if (normR < tol) break;
+        if (c->floor_aware && normR <= 1.5 * floor_now) break;   // at the fp64 resolution of the residual (only possible
+                                                             // when that resolution exceeds tol, i.e. grids >~ 600^2)
         const double normR_prev = normR;
         newton_linear_solve(c, Rp, Rm, a, phi, dt, st);
         // speculative full step: almost always alpha = 1 is both allowed by the ceiling and accepted by Armijo, so the
