@@ -240,8 +240,14 @@ def run_b200(args):
         top = next(iter(table))
         bpn = BYTES_PER_NODE.get(top, 16)
         ach = bpn * n / (rep[top][0] / rep[top][1] * 1e-3) / 1e9
+        traffic = None
+        try:    # DRAM bytes per launch of that kernel from the committed ncu --set full capture (profiles/)
+            with open(os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")) as fh:
+                traffic = json.load(fh)["kernels"].get(top) if N == 1024 else None
+        except Exception:
+            traffic = None
         roof = {"bound": "hbm", "kernel": top, "achieved": round(ach, 1), "peak": peak, "unit": "GB/s", "frac": round(ach / peak, 4),
-                "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": bpn * n,
+                "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": bpn * n,
                 "share_of_step": table[top]["share"], "profiled_steps": Mp, "kernels": table}
 
     # ---- end-to-end leg: the same call with HOST buffers (pinned), H2D/D2H inside the timed region
