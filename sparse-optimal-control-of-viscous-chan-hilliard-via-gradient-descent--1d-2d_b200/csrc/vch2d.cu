@@ -2,6 +2,7 @@
 // Host control flow lives here; all arithmetic is in the kernels of vch2d_kernels.cuh / vch_dct.cuh.
 #include "vch2d_kernels.cuh"
 #include <algorithm>
+#include <functional>
 #include <cstdlib>
 
 namespace vch {
@@ -34,6 +35,7 @@ struct vch2d_ctx {
     DevBuf phi, mu, phit, mut, w0, w1, cphi, cmu, Rphi, Rmu, a, RphiT, RmuT, aT;
     DevBuf kb, kx, kr, kr0, kp, kv, ks, kt, ktmp, kq, dmu;
     DevBuf adj_p[2], adj_q[2], adj_r[2], mu_old;
+    DevBuf stage[7];             // device staging of the host-buffer PGD iteration, kept across calls (no 50 GB malloc/free per step)
     DevBuf red_part;             // partials for grid reductions
     DevBuf small;                // small device vectors: weights, out4
     unsigned int* ticket = nullptr;
@@ -337,8 +339,11 @@ void post_step(vch2d_ctx* c, const double* phi_new, double* dst) {
     LAUNCH(c, mass_shift_kernel, c->eb(), 256, dst, c->g, c->ph, c->prm.Lx * c->prm.Ly, c->sc);
 }
 
+using LevelHook = std::function<void(int)>;
+
+// after_level(k): called once level k of phi_hist has been enqueued (streaming D2H of the trajectory hooks in here).
 void forward_dev(vch2d_ctx* c, const double* phi0, const double* u, int u_rows, int n_steps, const double* dt_steps,
-                 double* phi_hist, double* mu_hist, double* w_hist, vch_stats* st) {
+                 double* phi_hist, double* mu_hist, double* w_hist, vch_stats* st, const LevelHook& after_level = nullptr) {
     const long long n = c->g.n;
     const size_t bytes = n * sizeof(double);
     const int eb = c->eb();
@@ -361,12 +366,15 @@ void forward_dev(vch2d_ctx* c, const double* phi0, const double* u, int u_rows, 
         std::swap(c->w0.p, c->w1.p);
         if (mu_hist) VCH_CUDA(cudaMemcpyAsync(mu_hist + (size_t)s * n, mu_old, bytes, cudaMemcpyDeviceToDevice, c->stream));
         if (w_hist) VCH_CUDA(cudaMemcpyAsync(w_hist + (size_t)s * n, c->w0.p, bytes, cudaMemcpyDeviceToDevice, c->stream));
+        if (after_level) after_level(s + 1);
     }
     VCH_CUDA(cudaGetLastError());
 }
 
+// need_level(k): called before level k of phi_hist / phiQ is first read (streaming H2D hooks in here; levels descend).
 void adjoint_dev(vch2d_ctx* c, const double* phi_hist, int levels, const double* t_hist, double b1, double b2,
-                 const double* phiQ, const double* phiT, double* p_out, double* q_out, double* r_out, vch_stats* st) {
+                 const double* phiQ, const double* phiT, double* p_out, double* q_out, double* r_out, vch_stats* st,
+                 const LevelHook& need_level = nullptr) {
     const long long n = c->g.n;
     const size_t bytes = n * sizeof(double);
     const int eb = c->eb();
@@ -374,6 +382,7 @@ void adjoint_dev(vch2d_ctx* c, const double* phi_hist, int levels, const double*
     auto slot = [&](double* out, DevBuf (&ring)[2], int lvl) { return out ? out + (size_t)lvl * n : ring[lvl & 1].p; };
     const int M = levels - 1;
     double* pM = slot(p_out, c->adj_p, M); double* qM = slot(q_out, c->adj_q, M); double* rM = slot(r_out, c->adj_r, M);
+    if (need_level) need_level(M);
     LAUNCH(c, adj_terminal_rhs_kernel, eb, 256, phi_hist + (size_t)M * n, phiT, c->kb.p, n, b2);
     SymbolArgs sy{1.0, 0.0, nullptr, c->ph.tau, nullptr};
     c->dct.apply(c->stream, c->kb.p, pM, sy, nullptr);          // (I - tau L) p_M = b2 (phi_M - phi_T): exact in the DCT basis
@@ -388,6 +397,7 @@ void adjoint_dev(vch2d_ctx* c, const double* phi_hist, int levels, const double*
             VCH_CUDA(cudaMemcpyAsync(r0, r1, bytes, cudaMemcpyDeviceToDevice, c->stream));
             continue;
         }
+        if (need_level) need_level(k);
         const double* f1 = phi_hist + (size_t)(k + 1) * n; const double* f0 = phi_hist + (size_t)k * n;
         LAUNCH(c, adj_rhs_kernel, c->rb(), kRedThreads, p1, q1, f1, f0, phiQ ? phiQ + (size_t)(k + 1) * n : nullptr,
                phiQ ? phiQ + (size_t)k * n : nullptr, c->kb.p, c->a.p, c->g, c->ph, dt, b1, c->sc, c->red_part.p, c->ticket);
@@ -780,6 +790,94 @@ int vch_kkt_counts(void* stream, long long count, const double* u, const double*
     });
 }
 
+// Host-buffer path of vch2d_pgd_iteration: PCIe traffic is streamed under the compute instead of bracketing it.
+//   H2D on a copy stream: phi_T, then (phi_hist, phi_Q) chunks from the LAST level down — the order in which the adjoint
+//   sweep consumes them — then u; the sweep waits per chunk on events.  D2H: u_new right after the prox, phi_hist_new chunk
+//   by chunk while the forward solve is still producing later levels.  Full-duplex PCIe, both directions overlap compute
+//   when the caller's buffers are pinned (pageable buffers still work: the copies just stop overlapping).
+static void pgd_iteration_host_streamed(vch2d_ctx* c, int levels, const double* t_hist, const double* dt_steps, const double* x,
+                                        const double* y, const double* u, const double* phi_hist, const double* phiQ,
+                                        const double* phiT, double b1, double b2, double b3, double ksp, double umin,
+                                        double umax, double alpha, double* u_new_out, double* phi_hist_out, double* r_out,
+                                        double* J_out, double* red_out, vch_stats* s) {
+    const long long n = c->g.n;
+    const size_t fb = (size_t)n * sizeof(double), tot = (size_t)levels * n;
+    DevBuf &du = c->stage[0], &dh = c->stage[1], &dq = c->stage[2], &dT = c->stage[3], &dun = c->stage[4], &dhn = c->stage[5],
+           &dr = c->stage[6];
+    du.alloc(tot); dh.alloc(tot); dun.alloc(tot); dhn.alloc(tot); dr.alloc(tot);
+    if (phiQ) dq.alloc(tot);
+    if (phiT) dT.alloc(n);
+    cudaStream_t cp;
+    VCH_CUDA(cudaStreamCreateWithFlags(&cp, cudaStreamNonBlocking));
+    const int CH = 32;                                   // levels per chunk (269 MB at 1024^2)
+    const int nch = (levels + CH - 1) / CH;
+    std::vector<cudaEvent_t> ev_in(nch), ev_out(nch);
+    cudaEvent_t ev_u, ev_prox, ev_adj;
+    for (auto* v : {&ev_in, &ev_out}) for (auto& e : *v) VCH_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    for (cudaEvent_t* e : {&ev_u, &ev_prox, &ev_adj}) VCH_CUDA(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+    auto cleanup = [&] {
+        cudaStreamSynchronize(cp); cudaStreamSynchronize(c->stream);
+        for (auto* v : {&ev_in, &ev_out}) for (auto& e : *v) cudaEventDestroy(e);
+        cudaEventDestroy(ev_u); cudaEventDestroy(ev_prox); cudaEventDestroy(ev_adj);
+        cudaStreamDestroy(cp);
+    };
+    try {
+        // ---- enqueue every H2D copy up front, in consumption order
+        VCH_CUDA(cudaEventRecord(c->ev_in, c->stream));                 // buffers above were allocated; order cp after entry
+        VCH_CUDA(cudaStreamWaitEvent(cp, c->ev_in, 0));
+        if (phiT) VCH_CUDA(cudaMemcpyAsync(dT.p, phiT, fb, cudaMemcpyHostToDevice, cp));
+        for (int j = nch - 1; j >= 0; --j) {
+            const size_t lo = (size_t)j * CH, cnt = std::min<size_t>(CH, levels - lo);
+            VCH_CUDA(cudaMemcpyAsync(dh.p + lo * n, phi_hist + lo * n, cnt * fb, cudaMemcpyHostToDevice, cp));
+            if (phiQ) VCH_CUDA(cudaMemcpyAsync(dq.p + lo * n, phiQ + lo * n, cnt * fb, cudaMemcpyHostToDevice, cp));
+            VCH_CUDA(cudaEventRecord(ev_in[j], cp));
+        }
+        VCH_CUDA(cudaMemcpyAsync(du.p, u, tot * sizeof(double), cudaMemcpyHostToDevice, cp));
+        VCH_CUDA(cudaEventRecord(ev_u, cp));
+        // ---- (1) adjoint sweep, waiting chunk by chunk
+        int waited = nch;
+        auto need = [&](int k) {
+            const int j = k / CH;
+            while (waited > j) { --waited; VCH_CUDA(cudaStreamWaitEvent(c->stream, ev_in[waited], 0)); }
+        };
+        adjoint_dev(c, dh.p, levels, t_hist, b1, b2, phiQ ? dq.p : nullptr, phiT ? dT.p : nullptr, nullptr, nullptr, dr.p, s, need);
+        need(0);
+        VCH_CUDA(cudaEventRecord(ev_adj, c->stream));
+        // ---- (2) gradient + prox
+        VCH_CUDA(cudaStreamWaitEvent(c->stream, ev_u, 0));
+        LAUNCH(c, grad_prox_kernel, red_blocks((long long)tot), kRedThreads, du.p, dr.p, (double*)nullptr, dun.p, (long long)tot, b3,
+               alpha, ksp, umin, umax, c->out4 + 4, c->red_part.p, c->ticket);
+        VCH_CUDA(cudaEventRecord(ev_prox, c->stream));
+        VCH_CUDA(cudaStreamWaitEvent(cp, ev_prox, 0));
+        VCH_CUDA(cudaMemcpyAsync(u_new_out, dun.p, tot * sizeof(double), cudaMemcpyDeviceToHost, cp));
+        if (r_out) {
+            VCH_CUDA(cudaStreamWaitEvent(cp, ev_adj, 0));
+            VCH_CUDA(cudaMemcpyAsync(r_out, dr.p, tot * sizeof(double), cudaMemcpyDeviceToHost, cp));
+        }
+        // ---- (3) forward solve, trajectory streamed out chunk by chunk
+        auto after = [&](int k) {
+            if ((k + 1) % CH == 0 || k == levels - 1) {
+                const int j = k / CH;
+                const size_t lo = (size_t)j * CH, cnt = (size_t)k + 1 - lo;
+                VCH_CUDA(cudaEventRecord(ev_out[j], c->stream));
+                VCH_CUDA(cudaStreamWaitEvent(cp, ev_out[j], 0));
+                VCH_CUDA(cudaMemcpyAsync(phi_hist_out + lo * n, dhn.p + lo * n, cnt * fb, cudaMemcpyDeviceToHost, cp));
+            }
+        };
+        forward_dev(c, dh.p, dun.p, levels, levels - 1, dt_steps, dhn.p, nullptr, nullptr, s, after);
+        // ---- (4) cost
+        cost_dev(c, dhn.p, dun.p, phiQ ? dq.p : nullptr, phiT ? dT.p : nullptr, levels, x, y, t_hist, b1, b2, b3, ksp, J_out);
+        if (red_out) {
+            VCH_CUDA(cudaMemcpyAsync(c->out4_host + 4, c->out4 + 4, 4 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+            VCH_CUDA(cudaStreamSynchronize(c->stream));
+            for (int k = 0; k < 4; ++k) red_out[k] = c->out4_host[4 + k];
+        }
+        VCH_CUDA(cudaStreamSynchronize(cp));
+        VCH_CUDA(cudaStreamSynchronize(c->stream));
+    } catch (...) { cleanup(); throw; }
+    cleanup();
+}
+
 int vch2d_pgd_iteration(vch2d_ctx* c, int levels, const double* t_hist, const double* dt_steps, const double* x,
                         const double* y, const double* u, const double* phi_hist, const double* phiQ, const double* phiT,
                         double b1, double b2, double b3, double ksp, double umin, double umax, double alpha,
@@ -792,13 +890,17 @@ int vch2d_pgd_iteration(vch2d_ctx* c, int levels, const double* t_hist, const do
         const long long n = c->g.n;
         const StatMark mark0 = stat_mark(c);
         const size_t tot = (size_t)levels * n;
-        Stager st(c->stream, mem);
-        const double *du = st.in(u, tot), *dh = st.in(phi_hist, tot), *dq = st.in(phiQ, tot), *dT = st.in(phiT, n);
-        double *dun = st.out(u_new_out, tot), *dhn = st.out(phi_hist_out, tot);
-        double* dr = st.out(r_out, tot);
+        vch_stats local{}; vch_stats* s = stats ? stats : &local;
+        if (mem == VCH_MEM_HOST) {
+            pgd_iteration_host_streamed(c, levels, t_hist, dt_steps, x, y, u, phi_hist, phiQ, phiT, b1, b2, b3, ksp, umin, umax,
+                                        alpha, u_new_out, phi_hist_out, r_out, J_out, red_out, s);
+            stat_collect(c, mark0, s);
+            return VCH_OK;
+        }
+        const double *du = u, *dh = phi_hist, *dq = phiQ, *dT = phiT;
+        double *dun = u_new_out, *dhn = phi_hist_out, *dr = r_out;
         DevBuf rscratch;
         if (!dr) { rscratch.alloc(tot); dr = rscratch.p; }
-        vch_stats local{}; vch_stats* s = stats ? stats : &local;
         // (1) adjoint sweep over the stored trajectory                       GD2_configured.py:299
         adjoint_dev(c, dh, levels, t_hist, b1, b2, dq, dT, nullptr, nullptr, dr, s);
         // (2) gradient + soft-threshold prox + box, with the driver's norms  GD2_configured.py:304-305, :375
@@ -813,7 +915,7 @@ int vch2d_pgd_iteration(vch2d_ctx* c, int levels, const double* t_hist, const do
             VCH_CUDA(cudaStreamSynchronize(c->stream));
             for (int k = 0; k < 4; ++k) red_out[k] = c->out4_host[4 + k];
         }
-        st.finish();
+        VCH_CUDA(cudaStreamSynchronize(c->stream));
         stat_collect(c, mark0, s);
         return VCH_OK;
     });
