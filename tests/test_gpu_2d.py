@@ -233,3 +233,82 @@ def test_dct_fast_solve_is_exact_for_constant_coefficients(native, N):
     ref = dctn(dctn(b, type=1) / sym, type=1) / (4 * N * N)
     assert rel(dphi, ref) < 1e-10
     assert rel(dmu, 2 * (a * ref - 0.5 * P.kappa * apply_L(ref) + Rp)) < 1e-7     # L amplifies rounding by 1/h^2 (4e6 at N = 2048)
+
+
+def test_forward_matches_reference_golden_256(native, golden):
+    """Largest grid pinned directly to the unmodified reference: 256^2, two CN steps, adjoint and one PGD iteration."""
+    g = golden("g2d_256")
+    P = O.from_json(O.Phys2D, g["cfg_json"])
+    Op = O.from_json(O.Opt2D, g["opt_json"])
+    c = make_ctx(native, P)
+    dts = dt_list(P)
+    hist, mu, _ = c.forward(O.init_phi_2d(P.Nx, P.Ny), None, dts, want_mu=True)
+    assert rel(hist[g["keep"]], g["phi0"]) < TOL_TRAJ and rel(mu[[0, 1]], g["mu0"]) < TOL_TRAJ
+    phiT, phiQ = O.targets_2d(g["x"], g["y"], g["t"], hist[0], P.Lx, P.Ly, P.T)
+    _, _, r = c.adjoint(hist, g["t"], Op.b1, Op.b2, phiQ, phiT, want_pq=False)
+    assert rel(r[g["keep"]], g["r0"]) < TOL_GRAD
+    u1, hist1, J, _, _ = c.pgd_iteration(np.zeros_like(hist), hist, phiQ, phiT, g["t"], dts, g["x"], g["y"], Op.b1, Op.b2, Op.b3,
+                                         Op.kappa_sparsity, Op.u_min, Op.u_max, Op.alpha_max)
+    assert rel(u1[g["keep"]], g["u1"]) < TOL_GRAD and np.array_equal(u1[g["keep"]] != 0, g["u1"] != 0)
+    assert rel(hist1[g["keep"]], g["phi1"]) < TOL_TRAJ and abs(J[0] - g["J"][1]) <= TOL_J * abs(g["J"][1])
+
+
+def test_full_size_1024_properties(native):
+    """BASELINE grid (1024^2, device-resident): size-independent identities that need no CPU oracle.
+    (a) the linear solve satisfies the Schur system  (1/dt) dphi - L(a dphi - kappa/2 L dphi) = -R_mu + L R_phi  and
+        dmu = 2(a dphi - kappa/2 L dphi + R_phi), evaluated with the stencil kernel;
+    (b) every time step conserves the trapezoid mass to round-off and keeps |phi| <= 1 - delta;
+    (c) the adjoint levels satisfy  q = -L p  and the CN recursion for r;
+    (d) prox: u_new is in the box, support == {|u - alpha g| > alpha kappa}, fused norms agree with torch."""
+    import torch
+    N = 1024
+    P = O.Phys2D(Nx=N, Ny=N)
+    c = make_ctx(native, P)
+    dev = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    L = lambda v: c.apply_laplacian(v)
+    rng = np.random.default_rng(0)
+    x = np.linspace(0, 1, N + 1)
+    X, Y = np.meshgrid(x, x, indexing="ij")
+    phi = dev(0.6 * np.tanh(4 * np.sin(6 * np.pi * X) * np.cos(4 * np.pi * Y)) + 0.05 * rng.standard_normal(X.shape))
+    Rp, Rm = dev(rng.standard_normal(X.shape)), dev(rng.standard_normal(X.shape))
+    dt = 1e-2
+    dphi, dmu, its = c.jacobian_solve(phi, dt, Rp, Rm)
+    a = P.tau / dt + 2 * P.c1 / (1 - torch.clamp(phi * phi, max=1 - 1e-4))
+    K = a * dphi - 0.5 * P.kappa * L(dphi)
+    lhs, rhs = dphi / dt - L(K), L(Rp) - Rm
+    # compared in the preconditioned (error-like) sense: residual relative to the operator scale on dphi
+    assert float((lhs - rhs).norm() / rhs.norm()) < 1e-7 and 1 <= its <= 40
+    assert float((dmu - 2 * (K + Rp)).norm() / dmu.norm()) < 1e-12
+    # (b) forward steps
+    M = 6
+    dts = np.full(M, dt)
+    phi0 = dev(O.init_phi_2d(N, N))
+    hist, _, _ = c.forward(phi0, None, dts)
+    w = torch.ones(N + 1, dtype=torch.float64, device="cuda"); w[0] = w[-1] = 0.5
+    mass = torch.einsum("tij,i,j->t", hist, w, w) / N ** 2
+    assert float((mass - mass[0]).abs().max()) < 1e-11 and float(hist.abs().max()) <= 0.99
+    assert c.last_stats["krylov_stalls"] == 0 and c.last_stats["newton_linear_solves"] <= 3 * M
+    # (c) adjoint identities
+    t = dt * np.arange(M + 1)
+    phiT = dev(0.7 * np.sin(2 * np.pi * X) * np.cos(np.pi * Y))
+    s = dev(t / t[-1])[:, None, None]
+    phiQ = (1 - s) * hist[0] + s * phiT
+    p, q, r = c.adjoint(hist, t, 5.0, 10.0, phiQ, phiT)
+    for k in (0, 3, M):
+        assert float((q[k] + L(p[k])).norm() / q[k].norm()) < 1e-12
+    g_, den = P.gamma, P.gamma + 0.5 * dt
+    for k in (0, 2, M - 1):
+        rk = (g_ - 0.5 * dt) / den * r[k + 1] + 0.5 * dt / den * (q[k] + q[k + 1])
+        assert float((r[k] - rk).norm() / r[k].norm()) < 1e-12
+    assert float(r[M].abs().max()) == 0.0
+    # terminal solve (I - tau L) p_M = b2 (phi_M - phi_T), exact in the DCT basis
+    resid = p[M] - P.tau * L(p[M]) - 10.0 * (hist[M] - phiT)
+    assert float(resid.norm() / (10.0 * (hist[M] - phiT)).norm()) < 1e-9
+    # (d) prox
+    u = 0.3 * torch.randn_like(hist)
+    un, grad, red = native.grad_prox(u, r, 1e-4, 50.0, 1e-4, -1.0, 1.0, want_grad=True)
+    y = u - 50.0 * grad
+    assert float(un.abs().max()) <= 1.0
+    assert bool(((un != 0) == (y.abs() - 50.0 * 1e-4 > 0)).all())
+    assert abs(red[0] - float(((un - u) ** 2).sum())) <= 1e-9 * red[0] and abs(red[1] - float((u ** 2).sum())) <= 1e-9 * red[1]
+    assert red[2] == float((un != 0).sum())
