@@ -258,7 +258,10 @@ def run_b200(args):
             need = 5 * lv * field_bytes                      # pinned host buffers of this rank
             with open("/proc/meminfo") as fh:
                 avail = next(int(l.split()[1]) * 1024 for l in fh if l.startswith("MemAvailable"))
-            if need * world > 0.8 * avail:                   # all ranks share one host; never drive the box out of memory
+            fits = torch.tensor([1 if need * world <= 0.8 * avail else 0], device=dev)
+            if world > 1:
+                dist.all_reduce(fits, op=dist.ReduceOp.MIN)  # one decision for all ranks (collectives below must match)
+            if int(fits.item()) == 0:                        # all ranks share one host; never drive the box out of memory
                 raise MemoryError(f"e2e leg skipped: needs {need * world / 1e9:.0f} GB pinned host memory, {avail / 1e9:.0f} GB available")
             pin = lambda tns: tns.cpu().pin_memory()
             hu, hh, hq, hT = pin(state["u"]), pin(state["h"]), pin(phiQ), pin(phiT)

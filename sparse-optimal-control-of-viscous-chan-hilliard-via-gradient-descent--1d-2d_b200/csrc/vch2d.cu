@@ -206,6 +206,7 @@ int krylov_solve(vch2d_ctx* c, const double* b, const double* a, vch_stats* st) 
 struct StatMark { long long its, solves, stalls, launches, glaunches; };
 StatMark stat_mark(vch2d_ctx* c) {
     fetch_scalars(c);
+    VCH_CUDA(cudaMemsetAsync(&c->sc->iters_max, 0, sizeof(int), c->stream));   // per-call maximum
     return {c->sc_host->iters_total, c->sc_host->solves, c->sc_host->stalls, c->log.count, c->sc_host->g_launches};
 }
 void stat_collect(vch2d_ctx* c, const StatMark& m0, vch_stats* st) {
@@ -216,6 +217,9 @@ void stat_collect(vch2d_ctx* c, const StatMark& m0, vch_stats* st) {
     st->krylov_iterations += its;
     st->newton_linear_solves += solves;
     st->krylov_stalls += c->sc_host->stalls - m0.stalls;
+    if (c->sc_host->stalls > m0.stalls)    // never silent: the direct solver this replaces cannot stall
+        fprintf(stderr, "[vch_b200] warning: %lld linear solve(s) stopped above the Krylov tolerance (max_iter %d); see vch_stats.krylov_stalls\n",
+                (long long)(c->sc_host->stalls - m0.stalls), c->krylov_maxit);
     st->krylov_max_iterations = std::max<long long>(st->krylov_max_iterations, c->sc_host->iters_max);
     // kernels inside solve graphs are not seen by the launch log: 4 prologue kernels per solve + 11 per iteration
     st->kernel_launches += (c->log.count - m0.launches) + (c->sc_host->g_launches - m0.glaunches);
