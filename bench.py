@@ -35,8 +35,10 @@ UNIT = "it/s"
 BYTES_PER_NODE = {
     "op_apply_fwd": 24, "op_apply_adj": 24,            # read x, a; write y
     "dct_rows_fft": 16, "dct_cols_fft_solve": 16,      # read + write the field once
+    "dct_rows_fft_pro": 40,                            # read r, q|v, a; write p|s and the transform
+    "dct_rows_fft_epi1": 32, "dct_rows_fft_epi2": 24,  # read transform input, addend (, r0); write v|t
     "residual_kernel": 56,                             # read phi, mu, cphi, cmu; write Rphi, Rmu, a
-    "bicg_x_kernel": 56, "bicg_p_kernel": 32, "bicg_s_kernel": 24, "bicg_dot1_kernel": 16, "bicg_dot2_kernel": 16,
+    "bicg_x_kernel": 72, "bicg_p_kernel": 32, "bicg_s_kernel": 24, "bicg_dot1_kernel": 16, "bicg_dot2_kernel": 16,
     "bicg_init_kernel": 40, "schur_rhs_kernel": 24, "dmu_ceiling_kernel": 40, "trial_kernel": 48,
     "step_setup_kernel": 56, "solve_w_kernel": 32, "clip_mass_kernel": 16, "mass_shift_kernel": 16,
     "adj_rhs_kernel": 64, "adj_qr_kernel": 40, "adj_terminal_rhs_kernel": 24, "mu_init_kernel": 24,
@@ -243,10 +245,16 @@ def run_b200(args):
         traffic = None
         try:    # DRAM bytes per launch of that kernel from the committed ncu --set full capture (profiles/)
             with open(os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")) as fh:
-                traffic = json.load(fh)["kernels"].get(top) if N == 1024 else None
+                traffic = json.load(fh)["kernels"].get("dct_rows_fft" if top.startswith("dct_rows_fft") else top) if N == 1024 else None
         except Exception:
             traffic = None
+        # whole iteration: sum of algorithmic bytes of every profiled launch over the summed kernel time
+        all_bytes = sum(BYTES_PER_NODE.get(k, 0) * n * cnt for k, (tms, cnt) in rep.items())
+        all_bytes += sum(24 * (Mp + 1) * n for k in rep if k in ("grad_prox_kernel", "cost_kernel"))
         roof = {"bound": "hbm", "kernel": top, "achieved": round(ach, 1), "peak": peak, "unit": "GB/s", "frac": round(ach / peak, 4),
+                "frac_of_nominal_8000": round(ach / 8000.0, 4),
+                "whole_iteration": {"algorithmic_GB": round(all_bytes / 1e9, 2), "GBps": round(all_bytes / (tot * 1e-3) / 1e9, 1),
+                                    "frac": round(all_bytes / (tot * 1e-3) / 1e9 / peak, 4)},
                 "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": bpn * n,
                 "share_of_step": table[top]["share"], "profiled_steps": Mp, "kernels": table}
 

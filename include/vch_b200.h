@@ -124,7 +124,9 @@ int vch2d_adjoint(vch2d_ctx* c, const double* phi_hist, int levels, const double
                   const double* phiQ, const double* phiT, double* p_out, double* q_out, double* r_out,
                   vch_stats* stats, int mem);
 /* calculate_cost                                      2D/Vch_control_2D/cost2_and_function.py:80-108
- *   x (host, Nx+1), y (host, Ny+1), t_hist (host, levels): np.trapz abscissae;  J_out (host, 5) = J, J1..J4 */
+ *   x (host, Nx+1), y (host, Ny+1), t_hist (host, levels): np.trapz abscissae
+ *   J_out (host, 9) = J, J1..J4, then the raw trapezoid integrals  int|phi-phi_Q|^2, int|phi(T)-phi_T|^2, int u^2, int|u|
+ *   (the driver's tracking / terminal error norms, GD2_configured.py:336-363, are square roots of the first two) */
 int vch2d_cost(vch2d_ctx* c, const double* phi_hist, const double* u, const double* phiQ, const double* phiT,
                int levels, const double* x, const double* y, const double* t_hist,
                double b1, double b2, double b3, double kappa_sp, double* J_out, int mem);
@@ -141,7 +143,7 @@ int vch_kkt_counts(void* cuda_stream, long long count, const double* u, const do
 /* One optimistic PGD iteration                        GD2_configured.py:299-313
  *   adjoint(phi_hist) -> r;  u_new = prox(u - alpha (r + b3 u));  forward(u_new) -> phi_hist_out;  J(u_new).
  *   levels = n_steps+1 = rows of u, phi_hist, phiQ.  phi0 = phi_hist level 0.  r_out may be NULL (device scratch is used).
- *   J_out (host, 5), red_out (host, 4) as above. */
+ *   J_out (host, 9), red_out (host, 4) as above. */
 int vch2d_pgd_iteration(vch2d_ctx* c, int levels, const double* t_hist, const double* dt_steps,
                         const double* x, const double* y,
                         const double* u, const double* phi_hist, const double* phiQ, const double* phiT,

@@ -136,6 +136,7 @@ def optimize(fwd_config: ForwardSolverConfig, opt_config: OptimizationConfig, ch
     denQ = float(np.sqrt(max(np.dot(wt, _trapz_l2_sq(phi_Q, x, y)), 0.0)))
     denQ = rms if denQ < 1e-9 * rms else denQ
     denT = float(np.sqrt(max(_trapz_l2_sq(phi_T, x, y), 0.0))) + 1e-12
+    raw_track = raw_term = None          # raw integrals of the accepted iterate (device-resident path)
     for k in range(n_iter):
         it0 = time.perf_counter()
         if verbose:
@@ -168,26 +169,53 @@ def optimize(fwd_config: ForwardSolverConfig, opt_config: OptimizationConfig, ch
             if device_resident:
                 d_u, d_un = d_un, d_u
                 d_phi, d_phin = d_phin, d_phi
+                raw_track, raw_term = float(J[5]), float(J[6])
             else:
                 change_sq, unorm_sq = float(np.sum((u_try - u_k) ** 2)), float(np.sum(u_k ** 2))
                 u_k, phi_k = u_try, phi_try
+        elif device_resident:
+            # backtracking on device-resident state (reference :71-146): prox kernel -> forward -> cost, nothing leaves HBM
+            if verbose:
+                print("   ⚠ Optimistic step failed. Backtracking...")
+            ls0 = time.perf_counter()
+            alpha_k, cost_next = alpha_prev * 0.8, cost_k
+            hist["ls_calls"] += 1
+            for attempt in range(1, 11):
+                hist["ls_attempts"] += 1
+                d_un, _, red = _nat.grad_prox(d_u, d_r, b3, alpha_k, ksp, opt_config.u_min, opt_config.u_max)
+                d_phin, _, _ = ctx.forward(d_phi[0].contiguous(), d_un, dts)
+                J = ctx.cost(d_phin, d_un, d_Q, d_T, x, y, t_hist, b1, b2, b3, ksp)
+                cost_next = float(J[0])
+                if cost_next < cost_k:
+                    if verbose:
+                        print(f"   ✓ Backtracking found a good step (α = {alpha_k:.4f}) after {attempt} attempts.")
+                    break
+                if attempt < 10:
+                    alpha_k *= 0.8
+            else:
+                alpha_k *= 0.8           # the reference returns the shrunk alpha with the last trial
+                print("[Warning] Line search could not find a step that reduces cost. Returning last try.")
+            hist["t_linesearch"] += time.perf_counter() - ls0
+            change_sq, unorm_sq = float(red[0]), float(red[1])
+            d_u, d_phi = d_un, d_phin
+            d_un, d_phin = torch.empty_like(d_u), torch.empty_like(d_u)
+            raw_track, raw_term = float(J[5]), float(J[6])
         else:
             if verbose:
                 print("   ⚠ Optimistic step failed. Backtracking...")
-            if device_resident:
-                u_k, r_k = d_u.cpu().numpy(), d_r.cpu().numpy()
             grad = calculate_gradient(r_k, u_k, opt_config)
             alpha_k, u_next, cost_next, phi_next, _, secs, attempts = perform_backtracking_line_search_2D(
                 u_k, cost_k, grad, phi_Q, phi_T, x, y, fwd_config, opt_config, alpha_init=alpha_prev * 0.8)
             hist["t_linesearch"] += secs; hist["ls_calls"] += 1; hist["ls_attempts"] += attempts
             change_sq, unorm_sq = float(np.sum((u_next - u_k) ** 2)), float(np.sum(u_k ** 2))
             u_k, phi_k = u_next, phi_next
-            if device_resident:
-                d_u.copy_(dev(u_k)); d_phi.copy_(dev(phi_k))
         hist["cost"].append(cost_next); hist["alpha"].append(alpha_k)
-        phi_now = d_phi.cpu().numpy() if device_resident else phi_k
-        hist["track"].append(float(np.sqrt(max(np.dot(wt, _trapz_l2_sq(phi_now - phi_Q, x, y)), 0.0))) / (denQ + 1e-12))
-        hist["term"].append(float(np.sqrt(max(_trapz_l2_sq(phi_now[-1] - phi_T, x, y), 0.0))) / denT)
+        if device_resident:              # monitoring norms = square roots of the cost kernel's raw integrals (no extra pass)
+            hist["track"].append(float(np.sqrt(max(raw_track, 0.0))) / (denQ + 1e-12))
+            hist["term"].append(float(np.sqrt(max(raw_term, 0.0))) / denT)
+        else:
+            hist["track"].append(float(np.sqrt(max(np.dot(wt, _trapz_l2_sq(phi_k - phi_Q, x, y)), 0.0))) / (denQ + 1e-12))
+            hist["term"].append(float(np.sqrt(max(_trapz_l2_sq(phi_k[-1] - phi_T, x, y), 0.0))) / denT)
         plateau = plateau + 1 if (k > 0 and abs(hist["cost"][-1] - hist["cost"][-2]) < 1e-5) else 0
         if plateau >= 5:
             if verbose:

@@ -22,7 +22,7 @@ def calculate_cost(phi_hist, u, phi_Q_target, phi_T_target, x, y, t_hist, opt_co
     ctx = _nat.ctx2d(nx1 - 1, ny1 - 1, hx, hy, (nx1 - 1) * hx, (ny1 - 1) * hy, 0.05, 10.0, 0.75, 1.0, 1e-4, 1e-2)
     J = ctx.cost(_f64(phi_hist), _f64(u), _f64(phi_Q_target), _f64(phi_T_target), _f64(x), _f64(y), _f64(t_hist),
                  float(opt_config.b1), float(opt_config.b2), float(opt_config.b3), float(opt_config.kappa_sparsity))
-    total, c1, c2, c3, c4 = (float(v) for v in J)
+    total, c1, c2, c3, c4 = (float(v) for v in J[:5])
     print(f"  Tracking Cost (J1): {c1:.6g}")
     print(f"  Terminal Cost (J2): {c2:.6g}")
     print(f"  Control Energy (J3): {c3:.6g}")

@@ -438,6 +438,7 @@ void cost_dev(vch2d_ctx* c, const double* phi_hist, const double* u, const doubl
     const double J1 = 0.5 * b1 * c->out4_host[0], J2 = 0.5 * b2 * c->out4_host[1], J3 = 0.5 * b3 * c->out4_host[2],
                  J4 = ksp * c->out4_host[3];
     J_out[0] = J1 + J2 + J3 + J4; J_out[1] = J1; J_out[2] = J2; J_out[3] = J3; J_out[4] = J4;
+    for (int k = 0; k < 4; ++k) J_out[5 + k] = c->out4_host[k];   // raw integrals: the driver's monitoring norms (D1) come for free
 }
 
 struct SmallScratch {   // context-free reductions (vch_grad_prox / vch_kkt_counts / vch_solve_w)

@@ -542,13 +542,13 @@ inline void DctPlan::apply(cudaStream_t s, const double* in, double* out, const 
 
     if (all_fft) {
         // rows (prologue fused) -> fused column solve in place on the pitched buffer -> rows (addend + dots fused)
-        log->begin("dct_rows_fft", s);
+        log->begin(pro.mode ? "dct_rows_fft_pro" : "dct_rows_fft", s);
         fft_launch(false, inner, rgrid, rthreads, dct_smem(inner, rppb), in, t1, no, ni, ni, 1, P, 1, nullptr, nullptr, nosym, 1.0, 0, pro, DotEpilogue());
         log->end(s);
         log->begin("dct_cols_fft_solve", s);
         fft_launch(true, outer, cgrid, cthreads, dct_smem(outer, cppb), t1, t1, ni, no, 1, P, 1, P, inner.lam, outer.lam, sym, norm, scale_mode, RowPrologue(), DotEpilogue());
         log->end(s);
-        log->begin("dct_rows_fft", s);
+        log->begin(epi.mode == 1 ? "dct_rows_fft_epi1" : (epi.mode == 2 ? "dct_rows_fft_epi2" : "dct_rows_fft"), s);
         fft_launch(false, inner, rgrid, rthreads, dct_smem(inner, rppb), t1, out, no, ni, P, 1, ni, 1, nullptr, nullptr, nosym, 1.0, 0, RowPrologue(), epi);
         log->end(s);
         VCH_CUDA(cudaGetLastError());

@@ -323,7 +323,7 @@ class Ctx2D:
         s = self.shape
         lv = int(phi_hist.shape[0])
         full = (lv,) + s
-        J = np.zeros(5)
+        J = np.zeros(9)
         _check(lib().vch2d_cost(self.h, a.inp(phi_hist, full), a.inp(u, full), a.inp(phiQ, full), a.inp(phiT, s), lv,
                                 a.host(x), a.host(y), a.host(t_hist), C.c_double(b1), C.c_double(b2), C.c_double(b3),
                                 C.c_double(kappa_sp), J.ctypes.data_as(C.c_void_p), _mem_of(phi_hist, u, phiQ, phiT)))
@@ -345,7 +345,7 @@ class Ctx2D:
         else:
             phn = a.inp(phi_out, full)
         pr = a.inp(r_out, full) if r_out is not None else C.c_void_p(None)
-        J = np.zeros(5); red = np.zeros(4); st = Stats()
+        J = np.zeros(9); red = np.zeros(4); st = Stats()
         _check(lib().vch2d_pgd_iteration(self.h, lv, a.host(t_hist), a.host(dt_steps), a.host(x), a.host(y),
                                          a.inp(u, full), a.inp(phi_hist, full), a.inp(phiQ, full), a.inp(phiT, s),
                                          C.c_double(b1), C.c_double(b2), C.c_double(b3), C.c_double(kappa_sp),

@@ -166,3 +166,21 @@ def test_default_config_first_iteration_matches_reference(m, golden):
     keep = g["keep"]
     assert rel(res["phi_hist"][keep], g["phi1"]) < 1e-8
     assert rel(res["u"][keep], g["u1"]) < 1e-7 and np.array_equal(res["u"][keep] != 0, g["u1"] != 0)
+
+
+def test_driver_loop_matches_reference_loop(m, golden):
+    """K iterations of the reference's own PGD loop (oracle/make_golden_loop.py, default 128^2 config): cost, step-size and
+    control-change histories, line-search events included, reproduced by the device-resident driver."""
+    import os
+    from conftest import ROOT
+    if not os.path.exists(os.path.join(ROOT, "tests", "golden", "g2d_128_loop.npz")):
+        pytest.skip("loop golden not generated")
+    g = golden("g2d_128_loop")
+    G, C = m["GD2_configured"], m["config"]
+    K = len(g["J"]) - 1
+    res = quiet(G.optimize, C.ForwardSolverConfig(), C.OptimizationConfig(), 1, 1, max_iter=K, device_resident=True, verbose=False)
+    np.testing.assert_allclose(res["cost_history"], g["J"], rtol=1e-7)
+    np.testing.assert_allclose(res["alpha_history"], g["alpha"], rtol=1e-12)
+    assert res["timers"]["ls_attempts"] == int(g["ls_attempts"].sum())
+    assert rel(res["u"][[1, 50, 99]][:, ::4, ::4], g["u_final_sub"]) < 1e-6
+    assert rel(res["phi_hist"][-1], g["phi_final_T"]) < 1e-7
