@@ -432,6 +432,8 @@ class Ctx1D:
             if ub.ndim != 3 or ub.shape[0] != B or ub.shape[2] != self.n:
                 raise ValueError(f"control_input must have shape (rows, {self.n})")
             rows = int(ub.shape[1])
+            if M > rows:     # the reference indexes control_input[step] for every step (Forward_solver.py:347-353)
+                raise IndexError(f"index {rows} is out of bounds for axis 0 with size {rows}")
         else:
             ub = None
         hist, ph = a.out(phi0, (B, M + 2, self.n))

@@ -1,0 +1,84 @@
+"""GPU edge cases through the C ABI: ragged sizes, single levels, empty horizons, argument errors — the shapes the
+reference's tests poke at (tiny synthetic grids, M = 5) and the limits of the kernels' grid-stride / tail handling."""
+import numpy as np
+import pytest
+
+import vch_oracle as O
+from conftest import rel
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("count", [1, 2, 31, 255, 256, 257, 1025, 70001])
+def test_prox_kkt_solve_w_ragged_counts(native, count):
+    rng = np.random.default_rng(count)
+    u, r = rng.standard_normal(count), 0.01 * rng.standard_normal(count)
+    un, g, red = native.grad_prox(u, r, 0.3, 0.7, 0.05, -0.8, 0.9, want_grad=True)
+    ref = O.soft_prox(u, r + 0.3 * u, 0.7, 0.05, -0.8, 0.9)
+    assert np.array_equal(un, ref) and np.array_equal(g, r + 0.3 * u)
+    assert red[2] == np.count_nonzero(ref) and abs(red[1] - np.sum(u * u)) <= 1e-12 * max(1.0, red[1])
+    assert native.kkt_counts(un, r, 0.05) == O.kkt_counts(un, r, 0.05)
+    w = native.solve_w(u, 1e-2, 10.0, r, un)
+    assert np.array_equal(w, O.w_update(u, 1e-2, 10.0, r, un))
+
+
+def test_degenerate_horizons_and_shapes(native):
+    P = O.Phys2D(Nx=16, Ny=12, T=0.02)
+    c = native.Ctx2D(P.Nx, P.Ny, 1 / 16, 1 / 12, 1.0, 1.0, P.tau, P.gamma, P.c1, P.c2, P.kappa)
+    phi0 = O.init_phi_2d(16, 12)
+    h0, _, _ = c.forward(phi0, None, np.zeros(0))                    # empty horizon: only level 0
+    assert h0.shape == (1, 17, 13) and np.array_equal(h0[0], phi0)
+    # control shorter than the horizon: rows beyond the end act as zeros (Forward2_solver.py:545-548)
+    u_short = 0.3 * np.ones((2, 17, 13))
+    dts = np.full(3, 1e-2)
+    h_a, _, w_a = c.forward(phi0, u_short, dts, want_w=True)
+    u_full = np.concatenate([u_short, np.zeros((2, 17, 13))])
+    u_full[2:] = 0.0
+    fw = O.forward_2d(O.Phys2D(Nx=16, Ny=12, T=0.03), u_short)
+    assert rel(h_a, fw["phi"]) < 1e-8 and rel(w_a, fw["w"]) < 1e-12
+    # single-level adjoint / cost
+    x, y = np.linspace(0, 1, 17), np.linspace(0, 1, 13)
+    p, q, r = c.adjoint(h_a[:1], np.zeros(1), 5.0, 10.0, None, None)
+    po, qo, ro = O.adjoint_2d(P, h_a[:1], x, y, np.zeros(1), 5.0, 10.0)
+    assert rel(p, po) < 1e-9 and rel(q, qo) < 1e-9 and np.abs(r).max() == 0
+    J = c.cost(h_a[:1], 0 * h_a[:1], 0 * h_a[:1], 0 * phi0, x, y, np.zeros(1), 1.0, 2.0, 3.0, 4.0)
+    Jo, parts = O.cost_2d(h_a[:1], 0 * h_a[:1], 0 * h_a[:1], 0 * phi0, x, y, np.zeros(1), O.Opt2D(b1=1, b2=2, b3=3, kappa_sparsity=4))
+    assert abs(J[0] - Jo) <= 1e-12 * abs(Jo) and J[1] == 0.0
+    # repeated time stamps: the adjoint copies the level (backward2_solver.py:214-216)
+    t_rep = np.array([0.0, 0.01, 0.01, 0.02])
+    p2, q2, r2 = c.adjoint(h_a, t_rep, 5.0, 10.0, None, None)
+    assert np.array_equal(p2[1], p2[2]) and np.array_equal(r2[1], r2[2])
+    po2, _, ro2 = O.adjoint_2d(P, h_a, x, y, t_rep, 5.0, 10.0)
+    assert rel(p2, po2) < 1e-9 and rel(r2, ro2) < 1e-9
+    with pytest.raises(ValueError):
+        c.forward(phi0, np.zeros((3, 5, 5)), dts)
+    with pytest.raises(ValueError):
+        c.adjoint(np.zeros((4, 3, 3)), t_rep, 1.0, 1.0)
+    with pytest.raises(TypeError):
+        import torch
+        c.residual(phi0, torch.zeros(17, 13, dtype=torch.float64, device="cuda"), phi0, phi0, phi0, phi0, 1e-2)
+
+
+def test_1d_edge_cases(native):
+    P = O.Phys1D(N=40, T=0.03)
+    c = native.Ctx1D(P.N, P.Lx / P.N, P.Lx, P.tau, P.gamma, P.c1, P.c2, P.kappa)
+    phi0 = O.init_phi_1d(40)
+    h0, _, _ = c.forward(phi0, None, np.zeros(0))
+    assert h0.shape == (2, 41) and np.array_equal(h0[0], phi0) and np.array_equal(h0[1], phi0)
+    dts = np.full(3, 1e-2)
+    u = 0.2 * np.sin(np.arange(5 * 41)).reshape(5, 41)
+    h, mu, w = c.forward(phi0, u, dts, want_mu=True, want_w=True)
+    fw = O.forward_1d(P, u)
+    assert rel(h, fw["phi"]) < 1e-8 and rel(w, fw["w"]) < 1e-12
+    u3 = u[:3]                                                        # rows == steps: the last row repeats (Forward_solver.py:351-353)
+    h1, _, w1 = c.forward(phi0, u3, dts, want_w=True)
+    fw1 = O.forward_1d(P, u3)
+    assert rel(h1, fw1["phi"]) < 1e-8 and rel(w1, fw1["w"]) < 1e-12
+    with pytest.raises(IndexError):                                   # fewer rows than steps: IndexError, like the reference
+        c.forward(phi0, u[:2], dts)
+    with pytest.raises(ValueError):
+        c.forward(phi0, np.zeros((3, 7)), dts)
+    big = native.Ctx1D(512, 1 / 512, 1.0, P.tau, P.gamma, P.c1, P.c2, P.kappa)      # N = 512 as in the reference's order test
+    hb, _, _ = big.forward(O.init_phi_1d(512), None, np.full(2, 1e-3))
+    fb = O.forward_1d(O.Phys1D(N=512, T=2e-3, dt_initial=1e-3))
+    assert rel(hb, fb["phi"]) < 1e-8
