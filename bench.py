@@ -323,6 +323,67 @@ def run_b200(args):
         dist.destroy_process_group()
 
 
+def run_ensemble1d(args):
+    """Secondary workload (BASELINE config 4): B independent 1D control problems on the default 1D grid, varied targets and
+    weights, one optimistic PGD iteration per step for the WHOLE ensemble (4 launches).  The batch is split across ranks
+    with no communication (strong scaling: B is fixed); only the per-problem costs are gathered."""
+    import torch
+    import torch.distributed as dist
+    sys.path.insert(0, os.path.join(PKG, "Vch_control_1D"))
+    import vch_b200_native as nat
+    import GD_1D as G
+    rank, world, local = (int(os.environ.get(k, d)) for k, d in (("RANK", "0"), ("WORLD_SIZE", "1"), ("LOCAL_RANK", "0")))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+    B = args.batch
+    cfg = G.ForwardSolverConfig()
+    ens = G.make_ensemble(B)
+    lo, hi = G.shard_range(B, rank, world)
+    ctx = nat.Ctx1D(cfg.N, cfg.Lx / cfg.N, cfg.Lx, cfg.tau, cfg.gamma, cfg.c1, cfg.c2, cfg.kappa, device=local)
+    up = lambda a: torch.from_numpy(np.ascontiguousarray(a[lo:hi])).to(dev)
+    phi_init, phiQ, phiT = up(ens["phi_init"]), up(ens["phi_Q"]), up(ens["phi_T"])
+    w = {k: np.ascontiguousarray(ens[k][lo:hi]) for k in ("b1", "b2", "b3", "ksp")}
+    hist, _, _ = ctx.forward(phi_init, None, ens["dts"])
+    state = {"u": torch.zeros_like(hist), "h": hist, "J": None}
+
+    def step():
+        u1, h1, J, red, _ = G.optimistic_iteration_ensemble(ctx, ctx, state["u"], state["h"], phiQ, phiT, ens["x"], ens["t_hist"],
+                                                            ens["dts"], phi_init, w["b1"], w["b2"], w["b3"], w["ksp"], 100.0)
+        state.update(u=u1, h=h1, J=J)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    l0 = ctx.launches()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    barrier()
+    ms = torch.tensor([e0.elapsed_time(e1) / args.steps], device=dev, dtype=torch.float64)
+    Jsum = torch.tensor([float(state["J"][:, 0].sum())], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(Jsum, op=dist.ReduceOp.SUM)
+    if rank == 0:
+        print(json.dumps({"metric": "1D ensemble problem-iterations/s (config 4)", "value": B * 1e3 / float(ms.item()), "unit": "problem-it/s",
+                          "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": float(ms.item()),
+                          "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                          "config": {"workload": f"{B} independent 1D problems (N=128, 100 steps), make_ensemble(seed 1234), one optimistic PGD iteration each",
+                                     "problems_per_gpu": hi - lo},
+                          "gpu_launches": int(ctx.launches() - l0), "sum_J": float(Jsum.item())}), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -335,8 +396,12 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--workload", default="pgd2d", choices=["pgd2d", "ensemble1d"], help="pgd2d = BASELINE metric (default); ensemble1d = config 4")
+    ap.add_argument("--batch", type=int, default=1024, help="ensemble1d: number of problems")
     args = ap.parse_args()
-    if args.impl == "reference":
+    if args.workload == "ensemble1d":
+        run_ensemble1d(args)
+    elif args.impl == "reference":
         run_reference(args)
     else:
         run_b200(args)
