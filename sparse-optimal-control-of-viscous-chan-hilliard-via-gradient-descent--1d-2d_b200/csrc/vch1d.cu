@@ -11,9 +11,27 @@ using namespace vch;
 struct vch1d_ctx {
     vch1d_params prm;
     int device = 0;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr;   // private non-blocking work stream (the legacy default stream serialises against every
+                                     // other blocking stream of the process, e.g. NCCL's)
+    cudaStream_t user = nullptr;     // caller's stream; ordered with `stream` by events at entry/exit of every call
+    cudaEvent_t ev_in = nullptr, ev_out = nullptr;
     long long launches = 0;
 };
+
+namespace {
+struct Scope1D {
+    vch1d_ctx* c;
+    explicit Scope1D(vch1d_ctx* ctx) : c(ctx) {
+        VCH_CUDA(cudaSetDevice(c->device));
+        VCH_CUDA(cudaEventRecord(c->ev_in, c->user));
+        VCH_CUDA(cudaStreamWaitEvent(c->stream, c->ev_in, 0));
+    }
+    ~Scope1D() {
+        cudaEventRecord(c->ev_out, c->stream);
+        cudaStreamWaitEvent(c->user, c->ev_out, 0);
+    }
+};
+}  // namespace
 
 namespace {
 
@@ -446,13 +464,22 @@ int vch1d_create(const vch1d_params* p, int device, vch1d_ctx** out) {
         VCH_CUDA(cudaSetDevice(device));
         auto* c = new vch1d_ctx();
         c->prm = *p; c->device = device;
+        VCH_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+        VCH_CUDA(cudaEventCreateWithFlags(&c->ev_in, cudaEventDisableTiming));
+        VCH_CUDA(cudaEventCreateWithFlags(&c->ev_out, cudaEventDisableTiming));
         *out = c;
         return VCH_OK;
     });
 }
-void vch1d_destroy(vch1d_ctx* c) { delete c; }
+void vch1d_destroy(vch1d_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    cudaEventDestroy(c->ev_in); cudaEventDestroy(c->ev_out); cudaStreamDestroy(c->stream);
+    delete c;
+}
 int vch1d_set_stream(vch1d_ctx* c, void* s) {
-    return guarded([&] { VCH_REQUIRE(c, VCH_E_ARG, "null ctx"); c->stream = (cudaStream_t)s; return VCH_OK; });
+    return guarded([&] { VCH_REQUIRE(c, VCH_E_ARG, "null ctx"); c->user = (cudaStream_t)s; return VCH_OK; });
 }
 long long vch1d_launch_count(vch1d_ctx* c) { return c ? c->launches : 0; }
 
@@ -465,6 +492,7 @@ int vch1d_residual(vch1d_ctx* c, int batch, const double* phi_new, const double*
         VCH_CUDA(cudaSetDevice(c->device));
         const P1 p = make_p1(c->prm);
         const long long tot = (long long)batch * p.n;
+        Scope1D scope(c);
         Stager st(c->stream, mem);
         const double *a = st.in(phi_new, tot), *b = st.in(phi_old, tot), *m1 = st.in(mu_new, tot), *m0 = st.in(mu_old, tot),
                      *w1 = st.in(w_new, tot), *w0 = st.in(w_old, tot);
@@ -483,6 +511,7 @@ int vch1d_initialize_mu(vch1d_ctx* c, int batch, const double* phi, const double
         VCH_CUDA(cudaSetDevice(c->device));
         const P1 p = make_p1(c->prm);
         const long long tot = (long long)batch * p.n;
+        Scope1D scope(c);
         Stager st(c->stream, mem);
         const double *a = st.in(phi, tot), *b = st.in(w, tot);
         double* o = st.out(mu_out, tot);
@@ -503,6 +532,7 @@ int vch1d_newton(vch1d_ctx* c, int batch, const double* phi_old, const double* m
         const P1 p = make_p1(c->prm);
         prep(c, (const void*)newton1d_kernel, p.n);
         const size_t tot = (size_t)batch * p.n;
+        Scope1D scope(c);
         Stager st(c->stream, mem);
         const double *p0 = st.in(phi_old, tot), *m0 = st.in(mu_old, tot), *w0 = st.in(w_old, tot), *w1 = st.in(w_new, tot);
         double *po = st.out(phi_new_out, tot), *mo = st.out(mu_new_out, tot);
@@ -529,6 +559,7 @@ int vch1d_forward(vch1d_ctx* c, int batch, const double* phi0, const double* u, 
         const P1 p = make_p1(c->prm);
         prep(c, (const void*)forward1d_kernel, p.n);
         const size_t n = p.n;
+        Scope1D scope(c);
         Stager st(c->stream, mem);
         const double* d0 = st.in(phi0, (size_t)batch * n);
         const double* du = st.in(u, (size_t)batch * u_rows * n);
@@ -559,6 +590,7 @@ int vch1d_adjoint(vch1d_ctx* c, int batch, const double* phi_hist, int levels, c
         const P1 p = make_p1(c->prm);
         prep(c, (const void*)adjoint1d_kernel, p.n);
         const size_t n = p.n, tot = (size_t)batch * levels * n;
+        Scope1D scope(c);
         Stager st(c->stream, mem);
         const double *dh = st.in(phi_hist, tot), *dq = st.in(phiQ, tot), *dT = st.in(phiT, (size_t)batch * n);
         double *po = st.out(p_out, tot), *qo = st.out(q_out, tot), *ro = st.out(r_out, tot);
@@ -585,6 +617,7 @@ int vch1d_cost(vch1d_ctx* c, int batch, const double* phi_hist, const double* u,
         VCH_CUDA(cudaSetDevice(c->device));
         const int n = c->prm.N + 1;
         const size_t tot = (size_t)batch * levels * n;
+        Scope1D scope(c);
         Stager st(c->stream, mem);
         const double *dh = st.in(phi_hist, tot), *du = st.in(u, tot), *dq = st.in(phiQ, tot), *dT = st.in(phiT, (size_t)batch * n);
         std::vector<double> wx = trapz_w(x, n), wt = trapz_w(t_hist, levels);
@@ -609,6 +642,7 @@ int vch1d_grad_prox(vch1d_ctx* c, int batch, long long per_problem, const double
         VCH_REQUIRE(c && batch >= 1 && per_problem >= 1 && u && r && par && u_new_out, VCH_E_SHAPE, "grad_prox: bad arguments");
         VCH_CUDA(cudaSetDevice(c->device));
         const size_t tot = (size_t)batch * per_problem;
+        Scope1D scope(c);
         Stager st(c->stream, mem);
         const double *du = st.in(u, tot), *dr = st.in(r, tot);
         double* dn = st.out(u_new_out, tot);
