@@ -347,7 +347,8 @@ using LevelHook = std::function<void(int)>;
 
 // after_level(k): called once level k of phi_hist has been enqueued (streaming D2H of the trajectory hooks in here).
 void forward_dev(vch2d_ctx* c, const double* phi0, const double* u, int u_rows, int n_steps, const double* dt_steps,
-                 double* phi_hist, double* mu_hist, double* w_hist, vch_stats* st, const LevelHook& after_level = nullptr) {
+                 double* phi_hist, double* mu_hist, double* w_hist, vch_stats* st, const LevelHook& after_level = nullptr,
+                 const LevelHook& before_step = nullptr) {
     const long long n = c->g.n;
     const size_t bytes = n * sizeof(double);
     const int eb = c->eb();
@@ -360,6 +361,7 @@ void forward_dev(vch2d_ctx* c, const double* phi0, const double* u, int u_rows, 
            c->red_part.p, c->ticket);
     for (int s = 0; s < n_steps; ++s) {
         const double dt = dt_steps[s];
+        if (before_step) before_step(s);     // streaming path: makes sure control rows s and s+1 exist
         const double* un = nullptr; const double* un1 = nullptr;
         if (u && s < u_rows - 1) { un = u + (size_t)s * n; un1 = u + (size_t)(s + 1) * n; }
         LAUNCH(c, solve_w_kernel, eb, 256, c->w0.p, un, un1, c->w1.p, n, c->prm.gamma / dt);
@@ -837,8 +839,13 @@ static void pgd_iteration_host_streamed(vch2d_ctx* c, int levels, const double* 
             if (phiQ) VCH_CUDA(cudaMemcpyAsync(dq.p + lo * n, phiQ + lo * n, cnt * fb, cudaMemcpyHostToDevice, cp));
             VCH_CUDA(cudaEventRecord(ev_in[j], cp));
         }
-        VCH_CUDA(cudaMemcpyAsync(du.p, u, tot * sizeof(double), cudaMemcpyHostToDevice, cp));
-        VCH_CUDA(cudaEventRecord(ev_u, cp));
+        std::vector<cudaEvent_t> ev_uc(nch);
+        for (auto& e : ev_uc) VCH_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        for (int j = 0; j < nch; ++j) {                     // u in ASCENDING chunks: consumed just in time by the forward sweep
+            const size_t lo = (size_t)j * CH, cnt = std::min<size_t>(CH, levels - lo);
+            VCH_CUDA(cudaMemcpyAsync(du.p + lo * n, u + lo * n, cnt * fb, cudaMemcpyHostToDevice, cp));
+            VCH_CUDA(cudaEventRecord(ev_uc[j], cp));
+        }
         // ---- (1) adjoint sweep, waiting chunk by chunk
         int waited = nch;
         auto need = [&](int k) {
@@ -848,18 +855,27 @@ static void pgd_iteration_host_streamed(vch2d_ctx* c, int levels, const double* 
         adjoint_dev(c, dh.p, levels, t_hist, b1, b2, phiQ ? dq.p : nullptr, phiT ? dT.p : nullptr, nullptr, nullptr, dr.p, s, need);
         need(0);
         VCH_CUDA(cudaEventRecord(ev_adj, c->stream));
-        // ---- (2) gradient + prox
-        VCH_CUDA(cudaStreamWaitEvent(c->stream, ev_u, 0));
-        LAUNCH(c, grad_prox_kernel, red_blocks((long long)tot), kRedThreads, du.p, dr.p, (double*)nullptr, dun.p, (long long)tot, b3,
-               alpha, ksp, umin, umax, c->out4 + 4, c->red_part.p, c->ticket);
-        VCH_CUDA(cudaEventRecord(ev_prox, c->stream));
-        VCH_CUDA(cudaStreamWaitEvent(cp, ev_prox, 0));
-        VCH_CUDA(cudaMemcpyAsync(u_new_out, dun.p, tot * sizeof(double), cudaMemcpyDeviceToHost, cp));
         if (r_out) {
             VCH_CUDA(cudaStreamWaitEvent(cp, ev_adj, 0));
             VCH_CUDA(cudaMemcpyAsync(r_out, dr.p, tot * sizeof(double), cudaMemcpyDeviceToHost, cp));
         }
-        // ---- (3) forward solve, trajectory streamed out chunk by chunk
+        // ---- (2)+(3) gradient/prox chunk by chunk just ahead of the forward sweep; u_new and the trajectory stream out behind it
+        VCH_CUDA(cudaMemsetAsync(c->out4 + 4, 0, 4 * sizeof(double), c->stream));
+        int proxed = 0;                                      // chunks of u_new already produced
+        auto prox_upto = [&](int level) {
+            const int jmax = std::min(nch - 1, level / CH);
+            while (proxed <= jmax) {
+                const int j = proxed++;
+                const size_t lo = (size_t)j * CH, cnt = std::min<size_t>(CH, levels - lo);
+                VCH_CUDA(cudaStreamWaitEvent(c->stream, ev_uc[j], 0));
+                LAUNCH(c, grad_prox_kernel, red_blocks((long long)(cnt * n)), kRedThreads, du.p + lo * n, dr.p + lo * n, (double*)nullptr,
+                       dun.p + lo * n, (long long)(cnt * n), b3, alpha, ksp, umin, umax, c->out4 + 4, c->red_part.p, c->ticket, 1);
+                VCH_CUDA(cudaEventRecord(ev_prox, c->stream));
+                VCH_CUDA(cudaStreamWaitEvent(cp, ev_prox, 0));
+                VCH_CUDA(cudaMemcpyAsync(u_new_out + lo * n, dun.p + lo * n, cnt * fb, cudaMemcpyDeviceToHost, cp));
+            }
+        };
+        auto before = [&](int step) { prox_upto(step + 1); };
         auto after = [&](int k) {
             if ((k + 1) % CH == 0 || k == levels - 1) {
                 const int j = k / CH;
@@ -869,7 +885,9 @@ static void pgd_iteration_host_streamed(vch2d_ctx* c, int levels, const double* 
                 VCH_CUDA(cudaMemcpyAsync(phi_hist_out + lo * n, dhn.p + lo * n, cnt * fb, cudaMemcpyDeviceToHost, cp));
             }
         };
-        forward_dev(c, dh.p, dun.p, levels, levels - 1, dt_steps, dhn.p, nullptr, nullptr, s, after);
+        forward_dev(c, dh.p, dun.p, levels, levels - 1, dt_steps, dhn.p, nullptr, nullptr, s, after, before);
+        prox_upto(levels - 1);
+        for (auto& e : ev_uc) cudaEventDestroy(e);
         // ---- (4) cost
         cost_dev(c, dhn.p, dun.p, phiQ ? dq.p : nullptr, phiT ? dT.p : nullptr, levels, x, y, t_hist, b1, b2, b3, ksp, J_out);
         if (red_out) {

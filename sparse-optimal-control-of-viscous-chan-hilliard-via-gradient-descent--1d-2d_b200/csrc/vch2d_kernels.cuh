@@ -438,7 +438,7 @@ __global__ void cost_kernel(const double* __restrict__ phi, const double* __rest
 // g = r + b3 u ; v = u - alpha g ; soft threshold alpha*kappa ; box.  Also ||u_new-u||^2, ||u||^2, support and bound counts.
 __global__ void grad_prox_kernel(const double* __restrict__ u, const double* __restrict__ r, double* __restrict__ grad,
                                  double* __restrict__ un, long long n, double b3, double alpha, double ksp, double umin,
-                                 double umax, double* out4, double* part, unsigned int* ticket) {
+                                 double umax, double* out4, double* part, unsigned int* ticket, int accumulate = 0) {
     double v[4] = {0.0, 0.0, 0.0, 0.0};
     const double thr = alpha * ksp;
     for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (long long)gridDim.x * blockDim.x) {
@@ -459,7 +459,8 @@ __global__ void grad_prox_kernel(const double* __restrict__ u, const double* __r
     const int op[4] = {0, 0, 0, 0};
     double tot[4];
     if (grid_reduce<4>(v, op, part, ticket, tot) && threadIdx.x == 0) {
-        out4[0] = tot[0]; out4[1] = tot[1]; out4[2] = tot[2]; out4[3] = tot[3];
+        if (accumulate) { out4[0] += tot[0]; out4[1] += tot[1]; out4[2] += tot[2]; out4[3] += tot[3]; }   // chunked launches
+        else { out4[0] = tot[0]; out4[1] = tot[1]; out4[2] = tot[2]; out4[3] = tot[3]; }
     }
 }
 
