@@ -486,6 +486,7 @@ int vch2d_create(const vch2d_params* p, int device, vch2d_ctx** out) {
         c->prm = *p; c->device = device;
         c->debug = getenv("VCH_DEBUG") ? atoi(getenv("VCH_DEBUG")) : 0;
         if (getenv("VCH_NEWTON_STRICT")) c->floor_aware = 0;
+        if (getenv("VCH_KRYLOV_RTOL")) { const double t = atof(getenv("VCH_KRYLOV_RTOL")); if (t > 0 && t < 1) c->krylov_tol = t; }
         Geo& g = c->g;
         g.ni = p->Nx + 1; g.no = p->Ny + 1; g.nx1 = p->Nx + 1; g.ny1 = p->Ny + 1;
         g.n = (long long)g.ni * g.no;
