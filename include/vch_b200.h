@@ -35,6 +35,8 @@ extern "C" {
 #define VCH_E_NONFINITE   3   /* non-finite residual or mass defect (reference: RuntimeError, 1D Forward_solver.py:166-170) */
 #define VCH_E_KRYLOV      4   /* linear solve stalled above tolerance (the reference's direct solve has no analogue) */
 #define VCH_E_ARG         5
+#define VCH_E_COMM        6   /* slab mode: a peer rank did not arrive within the wait limit */
+#define VCH_IPC_HANDLE_BYTES 64
 
 typedef struct vch2d_ctx vch2d_ctx;
 typedef struct vch1d_ctx vch1d_ctx;
@@ -74,6 +76,21 @@ int  vch_version(void);
 /* ------------------------------------------------------------------ 2D context */
 int  vch2d_create(const vch2d_params* p, int device, vch2d_ctx** out);
 void vch2d_destroy(vch2d_ctx* c);
+
+/* ---- slab mode: ONE 2D problem decomposed into row slabs over 2/4/8 GPUs of one node, one process per GPU
+ * (BASELINE config 5).  The grid must be square with N = 2^k (32..4096).  Rank r owns rows
+ * [r*N/R, (r+1)*N/R) of every (N+1, N+1) field (the last rank one more); every array argument of the vch2d_* calls
+ * below is then the rank's slab (levels, rows, N+1), except x (cost / pgd_iteration), which stays the global abscissa
+ * vector.  All ranks must make the same calls in the same order (the kernels exchange halo rows, transposes of the
+ * spectral preconditioner and reduction partials through each other's memory over NVLink; there is no host-side
+ * collective).  Setup: every rank creates its context, publishes the 64-byte IPC handle of its arena, collects all
+ * ranks' handles (any host transport, e.g. torch.distributed.all_gather) and attaches.  vch2d_residual is not
+ * available in slab mode.  A rank that waits more than 10 s for a peer fails with VCH_E_COMM instead of hanging. */
+int  vch2d_slab_create(const vch2d_params* p_global, int device, int rank, int nranks, vch2d_ctx** out);
+int  vch2d_slab_rows(vch2d_ctx* c, int* row0_out, int* nrows_out);
+int  vch2d_slab_ipc_handle(vch2d_ctx* c, void* handle_out /* VCH_IPC_HANDLE_BYTES */);
+int  vch2d_slab_attach(vch2d_ctx* c, const void* handles /* nranks * VCH_IPC_HANDLE_BYTES, rank order */);
+int  vch2d_slab_selftest(vch2d_ctx* c, double* out5 /* sum, min, max of (rank+1); lower / upper ghost value */);
 int  vch2d_set_stream(vch2d_ctx* c, void* cuda_stream);          /* cudaStream_t; NULL = legacy default stream */
 int  vch2d_set_krylov(vch2d_ctx* c, double rel_tol, int max_iter);/* defaults 1e-11, 200 */
 /* Newton stop rule.  floor_aware = 1 (default): besides the reference's ||R||_2 < 1e-6 (Forward2_solver.py:353-365) the

@@ -36,7 +36,14 @@ struct vch2d_ctx {
     DevBuf kb, kx, kr, kr0, kp, kv, ks, kt, ktmp, kq, dmu;
     DevBuf adj_p[2], adj_q[2], adj_r[2], mu_old;
     DevBuf stage[7];             // device staging of the host-buffer PGD iteration, kept across calls (no 50 GB malloc/free per step)
-    DevBuf red_part;             // partials for grid reductions
+    RedBuf red;                  // partials for grid reductions (+ the Comm header the kernels read)
+    // slab mode (one rank of a row-slab decomposition of a square grid; see vch_common.cuh "slab mode")
+    bool slab = false;
+    Comm cm;                     // rank 0 of 1 unless slab
+    Arena arena;                 // every work vector lives here (ghost margins of 2 rows), peers address it over NVLink
+    int rows_lo = 0;             // rows owned by each rank but the last (the last owns rows_lo + 1)
+    std::vector<void*> peer_maps;   // cudaIpcOpenMemHandle mappings
+    bool attached = false;
     DevBuf small;                // small device vectors: weights, out4
     unsigned int* ticket = nullptr;
     Scal* sc = nullptr;          // device scalars
@@ -53,6 +60,7 @@ namespace {
 void fetch_scalars(vch2d_ctx* c) {
     VCH_CUDA(cudaMemcpyAsync(c->sc_host, c->sc, sizeof(Scal), cudaMemcpyDeviceToHost, c->stream));
     VCH_CUDA(cudaStreamSynchronize(c->stream));
+    if (c->sc_host->comm_err) throw Error(VCH_E_COMM, "slab mode: a peer rank did not arrive within the wait limit (ranks out of step or a peer failed)");
 }
 
 #define LAUNCH(c, kern, grid, block, ...)                       \
@@ -70,10 +78,28 @@ void op_apply(vch2d_ctx* c, const double* x, const double* a, double* y, const i
     c->log.end(c->stream);
 }
 
-// Left-preconditioned BiCGStab on  P^-1 A x = P^-1 b  with A = c0 I - {L diag(a) | diag(a) L} + c2 L^2 and
-// P the same operator with a replaced by the device scalar abar.  Scalars stay on the device; every kernel of
-// an iteration is gated on sc->done, so iterations are enqueued in batches and the host only polls.
-// Returns the number of iterations; result in c->kx.
+// Slab mode: ship the first / last `rows` owned rows of one or two fields into the neighbours' ghost rows.  The leading
+// barrier guarantees the neighbours have finished every kernel that still reads the old ghost rows, the trailing one that
+// the new rows have landed before anything reads them.  No-op outside slab mode.
+void halo_push(vch2d_ctx* c, const double* f0, const double* f1, int rows, const int* done = nullptr) {
+    if (!c->slab) return;
+    for (const double* f : {f0, f1})
+        if (f && (f < c->arena.base + kArenaHeader || f >= c->arena.base + c->arena.cap))
+            throw Error(VCH_E_ARG, "halo_push: field is not in the slab arena");
+    LAUNCH(c, xbar_kernel, 1, 32, c->cm, done);
+    const int blocks = std::max(1, std::min(32, (rows * c->g.ni + 255) / 256));
+    LAUNCH(c, halo_push_kernel, blocks, 256, c->cm, f0, f1, rows, c->g.no, c->rows_lo, c->g.ni, done);
+    LAUNCH(c, xbar_kernel, 1, 32, c->cm, done);
+}
+// Copy of a ghosted work vector including its ghost rows.
+void copy_ghosted(vch2d_ctx* c, double* dst, const double* src) {
+    const size_t m = c->slab ? 2 * (size_t)c->g.ni : 0;
+    VCH_CUDA(cudaMemcpyAsync(dst - m, src - m, ((size_t)c->g.n + 2 * m) * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+}
+// kernels per BiCGStab iteration / per solve prologue (accounting of launches inside solve graphs)
+template <bool ADJ> int iter_launches(const vch2d_ctx* c) { return ADJ ? (c->slab ? 11 + 6 + 6 : 11) : (c->slab ? 7 + 6 : 7); }
+int prologue_launches(const vch2d_ctx* c) { return c->slab ? 7 : 4; }
+
 // Orders the library's private stream after the caller's stream on entry and the caller's stream after ours on exit,
 // so callers see ordinary stream semantics (torch.cuda.Event on their stream brackets our kernels).
 struct StreamScope {
@@ -102,20 +128,22 @@ void enqueue_bicg_iteration(vch2d_ctx* c, const double* a, const SymbolArgs& sy,
     const int* done = &c->sc->done;
     if (ADJ) {
         LAUNCH(c, bicg_p_kernel, eb, 256, c->kr.p, c->kp.p, c->kv.p, n, c->sc);
+        halo_push(c, c->kp.p, nullptr, 2, done);
         op_apply<true>(c, c->kp.p, a, c->ktmp.p, done);
-        c->dct.apply(c->stream, c->ktmp.p, c->kv.p, sy, done, DotEpilogue{1, c->kr0.p, c->sc, c->red_part.p, c->ticket, nullptr});
+        c->dct.apply(c->stream, c->ktmp.p, c->kv.p, sy, done, DotEpilogue{1, c->kr0.p, c->sc, c->red.part, c->ticket, nullptr});
         LAUNCH(c, bicg_s_kernel, eb, 256, c->kr.p, c->kv.p, c->ks.p, n, c->sc);
+        halo_push(c, c->ks.p, nullptr, 2, done);
         op_apply<true>(c, c->ks.p, a, c->ktmp.p, done);
-        c->dct.apply(c->stream, c->ktmp.p, c->kt.p, sy, done, DotEpilogue{2, c->ks.p, c->sc, c->red_part.p, c->ticket, nullptr});
+        c->dct.apply(c->stream, c->ktmp.p, c->kt.p, sy, done, DotEpilogue{2, c->ks.p, c->sc, c->red.part, c->ticket, nullptr});
         LAUNCH(c, bicg_x_kernel, rb, kRedThreads, c->kx.p, c->kr.p, c->kp.p, c->ks.p, c->kt.p, c->kr0.p, (const double*)nullptr,
-               (double*)nullptr, n, c->sc, c->red_part.p, c->ticket, cond, use_cond);
+               (double*)nullptr, n, c->sc, c->red.part, c->ticket, cond, use_cond);
     } else {
-        c->dct.apply(c->stream, c->kr.p, c->kv.p, sy, done, DotEpilogue{1, c->kr0.p, c->sc, c->red_part.p, c->ticket, c->kp.p},
+        c->dct.apply(c->stream, c->kr.p, c->kv.p, sy, done, DotEpilogue{1, c->kr0.p, c->sc, c->red.part, c->ticket, c->kp.p},
                      RowPrologue{1, c->kr.p, c->kq.p, a, c->kp.p, c->sc}, 1);
-        c->dct.apply(c->stream, c->kr.p, c->kt.p, sy, done, DotEpilogue{2, c->ks.p, c->sc, c->red_part.p, c->ticket, c->ks.p},
+        c->dct.apply(c->stream, c->kr.p, c->kt.p, sy, done, DotEpilogue{2, c->ks.p, c->sc, c->red.part, c->ticket, c->ks.p},
                      RowPrologue{2, c->kr.p, c->kv.p, a, c->ks.p, c->sc}, 1);
         LAUNCH(c, bicg_x_kernel, rb, kRedThreads, c->kx.p, c->kr.p, c->kp.p, c->ks.p, c->kt.p, c->kr0.p, c->kv.p, c->kq.p, n, c->sc,
-               c->red_part.p, c->ticket, cond, use_cond);
+               c->red.part, c->ticket, cond, use_cond);
     }
 }
 
@@ -140,7 +168,7 @@ cudaGraphExec_t solve_graph(vch2d_ctx* c, const double* a) {
     VCH_CUDA(cudaStreamBeginCaptureToGraph(c->stream, graph, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal));
     c->dct.apply(c->stream, c->kb.p, c->kr.p, sy, nullptr);
     LAUNCH(c, bicg_init_kernel, c->rb(), kRedThreads, c->kr.p, c->kr0.p, c->kp.p, c->kv.p, c->kx.p, c->kq.p, n, c->sc,
-           c->red_part.p, c->ticket, cond, 4);
+           c->red.part, c->ticket, cond, prologue_launches(c));
     cudaStreamCaptureStatus st; const cudaGraphNode_t* deps = nullptr; size_t ndeps = 0;
     VCH_CUDA(cudaStreamGetCaptureInfo(c->stream, &st, nullptr, nullptr, &deps, &ndeps));
     std::vector<cudaGraphNode_t> leaf(deps, deps + ndeps);
@@ -156,7 +184,7 @@ cudaGraphExec_t solve_graph(vch2d_ctx* c, const double* a) {
     VCH_CUDA(cudaGraphAddNode(&wnode, graph, leaf.data(), leaf.size(), &np));
     cudaGraph_t body = np.conditional.phGraph_out[0];
     VCH_CUDA(cudaStreamBeginCaptureToGraph(c->stream, body, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal));
-    enqueue_bicg_iteration<ADJ>(c, a, sy, cond, ADJ ? 11 : 7);
+    enqueue_bicg_iteration<ADJ>(c, a, sy, cond, iter_launches<ADJ>(c));
     VCH_CUDA(cudaStreamEndCapture(c->stream, &tmp));
     cudaGraphExec_t exec;
     VCH_CUDA(cudaGraphInstantiate(&exec, graph, 0));
@@ -182,7 +210,7 @@ int krylov_solve(vch2d_ctx* c, const double* b, const double* a, vch_stats* st) 
     SymbolArgs sy{0.0, 0.0, &c->sc->abar, 0.0, &c->sc->c0};
     c->dct.apply(c->stream, c->kb.p, c->kr.p, sy, nullptr);
     LAUNCH(c, bicg_init_kernel, c->rb(), kRedThreads, c->kr.p, c->kr0.p, c->kp.p, c->kv.p, c->kx.p, c->kq.p, n, c->sc,
-           c->red_part.p, c->ticket, (cudaGraphConditionalHandle)0, 0);
+           c->red.part, c->ticket, (cudaGraphConditionalHandle)0, 0);
     int launched = 0, batch = 2;
     while (true) {
         for (int k = 0; k < batch; ++k) enqueue_bicg_iteration<ADJ>(c, a, sy, (cudaGraphConditionalHandle)0, 0);
@@ -227,16 +255,18 @@ void stat_collect(vch2d_ctx* c, const StatMark& m0, vch_stats* st) {
 
 void eval_residual(vch2d_ctx* c, const double* phi, const double* mu, double* Rphi, double* Rmu, double* a, double dt) {
     LAUNCH(c, residual_kernel, c->rb(), kRedThreads, phi, mu, c->cphi.p, c->cmu.p, Rphi, Rmu, a, c->g, c->ph, dt, c->sc,
-           c->red_part.p, c->ticket);
+           c->red.part, c->ticket);
 }
 
 // Solve J [dphi; dmu] = -[Rphi; Rmu] by Schur reduction:  (1/dt I - L(diag(a) - kappa/2 L)) dphi = -Rmu + L Rphi,
 // dmu = 2 (a dphi - kappa/2 L dphi + Rphi).   dphi -> c->kx, dmu -> c->dmu.  phi may be null (no ceiling minima).
 void newton_linear_solve(vch2d_ctx* c, const double* Rphi, const double* Rmu, const double* a, const double* phi,
                          double dt, vch_stats* st) {
+    halo_push(c, Rphi, nullptr, 1);
     LAUNCH(c, schur_rhs_kernel, c->eb(), 256, Rphi, Rmu, c->kb.p, c->g, c->sc, 1.0 / dt, 0.5 * c->ph.kappa);
     krylov_solve<false>(c, c->kb.p, a, st);
-    LAUNCH(c, dmu_ceiling_kernel, c->rb(), kRedThreads, c->kx.p, a, Rphi, phi, c->dmu.p, c->g, c->ph, c->sc, c->red_part.p,
+    halo_push(c, c->kx.p, nullptr, 1);
+    LAUNCH(c, dmu_ceiling_kernel, c->rb(), kRedThreads, c->kx.p, a, Rphi, phi, c->dmu.p, c->g, c->ph, c->sc, c->red.part,
            c->ticket);
 }
 
@@ -246,8 +276,15 @@ void newton_step(vch2d_ctx* c, const double* phi_old, const double* mu_old, cons
                  double dt, std::vector<double>* hist, vch_stats* st) {
     const long long n = c->g.n;
     const int eb = c->eb();
-    LAUNCH(c, step_setup_kernel, eb, 256, phi_old, mu_old, w_old, w_new, c->cphi.p, c->cmu.p, c->mu.p, c->g, c->ph, dt);
     VCH_CUDA(cudaMemcpyAsync(c->phi.p, phi_old, n * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+    if (c->slab && mu_old != c->mu_old.p) {   // test-level entry: bring mu_old into a ghosted work vector
+        c->mu_old.alloc(n);
+        VCH_CUDA(cudaMemcpyAsync(c->mu_old.p, mu_old, n * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+        mu_old = c->mu_old.p;
+        halo_push(c, c->phi.p, c->mu_old.p, 1);
+    } else halo_push(c, c->phi.p, nullptr, 1);
+    LAUNCH(c, step_setup_kernel, eb, 256, c->phi.p, mu_old, w_old, w_new, c->cphi.p, c->cmu.p, c->mu.p, c->g, c->ph, dt);
+    halo_push(c, c->mu.p, nullptr, 1);
     double *phi = c->phi.p, *mu = c->mu.p, *phit = c->phit.p, *mut = c->mut.p;
     double *Rp = c->Rphi.p, *Rm = c->Rmu.p, *a = c->a.p, *RpT = c->RphiT.p, *RmT = c->RmuT.p, *aT = c->aT.p;
     eval_residual(c, phi, mu, Rp, Rm, a, dt);
@@ -277,6 +314,7 @@ void newton_step(vch2d_ctx* c, const double* phi_old, const double* mu_old, cons
         // speculative full step: almost always alpha = 1 is both allowed by the ceiling and accepted by Armijo, so the
         // trial iterate and its residual are enqueued before the host has seen the ceiling -> ONE sync per Newton iteration
         LAUNCH(c, trial_kernel, eb, 256, phi, mu, c->kx.p, c->dmu.p, phit, mut, n, 1.0);
+        halo_push(c, phit, mut, 1);
         eval_residual(c, phit, mut, RpT, RmT, aT, dt);
         fetch_scalars(c);
         if (c->sc_host->nonfinite) throw Error(VCH_E_NONFINITE, "non-finite value in Krylov solve");
@@ -292,6 +330,7 @@ void newton_step(vch2d_ctx* c, const double* phi_old, const double* mu_old, cons
         for (int ls = 0; ls < 12; ++ls) {
             if (!have_trial) {
                 LAUNCH(c, trial_kernel, eb, 256, phi, mu, c->kx.p, c->dmu.p, phit, mut, n, alpha);
+                halo_push(c, phit, mut, 1);
                 eval_residual(c, phit, mut, RpT, RmT, aT, dt);
                 fetch_scalars(c);
                 if (st) st->newton_residual_evals += 1;
@@ -309,6 +348,7 @@ void newton_step(vch2d_ctx* c, const double* phi_old, const double* mu_old, cons
         if (!accepted) {
             if (best < normR) {   // fall back to the best trial (re-evaluated: same arithmetic, same values)
                 LAUNCH(c, trial_kernel, eb, 256, phi, mu, c->kx.p, c->dmu.p, phit, mut, n, best_alpha);
+                halo_push(c, phit, mut, 1);
                 eval_residual(c, phit, mut, RpT, RmT, aT, dt);
                 fetch_scalars(c);
                 normR = std::sqrt(c->sc_host->res2);
@@ -330,6 +370,7 @@ void newton_step(vch2d_ctx* c, const double* phi_old, const double* mu_old, cons
     if (phi != c->phi.p) {   // leave the result in c->phi / c->mu
         std::swap(c->phi.p, c->phit.p); std::swap(c->mu.p, c->mut.p);
         std::swap(c->phi.n, c->phit.n); std::swap(c->mu.n, c->mut.n);
+        std::swap(c->phi.view, c->phit.view); std::swap(c->mu.view, c->mut.view);
     }
     if (Rp != c->Rphi.p) {
         std::swap(c->Rphi.p, c->RphiT.p); std::swap(c->Rmu.p, c->RmuT.p); std::swap(c->a.p, c->aT.p);
@@ -339,7 +380,7 @@ void newton_step(vch2d_ctx* c, const double* phi_old, const double* mu_old, cons
 // Post-Newton clip + interior mass correction into `dst` (Forward2_solver.py:562-577).
 void post_step(vch2d_ctx* c, const double* phi_new, double* dst) {
     const double hxhy = c->prm.hx * c->prm.hy;
-    LAUNCH(c, clip_mass_kernel, c->rb(), kRedThreads, phi_new, dst, c->g, c->ph, hxhy, c->sc, 0, c->red_part.p, c->ticket);
+    LAUNCH(c, clip_mass_kernel, c->rb(), kRedThreads, phi_new, dst, c->g, c->ph, hxhy, c->sc, 0, c->red.part, c->ticket);
     LAUNCH(c, mass_shift_kernel, c->eb(), 256, dst, c->g, c->ph, c->prm.Lx * c->prm.Ly, c->sc);
 }
 
@@ -356,9 +397,16 @@ void forward_dev(vch2d_ctx* c, const double* phi0, const double* u, int u_rows, 
     VCH_CUDA(cudaMemsetAsync(c->w0.p, 0, bytes, c->stream));
     c->mu_old.alloc(n);
     double* mu_old = c->mu_old.p;   // mu_0 = initialize_mu(phi_0, w = 0), Forward2_solver.py:520
-    LAUNCH(c, mu_init_kernel, eb, 256, phi_hist, c->w0.p, mu_old, c->g, c->ph);
+    const double* phi_first = phi_hist;
+    if (c->slab) {   // the stencil needs ghost rows: work on a ghosted copy of level 0
+        VCH_CUDA(cudaMemcpyAsync(c->phi.p, phi0, bytes, cudaMemcpyDeviceToDevice, c->stream));
+        halo_push(c, c->phi.p, nullptr, 1);
+        phi_first = c->phi.p;
+    }
+    LAUNCH(c, mu_init_kernel, eb, 256, phi_first, c->w0.p, mu_old, c->g, c->ph);
+    halo_push(c, mu_old, nullptr, 1);
     LAUNCH(c, clip_mass_kernel, c->rb(), kRedThreads, phi_hist, (double*)nullptr, c->g, c->ph, c->prm.hx * c->prm.hy, c->sc, 1,
-           c->red_part.p, c->ticket);
+           c->red.part, c->ticket);
     for (int s = 0; s < n_steps; ++s) {
         const double dt = dt_steps[s];
         if (before_step) before_step(s);     // streaming path: makes sure control rows s and s+1 exist
@@ -368,7 +416,7 @@ void forward_dev(vch2d_ctx* c, const double* phi0, const double* u, int u_rows, 
         const double* phi_old = phi_hist + (size_t)s * n;
         newton_step(c, phi_old, mu_old, c->w0.p, c->w1.p, dt, nullptr, st);
         post_step(c, c->phi.p, phi_hist + (size_t)(s + 1) * n);
-        VCH_CUDA(cudaMemcpyAsync(mu_old, c->mu.p, bytes, cudaMemcpyDeviceToDevice, c->stream));
+        copy_ghosted(c, mu_old, c->mu.p);      // slab mode: the ghost rows of the accepted iterate travel along
         std::swap(c->w0.p, c->w1.p);
         if (mu_hist) VCH_CUDA(cudaMemcpyAsync(mu_hist + (size_t)s * n, mu_old, bytes, cudaMemcpyDeviceToDevice, c->stream));
         if (w_hist) VCH_CUDA(cudaMemcpyAsync(w_hist + (size_t)s * n, c->w0.p, bytes, cudaMemcpyDeviceToDevice, c->stream));
@@ -385,32 +433,49 @@ void adjoint_dev(vch2d_ctx* c, const double* phi_hist, int levels, const double*
     const size_t bytes = n * sizeof(double);
     const int eb = c->eb();
     for (int k = 0; k < 2; ++k) { c->adj_p[k].alloc(n); c->adj_q[k].alloc(n); c->adj_r[k].alloc(n); }
+    // slab mode: p and q feed stencils, so they always live in the ghosted ring and are copied out when asked for
     auto slot = [&](double* out, DevBuf (&ring)[2], int lvl) { return out ? out + (size_t)lvl * n : ring[lvl & 1].p; };
+    double* const p_user = c->slab ? p_out : nullptr; double* const q_user = c->slab ? q_out : nullptr;
+    if (c->slab) { p_out = nullptr; q_out = nullptr; }
+    auto copy_out = [&](int lvl, const double* pv, const double* qv) {
+        if (p_user) VCH_CUDA(cudaMemcpyAsync(p_user + (size_t)lvl * n, pv, bytes, cudaMemcpyDeviceToDevice, c->stream));
+        if (q_user) VCH_CUDA(cudaMemcpyAsync(q_user + (size_t)lvl * n, qv, bytes, cudaMemcpyDeviceToDevice, c->stream));
+    };
     const int M = levels - 1;
     double* pM = slot(p_out, c->adj_p, M); double* qM = slot(q_out, c->adj_q, M); double* rM = slot(r_out, c->adj_r, M);
     if (need_level) need_level(M);
     LAUNCH(c, adj_terminal_rhs_kernel, eb, 256, phi_hist + (size_t)M * n, phiT, c->kb.p, n, b2);
     SymbolArgs sy{1.0, 0.0, nullptr, c->ph.tau, nullptr};
     c->dct.apply(c->stream, c->kb.p, pM, sy, nullptr);          // (I - tau L) p_M = b2 (phi_M - phi_T): exact in the DCT basis
+    halo_push(c, pM, nullptr, 1);
     LAUNCH(c, adj_qr_kernel, eb, 256, pM, (const double*)nullptr, (const double*)nullptr, qM, rM, c->g, 0.0, 0.0);
+    halo_push(c, qM, nullptr, 1);
+    copy_out(M, pM, qM);
     for (int k = M - 1; k >= 0; --k) {
         const double dt = t_hist[k + 1] - t_hist[k];
         double *p0 = slot(p_out, c->adj_p, k), *q0 = slot(q_out, c->adj_q, k), *r0 = slot(r_out, c->adj_r, k);
         const double *p1 = slot(p_out, c->adj_p, k + 1), *q1 = slot(q_out, c->adj_q, k + 1), *r1 = slot(r_out, c->adj_r, k + 1);
         if (dt <= 1e-14) {   // backward2_solver.py:214-216
-            VCH_CUDA(cudaMemcpyAsync(p0, p1, bytes, cudaMemcpyDeviceToDevice, c->stream));
-            VCH_CUDA(cudaMemcpyAsync(q0, q1, bytes, cudaMemcpyDeviceToDevice, c->stream));
+            if (c->slab) { copy_ghosted(c, p0, p1); copy_ghosted(c, q0, q1); }
+            else {
+                VCH_CUDA(cudaMemcpyAsync(p0, p1, bytes, cudaMemcpyDeviceToDevice, c->stream));
+                VCH_CUDA(cudaMemcpyAsync(q0, q1, bytes, cudaMemcpyDeviceToDevice, c->stream));
+            }
             VCH_CUDA(cudaMemcpyAsync(r0, r1, bytes, cudaMemcpyDeviceToDevice, c->stream));
+            copy_out(k, p0, q0);
             continue;
         }
         if (need_level) need_level(k);
         const double* f1 = phi_hist + (size_t)(k + 1) * n; const double* f0 = phi_hist + (size_t)k * n;
         LAUNCH(c, adj_rhs_kernel, c->rb(), kRedThreads, p1, q1, f1, f0, phiQ ? phiQ + (size_t)(k + 1) * n : nullptr,
-               phiQ ? phiQ + (size_t)k * n : nullptr, c->kb.p, c->a.p, c->g, c->ph, dt, b1, c->sc, c->red_part.p, c->ticket);
+               phiQ ? phiQ + (size_t)k * n : nullptr, c->kb.p, c->a.p, c->g, c->ph, dt, b1, c->sc, c->red.part, c->ticket);
         krylov_solve<true>(c, c->kb.p, c->a.p, st);
         VCH_CUDA(cudaMemcpyAsync(p0, c->kx.p, bytes, cudaMemcpyDeviceToDevice, c->stream));
         const double den = c->ph.gamma + 0.5 * dt;
+        halo_push(c, p0, nullptr, 1);
         LAUNCH(c, adj_qr_kernel, eb, 256, p0, q1, r1, q0, r0, c->g, (c->ph.gamma - 0.5 * dt) / den, 0.5 * dt / den);
+        halo_push(c, q0, nullptr, 1);
+        copy_out(k, p0, q0);
     }
     VCH_CUDA(cudaGetLastError());
 }
@@ -424,8 +489,9 @@ std::vector<double> trapz_weights(const double* x, int n) {
 
 void cost_dev(vch2d_ctx* c, const double* phi_hist, const double* u, const double* phiQ, const double* phiT, int levels,
               const double* x, const double* y, const double* t, double b1, double b2, double b3, double ksp, double* J_out) {
-    const int nx1 = c->g.nx1, ny1 = c->g.ny1;
-    std::vector<double> w = trapz_weights(t, levels), wx = trapz_weights(x, nx1), wy = trapz_weights(y, ny1);
+    const int nx1 = c->g.nx1, ny1 = c->g.ny1;   // slab mode: x is the GLOBAL abscissa vector, this rank integrates rows [o0, o0 + nx1)
+    std::vector<double> w = trapz_weights(t, levels), wxg = trapz_weights(x, c->g.nxg), wy = trapz_weights(y, ny1);
+    std::vector<double> wx(wxg.begin() + c->g.o0, wxg.begin() + c->g.o0 + nx1);
     c->small.alloc((size_t)levels + nx1 + ny1);
     double *dwt = c->small.p, *dwx = dwt + levels, *dwy = dwx + nx1;
     VCH_CUDA(cudaMemcpyAsync(dwt, w.data(), levels * sizeof(double), cudaMemcpyHostToDevice, c->stream));
@@ -434,7 +500,7 @@ void cost_dev(vch2d_ctx* c, const double* phi_hist, const double* u, const doubl
     VCH_CUDA(cudaStreamSynchronize(c->stream));   // w/wx/wy are pageable host vectors
     const long long total = (long long)levels * c->g.n;
     LAUNCH(c, cost_kernel, red_blocks(total), kRedThreads, phi_hist, u, phiQ, phiT, levels, nx1, ny1, dwt, dwx, dwy, c->out4,
-           c->red_part.p, c->ticket);
+           c->red.part, c->ticket);
     VCH_CUDA(cudaMemcpyAsync(c->out4_host, c->out4, 4 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     VCH_CUDA(cudaStreamSynchronize(c->stream));
     const double J1 = 0.5 * b1 * c->out4_host[0], J2 = 0.5 * b2 * c->out4_host[1], J3 = 0.5 * b3 * c->out4_host[2],
@@ -444,10 +510,11 @@ void cost_dev(vch2d_ctx* c, const double* phi_hist, const double* u, const doubl
 }
 
 struct SmallScratch {   // context-free reductions (vch_grad_prox / vch_kkt_counts / vch_solve_w)
-    double* part = nullptr; unsigned int* ticket = nullptr; double* out = nullptr; double* out_host = nullptr;
+    RedBuf red; double* part = nullptr; unsigned int* ticket = nullptr; double* out = nullptr; double* out_host = nullptr;
     void ensure() {
         if (part) return;
-        VCH_CUDA(cudaMalloc(&part, 8 * kRedBlocksMax * sizeof(double)));
+        red.alloc(8 * kRedBlocksMax, Comm());
+        part = red.part;
         VCH_CUDA(cudaMalloc(&ticket, sizeof(unsigned int)));
         VCH_CUDA(cudaMemset(ticket, 0, sizeof(unsigned int)));
         VCH_CUDA(cudaMalloc(&out, 8 * sizeof(double)));
@@ -476,12 +543,20 @@ int vch_device_count(void) {
     return n;
 }
 
-int vch2d_create(const vch2d_params* p, int device, vch2d_ctx** out) {
+static int create_ctx(const vch2d_params* p, int device, int rank, int nranks, vch2d_ctx** out) {
     return guarded([&] {
         check_params(p);
         VCH_REQUIRE(out != nullptr, VCH_E_ARG, "null out");
         VCH_REQUIRE(vch_device_count() > device, VCH_E_CUDA, "no CUDA device: vch_b200 has no CPU fallback");
         VCH_CUDA(cudaSetDevice(device));
+        const bool slab = nranks > 1;
+        if (slab) {
+            const int N = p->Nx;
+            VCH_REQUIRE(p->Nx == p->Ny, VCH_E_SHAPE, "slab mode needs a square grid (Nx == Ny)");
+            VCH_REQUIRE((N & (N - 1)) == 0 && N >= 32 && N <= 4096, VCH_E_SHAPE, "slab mode needs N = 2^k, 32 <= N <= 4096");
+            VCH_REQUIRE(nranks == 2 || nranks == 4 || nranks == 8, VCH_E_ARG, "slab mode: 2, 4 or 8 ranks");
+            VCH_REQUIRE(rank >= 0 && rank < nranks && N / nranks >= 8, VCH_E_ARG, "slab mode: bad rank / fewer than 8 rows per rank");
+        }
         auto* c = new vch2d_ctx();
         c->prm = *p; c->device = device;
         c->debug = getenv("VCH_DEBUG") ? atoi(getenv("VCH_DEBUG")) : 0;
@@ -489,15 +564,40 @@ int vch2d_create(const vch2d_params* p, int device, vch2d_ctx** out) {
         if (getenv("VCH_KRYLOV_RTOL")) { const double t = atof(getenv("VCH_KRYLOV_RTOL")); if (t > 0 && t < 1) c->krylov_tol = t; }
         Geo& g = c->g;
         g.ni = p->Nx + 1; g.no = p->Ny + 1; g.nx1 = p->Nx + 1; g.ny1 = p->Ny + 1;
-        g.n = (long long)g.ni * g.no;
+        g.nxg = g.nx1; g.o0 = 0;
         g.ihi2 = 1.0 / (p->hx * p->hx); g.iho2 = 1.0 / (p->hy * p->hy);
+        DctSlab sl;
+        if (slab) {   // rows [o0, o0 + no) of the (N+1) x (N+1) grid; every rank but the last owns N / nranks rows
+            const int N = p->Nx, rw = N / nranks;
+            c->slab = true; c->rows_lo = rw;
+            c->cm.rank = rank; c->cm.nranks = nranks;
+            g.o0 = rank * rw; g.no = rw + (rank == nranks - 1 ? 1 : 0);
+            g.nx1 = g.no; g.nxg = N + 1;
+            g.glo = rank > 0; g.ghi = rank < nranks - 1;
+            sl.nloc = g.no; sl.o0 = g.o0; sl.wloc = g.no; sl.col0 = g.o0;
+            sl.shift = 0; while ((1 << sl.shift) < rw) ++sl.shift;
+            sl.p1 = rw + 2; sl.p2 = (g.ni + 3) & ~3;
+        }
+        g.n = (long long)g.ni * g.no;
         c->ph = Phys{p->tau, p->gamma, p->c1, p->c2, p->kappa, 1.0 - p->delta_sep, std::max(1e-8, 0.5 * p->delta_sep),
                      1.0 - p->delta_sep * p->delta_sep};
         const size_t n = (size_t)g.n;
-        for (DevBuf* b : {&c->phi, &c->mu, &c->phit, &c->mut, &c->w0, &c->w1, &c->cphi, &c->cmu, &c->Rphi, &c->Rmu, &c->a,
-                          &c->RphiT, &c->RmuT, &c->aT, &c->kb, &c->kx, &c->kr, &c->kr0, &c->kp, &c->kv, &c->ks, &c->kt,
-                          &c->ktmp, &c->kq, &c->dmu})
-            b->alloc(n);
+        std::vector<DevBuf*> fields = {&c->phi, &c->mu, &c->phit, &c->mut, &c->w0, &c->w1, &c->cphi, &c->cmu, &c->Rphi, &c->Rmu, &c->a,
+                                       &c->RphiT, &c->RmuT, &c->aT, &c->kb, &c->kx, &c->kr, &c->kr0, &c->kp, &c->kv, &c->ks, &c->kt,
+                                       &c->ktmp, &c->kq, &c->dmu};
+        if (slab) {
+            // identical arena layout on every rank: slots are sized for the largest slab (rows_lo + 1 rows)
+            for (int k = 0; k < 2; ++k) { fields.push_back(&c->adj_p[k]); fields.push_back(&c->adj_q[k]); fields.push_back(&c->adj_r[k]); }
+            fields.push_back(&c->mu_old);
+            const size_t nmax = (size_t)(c->rows_lo + 1) * g.ni, margin = 2 * (size_t)g.ni;
+            const size_t t1 = (size_t)(p->Nx + 1) * sl.p1, t2 = (size_t)(c->rows_lo + 1) * sl.p2;
+            c->arena.create(kArenaHeader + fields.size() * (nmax + 2 * margin + 64) + t1 + t2 + 256);
+            for (DevBuf* b : fields) c->arena.view(*b, nmax, margin);
+            sl.T1 = c->arena.carve(t1, 0); sl.T2 = c->arena.carve(t2, 0);
+            c->cm.peer[rank] = c->arena.base;
+        } else {
+            for (DevBuf* b : fields) b->alloc(n);
+        }
 
         VCH_CUDA(cudaMalloc(&c->ticket, sizeof(unsigned int)));
         VCH_CUDA(cudaMemset(c->ticket, 0, sizeof(unsigned int)));
@@ -506,8 +606,16 @@ int vch2d_create(const vch2d_params* p, int device, vch2d_ctx** out) {
         VCH_CUDA(cudaMallocHost(&c->sc_host, sizeof(Scal)));
         VCH_CUDA(cudaMalloc(&c->out4, 8 * sizeof(double)));
         VCH_CUDA(cudaMallocHost(&c->out4_host, 8 * sizeof(double)));
-        c->dct.init(g.no, g.ni, p->hy, p->hx, &c->log);
-        c->red_part.alloc(8 * (size_t)c->dct.max_grid());
+        if (slab) {
+            VCH_CUDA(cudaMalloc(&c->cm.seq, 2 * sizeof(unsigned long long)));
+            VCH_CUDA(cudaMemset(c->cm.seq, 0, 2 * sizeof(unsigned long long)));
+            c->cm.err = &c->sc->comm_err;
+            sl.cm = c->cm;
+            c->dct.init_slab(p->Nx + 1, p->hy, p->hx, &c->log, sl);
+        } else {
+            c->dct.init(g.no, g.ni, p->hy, p->hx, &c->log);
+        }
+        c->red.alloc(8 * (size_t)c->dct.max_grid(), c->cm);
         Scal init{}; init.tol2 = c->krylov_tol * c->krylov_tol; init.maxit = c->krylov_maxit;
         VCH_CUDA(cudaMemcpy(c->sc, &init, sizeof(Scal), cudaMemcpyHostToDevice));
         VCH_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
@@ -519,6 +627,82 @@ int vch2d_create(const vch2d_params* p, int device, vch2d_ctx** out) {
     });
 }
 
+int vch2d_create(const vch2d_params* p, int device, vch2d_ctx** out) { return create_ctx(p, device, 0, 1, out); }
+
+// ---- slab mode: one rank of a row-slab decomposition (one process per GPU; peers are reached through CUDA IPC)
+int vch2d_slab_create(const vch2d_params* p, int device, int rank, int nranks, vch2d_ctx** out) {
+    if (nranks < 2) { set_last_error("slab mode needs at least 2 ranks (use vch2d_create)"); return VCH_E_ARG; }
+    return create_ctx(p, device, rank, nranks, out);
+}
+
+int vch2d_slab_rows(vch2d_ctx* c, int* row0, int* nrows) {
+    return guarded([&] {
+        VCH_REQUIRE(c && row0 && nrows, VCH_E_ARG, "null argument");
+        *row0 = c->g.o0; *nrows = c->g.no;
+        return VCH_OK;
+    });
+}
+
+int vch2d_slab_ipc_handle(vch2d_ctx* c, void* handle_out) {
+    return guarded([&] {
+        VCH_REQUIRE(c && c->slab && handle_out, VCH_E_ARG, "not a slab context");
+        VCH_CUDA(cudaSetDevice(c->device));
+        cudaIpcMemHandle_t h;
+        VCH_CUDA(cudaIpcGetMemHandle(&h, c->arena.base));
+        static_assert(sizeof(h) == VCH_IPC_HANDLE_BYTES, "IPC handle size");
+        std::memcpy(handle_out, &h, sizeof(h));
+        return VCH_OK;
+    });
+}
+
+int vch2d_slab_attach(vch2d_ctx* c, const void* handles) {
+    return guarded([&] {
+        VCH_REQUIRE(c && c->slab && handles && !c->attached, VCH_E_ARG, "slab_attach: not a slab context / already attached");
+        VCH_CUDA(cudaSetDevice(c->device));
+        for (int r = 0; r < c->cm.nranks; ++r) {
+            if (r == c->cm.rank) continue;
+            cudaIpcMemHandle_t h;
+            std::memcpy(&h, (const char*)handles + (size_t)r * VCH_IPC_HANDLE_BYTES, sizeof(h));
+            void* ptr = nullptr;
+            VCH_CUDA(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
+            c->peer_maps.push_back(ptr);
+            c->cm.peer[r] = (double*)ptr;
+        }
+        c->red.set_comm(c->cm);
+        c->dct.slab.cm = c->cm;
+        c->attached = true;
+        return VCH_OK;
+    });
+}
+
+// Exercises the three cross-rank primitives: barrier, neighbour halo push, reduction (sum / min / max of rank + 1).
+// out (host, 5): sum, min, max, lower ghost value (rank of the neighbour below + 1, or 0), upper ghost value.
+__global__ void slab_selftest_kernel(double* field, int n, double val, double* out3, double* part, unsigned int* ticket) {
+    double v[3] = {0.0, INFINITY, -INFINITY};
+    if (blockIdx.x == 0 && threadIdx.x == 0) { v[0] = val; v[1] = val; v[2] = val; }
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) field[i] = val;
+    const int op[3] = {0, 1, 2};
+    double tot[3];
+    if (grid_reduce<3>(v, op, part, ticket, tot) && threadIdx.x == 0) { out3[0] = tot[0]; out3[1] = tot[1]; out3[2] = tot[2]; }
+}
+int vch2d_slab_selftest(vch2d_ctx* c, double* out5) {
+    return guarded([&] {
+        VCH_REQUIRE(c && c->slab && c->attached && out5, VCH_E_ARG, "slab_selftest: attach first");
+        StreamScope scope(c);
+        const int n = (int)c->g.n, ni = c->g.ni;
+        LAUNCH(c, slab_selftest_kernel, 8, 256, c->ktmp.p, n, (double)(c->cm.rank + 1), c->out4, c->red.part, c->ticket);
+        halo_push(c, c->ktmp.p, nullptr, 2);
+        double ghost[2] = {0.0, 0.0};
+        if (c->g.glo) VCH_CUDA(cudaMemcpyAsync(&ghost[0], c->ktmp.p - 2 * ni, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        if (c->g.ghi) VCH_CUDA(cudaMemcpyAsync(&ghost[1], c->ktmp.p + n + 2 * ni - 1, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        VCH_CUDA(cudaMemcpyAsync(c->out4_host, c->out4, 3 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        fetch_scalars(c);
+        for (int k = 0; k < 3; ++k) out5[k] = c->out4_host[k];
+        out5[3] = ghost[0]; out5[4] = ghost[1];
+        return VCH_OK;
+    });
+}
+
 void vch2d_destroy(vch2d_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
@@ -526,6 +710,9 @@ void vch2d_destroy(vch2d_ctx* c) {
     for (auto& g : c->graphs) { cudaGraphExecDestroy(g.exec); cudaGraphDestroy(g.g); }
     cudaEventDestroy(c->ev_in); cudaEventDestroy(c->ev_out); cudaStreamDestroy(c->stream);
     c->dct.destroy();
+    for (void* m : c->peer_maps) cudaIpcCloseMemHandle(m);
+    if (c->cm.seq) cudaFree(c->cm.seq);
+    c->arena.destroy();
     cudaFree(c->ticket); cudaFree(c->sc); cudaFreeHost(c->sc_host); cudaFree(c->out4); cudaFreeHost(c->out4_host);
     delete c;
 }
@@ -595,6 +782,11 @@ int vch2d_apply_laplacian(vch2d_ctx* c, const double* v, double* out, int mem) {
         StreamScope scope(c);
         Stager st(c->stream, mem);
         const double* dv = st.in(v, c->g.n); double* dout = st.out(out, c->g.n);
+        if (c->slab) {   // ghosted copy + halo rows from the neighbours
+            VCH_CUDA(cudaMemcpyAsync(c->ktmp.p, dv, c->g.n * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+            halo_push(c, c->ktmp.p, nullptr, 1);
+            dv = c->ktmp.p;
+        }
         LAUNCH(c, lap_kernel, c->eb(), 256, dv, dout, c->g, 1.0);
         VCH_CUDA(cudaGetLastError());
         st.finish();
@@ -608,6 +800,11 @@ int vch2d_initialize_mu(vch2d_ctx* c, const double* phi, const double* w, double
         StreamScope scope(c);
         Stager st(c->stream, mem);
         const double *dp = st.in(phi, c->g.n), *dw = st.in(w, c->g.n); double* dm = st.out(mu_out, c->g.n);
+        if (c->slab) {
+            VCH_CUDA(cudaMemcpyAsync(c->ktmp.p, dp, c->g.n * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+            halo_push(c, c->ktmp.p, nullptr, 1);
+            dp = c->ktmp.p;
+        }
         LAUNCH(c, mu_init_kernel, c->eb(), 256, dp, dw, dm, c->g, c->ph);
         VCH_CUDA(cudaGetLastError());
         st.finish();
@@ -637,6 +834,7 @@ int vch2d_residual(vch2d_ctx* c, const double* phi_new, const double* phi_old, c
     return guarded([&] {
         VCH_REQUIRE(c && phi_new && phi_old && mu_new && mu_old && w_new && w_old && Rphi_out && Rmu_out, VCH_E_SHAPE,
                     "residual: null array");
+        VCH_REQUIRE(!c->slab, VCH_E_ARG, "residual: test-level entry, not available in slab mode");
         StreamScope scope(c);
         const long long n = c->g.n;
         Stager st(c->stream, mem);
@@ -659,9 +857,13 @@ int vch2d_jacobian_solve(vch2d_ctx* c, const double* phi, double dt, const doubl
         Stager st(c->stream, mem);
         const double *dp = st.in(phi, n), *rp = st.in(Rphi, n), *rm = st.in(Rmu, n);
         double *o1 = st.out(dphi_out, n), *o2 = st.out(dmu_out, n);
-        LAUNCH(c, jac_diag_kernel, c->rb(), kRedThreads, dp, c->a.p, c->g, c->ph, dt, c->sc, c->red_part.p, c->ticket);
+        LAUNCH(c, jac_diag_kernel, c->rb(), kRedThreads, dp, c->a.p, c->g, c->ph, dt, c->sc, c->red.part, c->ticket);
         vch_stats s{};
         const StatMark mark0 = stat_mark(c);
+        if (c->slab) {   // R_phi feeds a stencil: it has to live in a ghosted work vector
+            VCH_CUDA(cudaMemcpyAsync(c->Rphi.p, rp, n * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+            rp = c->Rphi.p;
+        }
         newton_linear_solve(c, rp, rm, c->a.p, nullptr, dt, &s);
         VCH_CUDA(cudaMemcpyAsync(o1, c->kx.p, n * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
         VCH_CUDA(cudaMemcpyAsync(o2, c->dmu.p, n * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
@@ -870,7 +1072,7 @@ static void pgd_iteration_host_streamed(vch2d_ctx* c, int levels, const double* 
                 const size_t lo = (size_t)j * CH, cnt = std::min<size_t>(CH, levels - lo);
                 VCH_CUDA(cudaStreamWaitEvent(c->stream, ev_uc[j], 0));
                 LAUNCH(c, grad_prox_kernel, red_blocks((long long)(cnt * n)), kRedThreads, du.p + lo * n, dr.p + lo * n, (double*)nullptr,
-                       dun.p + lo * n, (long long)(cnt * n), b3, alpha, ksp, umin, umax, c->out4 + 4, c->red_part.p, c->ticket, 1);
+                       dun.p + lo * n, (long long)(cnt * n), b3, alpha, ksp, umin, umax, c->out4 + 4, c->red.part, c->ticket, 1);
                 VCH_CUDA(cudaEventRecord(ev_prox, c->stream));
                 VCH_CUDA(cudaStreamWaitEvent(cp, ev_prox, 0));
                 VCH_CUDA(cudaMemcpyAsync(u_new_out + lo * n, dun.p + lo * n, cnt * fb, cudaMemcpyDeviceToHost, cp));
@@ -929,7 +1131,7 @@ int vch2d_pgd_iteration(vch2d_ctx* c, int levels, const double* t_hist, const do
         adjoint_dev(c, dh, levels, t_hist, b1, b2, dq, dT, nullptr, nullptr, dr, s);
         // (2) gradient + soft-threshold prox + box, with the driver's norms  GD2_configured.py:304-305, :375
         LAUNCH(c, grad_prox_kernel, red_blocks((long long)tot), kRedThreads, du, dr, (double*)nullptr, dun, (long long)tot, b3,
-               alpha, ksp, umin, umax, c->out4 + 4, c->red_part.p, c->ticket);
+               alpha, ksp, umin, umax, c->out4 + 4, c->red.part, c->ticket);
         // (3) forward solve under the new control                            GD2_configured.py:309
         forward_dev(c, dh, dun, levels, levels - 1, dt_steps, dhn, nullptr, nullptr, s);
         // (4) cost functional                                                GD2_configured.py:312

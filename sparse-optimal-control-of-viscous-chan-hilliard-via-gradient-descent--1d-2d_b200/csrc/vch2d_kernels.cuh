@@ -10,10 +10,13 @@
 namespace vch {
 
 struct Geo {
-    int no, ni;          // Laplacian view
-    int nx1, ny1;        // array view (Nx+1, Ny+1) used by the trapezoid weights
+    int no, ni;          // Laplacian view (slab mode: no = rows owned by this rank)
+    int nx1, ny1;        // array view (Nx+1, Ny+1) used by the trapezoid weights (slab mode: nx1 = owned rows)
     long long n;
     double iho2, ihi2;   // 1/h_outer^2, 1/h_inner^2
+    // slab mode (square grids, rows [o0, o0+no) of nxg): ghost rows below (glo) / above (ghi) the owned rows hold the
+    // neighbour rank's boundary rows, so the outer-axis mirror rule applies only at the global boundary
+    int glo = 0, ghi = 0, o0 = 0, nxg = 0;
 };
 
 struct Phys {
@@ -21,12 +24,19 @@ struct Phys {
 };
 
 __device__ __forceinline__ double lap_g(const double* __restrict__ v, int o, int i, const Geo& g) {
-    const double c = v[(size_t)o * g.ni + i];
+    const double c = v[(long long)o * g.ni + i];
     const int im = (i > 0) ? i - 1 : 1, ip = (i < g.ni - 1) ? i + 1 : g.ni - 2;
-    const int om = (o > 0) ? o - 1 : 1, op = (o < g.no - 1) ? o + 1 : g.no - 2;
-    const double a = (v[(size_t)o * g.ni + ip] - c) + (v[(size_t)o * g.ni + im] - c);
-    const double b = (v[(size_t)op * g.ni + i] - c) + (v[(size_t)om * g.ni + i] - c);
+    const int om = (o > 0 || g.glo) ? o - 1 : 1, op = (o < g.no - 1 || g.ghi) ? o + 1 : g.no - 2;
+    const double a = (v[(long long)o * g.ni + ip] - c) + (v[(long long)o * g.ni + im] - c);
+    const double b = (v[(long long)op * g.ni + i] - c) + (v[(long long)om * g.ni + i] - c);
     return a * g.ihi2 + b * g.iho2;
+}
+
+// Outer-axis reflection that leaves ghost rows (slab mode) alone.
+__device__ __forceinline__ int mirror_o(int o, const Geo& g) {
+    if (o < 0 && !g.glo) o = -o;
+    if (o >= g.no && !g.ghi) o = 2 * (g.no - 1) - o;
+    return o;
 }
 
 __device__ __forceinline__ double flory_log(double phi, double eps) {
@@ -161,7 +171,7 @@ __global__ void __launch_bounds__(256) op_apply_kernel(const double* __restrict_
         const int ro = o0 - 2 + to, ri = i0 - 2 + ti;
         double val = 0.0;
         if (ro >= -2 && ro <= g.no + 1 && ri >= -2 && ri <= g.ni + 1)
-            val = x[(size_t)mirror(ro, g.no) * g.ni + mirror(ri, g.ni)];
+            val = x[(long long)mirror_o(ro, g) * g.ni + mirror(ri, g.ni)];
         sx[to][ti] = val;
     }
     __syncthreads();
@@ -174,7 +184,7 @@ __global__ void __launch_bounds__(256) op_apply_kernel(const double* __restrict_
         if (ADJ) z = lx;
         else {
             double av = 0.0;
-            if (ro >= -1 && ro <= g.no && ri >= -1 && ri <= g.ni) av = a[(size_t)mirror(ro, g.no) * g.ni + mirror(ri, g.ni)];
+            if (ro >= -1 && ro <= g.no && ri >= -1 && ri <= g.ni) av = a[(long long)mirror_o(ro, g) * g.ni + mirror(ri, g.ni)];
             z = av * c - c2 * lx;
         }
         sz[to][ti] = z;
@@ -333,7 +343,8 @@ __global__ void clip_mass_kernel(const double* __restrict__ phin, double* __rest
     const double thr = p.lim - 5e-3;
     for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < g.n; idx += (long long)gridDim.x * blockDim.x) {
         const int ix = (int)(idx / g.ny1), iy = (int)(idx - (long long)ix * g.ny1);
-        const double w = hxhy * ((ix == 0 || ix == g.nx1 - 1) ? 0.5 : 1.0) * ((iy == 0 || iy == g.ny1 - 1) ? 0.5 : 1.0);
+        const int ixg = ix + g.o0;
+        const double w = hxhy * ((ixg == 0 || ixg == g.nxg - 1) ? 0.5 : 1.0) * ((iy == 0 || iy == g.ny1 - 1) ? 0.5 : 1.0);
         double f = phin[idx];
         if (!set_mass0) { f = fmin(fmax(f, -p.lim), p.lim); phic[idx] = f; }
         v[0] += w * f;

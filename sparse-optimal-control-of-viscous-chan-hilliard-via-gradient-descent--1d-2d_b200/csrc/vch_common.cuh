@@ -41,13 +41,14 @@ static inline int guarded(F&& f) {
 struct DevBuf {
     double* p = nullptr;
     size_t n = 0;
+    bool view = false;          // carved out of an Arena (slab mode): not owned
     void alloc(size_t count) {
         if (count <= n && p) return;
         release();
         VCH_CUDA(cudaMalloc(&p, count * sizeof(double)));
         n = count;
     }
-    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+    void release() { if (p && !view) cudaFree(p); p = nullptr; n = 0; view = false; }
     ~DevBuf() { release(); }
     DevBuf() = default;
     DevBuf(const DevBuf&) = delete;
@@ -136,7 +137,89 @@ struct Scal {
     int done, iters, nonfinite, maxit;
     long long iters_total, solves, stalls;   // accumulated on the device (graph-driven solves are never polled)
     long long g_launches;                    // kernels that ran inside solve graphs (not seen by the host launch log)
-    int iters_max, pad;
+    int iters_max, comm_err;                 // comm_err: a bounded cross-rank wait expired (slab mode)
+};
+
+
+// ---------------------------------------------------------------- slab mode: peer-memory communication (one process per GPU)
+// Every rank owns one cudaMalloc'd ARENA with an identical layout; ranks exchange CUDA-IPC handles once and from then
+// on address each other's arena directly over NVLink (peer[r] + the same offset).  Three primitives, all device-side:
+//   * xrank_reduce  - inside grid_reduce: the last block of a reduction kernel writes its totals into every peer's slot,
+//                     waits for the peers' totals and combines them in rank order (deterministic, no extra launch);
+//   * xbar_kernel   - one-CTA barrier across ranks (monotone sequence flags in peer memory);
+//   * halo_push_kernel - writes this rank's boundary rows into the neighbours' ghost rows.
+// Waits are bounded (kSpinLimitNs): a timeout raises *err and lets the kernel finish, so a rank that lost its peers
+// fails loudly instead of hanging the GPU.
+constexpr int kMaxRanks = 8;
+constexpr int kRedK = 8;                                   // values per cross-rank reduction (max K of grid_reduce)
+constexpr size_t kSlotOff = 0;                             // [2 parities][kMaxRanks][kRedK + 1 (tag)] doubles
+constexpr size_t kFlagOff = 2 * kMaxRanks * (kRedK + 1);   // [kMaxRanks] barrier flags (unsigned long long)
+constexpr size_t kArenaHeader = 256;                       // doubles reserved at the start of every arena
+constexpr unsigned long long kSpinLimitNs = 10ull * 1000ull * 1000ull * 1000ull;
+
+struct Comm {
+    int rank = 0, nranks = 1;
+    double* peer[kMaxRanks] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    unsigned long long* seq = nullptr;   // local device counters: [0] reductions, [1] barriers
+    int* err = nullptr;                  // local device flag: a bounded wait expired
+};
+constexpr size_t kCommHeaderBytes = 256;   // the partials buffer of grid_reduce is preceded by a Comm (see comm_of)
+static_assert(sizeof(Comm) <= kCommHeaderBytes, "Comm must fit the header of the partials buffer");
+
+__device__ __forceinline__ const Comm* comm_of(const double* part) {
+    return reinterpret_cast<const Comm*>(reinterpret_cast<const char*>(part) - kCommHeaderBytes);
+}
+__device__ __forceinline__ unsigned long long global_ns() {
+    unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t;
+}
+// Spins until *flag >= want (monotone flags) or the limit expires.  Returns false on timeout.
+__device__ __forceinline__ bool spin_until(volatile unsigned long long* flag, unsigned long long want, int* err, bool exact) {
+    if (err && *reinterpret_cast<volatile int*>(err)) return false;   // an earlier wait already failed: do not wait again
+    const unsigned long long t0 = global_ns();
+    unsigned int polls = 0;
+    while (true) {
+        const unsigned long long v = *flag;
+        if (exact ? (v == want) : (v >= want)) return true;
+        if ((++polls & 1023u) == 0u && global_ns() - t0 > kSpinLimitNs) { if (err) *err = 1; return false; }
+    }
+}
+
+// Partials buffer with its Comm header (device memory).  `part` is what kernels receive.
+struct RedBuf {
+    char* base = nullptr;
+    double* part = nullptr;
+    void alloc(size_t doubles, const Comm& cm) {
+        release();
+        VCH_CUDA(cudaMalloc(&base, kCommHeaderBytes + doubles * sizeof(double)));
+        part = reinterpret_cast<double*>(base + kCommHeaderBytes);
+        set_comm(cm);
+    }
+    void set_comm(const Comm& cm) { VCH_CUDA(cudaMemcpy(base, &cm, sizeof(Comm), cudaMemcpyHostToDevice)); }
+    void release() { if (base) cudaFree(base); base = nullptr; part = nullptr; }
+    ~RedBuf() { release(); }
+    RedBuf() = default;
+    RedBuf(const RedBuf&) = delete;
+    RedBuf& operator=(const RedBuf&) = delete;
+};
+
+// One cudaMalloc per rank, carved identically on every rank (sizes must not depend on the rank).
+struct Arena {
+    double* base = nullptr;
+    size_t cap = 0, used = 0;    // doubles
+    void create(size_t doubles) {
+        VCH_CUDA(cudaMalloc(&base, doubles * sizeof(double)));
+        VCH_CUDA(cudaMemset(base, 0, doubles * sizeof(double)));
+        cap = doubles; used = kArenaHeader;
+    }
+    // `margin` doubles of ghost storage on both sides of the returned pointer
+    double* carve(size_t count, size_t margin) {
+        size_t start = (used + margin + 31) & ~size_t(31);          // 256-byte aligned payload
+        if (start + count + margin > cap) throw Error(VCH_E_ARG, "slab arena exhausted");
+        used = start + count + margin;
+        return base + start;
+    }
+    void view(DevBuf& b, size_t count, size_t margin) { b.release(); b.p = carve(count, margin); b.n = count; b.view = true; }
+    void destroy() { if (base) cudaFree(base); base = nullptr; cap = used = 0; }
 };
 
 // ---------------------------------------------------------------- launch geometry
@@ -180,6 +263,38 @@ template <int OP> __device__ __forceinline__ double block_red(double v, double* 
     return v;   // valid in warp 0 (all lanes)
 }
 
+// Cross-rank stage of a grid reduction (thread 0 of the last block).  Slots are double-buffered by sequence parity: a
+// rank cannot be two reductions ahead of a peer, because finishing reduction s+1 needs that peer's s+1 contribution.
+template <int K>
+__device__ __forceinline__ void xrank_reduce(double (&tot)[K], const int (&op)[K], const Comm& cm) {
+    static_assert(K <= kRedK, "too many values for a cross-rank reduction");
+    const unsigned long long s = ++cm.seq[0];
+    const size_t mine = kSlotOff + ((size_t)(s & 1ull) * kMaxRanks + cm.rank) * (kRedK + 1);
+    for (int r = 0; r < cm.nranks; ++r) {
+        volatile double* slot = cm.peer[r] + mine;
+#pragma unroll
+        for (int k = 0; k < K; ++k) slot[k] = tot[k];
+    }
+    __threadfence_system();
+    for (int r = 0; r < cm.nranks; ++r)
+        *reinterpret_cast<volatile unsigned long long*>(cm.peer[r] + mine + kRedK) = s;
+    double acc[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) acc[k] = (op[k] == 0) ? 0.0 : (op[k] == 1 ? INFINITY : -INFINITY);
+    for (int r = 0; r < cm.nranks; ++r) {
+        volatile double* slot = cm.peer[cm.rank] + kSlotOff + ((size_t)(s & 1ull) * kMaxRanks + r) * (kRedK + 1);
+        if (!spin_until(reinterpret_cast<volatile unsigned long long*>(slot + kRedK), s, cm.err, true)) break;
+        __threadfence_system();
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            const double x = slot[k];
+            acc[k] = (op[k] == 0) ? acc[k] + x : (op[k] == 1 ? fmin(acc[k], x) : fmax(acc[k], x));
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < K; ++k) tot[k] = acc[k];
+}
+
 // Returns true (block-uniform) in the last block; there tot[k] holds the grid-wide result (valid in thread 0).
 template <int K>
 __device__ __forceinline__ bool grid_reduce(double (&v)[K], const int (&op)[K], double* part, unsigned int* ticket,
@@ -208,7 +323,11 @@ __device__ __forceinline__ bool grid_reduce(double (&v)[K], const int (&op)[K], 
         }
         tot[k] = (op[k] == 0) ? block_red<0>(a, sh) : (op[k] == 1) ? block_red<1>(a, sh) : block_red<2>(a, sh);
     }
-    if (threadIdx.x == 0) *ticket = 0u;   // re-arm for the next launch on this stream
+    if (threadIdx.x == 0) {
+        *ticket = 0u;   // re-arm for the next launch on this stream
+        const Comm* cm = comm_of(part);
+        if (cm->nranks > 1) xrank_reduce<K>(tot, op, *cm);
+    }
     return true;
 }
 
@@ -217,6 +336,43 @@ __device__ __forceinline__ int mirror(int i, int n) {
     if (i < 0) i = -i;
     if (i >= n) i = 2 * (n - 1) - i;
     return i;
+}
+
+
+// One-CTA barrier across ranks: every rank announces its arrival in all peers' flag arrays and waits for everyone.
+// Stream order makes everything this rank enqueued before the barrier (including its peer writes) complete first.
+static __global__ void xbar_kernel(Comm cm, const int* __restrict__ done) {
+    if (done && *done) return;
+    __shared__ unsigned long long s;
+    if (threadIdx.x == 0) s = ++cm.seq[1];
+    __syncthreads();
+    const int r = threadIdx.x;
+    if (r < cm.nranks) {
+        __threadfence_system();
+        *reinterpret_cast<volatile unsigned long long*>(cm.peer[r] + kFlagOff + cm.rank) = s;
+        spin_until(reinterpret_cast<volatile unsigned long long*>(cm.peer[cm.rank] + kFlagOff + r), s, cm.err, false);
+    }
+    __syncthreads();
+    __threadfence_system();
+}
+
+// Writes the first / last `rows` owned rows of up to two fields into the neighbours' ghost rows (fields live at the same
+// arena offset on every rank; ranks below the last own `rows_lo` rows each).  Bracketed by xbar_kernel on both sides.
+static __global__ void halo_push_kernel(Comm cm, const double* f0, const double* f1, int rows, int nloc, int rows_lo, int ni,
+                                 const int* __restrict__ done) {
+    if (done && *done) return;
+    const long long cnt = (long long)rows * ni;
+    for (int w = 0; w < 2; ++w) {
+        const double* f = w ? f1 : f0;
+        if (!f) continue;
+        const size_t off = (size_t)(f - cm.peer[cm.rank]);
+        for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < cnt; e += (long long)gridDim.x * blockDim.x) {
+            if (cm.rank > 0)               // my first rows -> upper ghost rows of the rank below
+                cm.peer[cm.rank - 1][off + (size_t)rows_lo * ni + e] = f[e];
+            if (cm.rank < cm.nranks - 1)   // my last rows -> lower ghost rows [-rows, 0) of the rank above
+                *(cm.peer[cm.rank + 1] + (long long)off - cnt + e) = f[(long long)(nloc - rows) * ni + e];
+        }
+    }
 }
 
 }  // namespace vch

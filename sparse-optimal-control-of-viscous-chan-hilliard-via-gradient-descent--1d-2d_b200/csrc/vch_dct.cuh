@@ -62,12 +62,35 @@ struct RowPrologue {
     const Scal* sc = nullptr;
 };
 
+// Slab mode: the transposes between the row and the column transforms are done by the kernels' own stores, straight
+// into the peers' buffers over NVLink (no all-to-all pass).
+//   mode 1 (row kernel):    element kk of local line l  -> peer r = min(kk >> shift, nr-1):  T1[(base + l) * pitch + kk - (r << shift)]
+//   mode 2 (column kernel): element kk of local line pair l -> peer r = min(kk >> shift, nr-1):  T2[(kk - (r << shift)) * pitch + base + l]
+struct Scatter {
+    int mode = 0, shift = 0, nr = 1, base = 0, pitch = 0;
+    size_t off = 0;                       // arena offset (doubles) of the destination buffer, identical on every rank
+    double* peer[kMaxRanks] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+};
+
+struct DctSlab {
+    bool on = false;
+    Comm cm;
+    int nloc = 0, o0 = 0;        // owned rows [o0, o0 + nloc)
+    int wloc = 0, col0 = 0;      // owned columns of the transposed layout [col0, col0 + wloc)
+    int shift = 0;               // log2(N / nranks): rows per rank = columns per rank (the last rank has one more)
+    int p1 = 0, p2 = 0;          // pitches of T1 (global rows x owned columns) and T2 (owned rows x all columns)
+    double *T1 = nullptr, *T2 = nullptr;
+};
+
 struct DctPlan {
     DctAxis inner, outer;     // inner = contiguous axis (length ni), outer = strided axis (length no)
     int ni = 0, no = 0, pitch = 0;   // pitch of tmp1 (even, so column pairs are 16-byte aligned)
     DevBuf tmp1, tmp2;
     LaunchLog* log = nullptr;
+    DctSlab slab;             // slab mode: no = global rows; the plan transforms the owned rows / columns only
     void init(int no_, int ni_, double h_outer, double h_inner, LaunchLog* launch_log);
+    void init_slab(int n_global, double h_outer, double h_inner, LaunchLog* launch_log, const DctSlab& sl);
+    void barrier(cudaStream_t s, const int* done);
     void destroy();
     int max_grid() const;
     // out = P^-1 in   (in may equal out); epi = optional fused dots on `out`
@@ -226,7 +249,8 @@ template <int LOG2L, bool SOLVE, int MAXT>
 __global__ void __launch_bounds__(MAXT, VCH_FFT_MINB)
 dct_fft_kernel(const double* in, double* out, int nlines, int n, int in_ls, int in_es, int out_ls, int out_es, int ppb,
                const double2* __restrict__ twg, const double* __restrict__ lam_line, const double* __restrict__ lam_elem,
-               SymbolArgs sy, double norm, int scale_mode, RowPrologue pro, DotEpilogue epi, const int* __restrict__ done) {
+               SymbolArgs sy, double norm, int scale_mode, RowPrologue pro, DotEpilogue epi, const int* __restrict__ done,
+               Scatter sct) {
     using G = FftGeom<LOG2L>;
     constexpr int Lf = G::Lf, tpf = G::tpf, ld = G::ld;
     if (done && *done) return;
@@ -313,7 +337,17 @@ dct_fft_kernel(const double* in, double* out, int nlines, int n, int in_ls, int 
         const int kk = t + FftOut<LOG2L>::off(q);
         if (kk <= N) {
             const int off = kk * out_es;
-            if (SOLVE) {
+            if (sct.mode) {   // slab mode: transposing store into the owning peer's buffer
+                int r = kk >> sct.shift; if (r >= sct.nr) r = sct.nr - 1;
+                const int kl = kk - (r << sct.shift);
+                double* dst = sct.peer[r] + sct.off;
+                if (SOLVE) {
+                    if (va) *reinterpret_cast<double2*>(dst + (size_t)kl * sct.pitch + sct.base + la) = make_double2(z[q].x, vb ? z[q].y : 0.0);
+                } else {
+                    if (va) dst[(size_t)(sct.base + la) * sct.pitch + kl] = z[q].x;
+                    if (vb) dst[(size_t)(sct.base + lb) * sct.pitch + kl] = z[q].y;
+                }
+            } else if (SOLVE) {
                 if (va) *reinterpret_cast<double2*>(qa + off) = make_double2(z[q].x, vb ? z[q].y : 0.0);
             } else {
                 if (va) {
@@ -500,6 +534,19 @@ inline void DctPlan::init(int no_, int ni_, double h_outer, double h_inner, Laun
 #undef VCH_FFT_ATTR
 }
 
+// Slab mode: square global grid n_global x n_global (N = n_global - 1 a power of two), T1/T2 carved from the arena by the caller.
+inline void DctPlan::init_slab(int n_global, double h_outer, double h_inner, LaunchLog* launch_log, const DctSlab& sl) {
+    init(n_global, n_global, h_outer, h_inner, launch_log);
+    if (!(inner.fft && outer.fft)) throw Error(VCH_E_SHAPE, "slab mode needs N = 2^k, 32 <= N <= 4096");
+    tmp1.release(); tmp2.release();
+    slab = sl; slab.on = true;
+}
+inline void DctPlan::barrier(cudaStream_t s, const int* done) {
+    log->begin("xbar", s);
+    xbar_kernel<<<1, 32, 0, s>>>(slab.cm, done);
+    log->end(s);
+}
+
 inline int DctPlan::max_grid() const {
     int g = kRedBlocksMax;
     if (inner.fft) { const int ppb = dct_rows_ppb(inner, no); g = std::max(g, ((no + 1) / 2 + ppb - 1) / ppb); }
@@ -519,14 +566,14 @@ inline void DctPlan::apply(cudaStream_t s, const double* in, double* out, const 
     double* t2 = tmp2.p;
     auto fft_launch = [&](bool solve, const DctAxis& ax, int grid, int threads, size_t smem, const double* a, double* b, int nl,
                           int nn, int ils, int ies, int ols, int oes, const double* ll, const double* le, const SymbolArgs& sy,
-                          double nrm, int smode, const RowPrologue& pr, const DotEpilogue& ep) {
+                          double nrm, int smode, const RowPrologue& pr, const DotEpilogue& ep, const Scatter& sc8 = Scatter()) {
         const int ppb_ = threads / (ax.Lf >> 3);
 #define VCH_FFT_CASE(LG)                                                                                                      \
         case LG:                                                                                                              \
             if (solve) dct_fft_kernel<LG, true, ((1 << LG) / 8 <= 512 ? 512 : 1024)><<<grid, threads, smem, s>>>(              \
-                a, b, nl, nn, ils, ies, ols, oes, ppb_, ax.tw, ll, le, sy, nrm, smode, pr, ep, done);                          \
+                a, b, nl, nn, ils, ies, ols, oes, ppb_, ax.tw, ll, le, sy, nrm, smode, pr, ep, done, sc8);                     \
             else dct_fft_kernel<LG, false, ((1 << LG) / 8 <= 512 ? 512 : 1024)><<<grid, threads, smem, s>>>(                   \
-                a, b, nl, nn, ils, ies, ols, oes, ppb_, ax.tw, ll, le, sy, nrm, smode, pr, ep, done);                          \
+                a, b, nl, nn, ils, ies, ols, oes, ppb_, ax.tw, ll, le, sy, nrm, smode, pr, ep, done, sc8);                     \
             break;
         switch (ax.log2L) {
             VCH_FFT_CASE(6) VCH_FFT_CASE(7) VCH_FFT_CASE(8) VCH_FFT_CASE(9) VCH_FFT_CASE(10) VCH_FFT_CASE(11) VCH_FFT_CASE(12)
@@ -535,6 +582,33 @@ inline void DctPlan::apply(cudaStream_t s, const double* in, double* out, const 
         }
 #undef VCH_FFT_CASE
     };
+    if (slab.on) {
+        // rows of the owned slab, stored transposed into every peer's T1 | barrier | fused solve on the owned columns
+        // (all global rows), stored back into every peer's T2 | barrier | inverse rows from T2.  The leading barrier keeps
+        // a fast rank from overwriting T1/T2 of a peer that is still reading them from the previous application.
+        const DctSlab& sl = slab;
+        const int rp = dct_rows_ppb(inner, sl.nloc), rt = rp * (inner.Lf >> 3), rg = ((sl.nloc + 1) / 2 + rp - 1) / rp;
+        const int cp = dct_cols_ppb(outer, sl.wloc), ct = cp * (outer.Lf >> 3), cg = ((sl.wloc + 1) / 2 + cp - 1) / cp;
+        Scatter s1; s1.mode = 1; s1.shift = sl.shift; s1.nr = sl.cm.nranks; s1.base = sl.o0; s1.pitch = sl.p1;
+        s1.off = (size_t)(sl.T1 - sl.cm.peer[sl.cm.rank]);
+        Scatter s2; s2.mode = 2; s2.shift = sl.shift; s2.nr = sl.cm.nranks; s2.base = sl.col0; s2.pitch = sl.p2;
+        s2.off = (size_t)(sl.T2 - sl.cm.peer[sl.cm.rank]);
+        for (int r = 0; r < sl.cm.nranks; ++r) { s1.peer[r] = sl.cm.peer[r]; s2.peer[r] = sl.cm.peer[r]; }
+        barrier(s, done);
+        log->begin(pro.mode ? "dct_rows_fft_pro" : "dct_rows_fft", s);
+        fft_launch(false, inner, rg, rt, dct_smem(inner, rp), in, sl.T1, sl.nloc, ni, ni, 1, sl.p1, 1, nullptr, nullptr, nosym, 1.0, 0, pro, DotEpilogue(), s1);
+        log->end(s);
+        barrier(s, done);
+        log->begin("dct_cols_fft_solve", s);
+        fft_launch(true, outer, cg, ct, dct_smem(outer, cp), sl.T1, sl.T1, sl.wloc, no, 1, sl.p1, 1, sl.p1, inner.lam + sl.col0, outer.lam, sym, norm, scale_mode, RowPrologue(), DotEpilogue(), s2);
+        log->end(s);
+        barrier(s, done);
+        log->begin(epi.mode == 1 ? "dct_rows_fft_epi1" : (epi.mode == 2 ? "dct_rows_fft_epi2" : "dct_rows_fft"), s);
+        fft_launch(false, inner, rg, rt, dct_smem(inner, rp), sl.T2, out, sl.nloc, ni, sl.p2, 1, ni, 1, nullptr, nullptr, nosym, 1.0, 0, RowPrologue(), epi);
+        log->end(s);
+        VCH_CUDA(cudaGetLastError());
+        return;
+    }
     const int rppb = inner.fft ? dct_rows_ppb(inner, no) : 0, rthreads = inner.fft ? rppb * (inner.Lf >> 3) : 0;
     const int rgrid = inner.fft ? ((no + 1) / 2 + rppb - 1) / rppb : 0;
     const int cppb = outer.fft ? dct_cols_ppb(outer, ni) : 0, cthreads = outer.fft ? cppb * (outer.Lf >> 3) : 0;

@@ -51,6 +51,7 @@ EXPORTS = [
     "vch2d_apply_laplacian", "vch2d_initialize_mu", "vch_solve_w", "vch2d_residual", "vch2d_jacobian_solve",
     "vch2d_newton", "vch2d_forward", "vch2d_adjoint", "vch2d_cost", "vch_grad_prox", "vch_kkt_counts",
     "vch2d_pgd_iteration",
+    "vch2d_slab_create", "vch2d_slab_rows", "vch2d_slab_ipc_handle", "vch2d_slab_attach", "vch2d_slab_selftest",
     "vch1d_create", "vch1d_destroy", "vch1d_set_stream", "vch1d_launch_count", "vch1d_residual", "vch1d_initialize_mu", "vch1d_newton",
     "vch1d_forward", "vch1d_adjoint", "vch1d_cost", "vch1d_grad_prox",
 ]
@@ -354,6 +355,58 @@ class Ctx2D:
                                          _mem_of(u, phi_hist, phiQ, phiT)))
         self.last_stats = st.as_dict()
         return u_out, phi_out, J, red, self.last_stats
+
+
+class SlabCtx2D(Ctx2D):
+    """One rank of a row-slab decomposition of ONE square 2D problem over 2/4/8 GPUs (include/vch_b200.h, "slab mode").
+
+    Every array handed to the inherited methods is this rank's slab: (rows, N+1) fields, (levels, rows, N+1)
+    trajectories, rows = self.shape[0] starting at global row self.row0; `x` (cost / pgd_iteration) stays the global
+    abscissa vector.  All ranks must make the same calls in the same order."""
+
+    def __init__(self, N, h, L, tau, gamma, c1, c2, kappa, delta_sep, rank, nranks, device=0):
+        require_device()
+        self.p = Params2D(int(N), int(N), float(h), float(h), float(L), float(L), float(tau), float(gamma),
+                          float(c1), float(c2), float(kappa), float(delta_sep))
+        self.h = C.c_void_p()
+        self.rank, self.nranks = int(rank), int(nranks)
+        _check(lib().vch2d_slab_create(C.byref(self.p), int(device), self.rank, self.nranks, C.byref(self.h)))
+        r0, nr = C.c_int(0), C.c_int(0)
+        _check(lib().vch2d_slab_rows(self.h, C.byref(r0), C.byref(nr)))
+        self.row0, self.rows = r0.value, nr.value
+        self.shape = (self.rows, int(N) + 1)
+        self.last_stats = {}
+
+    def ipc_handle(self) -> bytes:
+        buf = C.create_string_buffer(64)
+        _check(lib().vch2d_slab_ipc_handle(self.h, buf))
+        return buf.raw
+
+    def attach(self, handles):
+        blob = b"".join(handles)
+        assert len(blob) == 64 * self.nranks
+        _check(lib().vch2d_slab_attach(self.h, C.c_char_p(blob)))
+
+    def selftest(self):
+        out = np.zeros(5)
+        self._stream()
+        _check(lib().vch2d_slab_selftest(self.h, out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    @classmethod
+    def create_distributed(cls, N, h, L, tau, gamma, c1, c2, kappa, delta_sep=1e-2, group=None, device=None):
+        """Collective over a torch.distributed group (any backend): creates the rank's context and wires the peers."""
+        import torch
+        import torch.distributed as dist
+        rank, nranks = dist.get_rank(group), dist.get_world_size(group)
+        if device is None:
+            device = torch.cuda.current_device()
+        c = cls(N, h, L, tau, gamma, c1, c2, kappa, delta_sep, rank, nranks, device)
+        handles = [None] * nranks
+        dist.all_gather_object(handles, c.ipc_handle(), group=group)
+        c.attach(handles)
+        dist.barrier(group)
+        return c
 
 
 # ------------------------------------------------------------------------------------------------ 1D context
