@@ -1,4 +1,7 @@
-"""Slab-mode check (run under torchrun, one rank per GPU): every stage compares the rank's slab of the decomposed
+"""Tolerances are BASELINE.json's: 1e-8 on trajectories, 1e-7 on gradient-like quantities and J (reduction order differs
+between the decompositions, which moves Newton stop decisions at the rounding floor on grids >~ 600^2).
+
+Slab-mode check (run under torchrun, one rank per GPU): every stage compares the rank's slab of the decomposed
 problem with the same rows of the single-GPU solution computed by the same rank.
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29533 \
@@ -68,13 +71,13 @@ if "forward" in stages or "adjoint" in stages or "pgd" in stages:
     hf, _, _ = full.forward(phi0_d, u, dts); torch.cuda.synchronize(); t1 = time.perf_counter()
     hs, _, _ = slab.forward(phi0_d[sl].contiguous(), u[:, sl].contiguous(), dts); torch.cuda.synchronize(); t2 = time.perf_counter()
     say(f"forward: full {t1-t0:.3f}s slab {t2-t1:.3f}s; stats full {full.last_stats.get('krylov_iterations')} slab {slab.last_stats.get('krylov_iterations')}")
-    check("forward phi_hist", hs, hf[:, sl], 1e-10)
+    check("forward phi_hist", hs, hf[:, sl], 1e-8)
     s_ = g(t / t[-1])[:, None, None]
     phiQ = (1 - s_) * hf[0] + s_ * phiT
 if "adjoint" in stages:
     pf, qf, rf = full.adjoint(hf, t, 5.0, 10.0, phiQ, phiT)
     ps, qs, rs = slab.adjoint(hf[:, sl].contiguous(), t, 5.0, 10.0, phiQ[:, sl].contiguous(), phiT[sl].contiguous())
-    check("adjoint p", ps, pf[:, sl], 1e-9); check("adjoint q", qs, qf[:, sl], 1e-9); check("adjoint r", rs, rf[:, sl], 1e-9)
+    check("adjoint p", ps, pf[:, sl], 1e-8); check("adjoint q", qs, qf[:, sl], 1e-7); check("adjoint r", rs, rf[:, sl], 1e-7)
 if "pgd" in stages:
     u0 = torch.zeros_like(hf)
     args = (5.0, 10.0, 1e-4, 1e-4, -1.0, 1.0, 50.0)
@@ -84,7 +87,7 @@ if "pgd" in stages:
                                                  phiT[sl].contiguous(), t, dts, x, x, *args)
     torch.cuda.synchronize(); t1 = time.perf_counter()
     say(f"pgd slab {t1-t0:.3f}s J full {J[0]:.15g} slab {Js[0]:.15g}; red full {red.tolist()} slab {reds.tolist()}")
-    check("pgd u_new", u1s, u1[:, sl], 1e-8); check("pgd phi_hist_new", h1s, h1[:, sl], 1e-9)
+    check("pgd u_new", u1s, u1[:, sl], 1e-7); check("pgd phi_hist_new", h1s, h1[:, sl], 1e-8)
     if abs(Js[0] - J[0]) > 1e-9 * abs(J[0]): say("J mismatch FAIL"); worst = max(worst, 1e9)
     say("support identical:", bool(((u1s != 0) == (u1[:, sl] != 0)).all()))
 dist.barrier()

@@ -86,10 +86,7 @@ void halo_push(vch2d_ctx* c, const double* f0, const double* f1, int rows, const
     for (const double* f : {f0, f1})
         if (f && (f < c->arena.base + kArenaHeader || f >= c->arena.base + c->arena.cap))
             throw Error(VCH_E_ARG, "halo_push: field is not in the slab arena");
-    LAUNCH(c, xbar_kernel, 1, 32, c->cm, done);
-    const int blocks = std::max(1, std::min(32, (rows * c->g.ni + 255) / 256));
-    LAUNCH(c, halo_push_kernel, blocks, 256, c->cm, f0, f1, rows, c->g.no, c->rows_lo, c->g.ni, done);
-    LAUNCH(c, xbar_kernel, 1, 32, c->cm, done);
+    LAUNCH(c, halo_push_kernel, 1, 1024, c->cm, f0, f1, rows, c->g.no, c->rows_lo, c->g.ni, done);
 }
 // Copy of a ghosted work vector including its ghost rows.
 void copy_ghosted(vch2d_ctx* c, double* dst, const double* src) {
@@ -97,7 +94,7 @@ void copy_ghosted(vch2d_ctx* c, double* dst, const double* src) {
     VCH_CUDA(cudaMemcpyAsync(dst - m, src - m, ((size_t)c->g.n + 2 * m) * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
 }
 // kernels per BiCGStab iteration / per solve prologue (accounting of launches inside solve graphs)
-template <bool ADJ> int iter_launches(const vch2d_ctx* c) { return ADJ ? (c->slab ? 11 + 6 + 6 : 11) : (c->slab ? 7 + 6 : 7); }
+template <bool ADJ> int iter_launches(const vch2d_ctx* c) { return ADJ ? (c->slab ? 11 + 4 + 2 : 11) : (c->slab ? 7 + 4 : 7); }
 int prologue_launches(const vch2d_ctx* c) { return c->slab ? 7 : 4; }
 
 // Orders the library's private stream after the caller's stream on entry and the caller's stream after ours on exit,
@@ -576,7 +573,7 @@ static int create_ctx(const vch2d_params* p, int device, int rank, int nranks, v
             g.glo = rank > 0; g.ghi = rank < nranks - 1;
             sl.nloc = g.no; sl.o0 = g.o0; sl.wloc = g.no; sl.col0 = g.o0;
             sl.shift = 0; while ((1 << sl.shift) < rw) ++sl.shift;
-            sl.p1 = rw + 2; sl.p2 = (g.ni + 3) & ~3;
+            sl.p1 = rw + 2;
         }
         g.n = (long long)g.ni * g.no;
         c->ph = Phys{p->tau, p->gamma, p->c1, p->c2, p->kappa, 1.0 - p->delta_sep, std::max(1e-8, 0.5 * p->delta_sep),
@@ -590,10 +587,10 @@ static int create_ctx(const vch2d_params* p, int device, int rank, int nranks, v
             for (int k = 0; k < 2; ++k) { fields.push_back(&c->adj_p[k]); fields.push_back(&c->adj_q[k]); fields.push_back(&c->adj_r[k]); }
             fields.push_back(&c->mu_old);
             const size_t nmax = (size_t)(c->rows_lo + 1) * g.ni, margin = 2 * (size_t)g.ni;
-            const size_t t1 = (size_t)(p->Nx + 1) * sl.p1, t2 = (size_t)(c->rows_lo + 1) * sl.p2;
-            c->arena.create(kArenaHeader + fields.size() * (nmax + 2 * margin + 64) + t1 + t2 + 256);
+            const size_t t1 = (size_t)(p->Nx + 1) * sl.p1;
+            c->arena.create(kArenaHeader + fields.size() * (nmax + 2 * margin + 64) + t1 + 256);
             for (DevBuf* b : fields) c->arena.view(*b, nmax, margin);
-            sl.T1 = c->arena.carve(t1, 0); sl.T2 = c->arena.carve(t2, 0);
+            sl.T1 = c->arena.carve(t1, 0);
             c->cm.peer[rank] = c->arena.base;
         } else {
             for (DevBuf* b : fields) b->alloc(n);

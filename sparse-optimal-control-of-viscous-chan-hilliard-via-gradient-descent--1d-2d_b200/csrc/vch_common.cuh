@@ -356,23 +356,42 @@ static __global__ void xbar_kernel(Comm cm, const int* __restrict__ done) {
     __threadfence_system();
 }
 
-// Writes the first / last `rows` owned rows of up to two fields into the neighbours' ghost rows (fields live at the same
-// arena offset on every rank; ranks below the last own `rows_lo` rows each).  Bracketed by xbar_kernel on both sides.
-static __global__ void halo_push_kernel(Comm cm, const double* f0, const double* f1, int rows, int nloc, int rows_lo, int ni,
-                                 const int* __restrict__ done) {
+// Barrier body for one CTA (thread r talks to rank r).  Must be called by every thread of the block.
+__device__ __forceinline__ void xbar_block(const Comm& cm, unsigned long long* s_shared) {
+    __syncthreads();
+    if (threadIdx.x == 0) *s_shared = ++cm.seq[1];
+    __syncthreads();
+    const int r = threadIdx.x;
+    if (r < cm.nranks) {
+        __threadfence_system();
+        *reinterpret_cast<volatile unsigned long long*>(cm.peer[r] + kFlagOff + cm.rank) = *s_shared;
+        spin_until(reinterpret_cast<volatile unsigned long long*>(cm.peer[cm.rank] + kFlagOff + r), *s_shared, cm.err, false);
+    }
+    __syncthreads();
+    __threadfence_system();
+}
+
+// ONE CTA: barrier (the neighbours have finished every kernel that still reads their old ghost rows) -> write the first /
+// last `rows` owned rows of up to two fields into the neighbours' ghost rows -> barrier (the rows have landed).  Fields live
+// at the same arena offset on every rank; ranks below the last own `rows_lo` rows each.
+static __global__ void __launch_bounds__(1024) halo_push_kernel(Comm cm, const double* f0, const double* f1, int rows, int nloc,
+                                                                int rows_lo, int ni, const int* __restrict__ done) {
     if (done && *done) return;
-    const long long cnt = (long long)rows * ni;
+    __shared__ unsigned long long s;
+    xbar_block(cm, &s);
+    const int cnt = rows * ni;
     for (int w = 0; w < 2; ++w) {
         const double* f = w ? f1 : f0;
         if (!f) continue;
         const size_t off = (size_t)(f - cm.peer[cm.rank]);
-        for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < cnt; e += (long long)gridDim.x * blockDim.x) {
+        for (int e = threadIdx.x; e < cnt; e += blockDim.x) {
             if (cm.rank > 0)               // my first rows -> upper ghost rows of the rank below
                 cm.peer[cm.rank - 1][off + (size_t)rows_lo * ni + e] = f[e];
             if (cm.rank < cm.nranks - 1)   // my last rows -> lower ghost rows [-rows, 0) of the rank above
                 *(cm.peer[cm.rank + 1] + (long long)off - cnt + e) = f[(long long)(nloc - rows) * ni + e];
         }
     }
+    xbar_block(cm, &s);
 }
 
 }  // namespace vch

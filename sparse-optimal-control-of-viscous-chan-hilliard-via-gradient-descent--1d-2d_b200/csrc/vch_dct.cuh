@@ -64,8 +64,10 @@ struct RowPrologue {
 
 // Slab mode: the transposes between the row and the column transforms are done by the kernels' own stores, straight
 // into the peers' buffers over NVLink (no all-to-all pass).
-//   mode 1 (row kernel):    element kk of local line l  -> peer r = min(kk >> shift, nr-1):  T1[(base + l) * pitch + kk - (r << shift)]
-//   mode 2 (column kernel): element kk of local line pair l -> peer r = min(kk >> shift, nr-1):  T2[(kk - (r << shift)) * pitch + base + l]
+//   mode 1 (forward row kernel, STORE): element kk of local line l -> peer r = min(kk >> shift, nr-1):
+//           T1_r[(base + l) * pitch + kk - (r << shift)]      (contiguous chunks of N/nr doubles: efficient remote writes)
+//   mode 3 (inverse row kernel, LOAD):  the same addresses are read back after the owners' in-place column solves
+//           (contiguous remote reads); the kernel's own output is an ordinary local store.
 struct Scatter {
     int mode = 0, shift = 0, nr = 1, base = 0, pitch = 0;
     size_t off = 0;                       // arena offset (doubles) of the destination buffer, identical on every rank
@@ -78,8 +80,8 @@ struct DctSlab {
     int nloc = 0, o0 = 0;        // owned rows [o0, o0 + nloc)
     int wloc = 0, col0 = 0;      // owned columns of the transposed layout [col0, col0 + wloc)
     int shift = 0;               // log2(N / nranks): rows per rank = columns per rank (the last rank has one more)
-    int p1 = 0, p2 = 0;          // pitches of T1 (global rows x owned columns) and T2 (owned rows x all columns)
-    double *T1 = nullptr, *T2 = nullptr;
+    int p1 = 0;                  // pitch of T1 (all global rows x owned columns)
+    double* T1 = nullptr;
 };
 
 struct DctPlan {
@@ -281,6 +283,12 @@ dct_fft_kernel(const double* in, double* out, int nlines, int n, int in_ls, int 
         const int off = (e <= N ? e : Lf - e) * in_es;
         if (SOLVE) {
             v[r] = va ? *reinterpret_cast<const double2*>(pa + off) : make_double2(0.0, 0.0);
+        } else if (sct.mode == 3) {   // slab mode: gather the row from the column owners' buffers
+            const int ee = (e <= N) ? e : Lf - e;
+            int rr = ee >> sct.shift; if (rr >= sct.nr) rr = sct.nr - 1;
+            const double* src = sct.peer[rr] + sct.off + (size_t)(sct.base + la) * sct.pitch + (ee - (rr << sct.shift));
+            v[r].x = va ? src[0] : 0.0;
+            v[r].y = vb ? src[sct.pitch] : 0.0;
         } else if (pro.mode == 0) {
             v[r].x = va ? pa[off] : 0.0;
             v[r].y = vb ? pb[off] : 0.0;
@@ -337,16 +345,12 @@ dct_fft_kernel(const double* in, double* out, int nlines, int n, int in_ls, int 
         const int kk = t + FftOut<LOG2L>::off(q);
         if (kk <= N) {
             const int off = kk * out_es;
-            if (sct.mode) {   // slab mode: transposing store into the owning peer's buffer
+            if (!SOLVE && sct.mode == 1) {   // slab mode: transposing store into the owning peer's buffer
                 int r = kk >> sct.shift; if (r >= sct.nr) r = sct.nr - 1;
                 const int kl = kk - (r << sct.shift);
                 double* dst = sct.peer[r] + sct.off;
-                if (SOLVE) {
-                    if (va) *reinterpret_cast<double2*>(dst + (size_t)kl * sct.pitch + sct.base + la) = make_double2(z[q].x, vb ? z[q].y : 0.0);
-                } else {
-                    if (va) dst[(size_t)(sct.base + la) * sct.pitch + kl] = z[q].x;
-                    if (vb) dst[(size_t)(sct.base + lb) * sct.pitch + kl] = z[q].y;
-                }
+                if (va) dst[(size_t)(sct.base + la) * sct.pitch + kl] = z[q].x;
+                if (vb) dst[(size_t)(sct.base + lb) * sct.pitch + kl] = z[q].y;
             } else if (SOLVE) {
                 if (va) *reinterpret_cast<double2*>(qa + off) = make_double2(z[q].x, vb ? z[q].y : 0.0);
             } else {
@@ -583,29 +587,29 @@ inline void DctPlan::apply(cudaStream_t s, const double* in, double* out, const 
 #undef VCH_FFT_CASE
     };
     if (slab.on) {
-        // rows of the owned slab, stored transposed into every peer's T1 | barrier | fused solve on the owned columns
-        // (all global rows), stored back into every peer's T2 | barrier | inverse rows from T2.  The leading barrier keeps
-        // a fast rank from overwriting T1/T2 of a peer that is still reading them from the previous application.
+        // rows of the owned slab, stored transposed into the column owners' T1 | barrier | fused solve in place on the owned
+        // columns (all global rows) | barrier | inverse rows, gathered back from the owners' T1.  Re-use of T1 by the next
+        // application is safe because a cross-rank synchronisation always follows: the fused dot-product reduction of the
+        // last kernel, or the explicit trailing barrier when there is none.
         const DctSlab& sl = slab;
         const int rp = dct_rows_ppb(inner, sl.nloc), rt = rp * (inner.Lf >> 3), rg = ((sl.nloc + 1) / 2 + rp - 1) / rp;
         const int cp = dct_cols_ppb(outer, sl.wloc), ct = cp * (outer.Lf >> 3), cg = ((sl.wloc + 1) / 2 + cp - 1) / cp;
         Scatter s1; s1.mode = 1; s1.shift = sl.shift; s1.nr = sl.cm.nranks; s1.base = sl.o0; s1.pitch = sl.p1;
         s1.off = (size_t)(sl.T1 - sl.cm.peer[sl.cm.rank]);
-        Scatter s2; s2.mode = 2; s2.shift = sl.shift; s2.nr = sl.cm.nranks; s2.base = sl.col0; s2.pitch = sl.p2;
-        s2.off = (size_t)(sl.T2 - sl.cm.peer[sl.cm.rank]);
-        for (int r = 0; r < sl.cm.nranks; ++r) { s1.peer[r] = sl.cm.peer[r]; s2.peer[r] = sl.cm.peer[r]; }
-        barrier(s, done);
+        for (int r = 0; r < sl.cm.nranks; ++r) s1.peer[r] = sl.cm.peer[r];
+        Scatter s3 = s1; s3.mode = 3;
         log->begin(pro.mode ? "dct_rows_fft_pro" : "dct_rows_fft", s);
         fft_launch(false, inner, rg, rt, dct_smem(inner, rp), in, sl.T1, sl.nloc, ni, ni, 1, sl.p1, 1, nullptr, nullptr, nosym, 1.0, 0, pro, DotEpilogue(), s1);
         log->end(s);
         barrier(s, done);
         log->begin("dct_cols_fft_solve", s);
-        fft_launch(true, outer, cg, ct, dct_smem(outer, cp), sl.T1, sl.T1, sl.wloc, no, 1, sl.p1, 1, sl.p1, inner.lam + sl.col0, outer.lam, sym, norm, scale_mode, RowPrologue(), DotEpilogue(), s2);
+        fft_launch(true, outer, cg, ct, dct_smem(outer, cp), sl.T1, sl.T1, sl.wloc, no, 1, sl.p1, 1, sl.p1, inner.lam + sl.col0, outer.lam, sym, norm, scale_mode, RowPrologue(), DotEpilogue());
         log->end(s);
         barrier(s, done);
         log->begin(epi.mode == 1 ? "dct_rows_fft_epi1" : (epi.mode == 2 ? "dct_rows_fft_epi2" : "dct_rows_fft"), s);
-        fft_launch(false, inner, rg, rt, dct_smem(inner, rp), sl.T2, out, sl.nloc, ni, sl.p2, 1, ni, 1, nullptr, nullptr, nosym, 1.0, 0, RowPrologue(), epi);
+        fft_launch(false, inner, rg, rt, dct_smem(inner, rp), sl.T1, out, sl.nloc, ni, sl.p1, 1, ni, 1, nullptr, nullptr, nosym, 1.0, 0, RowPrologue(), epi, s3);
         log->end(s);
+        if (!epi.mode) barrier(s, done);
         VCH_CUDA(cudaGetLastError());
         return;
     }
