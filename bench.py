@@ -384,6 +384,91 @@ def run_ensemble1d(args):
         dist.destroy_process_group()
 
 
+def run_slab2d(args):
+    """Secondary workload (BASELINE config 5): ONE 2D control problem decomposed into row slabs over the ranks (strong
+    scaling: the problem is fixed).  The kernels exchange halo rows, preconditioner transposes and reduction partials through
+    peer memory over NVLink (CUDA IPC); there is no host-side collective in the step.  At 1 rank the ordinary context runs the
+    same problem."""
+    import torch
+    import torch.distributed as dist
+    import vch_b200_native as nat
+    import vch_oracle as O
+    rank, world, local = (int(os.environ.get(k, d)) for k, d in (("RANK", "0"), ("WORLD_SIZE", "1"), ("LOCAL_RANK", "0")))
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+    N, M, dt = args.n, args.horizon, 1e-2
+    P = O.Phys2D(Nx=N, Ny=N, T=M * dt)
+    Op = O.Opt2D()
+    h = 1.0 / N
+    if world > 1:
+        ctx = nat.SlabCtx2D.create_distributed(N, h, 1.0, P.tau, P.gamma, P.c1, P.c2, P.kappa, 1e-2, device=local)
+        r0, nr = ctx.row0, ctx.rows
+    else:
+        ctx = nat.Ctx2D(N, N, h, h, 1.0, 1.0, P.tau, P.gamma, P.c1, P.c2, P.kappa, device=local)
+        r0, nr = 0, N + 1
+    dts = np.full(M, dt)
+    t_hist = np.concatenate([[0.0], np.minimum(np.cumsum(dts), P.T)])
+    x = np.linspace(0.0, 1.0, N + 1)
+    phi0 = torch.from_numpy(np.ascontiguousarray(O.init_phi_2d(N, N, seed=42)[r0:r0 + nr])).to(dev)   # every rank cuts the same global field
+    hist_a, _, _ = ctx.forward(phi0, None, dts)
+    xx, yy = torch.meshgrid(torch.from_numpy(x[r0:r0 + nr]).to(dev), torch.from_numpy(x).to(dev), indexing="ij")
+    phiT = (0.7 * torch.sin(2 * np.pi * xx) * torch.cos(np.pi * yy)).contiguous()
+    s = torch.from_numpy(t_hist / P.T).to(dev)[:, None, None]
+    phiQ = ((1 - s) * hist_a[0] + s * phiT).contiguous()
+    del s, xx, yy
+    state = {"u": torch.zeros_like(hist_a), "h": hist_a, "un": torch.empty_like(hist_a), "hn": torch.empty_like(hist_a), "J": None, "stats": None}
+    r_buf = torch.empty_like(hist_a)
+
+    def step():
+        _, _, J, red, st = ctx.pgd_iteration(state["u"], state["h"], phiQ, phiT, t_hist, dts, x, x, Op.b1, Op.b2, Op.b3,
+                                             Op.kappa_sparsity, Op.u_min, Op.u_max, Op.alpha_max, u_out=state["un"],
+                                             phi_out=state["hn"], r_out=r_buf)
+        state["u"], state["un"] = state["un"], state["u"]
+        state["h"], state["hn"] = state["hn"], state["h"]
+        state["J"], state["stats"] = J, st
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    sampler = ClockSampler(local)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    l0 = ctx.launches()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    ms = torch.tensor([e0.elapsed_time(e1) / args.steps], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        st = state["stats"]
+        print(json.dumps({"metric": "PGD iterations/s on ONE slab-decomposed 2D problem (config 5)", "value": 1e3 / float(ms.item()), "unit": "it/s",
+                          "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": float(ms.item()),
+                          "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                          "config": {"workload": f"ONE 2D {N}^2 grid ({N+1}^2 nodes), M={M} CN steps, row slabs over {world} GPU(s), reference 2D "
+                                                 "defaults, targets (1,1), chained optimistic PGD iterations from u0=0",
+                                     "rows_per_gpu": nr, "trajectory_GB_per_gpu": round(8.0 * (M + 1) * nr * (N + 1) / 1e9, 3),
+                                     "cache": "per-GPU trajectories exceed L2 (no flush needed)"},
+                          "gpu_launches": int(ctx.launches() - l0), "clocks": clocks, "J": float(state["J"][0]),
+                          "ms_per_time_step": float(ms.item()) / M,
+                          "solver": {k: st[k] for k in ("newton_residual_evals", "newton_linear_solves", "krylov_iterations", "krylov_stalls")}}),
+              flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -396,11 +481,14 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--workload", default="pgd2d", choices=["pgd2d", "ensemble1d"], help="pgd2d = BASELINE metric (default); ensemble1d = config 4")
+    ap.add_argument("--workload", default="pgd2d", choices=["pgd2d", "ensemble1d", "slab2d"],
+                    help="pgd2d = BASELINE metric (default); ensemble1d = config 4; slab2d = config 5 (one problem over all ranks)")
     ap.add_argument("--batch", type=int, default=1024, help="ensemble1d: number of problems")
     args = ap.parse_args()
     if args.workload == "ensemble1d":
         run_ensemble1d(args)
+    elif args.workload == "slab2d":
+        run_slab2d(args)
     elif args.impl == "reference":
         run_reference(args)
     else:

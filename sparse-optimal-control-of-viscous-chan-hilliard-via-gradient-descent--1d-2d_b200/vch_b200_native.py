@@ -357,6 +357,16 @@ class Ctx2D:
         return u_out, phi_out, J, red, self.last_stats
 
 
+def slab_partition(N, nranks):
+    """Row ranges [(row0, rows)] of the slab decomposition of an (N+1, N+1) field: N // nranks rows per rank, the last
+    rank one more (the same rule the library applies, csrc/vch2d.cu create_ctx)."""
+    N, nranks = int(N), int(nranks)
+    if nranks < 1 or N % nranks or (nranks > 1 and (N & (N - 1) or N < 32 or N > 4096 or nranks not in (2, 4, 8) or N // nranks < 8)):
+        raise ValueError("slab decomposition needs N = 2^k (32..4096) and 2, 4 or 8 ranks with at least 8 rows each")
+    rw = N // nranks
+    return [(r * rw, rw + (1 if r == nranks - 1 else 0)) for r in range(nranks)]
+
+
 class SlabCtx2D(Ctx2D):
     """One rank of a row-slab decomposition of ONE square 2D problem over 2/4/8 GPUs (include/vch_b200.h, "slab mode").
 
