@@ -475,7 +475,7 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--n", type=int, default=1024, help="grid intervals per side")
+    ap.add_argument("--n", "--grid", dest="n", type=int, default=1024, help="grid intervals per side (--grid: spelling that torchrun does not mistake for one of its own options)")
     ap.add_argument("--horizon", type=int, default=1000, help="CN time steps M")
     ap.add_argument("--profile-steps", type=int, default=20)
     ap.add_argument("--e2e-steps", type=int, default=2)

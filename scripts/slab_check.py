@@ -28,7 +28,7 @@ full = nat.Ctx2D(N, N, h, h, 1.0, 1.0, phys["tau"], phys["gamma"], phys["c1"], p
 r0, nr = slab.row0, slab.rows
 sl = slice(r0, r0 + nr)
 def say(*a):
-    print(f"[rank {rank}]", *a, flush=True)
+    sys.stdout.write(f"[rank {rank}] " + " ".join(str(v) for v in a) + "\n"); sys.stdout.flush()   # one write per line
 def rel(a, b):
     a = a.double().reshape(-1); b = b.double().reshape(-1)
     return float((a - b).norm() / max(float(b.norm()), 1e-300))

@@ -252,7 +252,7 @@ __global__ void __launch_bounds__(MAXT, VCH_FFT_MINB)
 dct_fft_kernel(const double* in, double* out, int nlines, int n, int in_ls, int in_es, int out_ls, int out_es, int ppb,
                const double2* __restrict__ twg, const double* __restrict__ lam_line, const double* __restrict__ lam_elem,
                SymbolArgs sy, double norm, int scale_mode, RowPrologue pro, DotEpilogue epi, const int* __restrict__ done,
-               Scatter sct) {
+               const __grid_constant__ Scatter sct) {   // __grid_constant__: sct.peer[r] is indexed straight from the constant bank
     using G = FftGeom<LOG2L>;
     constexpr int Lf = G::Lf, tpf = G::tpf, ld = G::ld;
     if (done && *done) return;
