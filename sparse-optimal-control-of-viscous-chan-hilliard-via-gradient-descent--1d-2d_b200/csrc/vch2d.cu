@@ -78,15 +78,15 @@ void op_apply(vch2d_ctx* c, const double* x, const double* a, double* y, const i
     c->log.end(c->stream);
 }
 
-// Slab mode: ship the first / last `rows` owned rows of one or two fields into the neighbours' ghost rows.  The leading
-// barrier guarantees the neighbours have finished every kernel that still reads the old ghost rows, the trailing one that
-// the new rows have landed before anything reads them.  No-op outside slab mode.
-void halo_push(vch2d_ctx* c, const double* f0, const double* f1, int rows, const int* done = nullptr) {
+// Slab mode: ship the first / last `rows` owned rows of one or two fields into the neighbours' ghost rows; a barrier inside
+// the kernel guarantees the rows have landed before anything reads them (lead = 1 adds a barrier in front, see
+// halo_push_kernel).  No-op outside slab mode.
+void halo_push(vch2d_ctx* c, const double* f0, const double* f1, int rows, const int* done = nullptr, int lead = 0) {
     if (!c->slab) return;
     for (const double* f : {f0, f1})
         if (f && (f < c->arena.base + kArenaHeader || f >= c->arena.base + c->arena.cap))
             throw Error(VCH_E_ARG, "halo_push: field is not in the slab arena");
-    LAUNCH(c, halo_push_kernel, 1, 1024, c->cm, f0, f1, rows, c->g.no, c->rows_lo, c->g.ni, done);
+    LAUNCH(c, halo_push_kernel, 1, 1024, c->cm, f0, f1, rows, c->g.no, c->rows_lo, c->g.ni, done, lead);
 }
 // Copy of a ghosted work vector including its ghost rows.
 void copy_ghosted(vch2d_ctx* c, double* dst, const double* src) {
@@ -688,7 +688,7 @@ int vch2d_slab_selftest(vch2d_ctx* c, double* out5) {
         StreamScope scope(c);
         const int n = (int)c->g.n, ni = c->g.ni;
         LAUNCH(c, slab_selftest_kernel, 8, 256, c->ktmp.p, n, (double)(c->cm.rank + 1), c->out4, c->red.part, c->ticket);
-        halo_push(c, c->ktmp.p, nullptr, 2);
+        halo_push(c, c->ktmp.p, nullptr, 2, nullptr, 1);
         double ghost[2] = {0.0, 0.0};
         if (c->g.glo) VCH_CUDA(cudaMemcpyAsync(&ghost[0], c->ktmp.p - 2 * ni, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
         if (c->g.ghi) VCH_CUDA(cudaMemcpyAsync(&ghost[1], c->ktmp.p + n + 2 * ni - 1, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
@@ -781,7 +781,7 @@ int vch2d_apply_laplacian(vch2d_ctx* c, const double* v, double* out, int mem) {
         const double* dv = st.in(v, c->g.n); double* dout = st.out(out, c->g.n);
         if (c->slab) {   // ghosted copy + halo rows from the neighbours
             VCH_CUDA(cudaMemcpyAsync(c->ktmp.p, dv, c->g.n * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
-            halo_push(c, c->ktmp.p, nullptr, 1);
+            halo_push(c, c->ktmp.p, nullptr, 1, nullptr, 1);
             dv = c->ktmp.p;
         }
         LAUNCH(c, lap_kernel, c->eb(), 256, dv, dout, c->g, 1.0);
@@ -799,7 +799,7 @@ int vch2d_initialize_mu(vch2d_ctx* c, const double* phi, const double* w, double
         const double *dp = st.in(phi, c->g.n), *dw = st.in(w, c->g.n); double* dm = st.out(mu_out, c->g.n);
         if (c->slab) {
             VCH_CUDA(cudaMemcpyAsync(c->ktmp.p, dp, c->g.n * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
-            halo_push(c, c->ktmp.p, nullptr, 1);
+            halo_push(c, c->ktmp.p, nullptr, 1, nullptr, 1);
             dp = c->ktmp.p;
         }
         LAUNCH(c, mu_init_kernel, c->eb(), 256, dp, dw, dm, c->g, c->ph);

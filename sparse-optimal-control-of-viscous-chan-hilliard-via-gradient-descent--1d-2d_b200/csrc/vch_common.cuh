@@ -371,14 +371,18 @@ __device__ __forceinline__ void xbar_block(const Comm& cm, unsigned long long* s
     __threadfence_system();
 }
 
-// ONE CTA: barrier (the neighbours have finished every kernel that still reads their old ghost rows) -> write the first /
-// last `rows` owned rows of up to two fields into the neighbours' ghost rows -> barrier (the rows have landed).  Fields live
-// at the same arena offset on every rank; ranks below the last own `rows_lo` rows each.
+// ONE CTA: [optional barrier] -> write the first / last `rows` owned rows of up to two fields into the neighbours' ghost
+// rows -> barrier (the rows have landed).  Fields live at the same arena offset on every rank; ranks below the last own
+// `rows_lo` rows each.
+// The leading barrier (lead = 1) protects ghost rows that a neighbour might still be reading.  The solver does not need it:
+// every kernel that reads ghost rows is followed — before the next push into the same buffer — by a cross-rank reduction
+// (grid_reduce) on every rank, and a rank can only pass reduction R after every peer has reached it, i.e. after the peers'
+// earlier kernels (stream order) have finished.  Callers outside that pattern pass lead = 1.
 static __global__ void __launch_bounds__(1024) halo_push_kernel(Comm cm, const double* f0, const double* f1, int rows, int nloc,
-                                                                int rows_lo, int ni, const int* __restrict__ done) {
+                                                                int rows_lo, int ni, const int* __restrict__ done, int lead) {
     if (done && *done) return;
     __shared__ unsigned long long s;
-    xbar_block(cm, &s);
+    if (lead) xbar_block(cm, &s);
     const int cnt = rows * ni;
     for (int w = 0; w < 2; ++w) {
         const double* f = w ? f1 : f0;

@@ -277,18 +277,37 @@ dct_fft_kernel(const double* in, double* out, int nlines, int n, int in_ls, int 
     // SOLVE (columns): the two lines of a pair are adjacent doubles of a pitched buffer whose pitch is even, so one
     // 16-byte access moves both.
     double2 v[8];
+    if (!SOLVE && sct.mode == 3) {
+        // slab mode: gather the row pair from the column owners' buffers.  Staged through shared memory with 16-byte loads so
+        // that every element crosses NVLink once (the direct path below re-reads each element for its mirror image, which
+        // is free from L1/L2 but doubles remote traffic).  The staging area is the FFT's own data buffer.
+        double* stg = reinterpret_cast<double*>(data);           // line a at [0, N], line b at [N + 2, 2N + 2]
+        for (int k = 2 * t; k <= N; k += 2 * tpf) {
+            int rr = k >> sct.shift; if (rr >= sct.nr) rr = sct.nr - 1;
+            const double* src = sct.peer[rr] + sct.off + (size_t)(sct.base + la) * sct.pitch + (k - (rr << sct.shift));
+            if (k < N) {
+                const double2 a2 = va ? *reinterpret_cast<const double2*>(src) : make_double2(0.0, 0.0);
+                const double2 b2 = vb ? *reinterpret_cast<const double2*>(src + sct.pitch) : make_double2(0.0, 0.0);
+                stg[k] = a2.x; stg[k + 1] = a2.y; stg[N + 2 + k] = b2.x; stg[N + 3 + k] = b2.y;
+            } else {
+                stg[k] = va ? src[0] : 0.0; stg[N + 2 + k] = vb ? src[sct.pitch] : 0.0;
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            const int e = t + r * tpf;
+            const int ee = (e <= N) ? e : Lf - e;
+            v[r] = make_double2(stg[ee], stg[N + 2 + ee]);
+        }
+        __syncthreads();                                          // staging is overwritten by the first-pass store
+    } else
 #pragma unroll
     for (int r = 0; r < 8; ++r) {
         const int e = t + r * tpf;
         const int off = (e <= N ? e : Lf - e) * in_es;
         if (SOLVE) {
             v[r] = va ? *reinterpret_cast<const double2*>(pa + off) : make_double2(0.0, 0.0);
-        } else if (sct.mode == 3) {   // slab mode: gather the row from the column owners' buffers
-            const int ee = (e <= N) ? e : Lf - e;
-            int rr = ee >> sct.shift; if (rr >= sct.nr) rr = sct.nr - 1;
-            const double* src = sct.peer[rr] + sct.off + (size_t)(sct.base + la) * sct.pitch + (ee - (rr << sct.shift));
-            v[r].x = va ? src[0] : 0.0;
-            v[r].y = vb ? src[sct.pitch] : 0.0;
         } else if (pro.mode == 0) {
             v[r].x = va ? pa[off] : 0.0;
             v[r].y = vb ? pb[off] : 0.0;
