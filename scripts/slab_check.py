@@ -16,7 +16,7 @@ import vch_b200_native as nat
 
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 128
 M = int(sys.argv[2]) if len(sys.argv) > 2 else 4
-stages = sys.argv[3:] or ["selftest", "lap", "jac", "forward", "adjoint", "pgd"]
+stages = sys.argv[3:] or ["selftest", "lap", "jac", "forward", "adjoint", "pgd", "host"]
 rank = int(os.environ.get("RANK", 0)); world = int(os.environ.get("WORLD_SIZE", 1))
 torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", 0)))
 dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -65,7 +65,7 @@ if "jac" in stages:
     check("jac dphi", e1, d1[sl], 1e-9); check("jac dmu", e2, d2[sl], 1e-9)
 dts = np.full(M, 1e-2); t = 1e-2 * np.arange(M + 1)
 phiT = g(0.7 * np.sin(2 * np.pi * xx) * np.cos(np.pi * yy))
-if "forward" in stages or "adjoint" in stages or "pgd" in stages:
+if any(k in stages for k in ("forward", "adjoint", "pgd", "host")):
     u = g(0.5 * np.sin(np.pi * xx)[None] * np.ones((M + 1, 1, 1)))
     torch.cuda.synchronize(); t0 = time.perf_counter()
     hf, _, _ = full.forward(phi0_d, u, dts); torch.cuda.synchronize(); t1 = time.perf_counter()
@@ -90,6 +90,15 @@ if "pgd" in stages:
     check("pgd u_new", u1s, u1[:, sl], 1e-7); check("pgd phi_hist_new", h1s, h1[:, sl], 1e-8)
     if abs(Js[0] - J[0]) > 1e-9 * abs(J[0]): say("J mismatch FAIL"); worst = max(worst, 1e9)
     say("support identical:", bool(((u1s != 0) == (u1[:, sl] != 0)).all()))
+if "host" in stages:    # host-buffer (streamed PCIe) entry point on the slab: NumPy in, NumPy out
+    u0 = torch.zeros_like(hf)
+    args = (5.0, 10.0, 1e-4, 1e-4, -1.0, 1.0, 50.0)
+    u1d, h1d, Jd, redd, _ = slab.pgd_iteration(u0[:, sl].contiguous(), hf[:, sl].contiguous(), phiQ[:, sl].contiguous(),
+                                               phiT[sl].contiguous(), t, dts, x, x, *args)
+    nph = lambda a: np.ascontiguousarray(a.cpu().numpy())
+    u1h, h1h, Jh, redh, _ = slab.pgd_iteration(nph(u0[:, sl]), nph(hf[:, sl]), nph(phiQ[:, sl]), nph(phiT[sl]), t, dts, x, x, *args)
+    check("host-path u_new", torch.from_numpy(u1h), u1d.cpu(), 1e-14); check("host-path phi_hist_new", torch.from_numpy(h1h), h1d.cpu(), 1e-14)
+    if abs(Jh[0] - Jd[0]) > 1e-14 * abs(Jd[0]): say("host-path J mismatch FAIL"); worst = max(worst, 1e9)
 dist.barrier()
 say("RESULT", "PASS" if worst <= 1.0 else "FAIL", f"(worst err/tol {worst:.2e})")
 dist.destroy_process_group()
