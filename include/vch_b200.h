@@ -98,6 +98,11 @@ int  vch2d_set_krylov(vch2d_ctx* c, double rel_tol, int max_iter);/* defaults 1e
  * reachable on grids >= 1024^2, where the reference's absolute tolerance lies below that resolution and its loop would spin
  * to max_iter = 500 on rounding noise.  floor_aware = 0: the reference's rule verbatim. */
 int  vch2d_set_newton(vch2d_ctx* c, int floor_aware);
+/* Device memory the HOST-buffer path of vch2d_pgd_iteration may use for staging.  0 (default): stage the whole
+ * trajectories when they fit, otherwise fall back to chunk rings sized to the free memory.  > 0: always walk the
+ * trajectories in chunks through rings of at most `bytes` in total (trajectories larger than HBM; results agree with the
+ * fully staged path to rounding of the cost sums). */
+int  vch2d_set_stream_budget(vch2d_ctx* c, long long bytes);
 long long vch2d_launch_count(vch2d_ctx* c);                        /* kernels launched since creation */
 /* Per-kernel device timing (bench.py's roofline leg).  While enabled every launch is bracketed by CUDA events on the
  * launching stream; the report returns ';'-joined kernel names with total milliseconds and launch counts. */

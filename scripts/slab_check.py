@@ -99,6 +99,11 @@ if "host" in stages:    # host-buffer (streamed PCIe) entry point on the slab: N
     u1h, h1h, Jh, redh, _ = slab.pgd_iteration(nph(u0[:, sl]), nph(hf[:, sl]), nph(phiQ[:, sl]), nph(phiT[sl]), t, dts, x, x, *args)
     check("host-path u_new", torch.from_numpy(u1h), u1d.cpu(), 1e-14); check("host-path phi_hist_new", torch.from_numpy(h1h), h1d.cpu(), 1e-14)
     if abs(Jh[0] - Jd[0]) > 1e-14 * abs(Jd[0]): say("host-path J mismatch FAIL"); worst = max(worst, 1e9)
+    slab.set_stream_budget(6 * 3 * 3 * 8 * slab.shape[0] * slab.shape[1])      # chunk rings of 3 levels: bounded-memory mode
+    u1b, h1b, Jb, redb, _ = slab.pgd_iteration(nph(u0[:, sl]), nph(hf[:, sl]), nph(phiQ[:, sl]), nph(phiT[sl]), t, dts, x, x, *args)
+    slab.set_stream_budget(0)
+    check("bounded-memory u_new", torch.from_numpy(u1b), u1d.cpu(), 1e-14); check("bounded-memory phi_hist_new", torch.from_numpy(h1b), h1d.cpu(), 1e-14)
+    if abs(Jb[0] - Jd[0]) > 1e-12 * abs(Jd[0]): say("bounded-memory J mismatch FAIL"); worst = max(worst, 1e9)
 dist.barrier()
 say("RESULT", "PASS" if worst <= 1.0 else "FAIL", f"(worst err/tol {worst:.2e})")
 dist.destroy_process_group()

@@ -36,6 +36,8 @@ struct vch2d_ctx {
     DevBuf kb, kx, kr, kr0, kp, kv, ks, kt, ktmp, kq, dmu;
     DevBuf adj_p[2], adj_q[2], adj_r[2], mu_old;
     DevBuf stage[7];             // device staging of the host-buffer PGD iteration, kept across calls (no 50 GB malloc/free per step)
+    long long stream_budget = 0; // bytes of device staging the host-buffer path may use; 0 = whatever fits (vch2d_set_stream_budget)
+    std::vector<double> r_host;  // host copy of the gradient trajectory for the bounded-memory path when the caller gives no r_out
     RedBuf red;                  // partials for grid reductions (+ the Comm header the kernels read)
     // slab mode (one rank of a row-slab decomposition of a square grid; see vch_common.cuh "slab mode")
     bool slab = false;
@@ -382,19 +384,26 @@ void post_step(vch2d_ctx* c, const double* phi_new, double* dst) {
 }
 
 using LevelHook = std::function<void(int)>;
+// level -> device address, for trajectories that live in chunk rings (bounded-memory streaming); unset entries fall back
+// to the dense arrays passed alongside
+struct LevelMap {
+    std::function<double*(int)> hist, Q, r, u, hist_new;
+};
 
 // after_level(k): called once level k of phi_hist has been enqueued (streaming D2H of the trajectory hooks in here).
 void forward_dev(vch2d_ctx* c, const double* phi0, const double* u, int u_rows, int n_steps, const double* dt_steps,
                  double* phi_hist, double* mu_hist, double* w_hist, vch_stats* st, const LevelHook& after_level = nullptr,
-                 const LevelHook& before_step = nullptr) {
+                 const LevelHook& before_step = nullptr, const LevelMap* lm = nullptr) {
     const long long n = c->g.n;
     const size_t bytes = n * sizeof(double);
     const int eb = c->eb();
-    VCH_CUDA(cudaMemcpyAsync(phi_hist, phi0, bytes, cudaMemcpyDeviceToDevice, c->stream));
+    auto HN = [&](int k) -> double* { return (lm && lm->hist_new) ? lm->hist_new(k) : phi_hist + (size_t)k * n; };
+    auto U = [&](int k) -> const double* { return (lm && lm->u) ? lm->u(k) : u + (size_t)k * n; };
+    VCH_CUDA(cudaMemcpyAsync(HN(0), phi0, bytes, cudaMemcpyDeviceToDevice, c->stream));
     VCH_CUDA(cudaMemsetAsync(c->w0.p, 0, bytes, c->stream));
     c->mu_old.alloc(n);
     double* mu_old = c->mu_old.p;   // mu_0 = initialize_mu(phi_0, w = 0), Forward2_solver.py:520
-    const double* phi_first = phi_hist;
+    const double* phi_first = HN(0);
     if (c->slab) {   // the stencil needs ghost rows: work on a ghosted copy of level 0
         VCH_CUDA(cudaMemcpyAsync(c->phi.p, phi0, bytes, cudaMemcpyDeviceToDevice, c->stream));
         halo_push(c, c->phi.p, nullptr, 1);
@@ -402,17 +411,17 @@ void forward_dev(vch2d_ctx* c, const double* phi0, const double* u, int u_rows, 
     }
     LAUNCH(c, mu_init_kernel, eb, 256, phi_first, c->w0.p, mu_old, c->g, c->ph);
     halo_push(c, mu_old, nullptr, 1);
-    LAUNCH(c, clip_mass_kernel, c->rb(), kRedThreads, phi_hist, (double*)nullptr, c->g, c->ph, c->prm.hx * c->prm.hy, c->sc, 1,
+    LAUNCH(c, clip_mass_kernel, c->rb(), kRedThreads, HN(0), (double*)nullptr, c->g, c->ph, c->prm.hx * c->prm.hy, c->sc, 1,
            c->red.part, c->ticket);
     for (int s = 0; s < n_steps; ++s) {
         const double dt = dt_steps[s];
         if (before_step) before_step(s);     // streaming path: makes sure control rows s and s+1 exist
         const double* un = nullptr; const double* un1 = nullptr;
-        if (u && s < u_rows - 1) { un = u + (size_t)s * n; un1 = u + (size_t)(s + 1) * n; }
+        if ((u || (lm && lm->u)) && s < u_rows - 1) { un = U(s); un1 = U(s + 1); }
         LAUNCH(c, solve_w_kernel, eb, 256, c->w0.p, un, un1, c->w1.p, n, c->prm.gamma / dt);
-        const double* phi_old = phi_hist + (size_t)s * n;
+        const double* phi_old = HN(s);
         newton_step(c, phi_old, mu_old, c->w0.p, c->w1.p, dt, nullptr, st);
-        post_step(c, c->phi.p, phi_hist + (size_t)(s + 1) * n);
+        post_step(c, c->phi.p, HN(s + 1));
         copy_ghosted(c, mu_old, c->mu.p);      // slab mode: the ghost rows of the accepted iterate travel along
         std::swap(c->w0.p, c->w1.p);
         if (mu_hist) VCH_CUDA(cudaMemcpyAsync(mu_hist + (size_t)s * n, mu_old, bytes, cudaMemcpyDeviceToDevice, c->stream));
@@ -425,10 +434,13 @@ void forward_dev(vch2d_ctx* c, const double* phi0, const double* u, int u_rows, 
 // need_level(k): called before level k of phi_hist / phiQ is first read (streaming H2D hooks in here; levels descend).
 void adjoint_dev(vch2d_ctx* c, const double* phi_hist, int levels, const double* t_hist, double b1, double b2,
                  const double* phiQ, const double* phiT, double* p_out, double* q_out, double* r_out, vch_stats* st,
-                 const LevelHook& need_level = nullptr) {
+                 const LevelHook& need_level = nullptr, const LevelMap* lm = nullptr) {
     const long long n = c->g.n;
     const size_t bytes = n * sizeof(double);
     const int eb = c->eb();
+    auto H = [&](int k) -> const double* { return (lm && lm->hist) ? lm->hist(k) : phi_hist + (size_t)k * n; };
+    const bool haveQ = phiQ || (lm && lm->Q);
+    auto Q = [&](int k) -> const double* { return !haveQ ? nullptr : ((lm && lm->Q) ? lm->Q(k) : phiQ + (size_t)k * n); };
     for (int k = 0; k < 2; ++k) { c->adj_p[k].alloc(n); c->adj_q[k].alloc(n); c->adj_r[k].alloc(n); }
     // slab mode: p and q feed stencils, so they always live in the ghosted ring and are copied out when asked for
     auto slot = [&](double* out, DevBuf (&ring)[2], int lvl) { return out ? out + (size_t)lvl * n : ring[lvl & 1].p; };
@@ -439,9 +451,10 @@ void adjoint_dev(vch2d_ctx* c, const double* phi_hist, int levels, const double*
         if (q_user) VCH_CUDA(cudaMemcpyAsync(q_user + (size_t)lvl * n, qv, bytes, cudaMemcpyDeviceToDevice, c->stream));
     };
     const int M = levels - 1;
-    double* pM = slot(p_out, c->adj_p, M); double* qM = slot(q_out, c->adj_q, M); double* rM = slot(r_out, c->adj_r, M);
+    auto rslot = [&](int lvl) -> double* { return (lm && lm->r) ? lm->r(lvl) : slot(r_out, c->adj_r, lvl); };
     if (need_level) need_level(M);
-    LAUNCH(c, adj_terminal_rhs_kernel, eb, 256, phi_hist + (size_t)M * n, phiT, c->kb.p, n, b2);
+    double* pM = slot(p_out, c->adj_p, M); double* qM = slot(q_out, c->adj_q, M); double* rM = rslot(M);
+    LAUNCH(c, adj_terminal_rhs_kernel, eb, 256, H(M), phiT, c->kb.p, n, b2);
     SymbolArgs sy{1.0, 0.0, nullptr, c->ph.tau, nullptr};
     c->dct.apply(c->stream, c->kb.p, pM, sy, nullptr);          // (I - tau L) p_M = b2 (phi_M - phi_T): exact in the DCT basis
     halo_push(c, pM, nullptr, 1);
@@ -450,8 +463,9 @@ void adjoint_dev(vch2d_ctx* c, const double* phi_hist, int levels, const double*
     copy_out(M, pM, qM);
     for (int k = M - 1; k >= 0; --k) {
         const double dt = t_hist[k + 1] - t_hist[k];
-        double *p0 = slot(p_out, c->adj_p, k), *q0 = slot(q_out, c->adj_q, k), *r0 = slot(r_out, c->adj_r, k);
-        const double *p1 = slot(p_out, c->adj_p, k + 1), *q1 = slot(q_out, c->adj_q, k + 1), *r1 = slot(r_out, c->adj_r, k + 1);
+        if (need_level) need_level(k);     // before the level's addresses are taken: ring slots may be recycled in here
+        double *p0 = slot(p_out, c->adj_p, k), *q0 = slot(q_out, c->adj_q, k), *r0 = rslot(k);
+        const double *p1 = slot(p_out, c->adj_p, k + 1), *q1 = slot(q_out, c->adj_q, k + 1), *r1 = rslot(k + 1);
         if (dt <= 1e-14) {   // backward2_solver.py:214-216
             if (c->slab) { copy_ghosted(c, p0, p1); copy_ghosted(c, q0, q1); }
             else {
@@ -462,10 +476,9 @@ void adjoint_dev(vch2d_ctx* c, const double* phi_hist, int levels, const double*
             copy_out(k, p0, q0);
             continue;
         }
-        if (need_level) need_level(k);
-        const double* f1 = phi_hist + (size_t)(k + 1) * n; const double* f0 = phi_hist + (size_t)k * n;
-        LAUNCH(c, adj_rhs_kernel, c->rb(), kRedThreads, p1, q1, f1, f0, phiQ ? phiQ + (size_t)(k + 1) * n : nullptr,
-               phiQ ? phiQ + (size_t)k * n : nullptr, c->kb.p, c->a.p, c->g, c->ph, dt, b1, c->sc, c->red.part, c->ticket);
+        const double* f1 = H(k + 1); const double* f0 = H(k);
+        LAUNCH(c, adj_rhs_kernel, c->rb(), kRedThreads, p1, q1, f1, f0, Q(k + 1), Q(k), c->kb.p, c->a.p, c->g, c->ph, dt, b1, c->sc,
+               c->red.part, c->ticket);
         krylov_solve<true>(c, c->kb.p, c->a.p, st);
         VCH_CUDA(cudaMemcpyAsync(p0, c->kx.p, bytes, cudaMemcpyDeviceToDevice, c->stream));
         const double den = c->ph.gamma + 0.5 * dt;
@@ -484,8 +497,9 @@ std::vector<double> trapz_weights(const double* x, int n) {
     return w;
 }
 
-void cost_dev(vch2d_ctx* c, const double* phi_hist, const double* u, const double* phiQ, const double* phiT, int levels,
-              const double* x, const double* y, const double* t, double b1, double b2, double b3, double ksp, double* J_out) {
+struct CostWeights { double *wt, *wx, *wy; };
+// Uploads the np.trapz weights (time, x, y) into c->small.  Synchronises the work stream (pageable host vectors).
+CostWeights cost_weights(vch2d_ctx* c, int levels, const double* x, const double* y, const double* t) {
     const int nx1 = c->g.nx1, ny1 = c->g.ny1;   // slab mode: x is the GLOBAL abscissa vector, this rank integrates rows [o0, o0 + nx1)
     std::vector<double> w = trapz_weights(t, levels), wxg = trapz_weights(x, c->g.nxg), wy = trapz_weights(y, ny1);
     std::vector<double> wx(wxg.begin() + c->g.o0, wxg.begin() + c->g.o0 + nx1);
@@ -494,10 +508,21 @@ void cost_dev(vch2d_ctx* c, const double* phi_hist, const double* u, const doubl
     VCH_CUDA(cudaMemcpyAsync(dwt, w.data(), levels * sizeof(double), cudaMemcpyHostToDevice, c->stream));
     VCH_CUDA(cudaMemcpyAsync(dwx, wx.data(), nx1 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
     VCH_CUDA(cudaMemcpyAsync(dwy, wy.data(), ny1 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
-    VCH_CUDA(cudaStreamSynchronize(c->stream));   // w/wx/wy are pageable host vectors
+    VCH_CUDA(cudaStreamSynchronize(c->stream));
+    return {dwt, dwx, dwy};
+}
+void cost_finish(vch2d_ctx* c, double b1, double b2, double b3, double ksp, double* J_out);
+
+void cost_dev(vch2d_ctx* c, const double* phi_hist, const double* u, const double* phiQ, const double* phiT, int levels,
+              const double* x, const double* y, const double* t, double b1, double b2, double b3, double ksp, double* J_out) {
+    const CostWeights cw = cost_weights(c, levels, x, y, t);
     const long long total = (long long)levels * c->g.n;
-    LAUNCH(c, cost_kernel, red_blocks(total), kRedThreads, phi_hist, u, phiQ, phiT, levels, nx1, ny1, dwt, dwx, dwy, c->out4,
-           c->red.part, c->ticket);
+    LAUNCH(c, cost_kernel, red_blocks(total), kRedThreads, phi_hist, u, phiQ, phiT, levels, c->g.nx1, c->g.ny1, cw.wt, cw.wx, cw.wy,
+           c->out4, c->red.part, c->ticket, -2, 0);
+    cost_finish(c, b1, b2, b3, ksp, J_out);
+}
+// Reads the four raw integrals from c->out4 and forms J, J1..J4.
+void cost_finish(vch2d_ctx* c, double b1, double b2, double b3, double ksp, double* J_out) {
     VCH_CUDA(cudaMemcpyAsync(c->out4_host, c->out4, 4 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     VCH_CUDA(cudaStreamSynchronize(c->stream));
     const double J1 = 0.5 * b1 * c->out4_host[0], J2 = 0.5 * b2 * c->out4_host[1], J3 = 0.5 * b3 * c->out4_host[2],
@@ -727,6 +752,15 @@ int vch2d_set_krylov(vch2d_ctx* c, double rel_tol, int max_iter) {
         VCH_CUDA(cudaStreamSynchronize(c->stream));
         VCH_CUDA(cudaMemcpy(&c->sc->tol2, &t2, sizeof(double), cudaMemcpyHostToDevice));
         VCH_CUDA(cudaMemcpy(&c->sc->maxit, &max_iter, sizeof(int), cudaMemcpyHostToDevice));
+        return VCH_OK;
+    });
+}
+
+int vch2d_set_stream_budget(vch2d_ctx* c, long long bytes) {
+    return guarded([&] {
+        VCH_REQUIRE(c && bytes >= 0, VCH_E_ARG, "bad stream budget");
+        if (bytes != c->stream_budget) for (auto& b : c->stage) b.release();
+        c->stream_budget = bytes;
         return VCH_OK;
     });
 }
@@ -1101,6 +1135,160 @@ static void pgd_iteration_host_streamed(vch2d_ctx* c, int levels, const double* 
     cleanup();
 }
 
+// Bounded-memory variant of the host-buffer path: no trajectory ever exists on the device in full.  Every array is
+// walked in chunks of CH levels through a ring of 3 chunk slots, in the order the sweeps consume / produce it:
+//   adjoint sweep (levels descending):  phi_hist, phi_Q chunks in;  r chunks out to the host
+//   prox + forward sweep (ascending):   u, r chunks in -> u_new chunk (out, and input of the time steps) -> phi_hist_new
+//                                       chunk out, with the cost integrals accumulated per chunk (phi_Q chunks in again)
+// so trajectories larger than HBM (2048^2 x 1000 on one GPU, 4096^2 x 3000 on eight) only need host memory and PCIe time.
+// A slot is recycled once its last consumer (kernel or copy) has been passed by an event; three slots suffice because
+// every stage touches at most two neighbouring chunks at a time.
+static void pgd_iteration_host_bounded(vch2d_ctx* c, int levels, const double* t_hist, const double* dt_steps, const double* x,
+                                       const double* y, const double* u, const double* phi_hist, const double* phiQ,
+                                       const double* phiT, double b1, double b2, double b3, double ksp, double umin,
+                                       double umax, double alpha, double* u_new_out, double* phi_hist_out, double* r_out,
+                                       double* J_out, double* red_out, vch_stats* s, size_t budget_bytes) {
+    const long long n = c->g.n;
+    const size_t fb = (size_t)n * sizeof(double), tot = (size_t)levels * n;
+    const int D = 3;
+    const int nrings = phiQ ? 6 : 5;
+    int CH = (int)std::min<size_t>((size_t)levels, std::max<size_t>(2, budget_bytes / ((size_t)nrings * D * fb)));
+    const int nch = (levels + CH - 1) / CH;
+    DevBuf &rU = c->stage[0], &rH = c->stage[1], &rQ = c->stage[2], &dT = c->stage[3], &rUN = c->stage[4], &rHN = c->stage[5],
+           &rR = c->stage[6];
+    const size_t ring = (size_t)D * CH * n;
+    rU.alloc(ring); rH.alloc(ring); rUN.alloc(ring); rHN.alloc(ring); rR.alloc(ring);
+    if (phiQ) rQ.alloc(ring);
+    if (phiT) dT.alloc(n);
+    auto at = [&](DevBuf& b, int level) { const int j = level / CH; return b.p + ((size_t)(j % D) * CH + (level - j * CH)) * n; };
+    auto lo_of = [&](int j) { return (size_t)j * CH; };
+    auto cnt_of = [&](int j) { return std::min<size_t>(CH, levels - lo_of(j)); };
+    double* rh = r_out;
+    if (!rh) { c->r_host.resize(tot); rh = c->r_host.data(); }
+
+    cudaStream_t cp;
+    VCH_CUDA(cudaStreamCreateWithFlags(&cp, cudaStreamNonBlocking));
+    enum { InA, FreeA, Rdone, Rsaved, InB, Prox, UNsaved, InQ, Cost, HNsaved, NKINDS };
+    std::vector<cudaEvent_t> ev((size_t)NKINDS * nch);
+    for (auto& e : ev) VCH_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    cudaEvent_t ev_misc[2];
+    for (auto& e : ev_misc) VCH_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    auto E = [&](int kind, int j) { return ev[(size_t)kind * nch + j]; };
+    auto rec = [&](int kind, int j, cudaStream_t st) { VCH_CUDA(cudaEventRecord(E(kind, j), st)); };
+    auto wait = [&](cudaStream_t st, int kind, int j) { VCH_CUDA(cudaStreamWaitEvent(st, E(kind, j), 0)); };
+    auto cleanup = [&] {
+        cudaStreamSynchronize(cp); cudaStreamSynchronize(c->stream);
+        for (auto& e : ev) cudaEventDestroy(e);
+        for (auto& e : ev_misc) cudaEventDestroy(e);
+        cudaStreamDestroy(cp);
+    };
+    try {
+        VCH_CUDA(cudaEventRecord(c->ev_in, c->stream));
+        VCH_CUDA(cudaStreamWaitEvent(cp, c->ev_in, 0));
+        if (phiT) {
+            VCH_CUDA(cudaMemcpyAsync(dT.p, phiT, fb, cudaMemcpyHostToDevice, cp));
+            VCH_CUDA(cudaEventRecord(ev_misc[0], cp));
+            VCH_CUDA(cudaStreamWaitEvent(c->stream, ev_misc[0], 0));
+        }
+        // ------------------------------------------------------------------ (1) adjoint sweep, levels descending
+        int nextLoadA = nch - 1, nextFreeA = nch - 1, waitedA = nch, rDone = nch, rEntered = nch;
+        auto loadA = [&](int j) {
+            if (j + D < nch) wait(cp, FreeA, j + D);
+            VCH_CUDA(cudaMemcpyAsync(at(rH, (int)lo_of(j)), phi_hist + lo_of(j) * n, cnt_of(j) * fb, cudaMemcpyHostToDevice, cp));
+            if (phiQ) VCH_CUDA(cudaMemcpyAsync(at(rQ, (int)lo_of(j)), phiQ + lo_of(j) * n, cnt_of(j) * fb, cudaMemcpyHostToDevice, cp));
+            rec(InA, j, cp);
+        };
+        auto save_r = [&](int j) {   // chunk j of r is complete on the device
+            rec(Rdone, j, c->stream); wait(cp, Rdone, j);
+            VCH_CUDA(cudaMemcpyAsync(rh + lo_of(j) * n, at(rR, (int)lo_of(j)), cnt_of(j) * fb, cudaMemcpyDeviceToHost, cp));
+            rec(Rsaved, j, cp);
+        };
+        auto needA = [&](int k) {    // called before level k (which reads levels k and k + 1) is processed
+            const int jk = k / CH;
+            while (nextFreeA >= 0 && lo_of(nextFreeA) > (size_t)k + 1) { rec(FreeA, nextFreeA, c->stream); --nextFreeA; }
+            while (rDone - 1 > jk) { --rDone; save_r(rDone); }
+            while (nextLoadA >= 0 && nextLoadA >= jk - 1) { loadA(nextLoadA); --nextLoadA; }
+            while (waitedA > jk) { --waitedA; wait(c->stream, InA, waitedA); }
+            while (rEntered > jk) { --rEntered; if (rEntered + D < nch) wait(c->stream, Rsaved, rEntered + D); }
+        };
+        LevelMap lmA;
+        lmA.hist = [&](int k) { return at(rH, k); };
+        if (phiQ) lmA.Q = [&](int k) { return at(rQ, k); };
+        lmA.r = [&](int k) { return at(rR, k); };
+        adjoint_dev(c, nullptr, levels, t_hist, b1, b2, nullptr, phiT ? dT.p : nullptr, nullptr, nullptr, nullptr, s, needA, &lmA);
+        while (rDone > 0) { --rDone; save_r(rDone); }
+        VCH_CUDA(cudaEventRecord(ev_misc[1], c->stream));           // phase (2) re-uses the Q and r rings
+        VCH_CUDA(cudaStreamWaitEvent(cp, ev_misc[1], 0));
+
+        // ------------------------------------------------------------------ (2) prox + forward sweep + cost, levels ascending
+        const CostWeights cw = cost_weights(c, levels, x, y, t_hist);
+        VCH_CUDA(cudaMemsetAsync(c->out4, 0, 8 * sizeof(double), c->stream));
+        int nextLoadB = 0, proxed = 0, nextLoadQ = 0, hnEntered = 0;
+        auto loadB = [&](int j) {
+            if (j - D >= 0) wait(cp, Prox, j - D);
+            VCH_CUDA(cudaMemcpyAsync(at(rU, (int)lo_of(j)), u + lo_of(j) * n, cnt_of(j) * fb, cudaMemcpyHostToDevice, cp));
+            VCH_CUDA(cudaMemcpyAsync(at(rR, (int)lo_of(j)), rh + lo_of(j) * n, cnt_of(j) * fb, cudaMemcpyHostToDevice, cp));
+            rec(InB, j, cp);
+        };
+        auto loadQ = [&](int j) {
+            if (!phiQ) return;
+            if (j - D >= 0) wait(cp, Cost, j - D);
+            VCH_CUDA(cudaMemcpyAsync(at(rQ, (int)lo_of(j)), phiQ + lo_of(j) * n, cnt_of(j) * fb, cudaMemcpyHostToDevice, cp));
+            rec(InQ, j, cp);
+        };
+        auto prox_upto = [&](int level) {
+            const int jmax = std::min(nch - 1, level / CH);
+            while (proxed <= jmax) {
+                const int j = proxed++;
+                while (nextLoadB < nch && nextLoadB <= j + 1) { loadB(nextLoadB); ++nextLoadB; }
+                wait(c->stream, InB, j);
+                if (j - D >= 0) wait(c->stream, UNsaved, j - D);
+                const long long cnt = (long long)cnt_of(j) * n;
+                LAUNCH(c, grad_prox_kernel, red_blocks(cnt), kRedThreads, at(rU, (int)lo_of(j)), at(rR, (int)lo_of(j)), (double*)nullptr,
+                       at(rUN, (int)lo_of(j)), cnt, b3, alpha, ksp, umin, umax, c->out4 + 4, c->red.part, c->ticket, 1);
+                rec(Prox, j, c->stream); wait(cp, Prox, j);
+                VCH_CUDA(cudaMemcpyAsync(u_new_out + lo_of(j) * n, at(rUN, (int)lo_of(j)), cnt_of(j) * fb, cudaMemcpyDeviceToHost, cp));
+                rec(UNsaved, j, cp);
+            }
+        };
+        auto before = [&](int step) {
+            prox_upto(step + 1);
+            const int j = (step + 1) / CH;       // slot that receives level step + 1
+            while (hnEntered <= j) { if (hnEntered - D >= 0) wait(c->stream, HNsaved, hnEntered - D); ++hnEntered; }
+        };
+        auto after = [&](int k) {                // level k of the new trajectory has been enqueued
+            if ((k + 1) % CH != 0 && k != levels - 1) return;
+            const int j = k / CH;
+            while (nextLoadQ < nch && nextLoadQ <= j + 1) { loadQ(nextLoadQ); ++nextLoadQ; }
+            if (phiQ) wait(c->stream, InQ, j);
+            const int cnt = (int)cnt_of(j);
+            LAUNCH(c, cost_kernel, red_blocks((long long)cnt * n), kRedThreads, at(rHN, (int)lo_of(j)), at(rUN, (int)lo_of(j)),
+                   phiQ ? at(rQ, (int)lo_of(j)) : (const double*)nullptr, phiT ? dT.p : (const double*)nullptr, cnt, c->g.nx1, c->g.ny1,
+                   cw.wt + lo_of(j), cw.wx, cw.wy, c->out4, c->red.part, c->ticket, (k == levels - 1) ? cnt - 1 : -1, 1);
+            rec(Cost, j, c->stream); wait(cp, Cost, j);
+            VCH_CUDA(cudaMemcpyAsync(phi_hist_out + lo_of(j) * n, at(rHN, (int)lo_of(j)), cnt_of(j) * fb, cudaMemcpyDeviceToHost, cp));
+            rec(HNsaved, j, cp);
+        };
+        loadQ(0); nextLoadQ = 1;
+        LevelMap lmB;
+        lmB.u = [&](int k) { return at(rUN, k); };
+        lmB.hist_new = [&](int k) { return at(rHN, k); };
+        hnEntered = 1;                                               // level 0 goes into a fresh slot
+        forward_dev(c, at(rH, 0), nullptr, levels, levels - 1, dt_steps, nullptr, nullptr, nullptr, s, after, before, &lmB);
+        prox_upto(levels - 1);
+        if (levels == 1) after(0);
+        cost_finish(c, b1, b2, b3, ksp, J_out);
+        if (red_out) {
+            VCH_CUDA(cudaMemcpyAsync(c->out4_host + 4, c->out4 + 4, 4 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+            VCH_CUDA(cudaStreamSynchronize(c->stream));
+            for (int k = 0; k < 4; ++k) red_out[k] = c->out4_host[4 + k];
+        }
+        VCH_CUDA(cudaStreamSynchronize(cp));
+        VCH_CUDA(cudaStreamSynchronize(c->stream));
+    } catch (...) { cleanup(); throw; }
+    cleanup();
+}
+
 int vch2d_pgd_iteration(vch2d_ctx* c, int levels, const double* t_hist, const double* dt_steps, const double* x,
                         const double* y, const double* u, const double* phi_hist, const double* phiQ, const double* phiT,
                         double b1, double b2, double b3, double ksp, double umin, double umax, double alpha,
@@ -1115,8 +1303,23 @@ int vch2d_pgd_iteration(vch2d_ctx* c, int levels, const double* t_hist, const do
         const size_t tot = (size_t)levels * n;
         vch_stats local{}; vch_stats* s = stats ? stats : &local;
         if (mem == VCH_MEM_HOST) {
-            pgd_iteration_host_streamed(c, levels, t_hist, dt_steps, x, y, u, phi_hist, phiQ, phiT, b1, b2, b3, ksp, umin, umax,
-                                        alpha, u_new_out, phi_hist_out, r_out, J_out, red_out, s);
+            // full device staging (5-6 trajectories) when it fits, chunk rings otherwise or when a budget was set
+            size_t freeb = 0, totalb = 0, held = 0;
+            VCH_CUDA(cudaMemGetInfo(&freeb, &totalb));
+            for (auto& b : c->stage) held += b.n * sizeof(double);
+            const size_t full = ((size_t)(phiQ ? 6 : 5) * tot + (size_t)n) * sizeof(double);
+            const bool bounded = c->stream_budget > 0 || full > (size_t)(0.92 * (double)(freeb + held));
+            if (bounded) {
+                if (c->stream_budget <= 0)      // the full-size staging of an earlier, smaller call is of no use here
+                    for (auto& b : c->stage) if (b.n > 0 && b.n * sizeof(double) > (size_t)(0.05 * (double)totalb)) b.release();
+                VCH_CUDA(cudaMemGetInfo(&freeb, &totalb));
+                const size_t budget = c->stream_budget > 0 ? (size_t)c->stream_budget : (size_t)(0.6 * (double)freeb);
+                pgd_iteration_host_bounded(c, levels, t_hist, dt_steps, x, y, u, phi_hist, phiQ, phiT, b1, b2, b3, ksp, umin, umax,
+                                           alpha, u_new_out, phi_hist_out, r_out, J_out, red_out, s, budget);
+            } else {
+                pgd_iteration_host_streamed(c, levels, t_hist, dt_steps, x, y, u, phi_hist, phiQ, phiT, b1, b2, b3, ksp, umin, umax,
+                                            alpha, u_new_out, phi_hist_out, r_out, J_out, red_out, s);
+            }
             stat_collect(c, mark0, s);
             return VCH_OK;
         }

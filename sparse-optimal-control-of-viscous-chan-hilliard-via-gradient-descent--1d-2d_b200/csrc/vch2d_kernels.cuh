@@ -425,8 +425,11 @@ __global__ void adj_qr_kernel(const double* __restrict__ p0, const double* __res
 __global__ void cost_kernel(const double* __restrict__ phi, const double* __restrict__ u, const double* __restrict__ Q,
                             const double* __restrict__ phiT, int levels, int nx1, int ny1,
                             const double* __restrict__ wt, const double* __restrict__ wx, const double* __restrict__ wy,
-                            double* out4, double* part, unsigned int* ticket) {
+                            double* out4, double* part, unsigned int* ticket, int term_level = -2, int accumulate = 0) {
+    // term_level: index (within the levels given) of the terminal level carrying the J2 term; -2 = the last one (whole
+    // trajectory in one launch), -1 = none (a chunk that does not contain the final time).  accumulate: add to out4.
     const long long n = (long long)nx1 * ny1, total = n * levels;
+    if (term_level == -2) term_level = levels - 1;
     double v[4] = {0.0, 0.0, 0.0, 0.0};
     for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
         const int t = (int)(idx / n);
@@ -436,13 +439,14 @@ __global__ void cost_kernel(const double* __restrict__ phi, const double* __rest
         const double f = phi[idx];
         const double e = f - (Q ? Q[idx] : 0.0);
         v[0] += w * e * e;
-        if (t == levels - 1) { const double d = f - (phiT ? phiT[node] : 0.0); v[1] += ws * d * d; }
+        if (t == term_level) { const double d = f - (phiT ? phiT[node] : 0.0); v[1] += ws * d * d; }
         if (u) { const double uv = u[idx]; v[2] += w * uv * uv; v[3] += w * fabs(uv); }
     }
     const int op[4] = {0, 0, 0, 0};
     double tot[4];
     if (grid_reduce<4>(v, op, part, ticket, tot) && threadIdx.x == 0) {
-        out4[0] = tot[0]; out4[1] = tot[1]; out4[2] = tot[2]; out4[3] = tot[3];
+        if (accumulate) { out4[0] += tot[0]; out4[1] += tot[1]; out4[2] += tot[2]; out4[3] += tot[3]; }
+        else { out4[0] = tot[0]; out4[1] = tot[1]; out4[2] = tot[2]; out4[3] = tot[3]; }
     }
 }
 

@@ -182,6 +182,40 @@ def test_device_resident_call_equals_host_call(native):
     assert np.array_equal(h_dev.cpu().numpy(), h_host)
 
 
+@pytest.mark.parametrize("budget_levels,with_Q,with_r", [(2, True, True), (5, True, False), (7, False, True), (1000, True, True)])
+def test_bounded_memory_streaming_equals_full_staging(native, budget_levels, with_Q, with_r):
+    """Host-buffer PGD iteration with the trajectories walked through chunk rings (vch2d_set_stream_budget; the mode for
+    trajectories larger than HBM) against the fully staged path: identical u_new / phi_hist_new / r bits, J to the rounding
+    of the chunked cost sums.  Chunk sizes that do not divide the number of levels, rings that wrap many times."""
+    P = O.Phys2D(Nx=32, Ny=24, Lx=1.0, Ly=0.75, T=0.23)          # 23 steps -> 24 levels
+    Op = O.Opt2D()
+    c = make_ctx(native, P)
+    rng = np.random.default_rng(5)
+    phi0 = O.init_phi_2d(P.Nx, P.Ny)
+    dts = dt_list(P)
+    t = np.concatenate([[0.0], np.cumsum(dts)])
+    hist, _, _ = c.forward(phi0, None, dts)
+    x, y = np.linspace(0, P.Lx, P.Nx + 1), np.linspace(0, P.Ly, P.Ny + 1)
+    phiT = 0.7 * np.sin(2 * np.pi * x)[:, None] * np.cos(np.pi * y)[None, :]
+    phiQ = (1 - t / t[-1])[:, None, None] * hist[0] + (t / t[-1])[:, None, None] * phiT if with_Q else None
+    u = 0.3 * rng.standard_normal(hist.shape)
+    args = (Op.b1, Op.b2, Op.b3, Op.kappa_sparsity, Op.u_min, Op.u_max, 20.0)
+    r_full = np.zeros_like(hist)
+    u1, h1, J, red, _ = c.pgd_iteration(u, hist, phiQ, phiT, t, dts, x, y, *args, r_out=r_full)
+    field = 8 * (P.Nx + 1) * (P.Ny + 1)
+    c.set_stream_budget((6 if with_Q else 5) * 3 * budget_levels * field)
+    try:
+        r_b = np.zeros_like(hist) if with_r else None
+        u2, h2, J2, red2, _ = c.pgd_iteration(u, hist, phiQ, phiT, t, dts, x, y, *args, r_out=r_b)
+    finally:
+        c.set_stream_budget(0)
+    assert np.array_equal(u2, u1) and np.array_equal(h2, h1)
+    if with_r:
+        assert np.array_equal(r_b, r_full)
+    np.testing.assert_allclose(J2[:5], J[:5], rtol=1e-13)
+    np.testing.assert_allclose(red2, red, rtol=1e-13)
+
+
 def test_adjoint_step_identity_small_rect(native):
     """A(phi_n) p_n = B(phi_{n+1}) p_{n+1} + src with independently assembled A, B (cf. test_2d_backward.py:209-246),
     on the reference test's own 7x6-node synthetic history."""
