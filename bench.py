@@ -279,10 +279,15 @@ def run_b200(args):
             state.clear()
             torch.cuda.empty_cache()
             reps = max(1, min(args.steps, args.e2e_steps))
+            bounded = args.stream_budget_gb > 0          # out-of-core mode: chunk rings instead of whole trajectories on the device
+            hr = torch.empty_like(hu).pin_memory() if bounded else None
+            if bounded:
+                ctx.set_stream_budget(int(args.stream_budget_gb * 1e9))
 
             def host_step():
                 return ctx.pgd_iteration(hu.numpy(), hh.numpy(), hq.numpy(), hT.numpy(), t_hist, dts, x, x, Op.b1, Op.b2, Op.b3,
-                                         Op.kappa_sparsity, Op.u_min, Op.u_max, alpha, u_out=hun.numpy(), phi_out=hhn.numpy())
+                                         Op.kappa_sparsity, Op.u_min, Op.u_max, alpha, u_out=hun.numpy(), phi_out=hhn.numpy(),
+                                         r_out=hr.numpy() if bounded else None)
             host_step()                                          # warm-up
             barrier()
             t0 = time.perf_counter()
@@ -292,8 +297,10 @@ def run_b200(args):
             tt = torch.tensor([(time.perf_counter() - t0) / reps], device=dev, dtype=torch.float64)
             if world > 1:
                 dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-            e2e = {"value": world / float(tt.item()), "unit": UNIT, "h2d_bytes_per_step": int((3 * lv + 1) * field_bytes),
-                   "d2h_bytes_per_step": int(2 * lv * field_bytes + 9 * 8), "steps": reps,
+            e2e = {"value": world / float(tt.item()), "unit": UNIT, "h2d_bytes_per_step": int(((5 if bounded else 3) * lv + 1) * field_bytes),
+                   "d2h_bytes_per_step": int((3 if bounded else 2) * lv * field_bytes + 9 * 8), "steps": reps,
+                   "device_staging": (f"chunk rings, {args.stream_budget_gb:g} GB budget (phi_Q is uploaded twice, r makes a round trip)"
+                                      if bounded else "whole trajectories"),
                    "call": "vch2d_pgd_iteration(mem=VCH_MEM_HOST): u, phi_hist, phi_Q, phi_T in; u_new, phi_hist_new, J, norms out"}
         except Exception as exc:   # report, do not hide
             e2e = {"value": None, "unit": UNIT, "error": repr(exc)}
@@ -480,6 +487,8 @@ def main():
     ap.add_argument("--profile-steps", type=int, default=20)
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--stream-budget-gb", type=float, default=0.0,
+                    help="e2e leg: cap the device staging (vch2d_set_stream_budget) -> bounded-memory chunk-ring mode; 0 = whole trajectories")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--workload", default="pgd2d", choices=["pgd2d", "ensemble1d", "slab2d"],
                     help="pgd2d = BASELINE metric (default); ensemble1d = config 4; slab2d = config 5 (one problem over all ranks)")
