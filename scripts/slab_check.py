@@ -104,6 +104,16 @@ if "host" in stages:    # host-buffer (streamed PCIe) entry point on the slab: N
     slab.set_stream_budget(0)
     check("bounded-memory u_new", torch.from_numpy(u1b), u1d.cpu(), 1e-14); check("bounded-memory phi_hist_new", torch.from_numpy(h1b), h1d.cpu(), 1e-14)
     if abs(Jb[0] - Jd[0]) > 1e-12 * abs(Jd[0]): say("bounded-memory J mismatch FAIL"); worst = max(worst, 1e9)
+if "desync" in stages:   # a rank that never arrives: the waiting rank must fail with VCH_E_COMM after the wait limit, not hang
+    if rank == 0:
+        t0 = time.perf_counter()
+        try:
+            slab.selftest()
+            say("desync: no error raised FAIL"); worst = 1e9
+        except RuntimeError as exc:
+            ok = "error 6" in str(exc) and time.perf_counter() - t0 < 60
+            say(f"desync: raised after {time.perf_counter() - t0:.1f}s: {exc} {'ok' if ok else 'FAIL'}")
+            if not ok: worst = 1e9
 dist.barrier()
 say("RESULT", "PASS" if worst <= 1.0 else "FAIL", f"(worst err/tol {worst:.2e})")
 dist.destroy_process_group()

@@ -50,3 +50,12 @@ def test_slab_context_rejects_bad_shapes():
     assert (c.row0, c.rows) == nat.slab_partition(128, 2)[1] == (64, 65)
     with pytest.raises(RuntimeError):       # but it cannot run collectives before the peers are attached
         c.selftest()
+
+
+def test_missing_peer_raises_instead_of_hanging():
+    """One rank skips a collective call: the other must come back with VCH_E_COMM once the 10 s wait limit expires."""
+    if _gpus() < 2:
+        pytest.skip("slab mode needs at least 2 GPUs")
+    out = _run(2, 128, 2, "desync", timeout=300)
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
+    assert "desync: raised after" in out.stdout and "FAIL" not in out.stdout, out.stdout[-3000:]
