@@ -301,6 +301,9 @@ __device__ __forceinline__ bool grid_reduce(double (&v)[K], const int (&op)[K], 
                                             double (&tot)[K]) {
     __shared__ double sh[32];
     __shared__ bool is_last;
+    // slab mode flag, fetched up front so that its latency hides under the block reduction instead of trailing the kernel
+    int nranks = 1;
+    if (threadIdx.x == 0) nranks = comm_of(part)->nranks;
 #pragma unroll
     for (int k = 0; k < K; ++k) {
         double r = (op[k] == 0) ? block_red<0>(v[k], sh) : (op[k] == 1) ? block_red<1>(v[k], sh) : block_red<2>(v[k], sh);
@@ -325,8 +328,7 @@ __device__ __forceinline__ bool grid_reduce(double (&v)[K], const int (&op)[K], 
     }
     if (threadIdx.x == 0) {
         *ticket = 0u;   // re-arm for the next launch on this stream
-        const Comm* cm = comm_of(part);
-        if (cm->nranks > 1) xrank_reduce<K>(tot, op, *cm);
+        if (nranks > 1) xrank_reduce<K>(tot, op, *comm_of(part));
     }
     return true;
 }

@@ -247,7 +247,8 @@ __device__ __forceinline__ void fft_last_pass(const double2* data, int t, const 
 #ifndef VCH_FFT_MINB
 #define VCH_FFT_MINB (1024 / MAXT)
 #endif
-template <int LOG2L, bool SOLVE, int MAXT>
+// XM: slab transposition mode of the row kernel, compile-time (0 none, 1 transposing store, 3 gathering load; see Scatter)
+template <int LOG2L, bool SOLVE, int MAXT, int XM = 0>
 __global__ void __launch_bounds__(MAXT, VCH_FFT_MINB)
 dct_fft_kernel(const double* in, double* out, int nlines, int n, int in_ls, int in_es, int out_ls, int out_es, int ppb,
                const double2* __restrict__ twg, const double* __restrict__ lam_line, const double* __restrict__ lam_elem,
@@ -277,7 +278,7 @@ dct_fft_kernel(const double* in, double* out, int nlines, int n, int in_ls, int 
     // SOLVE (columns): the two lines of a pair are adjacent doubles of a pitched buffer whose pitch is even, so one
     // 16-byte access moves both.
     double2 v[8];
-    if (!SOLVE && sct.mode == 3) {
+    if (!SOLVE && XM == 3) {
         // slab mode: gather the row pair from the column owners' buffers.  Staged through shared memory with 16-byte loads so
         // that every element crosses NVLink once (the direct path below re-reads each element for its mirror image, which
         // is free from L1/L2 but doubles remote traffic).  The staging area is the FFT's own data buffer.
@@ -364,7 +365,7 @@ dct_fft_kernel(const double* in, double* out, int nlines, int n, int in_ls, int 
         const int kk = t + FftOut<LOG2L>::off(q);
         if (kk <= N) {
             const int off = kk * out_es;
-            if (!SOLVE && sct.mode == 1) {   // slab mode: transposing store into the owning peer's buffer
+            if (!SOLVE && XM == 1) {   // slab mode: transposing store into the owning peer's buffer
                 int r = kk >> sct.shift; if (r >= sct.nr) r = sct.nr - 1;
                 const int kl = kk - (r << sct.shift);
                 double* dst = sct.peer[r] + sct.off;
@@ -545,6 +546,8 @@ inline void DctPlan::init(int no_, int ni_, double h_outer, double h_inner, Laun
     const int big = 200 * 1024;
 #define VCH_FFT_ATTR(LG)                                                                                                                        \
     VCH_CUDA(cudaFuncSetAttribute(dct_fft_kernel<LG, false, ((1 << LG) / 8 <= 512 ? 512 : 1024)>, cudaFuncAttributeMaxDynamicSharedMemorySize, big)); \
+    VCH_CUDA(cudaFuncSetAttribute(dct_fft_kernel<LG, false, ((1 << LG) / 8 <= 512 ? 512 : 1024), 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, big)); \
+    VCH_CUDA(cudaFuncSetAttribute(dct_fft_kernel<LG, false, ((1 << LG) / 8 <= 512 ? 512 : 1024), 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, big)); \
     VCH_CUDA(cudaFuncSetAttribute(dct_fft_kernel<LG, true, ((1 << LG) / 8 <= 512 ? 512 : 1024)>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
     for (const DctAxis* ax : {&inner, &outer}) {
         if (!ax->fft) continue;
@@ -594,6 +597,10 @@ inline void DctPlan::apply(cudaStream_t s, const double* in, double* out, const 
 #define VCH_FFT_CASE(LG)                                                                                                      \
         case LG:                                                                                                              \
             if (solve) dct_fft_kernel<LG, true, ((1 << LG) / 8 <= 512 ? 512 : 1024)><<<grid, threads, smem, s>>>(              \
+                a, b, nl, nn, ils, ies, ols, oes, ppb_, ax.tw, ll, le, sy, nrm, smode, pr, ep, done, sc8);                     \
+            else if (sc8.mode == 1) dct_fft_kernel<LG, false, ((1 << LG) / 8 <= 512 ? 512 : 1024), 1><<<grid, threads, smem, s>>>( \
+                a, b, nl, nn, ils, ies, ols, oes, ppb_, ax.tw, ll, le, sy, nrm, smode, pr, ep, done, sc8);                     \
+            else if (sc8.mode == 3) dct_fft_kernel<LG, false, ((1 << LG) / 8 <= 512 ? 512 : 1024), 3><<<grid, threads, smem, s>>>( \
                 a, b, nl, nn, ils, ies, ols, oes, ppb_, ax.tw, ll, le, sy, nrm, smode, pr, ep, done, sc8);                     \
             else dct_fft_kernel<LG, false, ((1 << LG) / 8 <= 512 ? 512 : 1024)><<<grid, threads, smem, s>>>(                   \
                 a, b, nl, nn, ils, ies, ols, oes, ppb_, ax.tw, ll, le, sy, nrm, smode, pr, ep, done, sc8);                     \
