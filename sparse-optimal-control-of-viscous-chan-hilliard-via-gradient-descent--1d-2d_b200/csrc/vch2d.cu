@@ -72,14 +72,6 @@ void fetch_scalars(vch2d_ctx* c) {
         (c)->log.end((c)->stream);                              \
     } while (0)
 
-template <bool ADJ>
-void op_apply(vch2d_ctx* c, const double* x, const double* a, double* y, const int* done) {
-    dim3 grid((c->g.ni + kTI - 1) / kTI, (c->g.no + kTO - 1) / kTO);
-    c->log.begin(ADJ ? "op_apply_adj" : "op_apply_fwd", c->stream);
-    op_apply_kernel<ADJ><<<grid, 256, 0, c->stream>>>(x, a, y, c->g, &c->sc->c0, done);
-    c->log.end(c->stream);
-}
-
 // Slab mode: ship the first / last `rows` owned rows of one or two fields into the neighbours' ghost rows; a barrier inside
 // the kernel guarantees the rows have landed before anything reads them (lead = 1 adds a barrier in front, see
 // halo_push_kernel).  No-op outside slab mode.
@@ -96,8 +88,10 @@ void copy_ghosted(vch2d_ctx* c, double* dst, const double* src) {
     VCH_CUDA(cudaMemcpyAsync(dst - m, src - m, ((size_t)c->g.n + 2 * m) * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
 }
 // kernels per BiCGStab iteration / per solve prologue (accounting of launches inside solve graphs)
-template <bool ADJ> int iter_launches(const vch2d_ctx* c) { return ADJ ? (c->slab ? 11 + 4 + 2 : 11) : (c->slab ? 7 + 4 : 7); }
-int prologue_launches(const vch2d_ctx* c) { return c->slab ? 7 : 4; }
+template <bool ADJ> int iter_launches(const vch2d_ctx* c) { return c->slab ? 7 + 4 : 7; }
+// FWD: P^-1 b (3 kernels) + init;  ADJ (right-preconditioned): init + the closing x = P^-1 y (3 kernels); slab mode adds the
+// barriers of one preconditioner application (2 + the trailing one)
+template <bool ADJ> int prologue_launches(const vch2d_ctx* c) { return 4 + (c->slab ? 3 : 0); }
 
 // Orders the library's private stream after the caller's stream on entry and the caller's stream after ours on exit,
 // so callers see ordinary stream semantics (torch.cuda.Event on their stream brackets our kernels).
@@ -114,36 +108,42 @@ struct StreamScope {
     }
 };
 
-// One BiCGStab iteration.
-//   Forward Schur operator (ADJ = false): A = P - L diag(a - abar), so P^-1 A x = x + DCT^-1[(lambda/sym) DCT((a - abar) x)]:
-//     no stencil kernel at all.  7 launches: rows[p = r + beta q; (a-abar)p] -> cols[lambda/sym] -> rows[+p, (r0,v)] ->
-//     rows[s = r - alpha v; (a-abar)s] -> cols -> rows[+s, (t,s),(t,t)] -> x/r/q update with (r,r),(r0,r).
-//   Adjoint operator (ADJ = true): A = P - diag(a - abar) L has the multiply on the other side, so it keeps the explicit
-//     two-level stencil: p-update, stencil, 3-kernel DCT solve (+dots), s-update, stencil, DCT solve, x/r update = 11 launches.
+// One BiCGStab iteration, stencil-free for both operators (7 launches):
+//   Forward Schur operator (ADJ = false), LEFT-preconditioned:  A = P - L diag(a - abar), so
+//     P^-1 A x = x + DCT^-1[(lambda/sym) DCT((a - abar) x)]      (coefficient multiply fused into the row prologue)
+//   Adjoint operator (ADJ = true), RIGHT-preconditioned:        A = P - diag(a - abar) L, so
+//     A P^-1 y = y + (a - abar) DCT^-1[(lambda/sym) DCT(y)]      (coefficient multiply fused into the row epilogue);
+//     the iteration runs on y with the TRUE residual b - A x, and x = P^-1 y closes the solve.
+//   rows[p = r + beta q (; (a-abar)p)] -> cols[lambda/sym] -> rows[(a-abar)z + p, (r0,v)] -> rows[s = r - alpha v ...] ->
+//   cols -> rows[... + s, (t,s),(t,t)] -> x/r/q update with (r,r),(r0,r).
 template <bool ADJ>
 void enqueue_bicg_iteration(vch2d_ctx* c, const double* a, const SymbolArgs& sy, cudaGraphConditionalHandle cond, int use_cond) {
     const long long n = c->g.n;
-    const int rb = c->rb(), eb = c->eb();
+    const int rb = c->rb();
     const int* done = &c->sc->done;
-    if (ADJ) {
-        LAUNCH(c, bicg_p_kernel, eb, 256, c->kr.p, c->kp.p, c->kv.p, n, c->sc);
-        halo_push(c, c->kp.p, nullptr, 2, done);
-        op_apply<true>(c, c->kp.p, a, c->ktmp.p, done);
-        c->dct.apply(c->stream, c->ktmp.p, c->kv.p, sy, done, DotEpilogue{1, c->kr0.p, c->sc, c->red.part, c->ticket, nullptr});
-        LAUNCH(c, bicg_s_kernel, eb, 256, c->kr.p, c->kv.p, c->ks.p, n, c->sc);
-        halo_push(c, c->ks.p, nullptr, 2, done);
-        op_apply<true>(c, c->ks.p, a, c->ktmp.p, done);
-        c->dct.apply(c->stream, c->ktmp.p, c->kt.p, sy, done, DotEpilogue{2, c->ks.p, c->sc, c->red.part, c->ticket, nullptr});
-        LAUNCH(c, bicg_x_kernel, rb, kRedThreads, c->kx.p, c->kr.p, c->kp.p, c->ks.p, c->kt.p, c->kr0.p, (const double*)nullptr,
-               (double*)nullptr, n, c->sc, c->red.part, c->ticket, cond, use_cond);
-    } else {
-        c->dct.apply(c->stream, c->kr.p, c->kv.p, sy, done, DotEpilogue{1, c->kr0.p, c->sc, c->red.part, c->ticket, c->kp.p},
-                     RowPrologue{1, c->kr.p, c->kq.p, a, c->kp.p, c->sc}, 1);
-        c->dct.apply(c->stream, c->kr.p, c->kt.p, sy, done, DotEpilogue{2, c->ks.p, c->sc, c->red.part, c->ticket, c->ks.p},
-                     RowPrologue{2, c->kr.p, c->kv.p, a, c->ks.p, c->sc}, 1);
-        LAUNCH(c, bicg_x_kernel, rb, kRedThreads, c->kx.p, c->kr.p, c->kp.p, c->ks.p, c->kt.p, c->kr0.p, c->kv.p, c->kq.p, n, c->sc,
-               c->red.part, c->ticket, cond, use_cond);
-    }
+    const double* pro_a = ADJ ? nullptr : a;     // multiply before the transform (forward) ...
+    const double* epi_a = ADJ ? a : nullptr;     // ... or after it (adjoint)
+    c->dct.apply(c->stream, c->kr.p, c->kv.p, sy, done, DotEpilogue{1, c->kr0.p, c->sc, c->red.part, c->ticket, c->kp.p, epi_a},
+                 RowPrologue{1, c->kr.p, c->kq.p, pro_a, c->kp.p, c->sc}, 1);
+    c->dct.apply(c->stream, c->kr.p, c->kt.p, sy, done, DotEpilogue{2, c->ks.p, c->sc, c->red.part, c->ticket, c->ks.p, epi_a},
+                 RowPrologue{2, c->kr.p, c->kv.p, pro_a, c->ks.p, c->sc}, 1);
+    LAUNCH(c, bicg_x_kernel, rb, kRedThreads, c->kx.p, c->kr.p, c->kp.p, c->ks.p, c->kt.p, c->kr0.p, c->kv.p, c->kq.p, n, c->sc,
+           c->red.part, c->ticket, cond, use_cond);
+}
+
+// Start of a solve: FWD r = P^-1 b; ADJ r = b.  Then r0 = r, x = q = 0 and the norms.
+template <bool ADJ>
+void enqueue_bicg_prologue(vch2d_ctx* c, const SymbolArgs& sy, cudaGraphConditionalHandle cond, int use_cond) {
+    const long long n = c->g.n;
+    if (ADJ) VCH_CUDA(cudaMemcpyAsync(c->kr.p, c->kb.p, n * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+    else c->dct.apply(c->stream, c->kb.p, c->kr.p, sy, nullptr);
+    LAUNCH(c, bicg_init_kernel, c->rb(), kRedThreads, c->kr.p, c->kr0.p, c->kp.p, c->kv.p, c->kx.p, c->kq.p, n, c->sc,
+           c->red.part, c->ticket, cond, use_cond);
+}
+// End of a solve: ADJ x = P^-1 y.
+template <bool ADJ>
+void enqueue_bicg_epilogue(vch2d_ctx* c, const SymbolArgs& sy) {
+    if (ADJ) c->dct.apply(c->stream, c->kx.p, c->kx.p, sy, nullptr);
 }
 
 // Whole linear solve as ONE CUDA graph: [P^-1 b, init] -> WHILE(not converged){ BiCGStab iteration } — the loop condition
@@ -156,7 +156,6 @@ cudaGraphExec_t solve_graph(vch2d_ctx* c, const double* a) {
         for (auto& g : c->graphs) { cudaGraphExecDestroy(g.exec); cudaGraphDestroy(g.g); }
         c->graphs.clear();
     }
-    const long long n = c->g.n;
     SymbolArgs sy{0.0, 0.0, &c->sc->abar, 0.0, &c->sc->c0};
     const long long count0 = c->log.count;
     cudaGraph_t graph;
@@ -165,9 +164,7 @@ cudaGraphExec_t solve_graph(vch2d_ctx* c, const double* a) {
     VCH_CUDA(cudaGraphConditionalHandleCreate(&cond, graph, 1, cudaGraphCondAssignDefault));
     // prologue nodes
     VCH_CUDA(cudaStreamBeginCaptureToGraph(c->stream, graph, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal));
-    c->dct.apply(c->stream, c->kb.p, c->kr.p, sy, nullptr);
-    LAUNCH(c, bicg_init_kernel, c->rb(), kRedThreads, c->kr.p, c->kr0.p, c->kp.p, c->kv.p, c->kx.p, c->kq.p, n, c->sc,
-           c->red.part, c->ticket, cond, prologue_launches(c));
+    enqueue_bicg_prologue<ADJ>(c, sy, cond, prologue_launches<ADJ>(c));
     cudaStreamCaptureStatus st; const cudaGraphNode_t* deps = nullptr; size_t ndeps = 0;
     VCH_CUDA(cudaStreamGetCaptureInfo(c->stream, &st, nullptr, nullptr, &deps, &ndeps));
     std::vector<cudaGraphNode_t> leaf(deps, deps + ndeps);
@@ -185,6 +182,11 @@ cudaGraphExec_t solve_graph(vch2d_ctx* c, const double* a) {
     VCH_CUDA(cudaStreamBeginCaptureToGraph(c->stream, body, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal));
     enqueue_bicg_iteration<ADJ>(c, a, sy, cond, iter_launches<ADJ>(c));
     VCH_CUDA(cudaStreamEndCapture(c->stream, &tmp));
+    if (ADJ) {   // closing x = P^-1 y, after the loop
+        VCH_CUDA(cudaStreamBeginCaptureToGraph(c->stream, graph, &wnode, nullptr, 1, cudaStreamCaptureModeThreadLocal));
+        enqueue_bicg_epilogue<ADJ>(c, sy);
+        VCH_CUDA(cudaStreamEndCapture(c->stream, &tmp));
+    }
     cudaGraphExec_t exec;
     VCH_CUDA(cudaGraphInstantiate(&exec, graph, 0));
     c->log.count = count0;            // capture launches nothing
@@ -207,9 +209,7 @@ int krylov_solve(vch2d_ctx* c, const double* b, const double* a, vch_stats* st) 
         return -1;
     }
     SymbolArgs sy{0.0, 0.0, &c->sc->abar, 0.0, &c->sc->c0};
-    c->dct.apply(c->stream, c->kb.p, c->kr.p, sy, nullptr);
-    LAUNCH(c, bicg_init_kernel, c->rb(), kRedThreads, c->kr.p, c->kr0.p, c->kp.p, c->kv.p, c->kx.p, c->kq.p, n, c->sc,
-           c->red.part, c->ticket, (cudaGraphConditionalHandle)0, 0);
+    enqueue_bicg_prologue<ADJ>(c, sy, (cudaGraphConditionalHandle)0, 0);
     int launched = 0, batch = 2;
     while (true) {
         for (int k = 0; k < batch; ++k) enqueue_bicg_iteration<ADJ>(c, a, sy, (cudaGraphConditionalHandle)0, 0);
@@ -218,6 +218,7 @@ int krylov_solve(vch2d_ctx* c, const double* b, const double* a, vch_stats* st) 
         if (c->sc_host->done || launched >= c->krylov_maxit) break;
         batch = (launched < 8) ? 2 : 4;
     }
+    enqueue_bicg_epilogue<ADJ>(c, sy);
     VCH_CUDA(cudaGetLastError());
     if (!c->sc_host->done) {   // mirror the device-side accounting of the graph path
         long long one = c->sc_host->stalls + 1;

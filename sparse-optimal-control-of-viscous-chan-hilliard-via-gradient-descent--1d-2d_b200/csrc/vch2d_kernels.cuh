@@ -32,13 +32,6 @@ __device__ __forceinline__ double lap_g(const double* __restrict__ v, int o, int
     return a * g.ihi2 + b * g.iho2;
 }
 
-// Outer-axis reflection that leaves ghost rows (slab mode) alone.
-__device__ __forceinline__ int mirror_o(int o, const Geo& g) {
-    if (o < 0 && !g.glo) o = -o;
-    if (o >= g.no && !g.ghi) o = 2 * (g.no - 1) - o;
-    return o;
-}
-
 __device__ __forceinline__ double flory_log(double phi, double eps) {
     const double s = fmin(fmax(phi, -1.0 + eps), 1.0 - eps);
     return log((1.0 + s) / (1.0 - s));
@@ -153,56 +146,6 @@ __global__ void schur_rhs_kernel(const double* __restrict__ Rphi, const double* 
     }
 }
 
-// Operator apply with a two-level shared-memory halo tile.
-//   ADJ = false (forward Schur complement):  z = a.x - c2 L x ;  y = c0 x - L z        (= (c0 I - L diag(a) + c2 L^2) x)
-//   ADJ = true  (adjoint CN operator):       z = L x          ;  y = c0 x - a.z + c2 L z (= (c0 I - diag(a) L + c2 L^2) x)
-constexpr int kTO = 16, kTI = 64;
-template <bool ADJ>
-__global__ void __launch_bounds__(256) op_apply_kernel(const double* __restrict__ x, const double* __restrict__ a,
-                                                        double* __restrict__ y, Geo g, const double* __restrict__ coef,
-                                                        const int* __restrict__ done) {
-    if (done && *done) return;
-    const double c0 = coef[0], c2 = coef[1];
-    __shared__ double sx[kTO + 4][kTI + 4];
-    __shared__ double sz[kTO + 2][kTI + 2];
-    const int o0 = blockIdx.y * kTO, i0 = blockIdx.x * kTI;
-    for (int e = threadIdx.x; e < (kTO + 4) * (kTI + 4); e += 256) {
-        const int to = e / (kTI + 4), ti = e - to * (kTI + 4);
-        const int ro = o0 - 2 + to, ri = i0 - 2 + ti;
-        double val = 0.0;
-        if (ro >= -2 && ro <= g.no + 1 && ri >= -2 && ri <= g.ni + 1)
-            val = x[(long long)mirror_o(ro, g) * g.ni + mirror(ri, g.ni)];
-        sx[to][ti] = val;
-    }
-    __syncthreads();
-    for (int e = threadIdx.x; e < (kTO + 2) * (kTI + 2); e += 256) {
-        const int to = e / (kTI + 2), ti = e - to * (kTI + 2);
-        const int ro = o0 - 1 + to, ri = i0 - 1 + ti;
-        const double c = sx[to + 1][ti + 1];
-        const double lx = ((sx[to + 1][ti + 2] - c) + (sx[to + 1][ti] - c)) * g.ihi2 + ((sx[to + 2][ti + 1] - c) + (sx[to][ti + 1] - c)) * g.iho2;
-        double z;
-        if (ADJ) z = lx;
-        else {
-            double av = 0.0;
-            if (ro >= -1 && ro <= g.no && ri >= -1 && ri <= g.ni) av = a[(long long)mirror_o(ro, g) * g.ni + mirror(ri, g.ni)];
-            z = av * c - c2 * lx;
-        }
-        sz[to][ti] = z;
-    }
-    __syncthreads();
-    for (int e = threadIdx.x; e < kTO * kTI; e += 256) {
-        const int to = e / kTI, ti = e - to * kTI;
-        const int o = o0 + to, i = i0 + ti;
-        if (o < g.no && i < g.ni) {
-            const double c = sz[to + 1][ti + 1];
-            const double lz = ((sz[to + 1][ti + 2] - c) + (sz[to + 1][ti] - c)) * g.ihi2 + ((sz[to + 2][ti + 1] - c) + (sz[to][ti + 1] - c)) * g.iho2;
-            const double xv = sx[to + 2][ti + 2];
-            const size_t idx = (size_t)o * g.ni + i;
-            y[idx] = ADJ ? (c0 * xv - a[idx] * c + c2 * lz) : (c0 * xv - lz);
-        }
-    }
-}
-
 // ---------------------------------------------------------------------------------- BiCGStab vector kernels
 // cond/use_cond: CUDA-graph WHILE handle of the enclosing solve graph (device-driven Krylov loop); ignored when use_cond = 0.
 __global__ void bicg_init_kernel(const double* __restrict__ r, double* __restrict__ r0, double* __restrict__ p,
@@ -229,51 +172,8 @@ __global__ void bicg_init_kernel(const double* __restrict__ r, double* __restric
     }
 }
 
-__global__ void bicg_p_kernel(const double* __restrict__ r, double* __restrict__ p, const double* __restrict__ v,
-                              long long n, const Scal* __restrict__ sc) {
-    if (sc->done) return;
-    const double beta = (sc->rho_new / sc->rho) * (sc->alpha / sc->omega), om = sc->omega;
-    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (long long)gridDim.x * blockDim.x)
-        p[idx] = r[idx] + beta * (p[idx] - om * v[idx]);
-}
-
-__global__ void bicg_dot1_kernel(const double* __restrict__ r0, const double* __restrict__ v, long long n, Scal* sc,
-                                 double* part, unsigned int* ticket) {
-    if (sc->done) return;
-    double acc[1] = {0.0};
-    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (long long)gridDim.x * blockDim.x)
-        acc[0] += r0[idx] * v[idx];
-    const int op[1] = {0};
-    double tot[1];
-    if (grid_reduce<1>(acc, op, part, ticket, tot) && threadIdx.x == 0) {
-        sc->r0v = tot[0]; sc->alpha = sc->rho_new / tot[0]; sc->rho = sc->rho_new;
-    }
-}
-
-__global__ void bicg_s_kernel(const double* __restrict__ r, const double* __restrict__ v, double* __restrict__ s,
-                              long long n, const Scal* __restrict__ sc) {
-    if (sc->done) return;
-    const double al = sc->alpha;
-    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (long long)gridDim.x * blockDim.x)
-        s[idx] = r[idx] - al * v[idx];
-}
-
-__global__ void bicg_dot2_kernel(const double* __restrict__ t, const double* __restrict__ s, long long n, Scal* sc,
-                                 double* part, unsigned int* ticket) {
-    if (sc->done) return;
-    double acc[2] = {0.0, 0.0};
-    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (long long)gridDim.x * blockDim.x) {
-        const double tv = t[idx];
-        acc[0] += tv * s[idx]; acc[1] += tv * tv;
-    }
-    const int op[2] = {0, 0};
-    double tot[2];
-    if (grid_reduce<2>(acc, op, part, ticket, tot) && threadIdx.x == 0) {
-        sc->ts = tot[0]; sc->tt = tot[1]; sc->omega = (tot[1] > 0.0) ? tot[0] / tot[1] : 0.0;
-    }
-}
-
-// q (optional) = p - omega v: the next iteration's fused prologue forms p = r + beta q without an in-place hazard.
+// x += alpha p + omega s, r = s - omega t, q = p - omega v (the next iteration's fused prologue forms p = r + beta q without an
+// in-place hazard), with (r,r) and (r0,r); the p- and s-updates and the other dot products live in the DCT row kernels.
 __global__ void bicg_x_kernel(double* __restrict__ x, double* __restrict__ r, const double* __restrict__ p,
                               const double* __restrict__ s, const double* __restrict__ t, const double* __restrict__ r0,
                               const double* __restrict__ v, double* __restrict__ q, long long n, Scal* sc, double* part,

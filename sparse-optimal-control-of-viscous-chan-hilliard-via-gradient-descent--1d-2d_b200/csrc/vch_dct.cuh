@@ -47,6 +47,8 @@ struct DotEpilogue {
     double* part = nullptr;
     unsigned int* ticket = nullptr;
     const double* addend = nullptr;
+    // right-preconditioned form (adjoint operator A P^-1 = I - diag(a - abar) L P^-1): out = addend + (mul_a - abar) * z
+    const double* mul_a = nullptr;
 };
 
 // Optional prologue of the first row transform (fused BiCGStab vector update + coefficient multiply):
@@ -57,7 +59,7 @@ struct RowPrologue {
     int mode = 0;
     const double* r = nullptr;
     const double* qv = nullptr;
-    const double* a = nullptr;
+    const double* a = nullptr;      // nullptr: x = w (no coefficient multiply; right-preconditioned form)
     double* w = nullptr;
     const Scal* sc = nullptr;
 };
@@ -319,8 +321,8 @@ dct_fft_kernel(const double* in, double* out, int nlines, int n, int in_ls, int 
             const double abar = sc->abar;
             const size_t ia = (size_t)la * in_ls + off, ib = (size_t)lb * in_ls + off;
             double xa = 0.0, xb = 0.0;
-            if (va) { const double w = pro.r[ia] + coef * pro.qv[ia]; if (e <= N) pro.w[ia] = w; xa = (pro.a[ia] - abar) * w; }
-            if (vb) { const double w = pro.r[ib] + coef * pro.qv[ib]; if (e <= N) pro.w[ib] = w; xb = (pro.a[ib] - abar) * w; }
+            if (va) { const double w = pro.r[ia] + coef * pro.qv[ia]; if (e <= N) pro.w[ia] = w; xa = pro.a ? (pro.a[ia] - abar) * w : w; }
+            if (vb) { const double w = pro.r[ib] + coef * pro.qv[ib]; if (e <= N) pro.w[ib] = w; xb = pro.a ? (pro.a[ib] - abar) * w : w; }
             v[r] = make_double2(xa, xb);
         }
     }
@@ -360,6 +362,7 @@ dct_fft_kernel(const double* in, double* out, int nlines, int n, int in_ls, int 
     const double* ob = epi.other + (size_t)lb * out_ls;
     const double* da = epi.addend + (size_t)la * out_ls;
     const double* db = epi.addend + (size_t)lb * out_ls;
+    const double eabar = epi.mul_a ? epi.sc->abar : 0.0;
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
         const int kk = t + FftOut<LOG2L>::off(q);
@@ -375,12 +378,14 @@ dct_fft_kernel(const double* in, double* out, int nlines, int n, int in_ls, int 
                 if (va) *reinterpret_cast<double2*>(qa + off) = make_double2(z[q].x, vb ? z[q].y : 0.0);
             } else {
                 if (va) {
-                    const double o = epi.addend ? z[q].x + da[off] : z[q].x;
+                    const double zx = epi.mul_a ? (epi.mul_a[(size_t)la * out_ls + off] - eabar) * z[q].x : z[q].x;
+                    const double o = epi.addend ? zx + da[off] : zx;
                     qa[off] = o;
                     if (epi.mode) { acc1 += oa[off] * o; acc2 += o * o; }
                 }
                 if (vb) {
-                    const double o = epi.addend ? z[q].y + db[off] : z[q].y;
+                    const double zy = epi.mul_a ? (epi.mul_a[(size_t)lb * out_ls + off] - eabar) * z[q].y : z[q].y;
+                    const double o = epi.addend ? zy + db[off] : zy;
                     qb[off] = o;
                     if (epi.mode) { acc1 += ob[off] * o; acc2 += o * o; }
                 }
@@ -442,13 +447,17 @@ __global__ void dct_prologue_kernel(RowPrologue pro, double* __restrict__ x, lon
     for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (long long)gridDim.x * blockDim.x) {
         const double w = pro.r[idx] + coef * pro.qv[idx];
         pro.w[idx] = w;
-        x[idx] = (pro.a[idx] - abar) * w;
+        x[idx] = pro.a ? (pro.a[idx] - abar) * w : w;
     }
 }
-__global__ void dct_addend_kernel(double* __restrict__ outv, const double* __restrict__ addend, long long n, const int* __restrict__ done) {
+__global__ void dct_addend_kernel(double* __restrict__ outv, const double* __restrict__ addend, const double* __restrict__ mul_a,
+                                  const Scal* __restrict__ sc, long long n, const int* __restrict__ done) {
     if (done && *done) return;
-    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (long long)gridDim.x * blockDim.x)
-        outv[idx] += addend[idx];
+    const double abar = mul_a ? sc->abar : 0.0;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (long long)gridDim.x * blockDim.x) {
+        const double z = mul_a ? (mul_a[idx] - abar) * outv[idx] : outv[idx];
+        outv[idx] = addend ? z + addend[idx] : z;
+    }
 }
 __global__ void dct_lambda_kernel(double* __restrict__ d, int no, int ni, const double* __restrict__ lam_o,
                                   const double* __restrict__ lam_i, const int* __restrict__ done) {
@@ -681,7 +690,7 @@ inline void DctPlan::apply(cudaStream_t s, const double* in, double* out, const 
     cols(t2, t1);
     rows(t1, t2);
     VCH_CUDA(cudaMemcpyAsync(out, t2, n * sizeof(double), cudaMemcpyDeviceToDevice, s));
-    if (epi.addend) { log->begin("dct_addend", s); dct_addend_kernel<<<red_blocks(n), 256, 0, s>>>(out, epi.addend, n, done); log->end(s); }
+    if (epi.addend || epi.mul_a) { log->begin("dct_addend", s); dct_addend_kernel<<<red_blocks(n), 256, 0, s>>>(out, epi.addend, epi.mul_a, epi.sc, n, done); log->end(s); }
     if (epi.mode) { log->begin("dct_dots", s); dct_dots_kernel<<<red_blocks(n), kRedThreads, 0, s>>>(out, epi, n, done); log->end(s); }
     VCH_CUDA(cudaGetLastError());
 }
