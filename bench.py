@@ -289,6 +289,15 @@ def run_b200(args):
                                          Op.kappa_sparsity, Op.u_min, Op.u_max, alpha, u_out=hun.numpy(), phi_out=hhn.numpy(),
                                          r_out=hr.numpy() if bounded else None)
             host_step()                                          # warm-up
+            # PCIe yardstick: the adjoint sweep cannot start before its inputs arrive, so H2D bandwidth bounds the e2e number
+            probe = torch.empty(min(hh.numel(), 1 << 28), dtype=torch.float64, device=dev)     # 2 GiB
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            probe.copy_(hh.view(-1)[:probe.numel()], non_blocking=True); torch.cuda.synchronize()
+            ev0.record(); probe.copy_(hh.view(-1)[:probe.numel()], non_blocking=True); ev1.record(); torch.cuda.synchronize()
+            h2d_gbps = probe.numel() * 8 / (ev0.elapsed_time(ev1) * 1e-3) / 1e9
+            ev0.record(); hhn.view(-1)[:probe.numel()].copy_(probe, non_blocking=True); ev1.record(); torch.cuda.synchronize()
+            d2h_gbps = probe.numel() * 8 / (ev0.elapsed_time(ev1) * 1e-3) / 1e9
+            del probe
             barrier()
             t0 = time.perf_counter()
             for _ in range(reps):
@@ -299,6 +308,8 @@ def run_b200(args):
                 dist.all_reduce(tt, op=dist.ReduceOp.MAX)
             e2e = {"value": world / float(tt.item()), "unit": UNIT, "h2d_bytes_per_step": int(((5 if bounded else 3) * lv + 1) * field_bytes),
                    "d2h_bytes_per_step": int((3 if bounded else 2) * lv * field_bytes + 9 * 8), "steps": reps,
+                   "pcie_GBps": {"h2d": round(h2d_gbps, 1), "d2h": round(d2h_gbps, 1),
+                                 "note": "the adjoint sweep consumes phi_hist and phi_Q (2/3 of the H2D bytes) before anything else can run"},
                    "device_staging": (f"chunk rings, {args.stream_budget_gb:g} GB budget (phi_Q is uploaded twice, r makes a round trip)"
                                       if bounded else "whole trajectories"),
                    "call": "vch2d_pgd_iteration(mem=VCH_MEM_HOST): u, phi_hist, phi_Q, phi_T in; u_new, phi_hist_new, J, norms out"}
