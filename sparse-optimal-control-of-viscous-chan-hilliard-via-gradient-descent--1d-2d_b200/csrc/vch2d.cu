@@ -3,6 +3,7 @@
 #include "vch2d_kernels.cuh"
 #include <algorithm>
 #include <functional>
+#include <chrono>
 #include <cstdlib>
 
 namespace vch {
@@ -59,18 +60,36 @@ struct vch2d_ctx {
 
 namespace {
 
-void fetch_scalars(vch2d_ctx* c) {
-    VCH_CUDA(cudaMemcpyAsync(c->sc_host, c->sc, sizeof(Scal), cudaMemcpyDeviceToHost, c->stream));
-    VCH_CUDA(cudaStreamSynchronize(c->stream));
-    if (c->sc_host->comm_err) throw Error(VCH_E_COMM, "slab mode: a peer rank did not arrive within the wait limit (ranks out of step or a peer failed)");
-}
-
 #define LAUNCH(c, kern, grid, block, ...)                       \
     do {                                                        \
         (c)->log.begin(#kern, (c)->stream);                     \
         kern<<<(grid), (block), 0, (c)->stream>>>(__VA_ARGS__); \
         (c)->log.end((c)->stream);                              \
     } while (0)
+
+// Device scalars -> pinned host mirror, written by a kernel straight into the (device-mapped) pinned page.  Not a
+// cudaMemcpyAsync: a 200-byte D2H memcpy is served by the D2H copy engine, where it queues behind the 270 MB trajectory chunks
+// of the streamed host-buffer path — once per Newton iteration (measured with a background D2H stream: 58 ms instead of
+// 1.3 ms per time step).
+__global__ void publish_scalars_kernel(const Scal* __restrict__ src, Scal* __restrict__ dst_host) {
+    static_assert(sizeof(Scal) % 8 == 0, "Scal is copied in 8-byte words");
+    const unsigned long long* s = reinterpret_cast<const unsigned long long*>(src);
+    unsigned long long* d = reinterpret_cast<unsigned long long*>(dst_host);
+    for (int i = threadIdx.x; i < (int)(sizeof(Scal) / 8); i += blockDim.x) d[i] = s[i];
+}
+
+void fetch_scalars(vch2d_ctx* c) {
+    LAUNCH(c, publish_scalars_kernel, 1, 32, c->sc, c->sc_host);
+    VCH_CUDA(cudaStreamSynchronize(c->stream));
+    if (c->sc_host->comm_err) throw Error(VCH_E_COMM, "slab mode: a peer rank did not arrive within the wait limit (ranks out of step or a peer failed)");
+}
+
+
+// Device-to-device field copy by a kernel (see copy_kernel).
+void dev_copy(vch2d_ctx* c, double* dst, const double* src, size_t count) {
+    if (dst == src || count == 0) return;
+    LAUNCH(c, copy_kernel, red_blocks((long long)count), kRedThreads, src, dst, (long long)count);
+}
 
 // Slab mode: ship the first / last `rows` owned rows of one or two fields into the neighbours' ghost rows; a barrier inside
 // the kernel guarantees the rows have landed before anything reads them (lead = 1 adds a barrier in front, see
@@ -85,13 +104,13 @@ void halo_push(vch2d_ctx* c, const double* f0, const double* f1, int rows, const
 // Copy of a ghosted work vector including its ghost rows.
 void copy_ghosted(vch2d_ctx* c, double* dst, const double* src) {
     const size_t m = c->slab ? 2 * (size_t)c->g.ni : 0;
-    VCH_CUDA(cudaMemcpyAsync(dst - m, src - m, ((size_t)c->g.n + 2 * m) * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+    dev_copy(c, dst - m, src - m, (size_t)c->g.n + 2 * m);
 }
 // kernels per BiCGStab iteration / per solve prologue (accounting of launches inside solve graphs)
 template <bool ADJ> int iter_launches(const vch2d_ctx* c) { return c->slab ? 7 + 4 : 7; }
 // FWD: P^-1 b (3 kernels) + init;  ADJ (right-preconditioned): init + the closing x = P^-1 y (3 kernels); slab mode adds the
 // barriers of one preconditioner application (2 + the trailing one)
-template <bool ADJ> int prologue_launches(const vch2d_ctx* c) { return 4 + (c->slab ? 3 : 0); }
+template <bool ADJ> int prologue_launches(const vch2d_ctx* c) { return (ADJ ? 5 : 4) + (c->slab ? 3 : 0); }   // ADJ: + the r = b copy kernel
 
 // Orders the library's private stream after the caller's stream on entry and the caller's stream after ours on exit,
 // so callers see ordinary stream semantics (torch.cuda.Event on their stream brackets our kernels).
@@ -135,7 +154,7 @@ void enqueue_bicg_iteration(vch2d_ctx* c, const double* a, const SymbolArgs& sy,
 template <bool ADJ>
 void enqueue_bicg_prologue(vch2d_ctx* c, const SymbolArgs& sy, cudaGraphConditionalHandle cond, int use_cond) {
     const long long n = c->g.n;
-    if (ADJ) VCH_CUDA(cudaMemcpyAsync(c->kr.p, c->kb.p, n * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+    if (ADJ) dev_copy(c, c->kr.p, c->kb.p, (size_t)n);
     else c->dct.apply(c->stream, c->kb.p, c->kr.p, sy, nullptr);
     LAUNCH(c, bicg_init_kernel, c->rb(), kRedThreads, c->kr.p, c->kr0.p, c->kp.p, c->kv.p, c->kx.p, c->kq.p, n, c->sc,
            c->red.part, c->ticket, cond, use_cond);
@@ -202,7 +221,7 @@ cudaGraphExec_t solve_graph(vch2d_ctx* c, const double* a) {
 template <bool ADJ>
 int krylov_solve(vch2d_ctx* c, const double* b, const double* a, vch_stats* st) {   // coefficients: sc->c0 / sc->c2, set by the rhs kernel
     const long long n = c->g.n;
-    if (b != c->kb.p) VCH_CUDA(cudaMemcpyAsync(c->kb.p, b, n * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+    if (b != c->kb.p) dev_copy(c, c->kb.p, b, (size_t)n);
     if (c->use_graphs && !c->log.profiling) {
         cudaGraphExec_t exec = solve_graph<ADJ>(c, a);
         VCH_CUDA(cudaGraphLaunch(exec, c->stream));
@@ -276,10 +295,10 @@ void newton_step(vch2d_ctx* c, const double* phi_old, const double* mu_old, cons
                  double dt, std::vector<double>* hist, vch_stats* st) {
     const long long n = c->g.n;
     const int eb = c->eb();
-    VCH_CUDA(cudaMemcpyAsync(c->phi.p, phi_old, n * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+    dev_copy(c, c->phi.p, phi_old, (size_t)n);
     if (c->slab && mu_old != c->mu_old.p) {   // test-level entry: bring mu_old into a ghosted work vector
         c->mu_old.alloc(n);
-        VCH_CUDA(cudaMemcpyAsync(c->mu_old.p, mu_old, n * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+        dev_copy(c, c->mu_old.p, mu_old, (size_t)n);
         mu_old = c->mu_old.p;
         halo_push(c, c->phi.p, c->mu_old.p, 1);
     } else halo_push(c, c->phi.p, nullptr, 1);
@@ -400,13 +419,13 @@ void forward_dev(vch2d_ctx* c, const double* phi0, const double* u, int u_rows, 
     const int eb = c->eb();
     auto HN = [&](int k) -> double* { return (lm && lm->hist_new) ? lm->hist_new(k) : phi_hist + (size_t)k * n; };
     auto U = [&](int k) -> const double* { return (lm && lm->u) ? lm->u(k) : u + (size_t)k * n; };
-    VCH_CUDA(cudaMemcpyAsync(HN(0), phi0, bytes, cudaMemcpyDeviceToDevice, c->stream));
+    dev_copy(c, HN(0), phi0, (size_t)n);
     VCH_CUDA(cudaMemsetAsync(c->w0.p, 0, bytes, c->stream));
     c->mu_old.alloc(n);
     double* mu_old = c->mu_old.p;   // mu_0 = initialize_mu(phi_0, w = 0), Forward2_solver.py:520
     const double* phi_first = HN(0);
     if (c->slab) {   // the stencil needs ghost rows: work on a ghosted copy of level 0
-        VCH_CUDA(cudaMemcpyAsync(c->phi.p, phi0, bytes, cudaMemcpyDeviceToDevice, c->stream));
+        dev_copy(c, c->phi.p, phi0, (size_t)n);
         halo_push(c, c->phi.p, nullptr, 1);
         phi_first = c->phi.p;
     }
@@ -425,8 +444,8 @@ void forward_dev(vch2d_ctx* c, const double* phi0, const double* u, int u_rows, 
         post_step(c, c->phi.p, HN(s + 1));
         copy_ghosted(c, mu_old, c->mu.p);      // slab mode: the ghost rows of the accepted iterate travel along
         std::swap(c->w0.p, c->w1.p);
-        if (mu_hist) VCH_CUDA(cudaMemcpyAsync(mu_hist + (size_t)s * n, mu_old, bytes, cudaMemcpyDeviceToDevice, c->stream));
-        if (w_hist) VCH_CUDA(cudaMemcpyAsync(w_hist + (size_t)s * n, c->w0.p, bytes, cudaMemcpyDeviceToDevice, c->stream));
+        if (mu_hist) dev_copy(c, mu_hist + (size_t)s * n, mu_old, (size_t)n);
+        if (w_hist) dev_copy(c, w_hist + (size_t)s * n, c->w0.p, (size_t)n);
         if (after_level) after_level(s + 1);
     }
     VCH_CUDA(cudaGetLastError());
@@ -437,7 +456,6 @@ void adjoint_dev(vch2d_ctx* c, const double* phi_hist, int levels, const double*
                  const double* phiQ, const double* phiT, double* p_out, double* q_out, double* r_out, vch_stats* st,
                  const LevelHook& need_level = nullptr, const LevelMap* lm = nullptr) {
     const long long n = c->g.n;
-    const size_t bytes = n * sizeof(double);
     const int eb = c->eb();
     auto H = [&](int k) -> const double* { return (lm && lm->hist) ? lm->hist(k) : phi_hist + (size_t)k * n; };
     const bool haveQ = phiQ || (lm && lm->Q);
@@ -448,8 +466,8 @@ void adjoint_dev(vch2d_ctx* c, const double* phi_hist, int levels, const double*
     double* const p_user = c->slab ? p_out : nullptr; double* const q_user = c->slab ? q_out : nullptr;
     if (c->slab) { p_out = nullptr; q_out = nullptr; }
     auto copy_out = [&](int lvl, const double* pv, const double* qv) {
-        if (p_user) VCH_CUDA(cudaMemcpyAsync(p_user + (size_t)lvl * n, pv, bytes, cudaMemcpyDeviceToDevice, c->stream));
-        if (q_user) VCH_CUDA(cudaMemcpyAsync(q_user + (size_t)lvl * n, qv, bytes, cudaMemcpyDeviceToDevice, c->stream));
+        if (p_user) dev_copy(c, p_user + (size_t)lvl * n, pv, (size_t)n);
+        if (q_user) dev_copy(c, q_user + (size_t)lvl * n, qv, (size_t)n);
     };
     const int M = levels - 1;
     auto rslot = [&](int lvl) -> double* { return (lm && lm->r) ? lm->r(lvl) : slot(r_out, c->adj_r, lvl); };
@@ -470,10 +488,10 @@ void adjoint_dev(vch2d_ctx* c, const double* phi_hist, int levels, const double*
         if (dt <= 1e-14) {   // backward2_solver.py:214-216
             if (c->slab) { copy_ghosted(c, p0, p1); copy_ghosted(c, q0, q1); }
             else {
-                VCH_CUDA(cudaMemcpyAsync(p0, p1, bytes, cudaMemcpyDeviceToDevice, c->stream));
-                VCH_CUDA(cudaMemcpyAsync(q0, q1, bytes, cudaMemcpyDeviceToDevice, c->stream));
+                dev_copy(c, p0, p1, (size_t)n);
+                dev_copy(c, q0, q1, (size_t)n);
             }
-            VCH_CUDA(cudaMemcpyAsync(r0, r1, bytes, cudaMemcpyDeviceToDevice, c->stream));
+            dev_copy(c, r0, r1, (size_t)n);
             copy_out(k, p0, q0);
             continue;
         }
@@ -481,7 +499,7 @@ void adjoint_dev(vch2d_ctx* c, const double* phi_hist, int levels, const double*
         LAUNCH(c, adj_rhs_kernel, c->rb(), kRedThreads, p1, q1, f1, f0, Q(k + 1), Q(k), c->kb.p, c->a.p, c->g, c->ph, dt, b1, c->sc,
                c->red.part, c->ticket);
         krylov_solve<true>(c, c->kb.p, c->a.p, st);
-        VCH_CUDA(cudaMemcpyAsync(p0, c->kx.p, bytes, cudaMemcpyDeviceToDevice, c->stream));
+        dev_copy(c, p0, c->kx.p, (size_t)n);
         const double den = c->ph.gamma + 0.5 * dt;
         halo_push(c, p0, nullptr, 1);
         LAUNCH(c, adj_qr_kernel, eb, 256, p0, q1, r1, q0, r0, c->g, (c->ph.gamma - 0.5 * dt) / den, 0.5 * dt / den);
@@ -626,7 +644,7 @@ static int create_ctx(const vch2d_params* p, int device, int rank, int nranks, v
         VCH_CUDA(cudaMemset(c->ticket, 0, sizeof(unsigned int)));
         VCH_CUDA(cudaMalloc(&c->sc, sizeof(Scal)));
         VCH_CUDA(cudaMemset(c->sc, 0, sizeof(Scal)));
-        VCH_CUDA(cudaMallocHost(&c->sc_host, sizeof(Scal)));
+        VCH_CUDA(cudaHostAlloc(&c->sc_host, sizeof(Scal), cudaHostAllocMapped));   // written by publish_scalars_kernel (UVA: same pointer)
         VCH_CUDA(cudaMalloc(&c->out4, 8 * sizeof(double)));
         VCH_CUDA(cudaMallocHost(&c->out4_host, 8 * sizeof(double)));
         if (slab) {
@@ -1063,8 +1081,12 @@ static void pgd_iteration_host_streamed(vch2d_ctx* c, int levels, const double* 
         cudaEventDestroy(ev_u); cudaEventDestroy(ev_prox); cudaEventDestroy(ev_adj);
         cudaStreamDestroy(cp);
     };
+    cudaEvent_t tph[4] = {nullptr, nullptr, nullptr, nullptr};           // VCH_DEBUG: phase times on the work stream
+    if (c->debug) for (auto& e : tph) cudaEventCreate(&e);
+    const auto host_t0 = std::chrono::steady_clock::now();
     try {
         // ---- enqueue every H2D copy up front, in consumption order
+        if (c->debug) cudaEventRecord(tph[0], c->stream);
         VCH_CUDA(cudaEventRecord(c->ev_in, c->stream));                 // buffers above were allocated; order cp after entry
         VCH_CUDA(cudaStreamWaitEvent(cp, c->ev_in, 0));
         if (phiT) VCH_CUDA(cudaMemcpyAsync(dT.p, phiT, fb, cudaMemcpyHostToDevice, cp));
@@ -1089,6 +1111,7 @@ static void pgd_iteration_host_streamed(vch2d_ctx* c, int levels, const double* 
         };
         adjoint_dev(c, dh.p, levels, t_hist, b1, b2, phiQ ? dq.p : nullptr, phiT ? dT.p : nullptr, nullptr, nullptr, dr.p, s, need);
         need(0);
+        if (c->debug) cudaEventRecord(tph[1], c->stream);
         VCH_CUDA(cudaEventRecord(ev_adj, c->stream));
         if (r_out) {
             VCH_CUDA(cudaStreamWaitEvent(cp, ev_adj, 0));
@@ -1122,6 +1145,7 @@ static void pgd_iteration_host_streamed(vch2d_ctx* c, int levels, const double* 
         };
         forward_dev(c, dh.p, dun.p, levels, levels - 1, dt_steps, dhn.p, nullptr, nullptr, s, after, before);
         prox_upto(levels - 1);
+        if (c->debug) cudaEventRecord(tph[2], c->stream);
         for (auto& e : ev_uc) cudaEventDestroy(e);
         // ---- (4) cost
         cost_dev(c, dhn.p, dun.p, phiQ ? dq.p : nullptr, phiT ? dT.p : nullptr, levels, x, y, t_hist, b1, b2, b3, ksp, J_out);
@@ -1130,10 +1154,21 @@ static void pgd_iteration_host_streamed(vch2d_ctx* c, int levels, const double* 
             VCH_CUDA(cudaStreamSynchronize(c->stream));
             for (int k = 0; k < 4; ++k) red_out[k] = c->out4_host[4 + k];
         }
-        VCH_CUDA(cudaStreamSynchronize(cp));
+        if (c->debug) cudaEventRecord(tph[3], c->stream);
         VCH_CUDA(cudaStreamSynchronize(c->stream));
-    } catch (...) { cleanup(); throw; }
+        const auto host_t1 = std::chrono::steady_clock::now();
+        VCH_CUDA(cudaStreamSynchronize(cp));
+        if (c->debug) {
+            float a = 0, f = 0, k = 0;
+            cudaEventElapsedTime(&a, tph[0], tph[1]); cudaEventElapsedTime(&f, tph[1], tph[2]); cudaEventElapsedTime(&k, tph[2], tph[3]);
+            const double wall = std::chrono::duration<double>(std::chrono::steady_clock::now() - host_t0).count();
+            const double work = std::chrono::duration<double>(host_t1 - host_t0).count();
+            fprintf(stderr, "[vch2d] streamed host path: adjoint %.3f s, prox+forward %.3f s, cost %.3f s on the work stream; work stream done "
+                            "at %.3f s, copies drained at %.3f s\n", a * 1e-3, f * 1e-3, k * 1e-3, work, wall);
+        }
+    } catch (...) { cleanup(); if (c->debug) for (auto& e : tph) cudaEventDestroy(e); throw; }
     cleanup();
+    if (c->debug) for (auto& e : tph) cudaEventDestroy(e);
 }
 
 // Bounded-memory variant of the host-buffer path: no trajectory ever exists on the device in full.  Every array is
