@@ -146,8 +146,8 @@ __global__ void jac_diag_kernel(const double* __restrict__ phi, double* __restri
 
 // Right-hand side of the Schur-reduced Newton system: b = -R_mu + L R_phi.
 __global__ void schur_rhs_kernel(const double* __restrict__ Rphi, const double* __restrict__ Rmu, double* __restrict__ b, Geo g,
-                                 Scal* sc, double c0, double c2) {
-    if (blockIdx.x == 0 && threadIdx.x == 0) { sc->c0 = c0; sc->c2 = c2; }   // coefficients of the solve that follows
+                                 Scal* sc, double c0, double c2, double tol2) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) { sc->c0 = c0; sc->c2 = c2; sc->tol2 = tol2; }   // coefficients and (squared) relative tolerance of the solve that follows
     for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < g.n; idx += (long long)gridDim.x * blockDim.x) {
         const int o = (int)(idx / g.ni), i = (int)(idx - (long long)o * g.ni);
         b[idx] = lap_g(Rphi, o, i, g) - Rmu[idx];
@@ -297,7 +297,7 @@ __global__ void adj_rhs_kernel(const double* __restrict__ p1, const double* __re
                                const double* __restrict__ phi1, const double* __restrict__ phi0,
                                const double* __restrict__ Q1, const double* __restrict__ Q0,
                                double* __restrict__ rhs, double* __restrict__ a, Geo g, Phys p, double dt, double b1,
-                               Scal* sc, double* part, unsigned int* ticket) {
+                               Scal* sc, double* part, unsigned int* ticket, double tol2) {
     double v[2] = {INFINITY, -INFINITY};
     const double hdt = 0.5 * dt;
     for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < g.n; idx += (long long)gridDim.x * blockDim.x) {
@@ -313,7 +313,7 @@ __global__ void adj_rhs_kernel(const double* __restrict__ p1, const double* __re
     if (grid_reduce<2>(v, op, part, ticket, tot) && threadIdx.x == 0) {
         sc->amin = tot[0]; sc->amax = tot[1];
         sc->abar = (tot[0] > 0.0) ? sqrt(tot[0] * tot[1]) : 0.5 * (tot[0] + tot[1]);
-        sc->c0 = 1.0; sc->c2 = hdt;                                            // coefficients of the solve that follows
+        sc->c0 = 1.0; sc->c2 = hdt; sc->tol2 = tol2;                           // coefficients / tolerance of the solve that follows
     }
 }
 

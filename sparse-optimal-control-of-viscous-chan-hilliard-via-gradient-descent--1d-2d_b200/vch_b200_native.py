@@ -47,7 +47,7 @@ class Stats(C.Structure):
 # every symbol include/vch_b200.h declares (tests check the library exports exactly these)
 EXPORTS = [
     "vch_last_error", "vch_device_count", "vch_version",
-    "vch2d_create", "vch2d_destroy", "vch2d_set_stream", "vch2d_set_krylov", "vch2d_set_newton", "vch2d_set_stream_budget", "vch2d_launch_count", "vch2d_profile", "vch2d_profile_report",
+    "vch2d_create", "vch2d_destroy", "vch2d_set_stream", "vch2d_set_krylov", "vch2d_set_krylov_first", "vch2d_set_newton", "vch2d_set_stream_budget", "vch2d_launch_count", "vch2d_profile", "vch2d_profile_report",
     "vch2d_apply_laplacian", "vch2d_initialize_mu", "vch_solve_w", "vch2d_residual", "vch2d_jacobian_solve",
     "vch2d_newton", "vch2d_forward", "vch2d_adjoint", "vch2d_cost", "vch_grad_prox", "vch_kkt_counts",
     "vch2d_pgd_iteration",
@@ -232,6 +232,10 @@ class Ctx2D:
     def set_stream_budget(self, nbytes=0):
         """Cap the device staging of the host-buffer pgd_iteration (0 = automatic); see include/vch_b200.h."""
         _check(lib().vch2d_set_stream_budget(self.h, C.c_longlong(int(nbytes))))
+
+    def set_krylov_first(self, rel_tol=1e-6):
+        """Tolerance of the first linear solve of each Newton solve in the time loop (0 = always the full tolerance)."""
+        _check(lib().vch2d_set_krylov_first(self.h, C.c_double(rel_tol)))
 
     def set_newton(self, floor_aware=True):
         _check(lib().vch2d_set_newton(self.h, 1 if floor_aware else 0))

@@ -287,6 +287,32 @@ def test_forward_matches_reference_golden_256(native, golden):
     assert rel(hist1[g["keep"]], g["phi1"]) < TOL_TRAJ and abs(J[0] - g["J"][1]) <= TOL_J * abs(g["J"][1])
 
 
+def test_inexact_first_newton_solve_keeps_trajectory_and_saves_iterations(native):
+    """Forcing term of the time loop (vch2d_set_krylov_first): the first linear solve of each Newton solve stops at 1e-6.
+    Against the all-1e-11 run of the same library: same number of Newton solves, trajectories equal
+    far inside BASELINE's 1e-8, fewer BiCGStab iterations.  Against the reference golden: unchanged tolerance."""
+    P = O.Phys2D(Nx=64, Ny=64, T=0.4)
+    dts = dt_list(P)
+    phi0 = O.init_phi_2d(P.Nx, P.Ny)
+    rng = np.random.default_rng(5)
+    u = 0.3 * rng.standard_normal((len(dts) + 1, P.Nx + 1, P.Ny + 1))
+    runs = {}
+    for name, tol in (("strict", 0.0), ("forced", 1e-6)):
+        c = make_ctx(native, P)
+        c.set_krylov_first(tol)
+        hist, mu, w = c.forward(phi0, u, dts, want_mu=True, want_w=True)
+        runs[name] = (hist, mu, dict(c.last_stats))
+    (h0, m0, s0), (h1, m1, s1) = runs["strict"], runs["forced"]
+    assert rel(h1, h0) < 1e-10 and rel(m1, m0) < 1e-10
+    assert abs(s1["newton_linear_solves"] - s0["newton_linear_solves"]) <= 2      # Newton itself is not slowed down
+    assert s1["krylov_iterations"] < 0.95 * s0["krylov_iterations"] and s1["krylov_stalls"] == 0
+    # a context whose overall tolerance is looser than the first-solve tolerance ignores the forcing term
+    c = make_ctx(native, P)
+    c.set_krylov(1e-5, 200)
+    h2, _, _ = c.forward(phi0, u, dts)
+    assert rel(h2, h0) < 1e-6
+
+
 def test_full_size_1024_properties(native):
     """BASELINE grid (1024^2, device-resident): size-independent identities that need no CPU oracle.
     (a) the linear solve satisfies the Schur system  (1/dt) dphi - L(a dphi - kappa/2 L dphi) = -R_mu + L R_phi  and
