@@ -349,7 +349,8 @@ def run_b200(args):
                 "config": {"workload": f"2D {N}^2 grid ({N+1}^2 nodes), M={M} CN steps (T={M*dt:g}), reference 2D defaults, "
                                        "targets build_targets(1,1), optimistic PGD iteration from u0=0",
                            "problems_per_gpu": 1, "l2": "inputs (8.4 GB trajectories) exceed the 126 MB L2; no flush needed",
-                           "newton": "reference rule + fp64-floor stop (DESIGN.md)", "krylov_rel_tol": 1e-11},
+                           "newton": "reference rule + fp64-floor stop (DESIGN.md)", "krylov_rel_tol": 1e-11,
+                           "krylov_first_solve_rel_tol": float(os.environ.get("VCH_KRYLOV_FIRST_RTOL", 1e-6))},
                 "gpu_launches": int(launches), "clocks": clocks, "e2e": e2e, "roofline": roof, "cpu_baseline": cpu,
                 "solver": {"linear_solves_per_iteration": agg["newton_linear_solves"] / args.steps,
                            "newton_residual_evals_per_time_step": agg["newton_residual_evals"] / (args.steps * M),
