@@ -67,6 +67,7 @@ typedef struct {
     long long kernel_launches;         /* kernels this library launched during the call */
     long long krylov_stalls;           /* solves that stopped above tolerance */
     double    last_newton_residual;
+    long long krylov_half_exits;       /* solves that ended after the first half of a BiCGStab iteration (counted as one iteration) */
 } vch_stats;
 
 const char* vch_last_error(void);

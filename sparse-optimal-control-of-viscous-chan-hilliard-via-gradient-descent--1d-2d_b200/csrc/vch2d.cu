@@ -31,6 +31,7 @@ struct vch2d_ctx {
     double krylov_first_tol = 1e-6;   // time loop only: relative tolerance of the FIRST linear solve of a Newton solve (0 = krylov_tol)
     int krylov_maxit = 200;
     int floor_aware = 1;         // fp64-resolution-aware Newton stop
+    int half_exit = 1;           // BiCGStab may stop after the first half of an iteration (VCH_NO_HALF_EXIT=1 disables)
     int debug = 0;
     DctPlan dct;
     // work vectors (n doubles each)
@@ -143,7 +144,7 @@ void enqueue_bicg_iteration(vch2d_ctx* c, const double* a, const SymbolArgs& sy,
     const int* done = &c->sc->done;
     const double* pro_a = ADJ ? nullptr : a;     // multiply before the transform (forward) ...
     const double* epi_a = ADJ ? a : nullptr;     // ... or after it (adjoint)
-    c->dct.apply(c->stream, c->kr.p, c->kv.p, sy, done, DotEpilogue{1, c->kr0.p, c->sc, c->red.part, c->ticket, c->kp.p, epi_a},
+    c->dct.apply(c->stream, c->kr.p, c->kv.p, sy, done, DotEpilogue{1, c->kr0.p, c->sc, c->red.part, c->ticket, c->kp.p, epi_a, c->half_exit ? c->kr.p : nullptr},
                  RowPrologue{1, c->kr.p, c->kq.p, pro_a, c->kp.p, c->sc}, 1);
     c->dct.apply(c->stream, c->kr.p, c->kt.p, sy, done, DotEpilogue{2, c->ks.p, c->sc, c->red.part, c->ticket, c->ks.p, epi_a},
                  RowPrologue{2, c->kr.p, c->kv.p, pro_a, c->ks.p, c->sc}, 1);
@@ -251,11 +252,12 @@ int krylov_solve(vch2d_ctx* c, const double* b, const double* a, vch_stats* st) 
 }
 
 // Device-side solver counters -> vch_stats (call after a fetch_scalars).
-struct StatMark { long long its, solves, stalls, launches, glaunches; };
+struct StatMark { long long its, solves, stalls, launches, glaunches, halves; };
 StatMark stat_mark(vch2d_ctx* c) {
     fetch_scalars(c);
     VCH_CUDA(cudaMemsetAsync(&c->sc->iters_max, 0, sizeof(int), c->stream));   // per-call maximum
-    return {c->sc_host->iters_total, c->sc_host->solves, c->sc_host->stalls, c->log.count, c->sc_host->g_launches};
+    return {c->sc_host->iters_total, c->sc_host->solves, c->sc_host->stalls, c->log.count, c->sc_host->g_launches,
+            c->sc_host->half_exits};
 }
 void stat_collect(vch2d_ctx* c, const StatMark& m0, vch_stats* st) {
     fetch_scalars(c);
@@ -265,6 +267,7 @@ void stat_collect(vch2d_ctx* c, const StatMark& m0, vch_stats* st) {
     st->krylov_iterations += its;
     st->newton_linear_solves += solves;
     st->krylov_stalls += c->sc_host->stalls - m0.stalls;
+    st->krylov_half_exits += c->sc_host->half_exits - m0.halves;
     if (c->sc_host->stalls > m0.stalls)    // never silent: the direct solver this replaces cannot stall
         fprintf(stderr, "[vch_b200] warning: %lld linear solve(s) stopped above the Krylov tolerance (max_iter %d); see vch_stats.krylov_stalls\n",
                 (long long)(c->sc_host->stalls - m0.stalls), c->krylov_maxit);
@@ -610,6 +613,7 @@ static int create_ctx(const vch2d_params* p, int device, int rank, int nranks, v
         c->prm = *p; c->device = device;
         c->debug = getenv("VCH_DEBUG") ? atoi(getenv("VCH_DEBUG")) : 0;
         if (getenv("VCH_NEWTON_STRICT")) c->floor_aware = 0;
+        if (getenv("VCH_NO_HALF_EXIT")) c->half_exit = 0;
         if (getenv("VCH_KRYLOV_FIRST_RTOL")) { const double t = atof(getenv("VCH_KRYLOV_FIRST_RTOL")); if (t >= 0 && t < 1) c->krylov_first_tol = t; }
         if (getenv("VCH_KRYLOV_RTOL")) { const double t = atof(getenv("VCH_KRYLOV_RTOL")); if (t > 0 && t < 1) c->krylov_tol = t; }
         Geo& g = c->g;

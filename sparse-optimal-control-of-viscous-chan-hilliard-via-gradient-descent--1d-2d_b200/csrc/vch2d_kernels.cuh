@@ -172,7 +172,7 @@ __global__ void bicg_init_kernel(const double* __restrict__ r, double* __restric
         sc->bnorm2 = tot[0]; sc->rr = tot[0]; sc->rho_new = tot[0];
         sc->rho = 1.0; sc->alpha = 1.0; sc->omega = 1.0;
         sc->thr2 = sc->tol2 * tot[0];
-        sc->iters = 0;
+        sc->iters = 0; sc->half = 0;
         sc->done = (tot[0] == 0.0 || !isfinite(tot[0])) ? 1 : 0;
         if (!isfinite(tot[0])) sc->nonfinite = 1;
         sc->solves += 1;
@@ -186,8 +186,22 @@ __global__ void bicg_x_kernel(double* __restrict__ x, double* __restrict__ r, co
                               const double* __restrict__ s, const double* __restrict__ t, const double* __restrict__ r0,
                               const double* __restrict__ v, double* __restrict__ q, long long n, Scal* sc, double* part,
                               unsigned int* ticket, cudaGraphConditionalHandle cond, int use_cond) {
-    if (sc->done) return;
+    const int half = sc->half;
+    if (sc->done && !half) return;
     const double al = sc->alpha, om = sc->omega;
+    if (half) {   // the solve converged at the half step (dots_finish): x += alpha p closes it; s, t were not formed
+        for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (long long)gridDim.x * blockDim.x)
+            x[idx] += al * p[idx];
+        double one[1] = {0.0};
+        const int op1[1] = {0};
+        double t1[1];
+        if (grid_reduce<1>(one, op1, part, ticket, t1) && threadIdx.x == 0) {   // last block: every block has read sc->half
+            sc->half = 0; sc->iters += 1; sc->iters_total += 1; sc->half_exits += 1;
+            if (sc->iters > sc->iters_max) sc->iters_max = sc->iters;
+            if (use_cond) { sc->g_launches += use_cond; cudaGraphSetConditional(cond, 0u); }
+        }
+        return;
+    }
     double acc[2] = {0.0, 0.0};
     for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (long long)gridDim.x * blockDim.x) {
         const double sv = s[idx], pv = p[idx];

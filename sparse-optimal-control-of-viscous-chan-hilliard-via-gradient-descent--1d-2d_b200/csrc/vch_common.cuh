@@ -137,7 +137,9 @@ struct Scal {
     int done, iters, nonfinite, maxit;
     long long iters_total, solves, stalls;   // accumulated on the device (graph-driven solves are never polled)
     long long g_launches;                    // kernels that ran inside solve graphs (not seen by the host launch log)
+    long long half_exits;                    // solves that stopped after the first half of a BiCGStab iteration (||s|| <= tol ||b||)
     int iters_max, comm_err;                 // comm_err: a bounded cross-rank wait expired (slab mode)
+    int half, pad_;                          // half = 1: converged at the half step, bicg_x_kernel only applies x += alpha p
 };
 
 

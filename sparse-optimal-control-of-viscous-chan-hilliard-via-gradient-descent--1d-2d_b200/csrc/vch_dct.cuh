@@ -49,7 +49,29 @@ struct DotEpilogue {
     const double* addend = nullptr;
     // right-preconditioned form (adjoint operator A P^-1 = I - diag(a - abar) L P^-1): out = addend + (mul_a - abar) * z
     const double* mul_a = nullptr;
+    // mode 1 only: the current residual r.  With (r, out) the kernel also knows ||s||^2 of s = r - alpha*out and can end the
+    // solve at the half step (dots_finish)
+    const double* rvec = nullptr;
 };
+
+// Last block of a dot-product epilogue: BiCGStab scalars from the grid-wide sums tot = {(other,out), (out,out), (r,out)}.
+// Half-step exit (mode 1): ||s||^2 = (r,r) - 2 alpha (r,v) + alpha^2 (v,v) for s = r - alpha v.  The three-term formula
+// carries a rounding error of ~1e-13 (r,r), so it is only trusted once (r,r) is within 1e6 of the threshold (a half step
+// gains 1e-2..1e-4 on ||.||^2); otherwise the iteration simply continues as before.  When it fires, done = half = 1: the
+// remaining transform kernels of the iteration return at once and bicg_x_kernel applies x += alpha p.
+__device__ __forceinline__ void dots_finish(const DotEpilogue& epi, const double (&tot)[3]) {
+    Scal* sc = epi.sc;
+    if (epi.mode == 1) {
+        const double al = sc->rho_new / tot[0];
+        sc->r0v = tot[0]; sc->alpha = al; sc->rho = sc->rho_new;
+        if (epi.rvec) {
+            const double ss = sc->rr - 2.0 * al * tot[2] + al * al * tot[1];
+            if (isfinite(ss) && ss <= sc->thr2 && sc->rr <= 1e6 * sc->thr2) { sc->half = 1; sc->done = 1; }
+        }
+    } else {
+        sc->ts = tot[0]; sc->tt = tot[1]; sc->omega = (tot[1] > 0.0) ? tot[0] / tot[1] : 0.0;
+    }
+}
 
 // Optional prologue of the first row transform (fused BiCGStab vector update + coefficient multiply):
 //   mode 0: x = in
@@ -355,7 +377,9 @@ dct_fft_kernel(const double* in, double* out, int nlines, int n, int in_ls, int 
         fft_last_pass<LOG2L>(data, t, tw, z);
     }
 
-    double acc1 = 0.0, acc2 = 0.0;
+    double acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;
+    const double* ra = epi.rvec + (size_t)la * out_ls;
+    const double* rb_ = epi.rvec + (size_t)lb * out_ls;
     double* qa = out + (size_t)la * out_ls;
     double* qb = out + (size_t)lb * out_ls;
     const double* oa = epi.other + (size_t)la * out_ls;
@@ -381,26 +405,22 @@ dct_fft_kernel(const double* in, double* out, int nlines, int n, int in_ls, int 
                     const double zx = epi.mul_a ? (epi.mul_a[(size_t)la * out_ls + off] - eabar) * z[q].x : z[q].x;
                     const double o = epi.addend ? zx + da[off] : zx;
                     qa[off] = o;
-                    if (epi.mode) { acc1 += oa[off] * o; acc2 += o * o; }
+                    if (epi.mode) { acc1 += oa[off] * o; acc2 += o * o; if (epi.rvec) acc3 += ra[off] * o; }
                 }
                 if (vb) {
                     const double zy = epi.mul_a ? (epi.mul_a[(size_t)lb * out_ls + off] - eabar) * z[q].y : z[q].y;
                     const double o = epi.addend ? zy + db[off] : zy;
                     qb[off] = o;
-                    if (epi.mode) { acc1 += ob[off] * o; acc2 += o * o; }
+                    if (epi.mode) { acc1 += ob[off] * o; acc2 += o * o; if (epi.rvec) acc3 += rb_[off] * o; }
                 }
             }
         }
     }
     if (epi.mode) {     // block-uniform: every thread of every CTA takes part in the reduction
-        double vals[2] = {acc1, acc2};
-        const int op[2] = {0, 0};
-        double tot[2];
-        if (grid_reduce<2>(vals, op, epi.part, epi.ticket, tot) && threadIdx.x == 0) {
-            Scal* sc = epi.sc;
-            if (epi.mode == 1) { sc->r0v = tot[0]; sc->alpha = sc->rho_new / tot[0]; sc->rho = sc->rho_new; }
-            else { sc->ts = tot[0]; sc->tt = tot[1]; sc->omega = (tot[1] > 0.0) ? tot[0] / tot[1] : 0.0; }
-        }
+        double vals[3] = {acc1, acc2, acc3};
+        const int op[3] = {0, 0, 0};
+        double tot[3];
+        if (grid_reduce<3>(vals, op, epi.part, epi.ticket, tot) && threadIdx.x == 0) dots_finish(epi, tot);
     }
 }
 
@@ -470,18 +490,15 @@ __global__ void dct_lambda_kernel(double* __restrict__ d, int no, int ni, const 
 // Stand-alone BiCGStab dots for the paths without the fused epilogue.
 __global__ void dct_dots_kernel(const double* __restrict__ outv, DotEpilogue epi, long long n, const int* __restrict__ done) {
     if (done && *done) return;
-    double vals[2] = {0.0, 0.0};
+    double vals[3] = {0.0, 0.0, 0.0};
     for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (long long)gridDim.x * blockDim.x) {
         const double zz = outv[idx];
         vals[0] += epi.other[idx] * zz; vals[1] += zz * zz;
+        if (epi.rvec) vals[2] += epi.rvec[idx] * zz;
     }
-    const int op[2] = {0, 0};
-    double tot[2];
-    if (grid_reduce<2>(vals, op, epi.part, epi.ticket, tot) && threadIdx.x == 0) {
-        Scal* sc = epi.sc;
-        if (epi.mode == 1) { sc->r0v = tot[0]; sc->alpha = sc->rho_new / tot[0]; sc->rho = sc->rho_new; }
-        else { sc->ts = tot[0]; sc->tt = tot[1]; sc->omega = (tot[1] > 0.0) ? tot[0] / tot[1] : 0.0; }
-    }
+    const int op[3] = {0, 0, 0};
+    double tot[3];
+    if (grid_reduce<3>(vals, op, epi.part, epi.ticket, tot) && threadIdx.x == 0) dots_finish(epi, tot);
 }
 
 // ------------------------------------------------------------------------------------------------ host side

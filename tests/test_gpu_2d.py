@@ -313,6 +313,41 @@ def test_inexact_first_newton_solve_keeps_trajectory_and_saves_iterations(native
     assert rel(h2, h0) < 1e-6
 
 
+def test_bicgstab_half_step_exit(native, monkeypatch):
+    """BiCGStab may end a solve after the first half of an iteration (||s|| <= tol ||b||, from three fused dot products).
+    Same trajectories and adjoint states as with the exit disabled (VCH_NO_HALF_EXIT=1), no stalls, and the polled
+    (VCH_NO_GRAPHS=1) path runs the same kernels as the graph path: bit-identical."""
+    P = O.Phys2D(Nx=64, Ny=64, T=0.3)
+    dts = dt_list(P)
+    t = np.concatenate([[0.0], np.cumsum(dts)])
+    phi0 = O.init_phi_2d(P.Nx, P.Ny)
+    rng = np.random.default_rng(9)
+    u = 0.3 * rng.standard_normal((len(dts) + 1, P.Nx + 1, P.Ny + 1))
+
+    def run(env):
+        for k in ("VCH_NO_HALF_EXIT", "VCH_NO_GRAPHS"):
+            monkeypatch.delenv(k, raising=False)
+        for k in env:
+            monkeypatch.setenv(k, "1")
+        c = make_ctx(native, P)
+        hist, mu, _ = c.forward(phi0, u, dts, want_mu=True)
+        sf = dict(c.last_stats)
+        p, q, r = c.adjoint(hist, t, 5.0, 10.0, None, None)
+        sa = dict(c.last_stats)
+        return hist, mu, r, sf, sa
+
+    h0, m0, r0, sf0, sa0 = run(["VCH_NO_HALF_EXIT"])
+    h1, m1, r1, sf1, sa1 = run([])
+    h2, m2, r2, sf2, sa2 = run(["VCH_NO_GRAPHS"])
+    assert sf0["krylov_half_exits"] == 0 and sa0["krylov_half_exits"] == 0
+    assert sf1["krylov_half_exits"] + sa1["krylov_half_exits"] > 0
+    assert sf1["krylov_stalls"] == 0 and sa1["krylov_stalls"] == 0
+    assert rel(h1, h0) < 1e-10 and rel(m1, m0) < 1e-10 and rel(r1, r0) < 1e-9
+    assert sf1["krylov_iterations"] <= sf0["krylov_iterations"] and sa1["krylov_iterations"] <= sa0["krylov_iterations"]
+    assert np.array_equal(h2, h1) and np.array_equal(r2, r1)
+    assert sf2["krylov_iterations"] == sf1["krylov_iterations"] and sf2["krylov_half_exits"] == sf1["krylov_half_exits"]
+
+
 def test_full_size_1024_properties(native):
     """BASELINE grid (1024^2, device-resident): size-independent identities that need no CPU oracle.
     (a) the linear solve satisfies the Schur system  (1/dt) dphi - L(a dphi - kappa/2 L dphi) = -R_mu + L R_phi  and
