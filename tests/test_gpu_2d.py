@@ -314,9 +314,9 @@ def test_inexact_first_newton_solve_keeps_trajectory_and_saves_iterations(native
 
 
 def test_bicgstab_half_step_exit(native, monkeypatch):
-    """BiCGStab may end a solve after the first half of an iteration (||s|| <= tol ||b||, from three fused dot products).
-    Same trajectories and adjoint states as with the exit disabled (VCH_NO_HALF_EXIT=1), no stalls, and the polled
-    (VCH_NO_GRAPHS=1) path runs the same kernels as the graph path: bit-identical."""
+    """Forward BiCGStab may end a solve after the first half of an iteration (||s|| <= tol ||b||, from three fused dot
+    products; the adjoint solves never do).  Same trajectories as with the exit disabled (VCH_NO_HALF_EXIT=1), no stalls,
+    and the polled (VCH_NO_GRAPHS=1) path runs the same kernels as the graph path: bit-identical."""
     P = O.Phys2D(Nx=64, Ny=64, T=0.3)
     dts = dt_list(P)
     t = np.concatenate([[0.0], np.cumsum(dts)])
@@ -340,7 +340,7 @@ def test_bicgstab_half_step_exit(native, monkeypatch):
     h1, m1, r1, sf1, sa1 = run([])
     h2, m2, r2, sf2, sa2 = run(["VCH_NO_GRAPHS"])
     assert sf0["krylov_half_exits"] == 0 and sa0["krylov_half_exits"] == 0
-    assert sf1["krylov_half_exits"] + sa1["krylov_half_exits"] > 0
+    assert sf1["krylov_half_exits"] > 0 and sa1["krylov_half_exits"] == 0
     assert sf1["krylov_stalls"] == 0 and sa1["krylov_stalls"] == 0
     assert rel(h1, h0) < 1e-10 and rel(m1, m0) < 1e-10 and rel(r1, r0) < 1e-9
     assert sf1["krylov_iterations"] <= sf0["krylov_iterations"] and sa1["krylov_iterations"] <= sa0["krylov_iterations"]
