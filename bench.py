@@ -36,10 +36,13 @@ BYTES_PER_NODE = {
     "op_apply_fwd": 24, "op_apply_adj": 24,            # read x, a; write y
     "dct_rows_fft": 16, "dct_cols_fft_solve": 16,      # read + write the field once
     "dct_rows_fft_pro": 40,                            # read r, q|v, a; write p|s and the transform
-    "dct_rows_fft_epi1": 32, "dct_rows_fft_epi2": 24,  # read transform input, addend (, r0); write v|t
+    "dct_rows_fft_epi1": 40, "dct_rows_fft_epi2": 24,  # read transform input, addend (, r0, r); write v|t
     "residual_kernel": 56,                             # read phi, mu, cphi, cmu; write Rphi, Rmu, a
     "bicg_x_kernel": 72, "bicg_p_kernel": 32, "bicg_s_kernel": 24, "bicg_dot1_kernel": 16, "bicg_dot2_kernel": 16,
-    "bicg_init_kernel": 40, "schur_rhs_kernel": 24, "dmu_ceiling_kernel": 40, "trial_kernel": 48,
+    "bicg_init_kernel": 24,                            # read r; write r0, x (adjoint: + write r)
+    "schur_rhs_kernel": 24,
+    "dmu_ceiling_kernel": 64,                          # read dphi, a, Rphi, phi, mu; write dmu, phi_trial, mu_trial
+    "trial_kernel": 48,
     "step_setup_kernel": 56, "solve_w_kernel": 32, "clip_mass_kernel": 16, "mass_shift_kernel": 16,
     "adj_rhs_kernel": 64, "adj_qr_kernel": 40, "adj_terminal_rhs_kernel": 24, "mu_init_kernel": 24,
 }

@@ -83,10 +83,14 @@ __global__ void publish_scalars_kernel(const Scal* __restrict__ src, Scal* __res
     for (int i = threadIdx.x; i < (int)(sizeof(Scal) / 8); i += blockDim.x) d[i] = s[i];
 }
 
-void fetch_scalars(vch2d_ctx* c) {
-    LAUNCH(c, publish_scalars_kernel, 1, 32, c->sc, c->sc_host);
+// Waits for scalars that the last kernel on the stream has published itself (residual_kernel with publish = sc_host).
+void wait_scalars(vch2d_ctx* c) {
     VCH_CUDA(cudaStreamSynchronize(c->stream));
     if (c->sc_host->comm_err) throw Error(VCH_E_COMM, "slab mode: a peer rank did not arrive within the wait limit (ranks out of step or a peer failed)");
+}
+void fetch_scalars(vch2d_ctx* c) {
+    LAUNCH(c, publish_scalars_kernel, 1, 32, c->sc, c->sc_host);
+    wait_scalars(c);
 }
 
 
@@ -115,7 +119,7 @@ void copy_ghosted(vch2d_ctx* c, double* dst, const double* src) {
 template <bool ADJ> int iter_launches(const vch2d_ctx* c) { return c->slab ? 7 + 4 : 7; }
 // FWD: P^-1 b (3 kernels) + init;  ADJ (right-preconditioned): init + the closing x = P^-1 y (3 kernels); slab mode adds the
 // barriers of one preconditioner application (2 + the trailing one)
-template <bool ADJ> int prologue_launches(const vch2d_ctx* c) { return (ADJ ? 5 : 4) + (c->slab ? 3 : 0); }   // ADJ: + the r = b copy kernel
+template <bool ADJ> int prologue_launches(const vch2d_ctx* c) { return 4 + (c->slab ? 3 : 0); }
 
 // Orders the library's private stream after the caller's stream on entry and the caller's stream after ours on exit,
 // so callers see ordinary stream semantics (torch.cuda.Event on their stream brackets our kernels).
@@ -159,9 +163,8 @@ void enqueue_bicg_iteration(vch2d_ctx* c, const double* a, const SymbolArgs& sy,
 template <bool ADJ>
 void enqueue_bicg_prologue(vch2d_ctx* c, const SymbolArgs& sy, cudaGraphConditionalHandle cond, int use_cond) {
     const long long n = c->g.n;
-    if (ADJ) dev_copy(c, c->kr.p, c->kb.p, (size_t)n);
-    else c->dct.apply(c->stream, c->kb.p, c->kr.p, sy, nullptr);
-    LAUNCH(c, bicg_init_kernel, c->rb(), kRedThreads, c->kr.p, c->kr0.p, c->kp.p, c->kv.p, c->kx.p, c->kq.p, n, c->sc,
+    if (!ADJ) c->dct.apply(c->stream, c->kb.p, c->kr.p, sy, nullptr);
+    LAUNCH(c, bicg_init_kernel, c->rb(), kRedThreads, ADJ ? c->kb.p : c->kr.p, c->kr.p, c->kr0.p, c->kx.p, n, c->sc,
            c->red.part, c->ticket, cond, use_cond);
 }
 // End of a solve: ADJ x = P^-1 y.
@@ -279,22 +282,25 @@ void stat_collect(vch2d_ctx* c, const StatMark& m0, vch_stats* st) {
     st->kernel_launches += (c->log.count - m0.launches) + (c->sc_host->g_launches - m0.glaunches);
 }
 
-void eval_residual(vch2d_ctx* c, const double* phi, const double* mu, double* Rphi, double* Rmu, double* a, double dt) {
+// publish: the kernel's last block also writes the scalars into the pinned mirror (follow with wait_scalars, not fetch_scalars)
+void eval_residual(vch2d_ctx* c, const double* phi, const double* mu, double* Rphi, double* Rmu, double* a, double dt,
+                   bool publish = false) {
     LAUNCH(c, residual_kernel, c->rb(), kRedThreads, phi, mu, c->cphi.p, c->cmu.p, Rphi, Rmu, a, c->g, c->ph, dt, c->sc,
-           c->red.part, c->ticket);
+           c->red.part, c->ticket, publish ? c->sc_host : (Scal*)nullptr);
 }
 
 // Solve J [dphi; dmu] = -[Rphi; Rmu] by Schur reduction:  (1/dt I - L(diag(a) - kappa/2 L)) dphi = -Rmu + L Rphi,
 // dmu = 2 (a dphi - kappa/2 L dphi + Rphi).   dphi -> c->kx, dmu -> c->dmu.  phi may be null (no ceiling minima).
 void newton_linear_solve(vch2d_ctx* c, const double* Rphi, const double* Rmu, const double* a, const double* phi,
-                         double dt, vch_stats* st, double rel_tol = 0.0) {
+                         double dt, vch_stats* st, double rel_tol = 0.0, const double* mu = nullptr, double* phit = nullptr,
+                         double* mut = nullptr) {
     if (!(rel_tol > 0.0)) rel_tol = c->krylov_tol;
     halo_push(c, Rphi, nullptr, 1);
     LAUNCH(c, schur_rhs_kernel, c->eb(), 256, Rphi, Rmu, c->kb.p, c->g, c->sc, 1.0 / dt, 0.5 * c->ph.kappa, rel_tol * rel_tol);
     krylov_solve<false>(c, c->kb.p, a, st);
     halo_push(c, c->kx.p, nullptr, 1);
     LAUNCH(c, dmu_ceiling_kernel, c->rb(), kRedThreads, c->kx.p, a, Rphi, phi, c->dmu.p, c->g, c->ph, c->sc, c->red.part,
-           c->ticket);
+           c->ticket, mu, (phi && mu) ? phit : nullptr, (phi && mu) ? mut : nullptr);
 }
 
 // One Newton solve (Forward2_solver.py:323-427).  Inputs: device phi_old, mu_old, w_old, w_new.
@@ -320,8 +326,8 @@ void newton_step(vch2d_ctx* c, const double* phi_old, const double* mu_old, cons
     halo_push(c, c->mu.p, nullptr, 1);
     double *phi = c->phi.p, *mu = c->mu.p, *phit = c->phit.p, *mut = c->mut.p;
     double *Rp = c->Rphi.p, *Rm = c->Rmu.p, *a = c->a.p, *RpT = c->RphiT.p, *RmT = c->RmuT.p, *aT = c->aT.p;
-    eval_residual(c, phi, mu, Rp, Rm, a, dt);
-    fetch_scalars(c);
+    eval_residual(c, phi, mu, Rp, Rm, a, dt, true);
+    wait_scalars(c);
     if (st) st->newton_residual_evals += 1;
     double normR = std::sqrt(c->sc_host->res2);
     const double tol = 1e-6, eta = 1e-4;
@@ -343,13 +349,14 @@ void newton_step(vch2d_ctx* c, const double* phi_old, const double* mu_old, cons
         if (c->floor_aware && normR <= 1.5 * floor_now) break;   // at the fp64 resolution of the residual (only possible
                                                              // when that resolution exceeds tol, i.e. grids >~ 600^2)
         const double normR_prev = normR;
-        newton_linear_solve(c, Rp, Rm, a, phi, dt, st, (inexact_first && k == 0 && c->krylov_first_tol > c->krylov_tol) ? c->krylov_first_tol : 0.0);
         // speculative full step: almost always alpha = 1 is both allowed by the ceiling and accepted by Armijo, so the
-        // trial iterate and its residual are enqueued before the host has seen the ceiling -> ONE sync per Newton iteration
-        LAUNCH(c, trial_kernel, eb, 256, phi, mu, c->kx.p, c->dmu.p, phit, mut, n, 1.0);
+        // trial iterate (formed by the dmu kernel) and its residual are enqueued before the host has seen the ceiling
+        // -> ONE sync per Newton iteration
+        newton_linear_solve(c, Rp, Rm, a, phi, dt, st, (inexact_first && k == 0 && c->krylov_first_tol > c->krylov_tol) ? c->krylov_first_tol : 0.0,
+                            mu, phit, mut);
         halo_push(c, phit, mut, 1);
-        eval_residual(c, phit, mut, RpT, RmT, aT, dt);
-        fetch_scalars(c);
+        eval_residual(c, phit, mut, RpT, RmT, aT, dt, true);
+        wait_scalars(c);
         if (c->sc_host->nonfinite) throw Error(VCH_E_NONFINITE, "non-finite value in Krylov solve");
         if (st) st->newton_residual_evals += 1;
         double amax = 2.0;
@@ -364,8 +371,8 @@ void newton_step(vch2d_ctx* c, const double* phi_old, const double* mu_old, cons
             if (!have_trial) {
                 LAUNCH(c, trial_kernel, eb, 256, phi, mu, c->kx.p, c->dmu.p, phit, mut, n, alpha);
                 halo_push(c, phit, mut, 1);
-                eval_residual(c, phit, mut, RpT, RmT, aT, dt);
-                fetch_scalars(c);
+                eval_residual(c, phit, mut, RpT, RmT, aT, dt, true);
+                wait_scalars(c);
                 if (st) st->newton_residual_evals += 1;
             }
             have_trial = false;
@@ -382,8 +389,8 @@ void newton_step(vch2d_ctx* c, const double* phi_old, const double* mu_old, cons
             if (best < normR) {   // fall back to the best trial (re-evaluated: same arithmetic, same values)
                 LAUNCH(c, trial_kernel, eb, 256, phi, mu, c->kx.p, c->dmu.p, phit, mut, n, best_alpha);
                 halo_push(c, phit, mut, 1);
-                eval_residual(c, phit, mut, RpT, RmT, aT, dt);
-                fetch_scalars(c);
+                eval_residual(c, phit, mut, RpT, RmT, aT, dt, true);
+                wait_scalars(c);
                 normR = std::sqrt(c->sc_host->res2);
                 accepted = true;
             }

@@ -87,11 +87,20 @@ __global__ void step_setup_kernel(const double* __restrict__ phi0, const double*
     }
 }
 
+// Device scalars -> mapped pinned host mirror, by one thread (8-byte words; visible to the host after the stream synchronises).
+__device__ __forceinline__ void publish_scalars(const Scal* src, Scal* dst_host) {
+    static_assert(sizeof(Scal) % 8 == 0, "Scal is copied in 8-byte words");
+    const volatile unsigned long long* s = reinterpret_cast<const volatile unsigned long long*>(src);
+    volatile unsigned long long* d = reinterpret_cast<volatile unsigned long long*>(dst_host);
+    for (int i = 0; i < (int)(sizeof(Scal) / 8); ++i) d[i] = s[i];
+    __threadfence_system();
+}
+
 // [R_phi; R_mu], the Jacobian diagonal a = tau/dt + 2c1/(1 - min(phi^2, 1-delta^2)) and ||R||^2, min a, max a.
 __global__ void residual_kernel(const double* __restrict__ phi, const double* __restrict__ mu,
                                 const double* __restrict__ cphi, const double* __restrict__ cmu,
                                 double* __restrict__ Rphi, double* __restrict__ Rmu, double* __restrict__ a,
-                                Geo g, Phys p, double dt, Scal* sc, double* part, unsigned int* ticket) {
+                                Geo g, Phys p, double dt, Scal* sc, double* part, unsigned int* ticket, Scal* publish) {
     const double idt = 1.0 / dt, tdt = p.tau / dt;
     double v[4] = {0.0, INFINITY, -INFINITY, 0.0};
     for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < g.n; idx += (long long)gridDim.x * blockDim.x) {
@@ -111,6 +120,9 @@ __global__ void residual_kernel(const double* __restrict__ phi, const double* __
     if (grid_reduce<4>(v, op, part, ticket, tot) && threadIdx.x == 0) {
         sc->res2 = tot[0]; sc->amin = tot[1]; sc->amax = tot[2]; sc->abar = sqrt(tot[1] * tot[2]); sc->mu2 = tot[3];
         if (!isfinite(tot[0])) sc->nonfinite = 1;
+        // Newton's host-side decisions follow every residual evaluation: the last block writes the scalars straight into
+        // the mapped pinned mirror (saves the separate publish launch in front of the host's stream synchronisation)
+        if (publish) publish_scalars(sc, publish);
     }
 }
 
@@ -156,21 +168,24 @@ __global__ void schur_rhs_kernel(const double* __restrict__ Rphi, const double* 
 
 // ---------------------------------------------------------------------------------- BiCGStab vector kernels
 // cond/use_cond: CUDA-graph WHILE handle of the enclosing solve graph (device-driven Krylov loop); ignored when use_cond = 0.
-__global__ void bicg_init_kernel(const double* __restrict__ r, double* __restrict__ r0, double* __restrict__ p,
-                                 double* __restrict__ v, double* __restrict__ x, double* __restrict__ q, long long n, Scal* sc,
+__global__ void bicg_init_kernel(const double* r_in, double* r /* may equal r_in */, double* __restrict__ r0,
+                                 double* __restrict__ x, long long n, Scal* sc,
                                  double* part, unsigned int* ticket, cudaGraphConditionalHandle cond, int use_cond) {
+    // r = r0 = r_in, x = 0, (r,r).  p, v and q are NOT cleared: the first iteration forms p = r + beta*q with beta = 0
+    // (alpha starts at 0; the prologue skips the q term for a zero coefficient, so stale values cannot leak in), v is
+    // written by the first operator application before anything reads it, q by the first x/r update.
     double acc[1] = {0.0};
     for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (long long)gridDim.x * blockDim.x) {
-        const double rv = r[idx];
-        r0[idx] = rv; p[idx] = 0.0; v[idx] = 0.0; x[idx] = 0.0;
-        if (q) q[idx] = 0.0;
+        const double rv = r_in[idx];
+        if (r != r_in) r[idx] = rv;
+        r0[idx] = rv; x[idx] = 0.0;
         acc[0] += rv * rv;
     }
     const int op[1] = {0};
     double tot[1];
     if (grid_reduce<1>(acc, op, part, ticket, tot) && threadIdx.x == 0) {
         sc->bnorm2 = tot[0]; sc->rr = tot[0]; sc->rho_new = tot[0];
-        sc->rho = 1.0; sc->alpha = 1.0; sc->omega = 1.0;
+        sc->rho = 1.0; sc->alpha = 0.0; sc->omega = 1.0;
         sc->thr2 = sc->tol2 * tot[0];
         sc->iters = 0; sc->half = 0;
         sc->done = (tot[0] == 0.0 || !isfinite(tot[0])) ? 1 : 0;
@@ -232,14 +247,19 @@ __global__ void bicg_x_kernel(double* __restrict__ x, double* __restrict__ r, co
 // dmu = 2 (a dphi - kappa/2 L dphi + R_phi) and the step ceiling minima (Forward2_solver.py:377-391).
 __global__ void dmu_ceiling_kernel(const double* __restrict__ dphi, const double* __restrict__ a,
                                    const double* __restrict__ Rphi, const double* __restrict__ phi,
-                                   double* __restrict__ dmu, Geo g, Phys p, Scal* sc, double* part, unsigned int* ticket) {
+                                   double* __restrict__ dmu, Geo g, Phys p, Scal* sc, double* part, unsigned int* ticket,
+                                   const double* __restrict__ mu, double* __restrict__ phit, double* __restrict__ mut) {
+    // phit/mut (optional, need phi and mu): the full-step trial iterate phi + dphi, mu + dmu — what trial_kernel(alpha = 1)
+    // computes — so the speculative first Armijo trial costs no launch of its own
     double v[2] = {INFINITY, INFINITY};
     for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < g.n; idx += (long long)gridDim.x * blockDim.x) {
         const int o = (int)(idx / g.ni), i = (int)(idx - (long long)o * g.ni);
         const double d = dphi[idx];
-        dmu[idx] = 2.0 * (a[idx] * d - 0.5 * p.kappa * lap_g(dphi, o, i, g) + Rphi[idx]);
+        const double dm = 2.0 * (a[idx] * d - 0.5 * p.kappa * lap_g(dphi, o, i, g) + Rphi[idx]);
+        dmu[idx] = dm;
         if (phi) {
             const double f = phi[idx];
+            if (phit) { phit[idx] = f + 1.0 * d; mut[idx] = mu[idx] + 1.0 * dm; }
             if (d > 0.0) v[0] = fmin(v[0], (p.lim - f) / d);
             else if (d < 0.0) v[1] = fmin(v[1], (-p.lim - f) / d);
         }

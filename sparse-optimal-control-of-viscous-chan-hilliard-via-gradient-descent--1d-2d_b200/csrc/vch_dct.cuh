@@ -343,8 +343,9 @@ dct_fft_kernel(const double* in, double* out, int nlines, int n, int in_ls, int 
             const double abar = sc->abar;
             const size_t ia = (size_t)la * in_ls + off, ib = (size_t)lb * in_ls + off;
             double xa = 0.0, xb = 0.0;
-            if (va) { const double w = pro.r[ia] + coef * pro.qv[ia]; if (e <= N) pro.w[ia] = w; xa = pro.a ? (pro.a[ia] - abar) * w : w; }
-            if (vb) { const double w = pro.r[ib] + coef * pro.qv[ib]; if (e <= N) pro.w[ib] = w; xb = pro.a ? (pro.a[ib] - abar) * w : w; }
+            // coef == 0 (first iteration: beta = 0): qv is not read — it may hold anything (bicg_init_kernel does not clear it)
+            if (va) { const double w = (coef != 0.0) ? pro.r[ia] + coef * pro.qv[ia] : pro.r[ia]; if (e <= N) pro.w[ia] = w; xa = pro.a ? (pro.a[ia] - abar) * w : w; }
+            if (vb) { const double w = (coef != 0.0) ? pro.r[ib] + coef * pro.qv[ib] : pro.r[ib]; if (e <= N) pro.w[ib] = w; xb = pro.a ? (pro.a[ib] - abar) * w : w; }
             v[r] = make_double2(xa, xb);
         }
     }
@@ -465,7 +466,7 @@ __global__ void dct_prologue_kernel(RowPrologue pro, double* __restrict__ x, lon
     const double coef = (pro.mode == 1) ? (sc->rho_new / sc->rho) * (sc->alpha / sc->omega) : -sc->alpha;
     const double abar = sc->abar;
     for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (long long)gridDim.x * blockDim.x) {
-        const double w = pro.r[idx] + coef * pro.qv[idx];
+        const double w = (coef != 0.0) ? pro.r[idx] + coef * pro.qv[idx] : pro.r[idx];
         pro.w[idx] = w;
         x[idx] = pro.a ? (pro.a[idx] - abar) * w : w;
     }
