@@ -31,6 +31,7 @@ struct vch2d_ctx {
     double krylov_first_tol = 1e-6;   // time loop only: relative tolerance of the FIRST linear solve of a Newton solve (0 = krylov_tol)
     int krylov_maxit = 200;
     int floor_aware = 1;         // fp64-resolution-aware Newton stop
+    int pdl = 0;                 // programmatic dependent launch for every kernel of the work stream (vch_common.cuh); VCH_PDL=0|1
     int half_exit = 1;           // forward BiCGStab may stop after the first half of an iteration (VCH_NO_HALF_EXIT=1 disables).
                                  // Not used for the adjoint: its tolerance is on the TRUE residual, whose error is ~1e3 larger;
                                  // the second half of its last iteration is what keeps the gradient at ~1e-12 of the reference's
@@ -68,7 +69,7 @@ namespace {
 #define LAUNCH(c, kern, grid, block, ...)                       \
     do {                                                        \
         (c)->log.begin(#kern, (c)->stream);                     \
-        kern<<<(grid), (block), 0, (c)->stream>>>(__VA_ARGS__); \
+        launch_pdl((c)->pdl != 0, kern, dim3(grid), dim3(block), 0, (c)->stream, __VA_ARGS__); \
         (c)->log.end((c)->stream);                              \
     } while (0)
 
@@ -77,6 +78,7 @@ namespace {
 // of the streamed host-buffer path — once per Newton iteration (measured with a background D2H stream: 58 ms instead of
 // 1.3 ms per time step).
 __global__ void publish_scalars_kernel(const Scal* __restrict__ src, Scal* __restrict__ dst_host) {
+    pdl_enter();
     static_assert(sizeof(Scal) % 8 == 0, "Scal is copied in 8-byte words");
     const unsigned long long* s = reinterpret_cast<const unsigned long long*>(src);
     unsigned long long* d = reinterpret_cast<unsigned long long*>(dst_host);
@@ -624,6 +626,7 @@ static int create_ctx(const vch2d_params* p, int device, int rank, int nranks, v
         c->debug = getenv("VCH_DEBUG") ? atoi(getenv("VCH_DEBUG")) : 0;
         if (getenv("VCH_NEWTON_STRICT")) c->floor_aware = 0;
         if (getenv("VCH_NO_HALF_EXIT")) c->half_exit = 0;
+        c->pdl = (getenv("VCH_PDL") ? atoi(getenv("VCH_PDL")) : 0) && !slab;   // slab mode: cross-rank waits inside kernels, keep full serialization
         if (getenv("VCH_KRYLOV_FIRST_RTOL")) { const double t = atof(getenv("VCH_KRYLOV_FIRST_RTOL")); if (t >= 0 && t < 1) c->krylov_first_tol = t; }
         if (getenv("VCH_KRYLOV_RTOL")) { const double t = atof(getenv("VCH_KRYLOV_RTOL")); if (t > 0 && t < 1) c->krylov_tol = t; }
         Geo& g = c->g;
@@ -678,6 +681,7 @@ static int create_ctx(const vch2d_params* p, int device, int rank, int nranks, v
             c->dct.init_slab(p->Nx + 1, p->hy, p->hx, &c->log, sl);
         } else {
             c->dct.init(g.no, g.ni, p->hy, p->hx, &c->log);
+            c->dct.pdl = c->pdl != 0;
         }
         c->red.alloc(8 * (size_t)c->dct.max_grid(), c->cm);
         Scal init{}; init.tol2 = c->krylov_tol * c->krylov_tol; init.maxit = c->krylov_maxit;
@@ -742,6 +746,7 @@ int vch2d_slab_attach(vch2d_ctx* c, const void* handles) {
 // Exercises the three cross-rank primitives: barrier, neighbour halo push, reduction (sum / min / max of rank + 1).
 // out (host, 5): sum, min, max, lower ghost value (rank of the neighbour below + 1, or 0), upper ghost value.
 __global__ void slab_selftest_kernel(double* field, int n, double val, double* out3, double* part, unsigned int* ticket) {
+    pdl_enter();
     double v[3] = {0.0, INFINITY, -INFINITY};
     if (blockIdx.x == 0 && threadIdx.x == 0) { v[0] = val; v[1] = val; v[2] = val; }
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) field[i] = val;
@@ -1398,7 +1403,7 @@ int vch2d_pgd_iteration(vch2d_ctx* c, int levels, const double* t_hist, const do
         adjoint_dev(c, dh, levels, t_hist, b1, b2, dq, dT, nullptr, nullptr, dr, s);
         // (2) gradient + soft-threshold prox + box, with the driver's norms  GD2_configured.py:304-305, :375
         LAUNCH(c, grad_prox_kernel, red_blocks((long long)tot), kRedThreads, du, dr, (double*)nullptr, dun, (long long)tot, b3,
-               alpha, ksp, umin, umax, c->out4 + 4, c->red.part, c->ticket);
+               alpha, ksp, umin, umax, c->out4 + 4, c->red.part, c->ticket, 0);
         // (3) forward solve under the new control                            GD2_configured.py:309
         forward_dev(c, dh, dun, levels, levels - 1, dt_steps, dhn, nullptr, nullptr, s);
         // (4) cost functional                                                GD2_configured.py:312

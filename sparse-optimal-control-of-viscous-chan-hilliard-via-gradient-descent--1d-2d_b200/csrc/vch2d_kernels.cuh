@@ -39,6 +39,7 @@ __device__ __forceinline__ double flory_log(double phi, double eps) {
 
 // ---------------------------------------------------------------------------------- elementwise / stencil
 __global__ void lap_kernel(const double* __restrict__ v, double* __restrict__ out, Geo g, double scale) {
+    pdl_enter();
     for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < g.n; idx += (long long)gridDim.x * blockDim.x) {
         const int o = (int)(idx / g.ni), i = (int)(idx - (long long)o * g.ni);
         out[idx] = scale * lap_g(v, o, i, g);
@@ -49,12 +50,14 @@ __global__ void lap_kernel(const double* __restrict__ v, double* __restrict__ ou
 // are served by a copy engine, where they queue behind the 270 MB host<->device chunks of the streamed host-buffer path and
 // stall the work stream for milliseconds (measured: adjoint sweep 0.55 s instead of 0.33 s).
 __global__ void copy_kernel(const double* __restrict__ src, double* __restrict__ dst, long long n) {
+    pdl_enter();
     for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (long long)gridDim.x * blockDim.x)
         dst[idx] = src[idx];
 }
 
 __global__ void solve_w_kernel(const double* __restrict__ w0, const double* __restrict__ un, const double* __restrict__ un1,
                                double* __restrict__ w1, long long n, double gdt) {
+    pdl_enter();
     for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (long long)gridDim.x * blockDim.x) {
         const double a = un ? un[idx] : 0.0, b = un1 ? un1[idx] : 0.0;
         // no FMA contraction: bit-identical to the reference's NumPy expression (its tests ask rtol 1e-15)
@@ -63,6 +66,7 @@ __global__ void solve_w_kernel(const double* __restrict__ w0, const double* __re
 }
 
 __global__ void mu_init_kernel(const double* __restrict__ phi, const double* __restrict__ w, double* __restrict__ mu, Geo g, Phys p) {
+    pdl_enter();
     for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < g.n; idx += (long long)gridDim.x * blockDim.x) {
         const int o = (int)(idx / g.ni), i = (int)(idx - (long long)o * g.ni);
         const double f = phi[idx];
@@ -76,6 +80,7 @@ __global__ void step_setup_kernel(const double* __restrict__ phi0, const double*
                                   const double* __restrict__ w0, const double* __restrict__ w1,
                                   double* __restrict__ cphi, double* __restrict__ cmu, double* __restrict__ mu_guess,
                                   Geo g, Phys p, double dt) {
+    pdl_enter();
     const double idt = 1.0 / dt;
     for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < g.n; idx += (long long)gridDim.x * blockDim.x) {
         const int o = (int)(idx / g.ni), i = (int)(idx - (long long)o * g.ni);
@@ -101,6 +106,7 @@ __global__ void residual_kernel(const double* __restrict__ phi, const double* __
                                 const double* __restrict__ cphi, const double* __restrict__ cmu,
                                 double* __restrict__ Rphi, double* __restrict__ Rmu, double* __restrict__ a,
                                 Geo g, Phys p, double dt, Scal* sc, double* part, unsigned int* ticket, Scal* publish) {
+    pdl_enter();
     const double idt = 1.0 / dt, tdt = p.tau / dt;
     double v[4] = {0.0, INFINITY, -INFINITY, 0.0};
     for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < g.n; idx += (long long)gridDim.x * blockDim.x) {
@@ -131,6 +137,7 @@ __global__ void residual_full_kernel(const double* __restrict__ phi, const doubl
                                      const double* __restrict__ mu, const double* __restrict__ mu0,
                                      const double* __restrict__ w1, const double* __restrict__ w0,
                                      double* __restrict__ Rphi, double* __restrict__ Rmu, Geo g, Phys p, double dt) {
+    pdl_enter();
     for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < g.n; idx += (long long)gridDim.x * blockDim.x) {
         const int o = (int)(idx / g.ni), i = (int)(idx - (long long)o * g.ni);
         const double f = phi[idx], f0 = phi0[idx];
@@ -143,6 +150,7 @@ __global__ void residual_full_kernel(const double* __restrict__ phi, const doubl
 // Jacobian diagonal only (test-level jacobian_solve).
 __global__ void jac_diag_kernel(const double* __restrict__ phi, double* __restrict__ a, Geo g, Phys p, double dt,
                                 Scal* sc, double* part, unsigned int* ticket) {
+    pdl_enter();
     double v[2] = {INFINITY, -INFINITY};
     for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < g.n; idx += (long long)gridDim.x * blockDim.x) {
         const double f = phi[idx];
@@ -159,6 +167,7 @@ __global__ void jac_diag_kernel(const double* __restrict__ phi, double* __restri
 // Right-hand side of the Schur-reduced Newton system: b = -R_mu + L R_phi.
 __global__ void schur_rhs_kernel(const double* __restrict__ Rphi, const double* __restrict__ Rmu, double* __restrict__ b, Geo g,
                                  Scal* sc, double c0, double c2, double tol2) {
+    pdl_enter();
     if (blockIdx.x == 0 && threadIdx.x == 0) { sc->c0 = c0; sc->c2 = c2; sc->tol2 = tol2; }   // coefficients and (squared) relative tolerance of the solve that follows
     for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < g.n; idx += (long long)gridDim.x * blockDim.x) {
         const int o = (int)(idx / g.ni), i = (int)(idx - (long long)o * g.ni);
@@ -171,6 +180,7 @@ __global__ void schur_rhs_kernel(const double* __restrict__ Rphi, const double* 
 __global__ void bicg_init_kernel(const double* r_in, double* r /* may equal r_in */, double* __restrict__ r0,
                                  double* __restrict__ x, long long n, Scal* sc,
                                  double* part, unsigned int* ticket, cudaGraphConditionalHandle cond, int use_cond) {
+    pdl_enter();
     // r = r0 = r_in, x = 0, (r,r).  p, v and q are NOT cleared: the first iteration forms p = r + beta*q with beta = 0
     // (alpha starts at 0; the prologue skips the q term for a zero coefficient, so stale values cannot leak in), v is
     // written by the first operator application before anything reads it, q by the first x/r update.
@@ -201,6 +211,7 @@ __global__ void bicg_x_kernel(double* __restrict__ x, double* __restrict__ r, co
                               const double* __restrict__ s, const double* __restrict__ t, const double* __restrict__ r0,
                               const double* __restrict__ v, double* __restrict__ q, long long n, Scal* sc, double* part,
                               unsigned int* ticket, cudaGraphConditionalHandle cond, int use_cond) {
+    pdl_enter();
     const int half = sc->half;
     if (sc->done && !half) return;
     const double al = sc->alpha, om = sc->omega;
@@ -249,6 +260,7 @@ __global__ void dmu_ceiling_kernel(const double* __restrict__ dphi, const double
                                    const double* __restrict__ Rphi, const double* __restrict__ phi,
                                    double* __restrict__ dmu, Geo g, Phys p, Scal* sc, double* part, unsigned int* ticket,
                                    const double* __restrict__ mu, double* __restrict__ phit, double* __restrict__ mut) {
+    pdl_enter();
     // phit/mut (optional, need phi and mu): the full-step trial iterate phi + dphi, mu + dmu — what trial_kernel(alpha = 1)
     // computes — so the speculative first Armijo trial costs no launch of its own
     double v[2] = {INFINITY, INFINITY};
@@ -272,6 +284,7 @@ __global__ void dmu_ceiling_kernel(const double* __restrict__ dphi, const double
 __global__ void trial_kernel(const double* __restrict__ phi, const double* __restrict__ mu, const double* __restrict__ dphi,
                              const double* __restrict__ dmu, double* __restrict__ phit, double* __restrict__ mut,
                              long long n, double alpha) {
+    pdl_enter();
     for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (long long)gridDim.x * blockDim.x) {
         phit[idx] = phi[idx] + alpha * dphi[idx];
         mut[idx] = mu[idx] + alpha * dmu[idx];
@@ -281,6 +294,7 @@ __global__ void trial_kernel(const double* __restrict__ phi, const double* __res
 // Weighted mass of clip(phi) and the interior weight (Forward2_solver.py:562-571).  WRITE_CLIP stores the clipped field.
 __global__ void clip_mass_kernel(const double* __restrict__ phin, double* __restrict__ phic, Geo g, Phys p, double hxhy,
                                  Scal* sc, int set_mass0, double* part, unsigned int* ticket) {
+    pdl_enter();
     double v[2] = {0.0, 0.0};
     const double thr = p.lim - 5e-3;
     for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < g.n; idx += (long long)gridDim.x * blockDim.x) {
@@ -302,6 +316,7 @@ __global__ void clip_mass_kernel(const double* __restrict__ phin, double* __rest
 
 // Interior-only mass shift (uniform shift + re-clip when there is no interior), Forward2_solver.py:566-577.
 __global__ void mass_shift_kernel(double* __restrict__ phi, Geo g, Phys p, double area, const Scal* __restrict__ sc) {
+    pdl_enter();
     const double err = sc->mass - sc->mass0;
     if (!(fabs(err) > 1e-16)) return;
     const double wint = sc->wint, thr = p.lim - 5e-3;
@@ -320,6 +335,7 @@ __device__ __forceinline__ double fpp_dev(double phi, double c1, double c2) {
 
 __global__ void adj_terminal_rhs_kernel(const double* __restrict__ phiM, const double* __restrict__ phiT,
                                         double* __restrict__ b, long long n, double b2) {
+    pdl_enter();
     for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (long long)gridDim.x * blockDim.x)
         b[idx] = b2 * (phiM[idx] - (phiT ? phiT[idx] : 0.0));
 }
@@ -332,6 +348,7 @@ __global__ void adj_rhs_kernel(const double* __restrict__ p1, const double* __re
                                const double* __restrict__ Q1, const double* __restrict__ Q0,
                                double* __restrict__ rhs, double* __restrict__ a, Geo g, Phys p, double dt, double b1,
                                Scal* sc, double* part, unsigned int* ticket, double tol2) {
+    pdl_enter();
     double v[2] = {INFINITY, -INFINITY};
     const double hdt = 0.5 * dt;
     for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < g.n; idx += (long long)gridDim.x * blockDim.x) {
@@ -354,6 +371,7 @@ __global__ void adj_rhs_kernel(const double* __restrict__ p1, const double* __re
 // q0 = -L p0 ;  r0 = fb r1 + fs (q0 + q1)      (backward2_solver.py:233-242).  r1 == nullptr: terminal level (r = 0).
 __global__ void adj_qr_kernel(const double* __restrict__ p0, const double* __restrict__ q1, const double* __restrict__ r1,
                               double* __restrict__ q0, double* __restrict__ r0, Geo g, double fb, double fs) {
+    pdl_enter();
     for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < g.n; idx += (long long)gridDim.x * blockDim.x) {
         const int o = (int)(idx / g.ni), i = (int)(idx - (long long)o * g.ni);
         const double qv = -lap_g(p0, o, i, g);
@@ -368,6 +386,7 @@ __global__ void cost_kernel(const double* __restrict__ phi, const double* __rest
                             const double* __restrict__ phiT, int levels, int nx1, int ny1,
                             const double* __restrict__ wt, const double* __restrict__ wx, const double* __restrict__ wy,
                             double* out4, double* part, unsigned int* ticket, int term_level = -2, int accumulate = 0) {
+    pdl_enter();
     // term_level: index (within the levels given) of the terminal level carrying the J2 term; -2 = the last one (whole
     // trajectory in one launch), -1 = none (a chunk that does not contain the final time).  accumulate: add to out4.
     const long long n = (long long)nx1 * ny1, total = n * levels;
@@ -396,6 +415,7 @@ __global__ void cost_kernel(const double* __restrict__ phi, const double* __rest
 __global__ void grad_prox_kernel(const double* __restrict__ u, const double* __restrict__ r, double* __restrict__ grad,
                                  double* __restrict__ un, long long n, double b3, double alpha, double ksp, double umin,
                                  double umax, double* out4, double* part, unsigned int* ticket, int accumulate = 0) {
+    pdl_enter();
     double v[4] = {0.0, 0.0, 0.0, 0.0};
     const double thr = alpha * ksp;
     for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (long long)gridDim.x * blockDim.x) {
@@ -423,6 +443,7 @@ __global__ void grad_prox_kernel(const double* __restrict__ u, const double* __r
 
 __global__ void kkt_kernel(const double* __restrict__ u, const double* __restrict__ r, long long n, double ksp, double tol,
                            double* out3, double* part, unsigned int* ticket) {
+    pdl_enter();
     double v[3] = {0.0, 0.0, 0.0};
     for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (long long)gridDim.x * blockDim.x) {
         const bool a = fabs(u[idx]) < tol, b = fabs(r[idx]) <= ksp;

@@ -8,6 +8,7 @@
 #include <string>
 #include <vector>
 #include <stdexcept>
+#include <utility>
 #include "../../include/vch_b200.h"
 
 namespace vch {
@@ -224,6 +225,31 @@ struct Arena {
     void destroy() { if (base) cudaFree(base); base = nullptr; cap = used = 0; }
 };
 
+// ---------------------------------------------------------------- programmatic dependent launch
+// The hot path is a chain of 10-25 us kernels, each depending on the one before.  Launched with programmatic stream
+// serialization, kernel N+1 is scheduled while kernel N is still running (its CTAs become resident as soon as every CTA
+// of N has passed pdl_enter) and parks in griddepcontrol.wait until N has completed and flushed its memory — the launch
+// latency and CTA ramp-up move under the predecessor instead of sitting between the two.  EVERY kernel of this library
+// begins with pdl_enter(): the wait makes the predecessor's writes (and, transitively, everything before it) visible, so
+// nothing is read or written ahead of time; in a kernel launched without the attribute both instructions are no-ops.
+__device__ __forceinline__ void pdl_enter() {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
+template <typename... KArgs, typename... Args>
+inline void launch_pdl(bool pdl, void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    if (pdl) {
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+    }
+    VCH_CUDA(cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...));
+}
+
 // ---------------------------------------------------------------- launch geometry
 constexpr int kSMs = 148;              // B200
 constexpr int kRedThreads = 256;
@@ -346,6 +372,7 @@ __device__ __forceinline__ int mirror(int i, int n) {
 // One-CTA barrier across ranks: every rank announces its arrival in all peers' flag arrays and waits for everyone.
 // Stream order makes everything this rank enqueued before the barrier (including its peer writes) complete first.
 static __global__ void xbar_kernel(Comm cm, const int* __restrict__ done) {
+    pdl_enter();
     if (done && *done) return;
     __shared__ unsigned long long s;
     if (threadIdx.x == 0) s = ++cm.seq[1];
@@ -384,6 +411,7 @@ __device__ __forceinline__ void xbar_block(const Comm& cm, unsigned long long* s
 // earlier kernels (stream order) have finished.  Callers outside that pattern pass lead = 1.
 static __global__ void __launch_bounds__(1024) halo_push_kernel(Comm cm, const double* f0, const double* f1, int rows, int nloc,
                                                                 int rows_lo, int ni, const int* __restrict__ done, int lead) {
+    pdl_enter();
     if (done && *done) return;
     __shared__ unsigned long long s;
     if (lead) xbar_block(cm, &s);

@@ -113,6 +113,7 @@ struct DctPlan {
     int ni = 0, no = 0, pitch = 0;   // pitch of tmp1 (even, so column pairs are 16-byte aligned)
     DevBuf tmp1, tmp2;
     LaunchLog* log = nullptr;
+    bool pdl = false;         // launch the transform kernels with programmatic stream serialization (see launch_pdl)
     DctSlab slab;             // slab mode: no = global rows; the plan transforms the owned rows / columns only
     void init(int no_, int ni_, double h_outer, double h_inner, LaunchLog* launch_log);
     void init_slab(int n_global, double h_outer, double h_inner, LaunchLog* launch_log, const DctSlab& sl);
@@ -278,6 +279,7 @@ dct_fft_kernel(const double* in, double* out, int nlines, int n, int in_ls, int 
                const double2* __restrict__ twg, const double* __restrict__ lam_line, const double* __restrict__ lam_elem,
                SymbolArgs sy, double norm, int scale_mode, RowPrologue pro, DotEpilogue epi, const int* __restrict__ done,
                const __grid_constant__ Scatter sct) {   // __grid_constant__: sct.peer[r] is indexed straight from the constant bank
+    pdl_enter();
     using G = FftGeom<LOG2L>;
     constexpr int Lf = G::Lf, tpf = G::tpf, ld = G::ld;
     if (done && *done) return;
@@ -428,6 +430,7 @@ dct_fft_kernel(const double* in, double* out, int nlines, int n, int in_ls, int 
 // Dense-table fallbacks for N that is not a power of two (small validation grids).
 __global__ void dct_rows_dense_kernel(const double* __restrict__ in, double* __restrict__ out, int lines, int n,
                                       const double* __restrict__ Tt, const int* __restrict__ done) {
+    pdl_enter();
     if (done && *done) return;
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (long long)lines * n) return;
@@ -439,6 +442,7 @@ __global__ void dct_rows_dense_kernel(const double* __restrict__ in, double* __r
 }
 __global__ void dct_cols_dense_kernel(const double* __restrict__ in, double* __restrict__ out, int no, int ni,
                                       const double* __restrict__ Tt, const int* __restrict__ done) {
+    pdl_enter();
     if (done && *done) return;
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (long long)no * ni) return;
@@ -450,6 +454,7 @@ __global__ void dct_cols_dense_kernel(const double* __restrict__ in, double* __r
 __global__ void dct_scale_kernel(double* __restrict__ d, int no, int ni, const double* __restrict__ lam_o,
                                  const double* __restrict__ lam_i, SymbolArgs sy, double norm,
                                  const int* __restrict__ done) {
+    pdl_enter();
     if (done && *done) return;
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (long long)no * ni) return;
@@ -461,6 +466,7 @@ __global__ void dct_scale_kernel(double* __restrict__ d, int no, int ni, const d
 }
 // Dense-path stand-ins for the fused prologue / epilogue / spectral factor.
 __global__ void dct_prologue_kernel(RowPrologue pro, double* __restrict__ x, long long n, const int* __restrict__ done) {
+    pdl_enter();
     if (done && *done) return;
     const Scal* sc = pro.sc;
     const double coef = (pro.mode == 1) ? (sc->rho_new / sc->rho) * (sc->alpha / sc->omega) : -sc->alpha;
@@ -473,6 +479,7 @@ __global__ void dct_prologue_kernel(RowPrologue pro, double* __restrict__ x, lon
 }
 __global__ void dct_addend_kernel(double* __restrict__ outv, const double* __restrict__ addend, const double* __restrict__ mul_a,
                                   const Scal* __restrict__ sc, long long n, const int* __restrict__ done) {
+    pdl_enter();
     if (done && *done) return;
     const double abar = mul_a ? sc->abar : 0.0;
     for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (long long)gridDim.x * blockDim.x) {
@@ -482,6 +489,7 @@ __global__ void dct_addend_kernel(double* __restrict__ outv, const double* __res
 }
 __global__ void dct_lambda_kernel(double* __restrict__ d, int no, int ni, const double* __restrict__ lam_o,
                                   const double* __restrict__ lam_i, const int* __restrict__ done) {
+    pdl_enter();
     if (done && *done) return;
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (long long)no * ni) return;
@@ -490,6 +498,7 @@ __global__ void dct_lambda_kernel(double* __restrict__ d, int no, int ni, const 
 }
 // Stand-alone BiCGStab dots for the paths without the fused epilogue.
 __global__ void dct_dots_kernel(const double* __restrict__ outv, DotEpilogue epi, long long n, const int* __restrict__ done) {
+    pdl_enter();
     if (done && *done) return;
     double vals[3] = {0.0, 0.0, 0.0};
     for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (long long)gridDim.x * blockDim.x) {
@@ -621,16 +630,14 @@ inline void DctPlan::apply(cudaStream_t s, const double* in, double* out, const 
                           int nn, int ils, int ies, int ols, int oes, const double* ll, const double* le, const SymbolArgs& sy,
                           double nrm, int smode, const RowPrologue& pr, const DotEpilogue& ep, const Scatter& sc8 = Scatter()) {
         const int ppb_ = threads / (ax.Lf >> 3);
+        const bool pd = pdl;
+#define VCH_FFT_ARGS a, b, nl, nn, ils, ies, ols, oes, ppb_, ax.tw, ll, le, sy, nrm, smode, pr, ep, done, sc8
 #define VCH_FFT_CASE(LG)                                                                                                      \
         case LG:                                                                                                              \
-            if (solve) dct_fft_kernel<LG, true, ((1 << LG) / 8 <= 512 ? 512 : 1024)><<<grid, threads, smem, s>>>(              \
-                a, b, nl, nn, ils, ies, ols, oes, ppb_, ax.tw, ll, le, sy, nrm, smode, pr, ep, done, sc8);                     \
-            else if (sc8.mode == 1) dct_fft_kernel<LG, false, ((1 << LG) / 8 <= 512 ? 512 : 1024), 1><<<grid, threads, smem, s>>>( \
-                a, b, nl, nn, ils, ies, ols, oes, ppb_, ax.tw, ll, le, sy, nrm, smode, pr, ep, done, sc8);                     \
-            else if (sc8.mode == 3) dct_fft_kernel<LG, false, ((1 << LG) / 8 <= 512 ? 512 : 1024), 3><<<grid, threads, smem, s>>>( \
-                a, b, nl, nn, ils, ies, ols, oes, ppb_, ax.tw, ll, le, sy, nrm, smode, pr, ep, done, sc8);                     \
-            else dct_fft_kernel<LG, false, ((1 << LG) / 8 <= 512 ? 512 : 1024)><<<grid, threads, smem, s>>>(                   \
-                a, b, nl, nn, ils, ies, ols, oes, ppb_, ax.tw, ll, le, sy, nrm, smode, pr, ep, done, sc8);                     \
+            if (solve) launch_pdl(pd, dct_fft_kernel<LG, true, ((1 << LG) / 8 <= 512 ? 512 : 1024)>, grid, threads, smem, s, VCH_FFT_ARGS); \
+            else if (sc8.mode == 1) launch_pdl(pd, dct_fft_kernel<LG, false, ((1 << LG) / 8 <= 512 ? 512 : 1024), 1>, grid, threads, smem, s, VCH_FFT_ARGS); \
+            else if (sc8.mode == 3) launch_pdl(pd, dct_fft_kernel<LG, false, ((1 << LG) / 8 <= 512 ? 512 : 1024), 3>, grid, threads, smem, s, VCH_FFT_ARGS); \
+            else launch_pdl(pd, dct_fft_kernel<LG, false, ((1 << LG) / 8 <= 512 ? 512 : 1024)>, grid, threads, smem, s, VCH_FFT_ARGS); \
             break;
         switch (ax.log2L) {
             VCH_FFT_CASE(6) VCH_FFT_CASE(7) VCH_FFT_CASE(8) VCH_FFT_CASE(9) VCH_FFT_CASE(10) VCH_FFT_CASE(11) VCH_FFT_CASE(12)
@@ -638,6 +645,7 @@ inline void DctPlan::apply(cudaStream_t s, const double* in, double* out, const 
             default: throw Error(VCH_E_ARG, "unsupported FFT length");
         }
 #undef VCH_FFT_CASE
+#undef VCH_FFT_ARGS
     };
     if (slab.on) {
         // rows of the owned slab, stored transposed into the column owners' T1 | barrier | fused solve in place on the owned
