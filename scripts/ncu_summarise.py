@@ -18,7 +18,7 @@ for r in rd:
     name = r["Kernel Name"]
     name = re.sub(r"^void |\(.*$", "", name)
     name = name.replace("vch::", "")
-    if not re.match(r"(dct_|bicg_|residual|dmu_|schur|trial|step_setup|adj_|clip_mass|mass_shift|solve_w|cost_|grad_prox|mu_init|xbar|halo|lap_|jac_|kkt)", name):
+    if not re.match(r"(dct_|bicg_|residual|dmu_|schur|trial|step_setup|adj_|clip_mass|mass_shift|solve_w|cost_|grad_prox|mu_init|xbar|halo|lap_|jac_|kkt|publish_scalars|copy_kernel)", name):
         name = "torch (setup: targets, zeros)"
     elif us < 4.5 and re.match(r"(dct_fft_kernel|bicg_x_kernel)", name):
         name += " [exits on done flag]"
