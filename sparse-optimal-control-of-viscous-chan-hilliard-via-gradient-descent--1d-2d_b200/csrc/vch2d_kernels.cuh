@@ -107,7 +107,9 @@ __device__ __forceinline__ void publish_scalars(const Scal* src, Scal* dst_host)
 }
 
 // [R_phi; R_mu], the Jacobian diagonal a = tau/dt + 2c1/(1 - min(phi^2, 1-delta^2)) and ||R||^2, min a, max a.
-__global__ void residual_kernel(const double* __restrict__ phi, const double* __restrict__ mu,
+// __launch_bounds__(256, 4): the grid is 4 CTAs per SM (red_blocks); at 67 registers only 3 fit and a quarter of the blocks ran as a
+// second, nearly empty wave
+__global__ void __launch_bounds__(kRedThreads, 4) residual_kernel(const double* __restrict__ phi, const double* __restrict__ mu,
                                 const double* __restrict__ cphi, const double* __restrict__ cmu,
                                 double* __restrict__ Rphi, double* __restrict__ Rmu, double* __restrict__ a,
                                 Geo g, Phys p, double dt, Scal* sc, double* part, unsigned int* ticket, Scal* publish) {
