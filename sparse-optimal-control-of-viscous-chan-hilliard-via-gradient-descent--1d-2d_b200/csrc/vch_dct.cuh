@@ -266,6 +266,86 @@ __device__ __forceinline__ void fft_last_pass(const double2* data, int t, const 
     }
 }
 
+// ---- EXPERIMENTAL, compiled only with -DVCH_ROW_PROLOGUE_V2 (round-2 candidate, NOT yet run on a GPU).
+// SASS of the default build shows the fused prologue as 16 dependent groups of 3 loads + 1 store per thread (the stores to w may
+// alias r/q/a as far as the compiler knows, so the next group's loads wait behind them) and the BiCGStab scalars reloaded and
+// re-divided for every point: rows_pro costs 17.4 us against 14.8 us for the plain transform.  The variant below reads the scalars
+// once and issues the 4-6 loads of a point (both lines) back to back.
+#ifdef VCH_ROW_PROLOGUE_V2
+// First-pass inputs of a row pair with the fused BiCGStab vector update (RowPrologue modes 1 and 2):
+//   w = r + coef*q (coef = 0: w = r, q is not read — it may hold anything, bicg_init_kernel does not clear it),
+//   stored once (the mirror images e > N are recomputed, not stored), x = (a - abar)*w or w.
+// A function of its own so that the pointers are restrict-qualified PARAMETERS: the kernel's struct members carry no such
+// promise, and without it every store to w ordered the loads of the next point behind it (8 dependent L2 round trips).
+// r, q|v, a and w are distinct work vectors (enqueue_bicg_iteration).
+template <int LOG2L, bool USEQ, bool HASA>
+__device__ __forceinline__ void row_prologue_load_impl(double2 (&v)[8], const double* __restrict__ pr, const double* __restrict__ pq,
+                                                       const double* __restrict__ pa, double* __restrict__ pw, double coef, double abar,
+                                                       bool va, bool vb, size_t base_a, size_t base_b, int t, int N, int in_es) {
+    using G = FftGeom<LOG2L>;
+    // an absent line (the odd line out of the last pair, idle FFT slots of the last CTA) is loaded from line 0 and discarded: no branch
+    // separates the loads, so the 4-6 loads of a point (both lines) are issued back to back and, the stores being known not to
+    // alias them, the next point's loads can follow at once
+    const size_t ba = va ? base_a : 0, bb = vb ? base_b : 0;   // line 0 always exists
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+        const int e = t + r * G::tpf;
+        const size_t o = (size_t)((e <= N ? e : G::Lf - e) * in_es);
+        const double ra = pr[ba + o], rb = pr[bb + o];
+        double qa = 0.0, qb = 0.0, aa = 0.0, ab = 0.0;
+        if (USEQ) { qa = pq[ba + o]; qb = pq[bb + o]; }
+        if (HASA) { aa = pa[ba + o]; ab = pa[bb + o]; }
+        const double wa = USEQ ? ra + coef * qa : ra, wb = USEQ ? rb + coef * qb : rb;
+        if (e <= N) { if (va) pw[ba + o] = wa; if (vb) pw[bb + o] = wb; }
+        const double xa = HASA ? (aa - abar) * wa : wa, xb = HASA ? (ab - abar) * wb : wb;
+        v[r] = make_double2(va ? xa : 0.0, vb ? xb : 0.0);
+    }
+}
+template <int LOG2L>
+__device__ __forceinline__ void row_prologue_load(double2 (&v)[8], const double* pr, const double* pq, const double* pa, double* pw,
+                                                  double coef, double abar, bool va, bool vb, size_t base_a, size_t base_b, int t,
+                                                  int N, int in_es) {
+    // coef == 0 (first iteration of a solve: beta = 0): q is not read — bicg_init_kernel does not clear it
+    if (coef != 0.0) {
+        if (pa) row_prologue_load_impl<LOG2L, true, true>(v, pr, pq, pa, pw, coef, abar, va, vb, base_a, base_b, t, N, in_es);
+        else row_prologue_load_impl<LOG2L, true, false>(v, pr, pq, pa, pw, coef, abar, va, vb, base_a, base_b, t, N, in_es);
+    } else {
+        if (pa) row_prologue_load_impl<LOG2L, false, true>(v, pr, pq, pa, pw, coef, abar, va, vb, base_a, base_b, t, N, in_es);
+        else row_prologue_load_impl<LOG2L, false, false>(v, pr, pq, pa, pw, coef, abar, va, vb, base_a, base_b, t, N, in_es);
+    }
+}
+
+
+// Same idea for the fused row epilogue (out = (mul_a - abar) z + addend, BiCGStab dot products): in the default build every
+// store to `out` holds back the loads of the next point (epi1 costs 20.6 us against 14.8 us for the plain transform).  Here
+// the up to 8 loads of a point (both lines: addend, other, r, a) are issued together; out, addend, other, r and a are distinct
+// work vectors (enqueue_bicg_iteration).  Absent lines read line 0 and are discarded.
+template <int LOG2L>
+__device__ __forceinline__ void row_epilogue_store(const double2 (&z)[8], double* __restrict__ out, const double* __restrict__ addend,
+                                                   const double* __restrict__ other, const double* __restrict__ rvec,
+                                                   const double* __restrict__ mul_a, double eabar, int mode, bool va, bool vb,
+                                                   size_t base_a, size_t base_b, int t, int N, int out_es,
+                                                   double& acc1, double& acc2, double& acc3) {
+    const size_t ba = va ? base_a : 0, bb = vb ? base_b : 0;
+    const bool has_add = addend != nullptr, has_mul = mul_a != nullptr, has_r = rvec != nullptr && mode != 0, has_o = mode != 0;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        const int kk = t + FftOut<LOG2L>::off(q);
+        if (kk <= N) {
+            const size_t off = (size_t)(kk * out_es);
+            const double ma = has_mul ? mul_a[ba + off] : 0.0, mb = has_mul ? mul_a[bb + off] : 0.0;
+            const double da = has_add ? addend[ba + off] : 0.0, db = has_add ? addend[bb + off] : 0.0;
+            const double oa = has_o ? other[ba + off] : 0.0, ob = has_o ? other[bb + off] : 0.0;
+            const double ra = has_r ? rvec[ba + off] : 0.0, rb = has_r ? rvec[bb + off] : 0.0;
+            const double zx = has_mul ? (ma - eabar) * z[q].x : z[q].x, zy = has_mul ? (mb - eabar) * z[q].y : z[q].y;
+            const double xo = has_add ? zx + da : zx, yo = has_add ? zy + db : zy;
+            if (va) { out[ba + off] = xo; if (has_o) { acc1 += oa * xo; acc2 += xo * xo; if (has_r) acc3 += ra * xo; } }
+            if (vb) { out[bb + off] = yo; if (has_o) { acc1 += ob * yo; acc2 += yo * yo; if (has_r) acc3 += rb * yo; } }
+        }
+    }
+}
+#endif   // VCH_ROW_PROLOGUE_V2
+
 // One CTA = ppb complex FFTs (2*ppb lines).  Line l, element e lives at base[l*line_stride + e*elem_stride].
 //   SOLVE = false: out = DCT-I(in) per line (unnormalised "FFT of the even extension").
 //   SOLVE = true : fused  forward transform -> divide by symbol -> inverse transform  (column solve, in place).
@@ -339,6 +419,7 @@ dct_fft_kernel(const double* in, double* out, int nlines, int n, int in_ls, int 
             v[r].x = va ? pa[off] : 0.0;
             v[r].y = vb ? pb[off] : 0.0;
         } else {
+#ifndef VCH_ROW_PROLOGUE_V2
             // fused vector update: every element is recomputed where its mirror image is needed; it is written once
             const Scal* sc = pro.sc;
             const double coef = (pro.mode == 1) ? (sc->rho_new / sc->rho) * (sc->alpha / sc->omega) : -sc->alpha;
@@ -349,8 +430,16 @@ dct_fft_kernel(const double* in, double* out, int nlines, int n, int in_ls, int 
             if (va) { const double w = (coef != 0.0) ? pro.r[ia] + coef * pro.qv[ia] : pro.r[ia]; if (e <= N) pro.w[ia] = w; xa = pro.a ? (pro.a[ia] - abar) * w : w; }
             if (vb) { const double w = (coef != 0.0) ? pro.r[ib] + coef * pro.qv[ib] : pro.r[ib]; if (e <= N) pro.w[ib] = w; xb = pro.a ? (pro.a[ib] - abar) * w : w; }
             v[r] = make_double2(xa, xb);
+#endif
         }
     }
+#ifdef VCH_ROW_PROLOGUE_V2
+    if (!SOLVE && XM != 3 && pro.mode != 0) {
+        const Scal* sc = pro.sc;
+        const double coef = (pro.mode == 1) ? (sc->rho_new / sc->rho) * (sc->alpha / sc->omega) : -sc->alpha;
+        row_prologue_load<LOG2L>(v, pro.r, pro.qv, pro.a, pro.w, coef, sc->abar, va, vb, (size_t)la * in_ls, (size_t)lb * in_ls, t, N, in_es);
+    }
+#endif
     fft_first_pass_store(data, v, t);
     fft_middle<LOG2L>(data, t, tw);
     double2 z[8];
@@ -404,6 +493,7 @@ dct_fft_kernel(const double* in, double* out, int nlines, int n, int in_ls, int 
             } else if (SOLVE) {
                 if (va) *reinterpret_cast<double2*>(qa + off) = make_double2(z[q].x, vb ? z[q].y : 0.0);
             } else {
+#ifndef VCH_ROW_PROLOGUE_V2
                 if (va) {
                     const double zx = epi.mul_a ? (epi.mul_a[(size_t)la * out_ls + off] - eabar) * z[q].x : z[q].x;
                     const double o = epi.addend ? zx + da[off] : zx;
@@ -416,9 +506,15 @@ dct_fft_kernel(const double* in, double* out, int nlines, int n, int in_ls, int 
                     qb[off] = o;
                     if (epi.mode) { acc1 += ob[off] * o; acc2 += o * o; if (epi.rvec) acc3 += rb_[off] * o; }
                 }
+#endif
             }
         }
     }
+#ifdef VCH_ROW_PROLOGUE_V2
+    if (!SOLVE && XM != 1)
+        row_epilogue_store<LOG2L>(z, out, epi.addend, epi.other, epi.rvec, epi.mul_a, eabar, epi.mode, va, vb, (size_t)la * out_ls,
+                                  (size_t)lb * out_ls, t, N, out_es, acc1, acc2, acc3);
+#endif
     if (epi.mode) {     // block-uniform: every thread of every CTA takes part in the reduction
         double vals[3] = {acc1, acc2, acc3};
         const int op[3] = {0, 0, 0};
