@@ -173,7 +173,11 @@ __device__ __forceinline__ const Comm* comm_of(const double* part) {
     return reinterpret_cast<const Comm*>(reinterpret_cast<const char*>(part) - kCommHeaderBytes);
 }
 __device__ __forceinline__ unsigned long long global_ns() {
+#ifdef VCH_CPU_EMU   // tests/emu: kernels compiled for the host by g++ (no PTX)
+    return 0ull;
+#else
     unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t;
+#endif
 }
 // Spins until *flag >= want (monotone flags) or the limit expires.  Returns false on timeout.
 __device__ __forceinline__ bool spin_until(volatile unsigned long long* flag, unsigned long long want, int* err, bool exact) {
@@ -233,10 +237,13 @@ struct Arena {
 // begins with pdl_enter(): the wait makes the predecessor's writes (and, transitively, everything before it) visible, so
 // nothing is read or written ahead of time; in a kernel launched without the attribute both instructions are no-ops.
 __device__ __forceinline__ void pdl_enter() {
+#ifndef VCH_CPU_EMU
     asm volatile("griddepcontrol.wait;" ::: "memory");
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
 }
 
+#ifndef VCH_CPU_EMU
 template <typename... KArgs, typename... Args>
 inline void launch_pdl(bool pdl, void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
     cudaLaunchConfig_t cfg = {};
@@ -249,6 +256,7 @@ inline void launch_pdl(bool pdl, void (*kern)(KArgs...), dim3 grid, dim3 block, 
     }
     VCH_CUDA(cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...));
 }
+#endif
 
 // ---------------------------------------------------------------- launch geometry
 constexpr int kSMs = 148;              // B200

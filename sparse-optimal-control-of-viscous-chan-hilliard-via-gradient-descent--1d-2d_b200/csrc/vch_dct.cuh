@@ -363,7 +363,11 @@ dct_fft_kernel(const double* in, double* out, int nlines, int n, int in_ls, int 
     using G = FftGeom<LOG2L>;
     constexpr int Lf = G::Lf, tpf = G::tpf, ld = G::ld;
     if (done && *done) return;
+#ifdef VCH_CPU_EMU
+    double2* sm = reinterpret_cast<double2*>(vch_emu::dynamic_smem());
+#else
     extern __shared__ double2 sm[];
+#endif
     const int N = n - 1;
     const int f = threadIdx.x / tpf, t = threadIdx.x - f * tpf;
     // twiddle tables first (visible after the first-pass barrier), FFT buffers behind them
@@ -613,6 +617,7 @@ __global__ void dct_dots_kernel(const double* __restrict__ outv, DotEpilogue epi
 }
 
 // ------------------------------------------------------------------------------------------------ host side
+#ifndef VCH_CPU_EMU   // (the CPU emulation harness of tests/emu drives the kernels above directly)
 static inline void dct_axis_init(DctAxis& ax, int n, double h) {
     const int N = n - 1;
     ax.n = n;
@@ -831,5 +836,6 @@ inline void DctPlan::destroy() {
     }
     tmp1.release(); tmp2.release();
 }
+#endif   // VCH_CPU_EMU
 
 }  // namespace vch

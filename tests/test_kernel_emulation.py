@@ -1,0 +1,123 @@
+"""The CUDA transform kernels themselves, run on the CPU (tests/emu/cuda_emu.h: blocks as groups of fibers, barriers, warp
+shuffles, shared memory) and checked against NumPy/SciPy:
+
+  * `dct_fft_kernel` rows + fused column solve = the exact constant-coefficient solve P^-1 (and lambda P^-1);
+  * the fused BiCGStab prologues (p = r + beta q, s = r - alpha v, coefficient multiply) and epilogues (+addend, adjoint-side
+    multiply, dot products -> alpha / omega, half-step exit, done-flag gating), forward and adjoint form;
+  * the experimental kernel variants (-DVCH_ROW_PROLOGUE_V2, -DVCH_FAST_SYMBOL) against the default build:
+    bit-identical resp. to round-off.
+
+The emulation pins kernel LOGIC (index maps, flag protocol, reductions); memory ordering and timing need the GPU suite."""
+import os
+import struct
+import subprocess
+
+import numpy as np
+import pytest
+import scipy.fft as sf
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EMU = os.path.join(ROOT, "tests", "emu")
+CUDA_INC = os.environ.get("CUDA_HOME", "/usr/local/cuda") + "/include"
+CUDA_LIB = os.environ.get("CUDA_HOME", "/usr/local/cuda") + "/lib64"
+
+
+def _build(tmp, name, flags):
+    exe = os.path.join(tmp, name)
+    cmd = ["g++", "-std=c++17", "-O1", "-I" + CUDA_INC] + flags + [os.path.join(EMU, "dct_emu_harness.cpp"), "-o", exe,
+           "-L" + CUDA_LIB, "-lcudart", "-Wl,-rpath," + CUDA_LIB]
+    subprocess.run(cmd, check=True, capture_output=True)
+    return exe
+
+
+def _run(exe, lg, tmp, tag):
+    out = os.path.join(tmp, f"out_{tag}_{lg}.bin")
+    subprocess.run([exe, str(lg), out], check=True, timeout=600)
+    res = {}
+    with open(out, "rb") as fh:
+        while True:
+            hdr = fh.read(40)
+            if len(hdr) < 40:
+                break
+            name = hdr[:32].split(b"\0")[0].decode()
+            (cnt,) = struct.unpack("<Q", hdr[32:])
+            res[name] = np.frombuffer(fh.read(8 * cnt), dtype=np.float64).copy()
+    return res
+
+
+@pytest.fixture(scope="module")
+def builds(tmp_path_factory):
+    if not os.path.exists(os.path.join(CUDA_INC, "cuda_runtime.h")):
+        pytest.skip("CUDA headers not found")
+    tmp = str(tmp_path_factory.mktemp("emu"))
+    return tmp, {"default": _build(tmp, "h_default", []),
+                 "v2": _build(tmp, "h_v2", ["-DVCH_ROW_PROLOGUE_V2"]),
+                 "fast": _build(tmp, "h_fast", ["-DVCH_FAST_SYMBOL"])}
+
+
+rel = lambda a, b: float(np.linalg.norm(a - b) / np.linalg.norm(b))
+
+
+@pytest.mark.parametrize("lg", [6, 7])
+def test_transform_kernels_on_cpu_match_numpy(builds, lg):
+    tmp, exe = builds
+    R = _run(exe["default"], lg, tmp, "default")
+    N = (1 << lg) // 2
+    n = N + 1
+    pitch = (n + 3) & ~3
+    sq = lambda k: R[k].reshape(n, n)
+    x, r, q, r0, a, lam = sq("in"), sq("r"), sq("q"), sq("r0"), sq("a"), R["lam"]
+    L = lam[:, None] + lam[None, :]
+    # A. row transform = unnormalised DCT-I of every line; fused solve = exact inverse of c0 + abar*lam + c2*lam^2
+    rows = R["A_rows"].reshape(n, pitch)[:, :n]
+    assert rel(rows, sf.dct(x, type=1, axis=1)) < 1e-14
+    sym = 100.0 + L * (7.5 + 5e-5 * L)
+    assert rel(sq("A_solve"), sf.idctn(sf.dctn(x, type=1) / sym, type=1)) < 1e-13
+    assert rel(sq("A_lamsolve"), sf.idctn(sf.dctn(x, type=1) * L / sym, type=1)) < 1e-13
+    # B/C. forward operator applications with the fused vector updates and dot products
+    abar = 7.25
+    symb = 100.0 + L * (abar + 5e-5 * L)
+    K = lambda y: sf.idctn(sf.dctn(y, type=1) * L / symb, type=1)
+    beta = (1.7 / 0.9) * (0.6 / 1.3)
+    p = r + beta * q
+    v = K((a - abar) * p) + p
+    assert rel(sq("B_p"), p) < 1e-15 and rel(sq("B_v"), v) < 1e-13
+    alpha, r0v, rho, done, half = R["B_scal"][:5]
+    assert abs(r0v - np.vdot(r0, v)) < 1e-11 * abs(r0v) and abs(alpha - 1.7 / r0v) < 1e-12 * abs(alpha) and rho == 1.7
+    assert done == 0 and half == 0
+    s = r - 0.6 * q
+    t = K((a - abar) * s) + s
+    assert rel(sq("C_s"), s) < 1e-15 and rel(sq("C_t"), t) < 1e-13
+    omega, ts, tt = R["C_scal"][:3]
+    assert abs(ts - np.vdot(t, s)) < 1e-11 * abs(ts) and abs(tt - np.vdot(t, t)) < 1e-11 * tt and abs(omega - ts / tt) < 1e-12 * abs(omega)
+    # D. beta = 0: p = r bit for bit, nothing of the poisoned q arrives anywhere
+    assert np.array_equal(sq("D_p"), r) and np.isfinite(sq("D_v")).all()
+    assert rel(sq("D_v"), K((a - abar) * r) + r) < 1e-13
+    # E. adjoint (right-preconditioned) form: multiply after the transform
+    pa = r + beta * q
+    va = (a - abar) * K(pa) + pa
+    assert rel(sq("E_p"), pa) < 1e-15 and rel(sq("E_v"), va) < 1e-13
+    al = R["E_scal"][0]
+    assert abs(al - 1.7 / np.vdot(r0, va)) < 1e-11 * abs(al)
+    sa = r - al * va
+    ta = (a - abar) * K(sa) + sa
+    assert rel(sq("E_s"), sa) < 1e-12 and rel(sq("E_t"), ta) < 1e-12
+    assert abs(R["E_scal2"][0] - np.vdot(ta, sa) / np.vdot(ta, ta)) < 1e-10 * abs(R["E_scal2"][0])
+    # F. half-step exit fires, and kernels gated on the done flag leave their outputs alone
+    alpha_f, done_f, half_f, r0v_rel = R["F_scal"][:4]
+    assert abs(alpha_f - 1.0) < 1e-12 and done_f == 1 and half_f == 1 and abs(r0v_rel - 1.0) < 1e-12
+    assert np.all(R["F_keep"] == 42.0) and np.all(R["F_keepw"] == 43.0)
+
+
+@pytest.mark.parametrize("lg", [6, 7])
+def test_experimental_kernel_variants_equal_the_default_build(builds, lg):
+    tmp, exe = builds
+    D = _run(exe["default"], lg, tmp, "default")
+    V = _run(exe["v2"], lg, tmp, "v2")
+    F = _run(exe["fast"], lg, tmp, "fast")
+    assert D.keys() == V.keys() == F.keys()
+    for k in D:
+        # restrict-qualified fused prologue / epilogue: same arithmetic in the same order -> identical bits, NaNs included
+        assert np.array_equal(D[k], V[k], equal_nan=True), k
+        # reciprocal-multiply spectral factor: <= 1 ulp per factor
+        assert np.allclose(D[k], F[k], rtol=1e-13, atol=1e-13 * max(1.0, float(np.abs(D[k]).max()))), k
