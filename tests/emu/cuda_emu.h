@@ -133,7 +133,7 @@ inline void launch(unsigned grid, unsigned block, size_t smem_bytes, const std::
         for (unsigned t = 0; t < block; ++t) {
             Fiber& f = blk.fibers[t];
             f.tid = t;
-            f.stack.resize(256 * 1024);
+            f.stack.resize(96 * 1024);
             getcontext(&f.ctx);
             f.ctx.uc_stack.ss_sp = f.stack.data();
             f.ctx.uc_stack.ss_size = f.stack.size();
@@ -176,6 +176,7 @@ template <typename T> inline T __ldcg(const T* p) { return *p; }
 inline unsigned int atomicAdd(unsigned int* p, unsigned int v) { const unsigned int o = *p; *p = o + v; return o; }
 inline double __dmul_rn(double a, double b) { volatile double r = a * b; return r; }
 inline double __dadd_rn(double a, double b) { volatile double r = a + b; return r; }
+inline double __dsub_rn(double a, double b) { volatile double r = a - b; return r; }
 inline double __ddiv_rn(double a, double b) { volatile double r = a / b; return r; }
 inline double __drcp_rn(double a) { volatile double r = 1.0 / a; return r; }
 typedef unsigned long long cudaGraphConditionalHandle_emu;

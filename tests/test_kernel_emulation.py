@@ -121,3 +121,86 @@ def test_experimental_kernel_variants_equal_the_default_build(builds, lg):
         assert np.array_equal(D[k], V[k], equal_nan=True), k
         # reciprocal-multiply spectral factor: <= 1 ulp per factor
         assert np.allclose(D[k], F[k], rtol=1e-13, atol=1e-13 * max(1.0, float(np.abs(D[k]).max()))), k
+
+
+# ------------------------------------------------------------------------------------------------ Newton linear solve / adjoint step
+import sys
+sys.path.insert(0, os.path.join(ROOT, "scripts"))
+import krylov_proto as KP   # noqa: E402  (NumPy model of the algorithm; here only its stencil and spectral helpers)
+
+
+@pytest.fixture(scope="module")
+def krylov_exe(tmp_path_factory):
+    if not os.path.exists(os.path.join(CUDA_INC, "cuda_runtime.h")):
+        pytest.skip("CUDA headers not found")
+    tmp = str(tmp_path_factory.mktemp("emuk"))
+    exe = os.path.join(tmp, "k_default")
+    subprocess.run(["g++", "-std=c++17", "-O1", "-I" + CUDA_INC, os.path.join(EMU, "krylov_emu_harness.cpp"), "-o", exe,
+                    "-L" + CUDA_LIB, "-lcudart", "-Wl,-rpath," + CUDA_LIB], check=True, capture_output=True)
+    return tmp, exe
+
+
+def _read(path):
+    res = {}
+    with open(path, "rb") as fh:
+        while True:
+            hdr = fh.read(40)
+            if len(hdr) < 40:
+                break
+            (cnt,) = struct.unpack("<Q", hdr[32:])
+            res[hdr[:32].split(b"\0")[0].decode()] = np.frombuffer(fh.read(8 * cnt), dtype=np.float64).copy()
+    return res
+
+
+@pytest.mark.parametrize("lg,tol,half", [(6, 1e-11, 1), (6, 1e-11, 0), (6, 1e-6, 1), (7, 1e-11, 1)])
+def test_newton_linear_solve_and_adjoint_step_on_cpu(krylov_exe, lg, tol, half):
+    """residual -> Schur rhs -> P^-1 b -> BiCGStab (device-side done / half-step flags) -> delta-mu, ceiling, trial iterate, and one
+    adjoint step, through the real kernels on the CPU emulator, against NumPy."""
+    tmp, exe = krylov_exe
+    out = os.path.join(tmp, f"k_{lg}_{tol}_{half}.bin")
+    subprocess.run([exe, str(lg), repr(tol), str(half), out], check=True, timeout=900)
+    R = _read(out)
+    N = (1 << lg) // 2
+    n = N + 1
+    G = KP.Grid(N, kappa=1e-4, tau=0.05, gamma=10.0, c1=0.75, c2=1.0, dt=1e-2)
+    sq = lambda k: R[k].reshape(n, n)
+    phi, mu, cphi, cmu = sq("phi"), sq("mu"), sq("cphi"), sq("cmu")
+    dt, tdt = 1e-2, 0.05 / 1e-2
+    # residual, Jacobian diagonal, reductions, published mirror
+    rp = tdt * phi - 0.5 * G.kappa * G.lap(phi) + G.c1 * G.flog(phi) - 0.5 * mu + cphi
+    rm = phi / dt - 0.5 * G.lap(mu) + cmu
+    a = tdt + 2 * G.c1 / (1 - np.minimum(phi ** 2, 1 - 1e-4))
+    assert rel(sq("Rphi"), rp) < 1e-13 and rel(sq("Rmu"), rm) < 1e-13 and rel(sq("a"), a) < 1e-15
+    res2, amin, amax, abar, mu2, mirror_ok = R["res_scal"]
+    assert abs(res2 - (np.sum(rp ** 2) + np.sum(rm ** 2))) < 1e-12 * res2 and amin == sq("a").min() and amax == sq("a").max()
+    assert abs(abar - np.sqrt(amin * amax)) < 1e-15 * abar and abs(mu2 - np.sum(mu ** 2)) < 1e-12 * mu2 and mirror_ok == 1
+    # Schur right-hand side and the solve
+    b = G.lap(sq("Rphi")) - sq("Rmu")
+    assert rel(sq("b"), b) < 1e-12
+    A = lambda x: x / dt - G.lap(sq("a") * x) + 0.5 * G.kappa * G.lap(G.lap(x))
+    dphi = sq("dphi")
+    x_ref, its_ref = KP.bicgstab(G, sq("a"), sq("b"), abar, tol=tol)
+    its, done, half_exits, half_flag, solves, launched, unchanged, nonfinite = R["fwd_scal"]
+    assert done == 1 and half_flag == 0 and solves == 1 and unchanged == 1 and nonfinite == 0
+    assert its == np.ceil(its_ref) if half else its >= np.ceil(its_ref)
+    assert half_exits == (1 if (half and its_ref != np.floor(its_ref)) else 0)
+    assert rel(dphi, x_ref) < 50 * tol and np.linalg.norm(A(dphi) - sq("b")) < 1e3 * tol * np.linalg.norm(sq("b"))
+    # delta-mu, full-step trial iterate, step ceiling
+    dmu = 2 * (sq("a") * dphi - 0.5 * G.kappa * G.lap(dphi) + sq("Rphi"))
+    assert rel(sq("dmu"), dmu) < 1e-12
+    assert np.array_equal(sq("phit"), phi + dphi) and np.array_equal(sq("mut"), mu + sq("dmu"))
+    pos, neg = dphi > 0, dphi < 0
+    assert abs(R["ceil"][0] - np.min((0.99 - phi[pos]) / dphi[pos])) < 1e-12 * abs(R["ceil"][0])
+    assert abs(R["ceil"][1] - np.min((-0.99 - phi[neg]) / dphi[neg])) < 1e-12 * abs(R["ceil"][1])
+    # adjoint step
+    fpp = lambda f: 2 * G.c1 / (1 - np.clip(f, -(1 - 1e-8), 1 - 1e-8) ** 2) - 2 * G.c2
+    p1, q1, phi1 = sq("p1"), sq("q1"), sq("phi1")
+    assert rel(q1, -G.lap(p1)) < 1e-13
+    rhs = p1 + 0.05 * q1 + 0.5 * dt * G.lap(q1) - 0.5 * dt * fpp(phi1) * q1 + 0.5 * dt * 5.0 * (phi + phi1)
+    aa = 0.05 + 0.5 * dt * fpp(phi)
+    assert rel(sq("adj_rhs"), rhs) < 1e-12 and rel(sq("adj_a"), aa) < 1e-14
+    Aadj = lambda p: p - sq("adj_a") * G.lap(p) + 0.5 * dt * G.lap(G.lap(p))
+    ap = sq("adj_p")
+    assert np.linalg.norm(Aadj(ap) - sq("adj_rhs")) < 1e-10 * np.linalg.norm(sq("adj_rhs"))
+    a_its, a_done, a_half, a_abar = R["adj_scal"]
+    assert a_done == 1 and a_half == half_exits and 1 <= a_its <= 6      # the counter is cumulative: the adjoint solve adds no half-step exit and abs(a_abar - np.sqrt(aa.min() * aa.max())) < 1e-14 * a_abar
