@@ -256,6 +256,11 @@ inline void launch_pdl(bool pdl, void (*kern)(KArgs...), dim3 grid, dim3 block, 
     }
     VCH_CUDA(cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...));
 }
+#else   // tests/emu: the same funnel runs the kernel on the CPU emulator (vch_emu::launch_kernel, cuda_emu.h)
+template <typename... KArgs, typename... Args>
+inline void launch_pdl(bool, void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t, Args&&... args) {
+    vch_emu::launch_kernel(kern, grid.x, block.x, smem, std::forward<Args>(args)...);
+}
 #endif
 
 // ---------------------------------------------------------------- launch geometry

@@ -617,7 +617,7 @@ __global__ void dct_dots_kernel(const double* __restrict__ outv, DotEpilogue epi
 }
 
 // ------------------------------------------------------------------------------------------------ host side
-#ifndef VCH_CPU_EMU   // (the CPU emulation harness of tests/emu drives the kernels above directly)
+#ifndef VCH_CPU_EMU_KERNELS_ONLY   // (the kernel-level CPU emulation harnesses of tests/emu drive the kernels above directly)
 static inline void dct_axis_init(DctAxis& ax, int n, double h) {
     const int N = n - 1;
     ax.n = n;
@@ -836,6 +836,6 @@ inline void DctPlan::destroy() {
     }
     tmp1.release(); tmp2.release();
 }
-#endif   // VCH_CPU_EMU
+#endif   // VCH_CPU_EMU_KERNELS_ONLY
 
 }  // namespace vch

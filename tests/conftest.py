@@ -14,6 +14,13 @@ for p in (PKG, os.path.join(ROOT, "oracle"), ROOT):
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+    # tests/test_library_emulation.py re-runs part of the GPU suite in a subprocess against the CPU-emulation build of the
+    # library (tests/emu): TEST plumbing only — the product binding has no such switch and no CPU fallback.
+    emu = os.environ.get("VCH_TEST_EMU_LIB")
+    if emu:
+        os.environ["VCH_NO_GRAPHS"] = "1"          # the emulated runtime has no CUDA graphs
+        import vch_b200_native as nat
+        nat.LIB_PATH = emu
 
 
 def rel(a, b):

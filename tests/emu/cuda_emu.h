@@ -18,6 +18,9 @@
 #include <cstdlib>
 #include <cstring>
 #include <functional>
+#include <tuple>
+#include <type_traits>
+#include <utility>
 #include <vector>
 
 #undef __shared__
@@ -36,10 +39,16 @@ inline Dim3 g_threadIdx, g_blockIdx, g_blockDim, g_gridDim;
 
 struct Fiber {
     ucontext_t ctx;
-    std::vector<char> stack;
     bool done = false;
     unsigned tid = 0;
 };
+constexpr size_t kStackBytes = 96 * 1024;
+// fiber stacks are reused across launches (thread t of every block runs on stack t; allocated once, never cleared)
+inline char* fiber_stack(unsigned t) {
+    static std::vector<char*> pool;
+    while (pool.size() <= t) pool.push_back(static_cast<char*>(std::malloc(kStackBytes)));
+    return pool[t];
+}
 
 struct Block {
     std::vector<Fiber> fibers;
@@ -52,6 +61,7 @@ struct Block {
     std::vector<unsigned> shfl_arrived, shfl_gen;
     std::function<void()> body;
     std::vector<char> dyn_smem;
+    unsigned live = 0;             // threads that have not returned from the kernel yet
 };
 inline Block* g_block = nullptr;
 
@@ -67,14 +77,11 @@ inline void fiber_entry() {
     Block* b = g_block;
     b->body();
     b->fibers[b->current].done = true;
+    b->live -= 1;
     yield();
 }
 
-inline unsigned live_threads(Block* b) {
-    unsigned n = 0;
-    for (auto& f : b->fibers) n += f.done ? 0u : 1u;
-    return n;
-}
+inline unsigned live_threads(Block* b) { return b->live; }
 
 // All threads of the block must arrive (threads that have already returned from the kernel are not waited for, which is
 // what the hardware does as well).
@@ -123,6 +130,7 @@ inline void launch(unsigned grid, unsigned block, size_t smem_bytes, const std::
         Block blk;
         blk.body = body;
         blk.fibers.resize(block);
+        blk.live = block;
         blk.dyn_smem.assign(smem_bytes + 64, 0);
         const unsigned nwarps = (block + 31u) / 32u;
         blk.shfl_val.assign(nwarps * 32u, 0.0);
@@ -133,10 +141,9 @@ inline void launch(unsigned grid, unsigned block, size_t smem_bytes, const std::
         for (unsigned t = 0; t < block; ++t) {
             Fiber& f = blk.fibers[t];
             f.tid = t;
-            f.stack.resize(96 * 1024);
             getcontext(&f.ctx);
-            f.ctx.uc_stack.ss_sp = f.stack.data();
-            f.ctx.uc_stack.ss_size = f.stack.size();
+            f.ctx.uc_stack.ss_sp = fiber_stack(t);
+            f.ctx.uc_stack.ss_size = kStackBytes;
             f.ctx.uc_link = &blk.sched;
             makecontext(&f.ctx, (void (*)())fiber_entry, 0);
         }
@@ -158,6 +165,27 @@ inline void launch(unsigned grid, unsigned block, size_t smem_bytes, const std::
     }
 }
 
+// Kernel launch by function pointer (the library's launch_pdl funnel): arguments are converted to the kernel's parameter types
+// and copied, as a launch does; trailing parameters the call site leaves to their C++ defaults are value-initialised (every
+// such default in the library is 0).
+template <typename Tuple, typename... KArgs, size_t... I>
+inline void call_with_tuple(void (*kern)(KArgs...), Tuple& t, std::index_sequence<I...>) { kern(std::get<I>(t)...); }
+template <size_t I, typename Tuple> inline void fill_from(Tuple&) {}
+template <size_t I, typename Tuple, typename A, typename... Rest>
+inline void fill_from(Tuple& t, A&& a, Rest&&... rest) {
+    std::get<I>(t) = static_cast<std::tuple_element_t<I, Tuple>>(a);
+    fill_from<I + 1>(t, std::forward<Rest>(rest)...);
+}
+template <typename... KArgs, typename... Args>
+inline void launch_kernel(void (*kern)(KArgs...), unsigned grid, unsigned block, size_t smem, Args&&... args) {
+    static_assert(sizeof...(Args) <= sizeof...(KArgs), "too many kernel arguments");
+    std::tuple<std::remove_cv_t<std::remove_reference_t<KArgs>>...> t{};
+    fill_from<0>(t, std::forward<Args>(args)...);
+    launch(grid, block, smem, [&] { call_with_tuple(kern, t, std::index_sequence_for<KArgs...>{}); });
+}
+
+template <typename F> inline cudaError_t func_set_attribute(F, cudaFuncAttribute, int) { return cudaSuccess; }
+
 }  // namespace vch_emu
 
 // ---- the names kernels use
@@ -167,6 +195,8 @@ inline void launch(unsigned grid, unsigned block, size_t smem_bytes, const std::
 #define gridDim vch_emu::g_gridDim
 
 using std::isfinite;
+inline int min(int a, int b) { return a < b ? a : b; }
+inline int max(int a, int b) { return a > b ? a : b; }
 inline void __syncthreads() { vch_emu::syncthreads(); }
 inline double __shfl_xor_sync(unsigned, double v, int m) { return vch_emu::shfl_xor(v, m); }
 inline void __threadfence() {}

@@ -1,0 +1,54 @@
+// Host-memory stand-in for the CUDA runtime calls the library makes — TEST INFRASTRUCTURE ONLY (tests/emu).
+// Linked INSTEAD of libcudart into the emulation build of the library (tests/emu/build_emu_lib.py): "device" memory is host
+// memory, streams and events are ordering no-ops (the emulator runs every kernel synchronously at launch), CUDA graphs and IPC
+// are not available (the library is run with VCH_NO_GRAPHS=1, single rank).  Nothing here is ever loaded by the product.
+#include <cuda_runtime.h>
+#include <cstdlib>
+#include <cstring>
+
+extern "C" {
+
+cudaError_t cudaGetDeviceCount(int* n) { *n = 1; return cudaSuccess; }
+cudaError_t cudaSetDevice(int) { return cudaSuccess; }
+cudaError_t cudaGetLastError(void) { return cudaSuccess; }
+const char* cudaGetErrorString(cudaError_t) { return "cuda_emu"; }
+cudaError_t cudaMemGetInfo(size_t* free_b, size_t* total_b) { *free_b = (size_t)8 << 30; *total_b = (size_t)16 << 30; return cudaSuccess; }
+
+cudaError_t cudaMalloc(void** p, size_t bytes) { *p = std::malloc(bytes ? bytes : 1); return *p ? cudaSuccess : cudaErrorMemoryAllocation; }
+cudaError_t cudaFree(void* p) { std::free(p); return cudaSuccess; }
+cudaError_t cudaMallocHost(void** p, size_t bytes) { return cudaMalloc(p, bytes); }
+cudaError_t cudaHostAlloc(void** p, size_t bytes, unsigned int) { return cudaMalloc(p, bytes); }
+cudaError_t cudaFreeHost(void* p) { std::free(p); return cudaSuccess; }
+cudaError_t cudaMemcpy(void* d, const void* s, size_t n, cudaMemcpyKind) { std::memmove(d, s, n); return cudaSuccess; }
+cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, cudaMemcpyKind, cudaStream_t) { std::memmove(d, s, n); return cudaSuccess; }
+cudaError_t cudaMemset(void* d, int v, size_t n) { std::memset(d, v, n); return cudaSuccess; }
+cudaError_t cudaMemsetAsync(void* d, int v, size_t n, cudaStream_t) { std::memset(d, v, n); return cudaSuccess; }
+
+cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, unsigned int) { *s = reinterpret_cast<cudaStream_t>(std::malloc(8)); return cudaSuccess; }
+cudaError_t cudaStreamDestroy(cudaStream_t s) { std::free(s); return cudaSuccess; }
+cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
+cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned int) { return cudaSuccess; }
+cudaError_t cudaEventCreate(cudaEvent_t* e) { *e = reinterpret_cast<cudaEvent_t>(std::malloc(8)); return cudaSuccess; }
+cudaError_t cudaEventCreateWithFlags(cudaEvent_t* e, unsigned int) { return cudaEventCreate(e); }
+cudaError_t cudaEventDestroy(cudaEvent_t e) { std::free(e); return cudaSuccess; }
+cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t) { return cudaSuccess; }
+cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }
+cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t, cudaEvent_t) { *ms = 0.f; return cudaSuccess; }
+cudaError_t cudaFuncSetAttribute(const void*, cudaFuncAttribute, int) { return cudaSuccess; }
+
+// not available under emulation: the library is run with VCH_NO_GRAPHS=1 on one rank, so none of these is reached
+cudaError_t cudaGraphCreate(cudaGraph_t*, unsigned int) { return cudaErrorNotSupported; }
+cudaError_t cudaGraphDestroy(cudaGraph_t) { return cudaSuccess; }
+cudaError_t cudaGraphExecDestroy(cudaGraphExec_t) { return cudaSuccess; }
+cudaError_t cudaGraphConditionalHandleCreate(cudaGraphConditionalHandle*, cudaGraph_t, unsigned int, unsigned int) { return cudaErrorNotSupported; }
+cudaError_t cudaStreamBeginCaptureToGraph(cudaStream_t, cudaGraph_t, const cudaGraphNode_t*, const cudaGraphEdgeData*, size_t, cudaStreamCaptureMode) { return cudaErrorNotSupported; }
+cudaError_t cudaStreamEndCapture(cudaStream_t, cudaGraph_t*) { return cudaErrorNotSupported; }
+cudaError_t cudaStreamGetCaptureInfo(cudaStream_t, cudaStreamCaptureStatus*, unsigned long long*, cudaGraph_t*, const cudaGraphNode_t**, size_t*) { return cudaErrorNotSupported; }
+cudaError_t cudaGraphAddNode(cudaGraphNode_t*, cudaGraph_t, const cudaGraphNode_t*, size_t, cudaGraphNodeParams*) { return cudaErrorNotSupported; }
+cudaError_t cudaGraphInstantiate(cudaGraphExec_t*, cudaGraph_t, unsigned long long) { return cudaErrorNotSupported; }
+cudaError_t cudaGraphLaunch(cudaGraphExec_t, cudaStream_t) { return cudaErrorNotSupported; }
+cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t*, void*) { return cudaErrorNotSupported; }
+cudaError_t cudaIpcOpenMemHandle(void**, cudaIpcMemHandle_t, unsigned int) { return cudaErrorNotSupported; }
+cudaError_t cudaIpcCloseMemHandle(void*) { return cudaErrorNotSupported; }
+
+}  // extern "C"

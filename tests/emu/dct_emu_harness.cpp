@@ -4,6 +4,7 @@
 // logic is pinned on the CPU) and the experimental build with the default build.
 //   usage: dct_emu_harness <log2L: 6|7> <out.bin>
 #define VCH_CPU_EMU 1
+#define VCH_CPU_EMU_KERNELS_ONLY 1
 #include "cuda_emu.h"
 #include "../../sparse-optimal-control-of-viscous-chan-hilliard-via-gradient-descent--1d-2d_b200/csrc/vch_dct.cuh"
 

@@ -3,6 +3,7 @@
 // right-hand side -> right-preconditioned BiCGStab -> closing P^-1 y), under tests/emu/cuda_emu.h.  TEST INFRASTRUCTURE.
 //   usage: krylov_emu_harness <log2L: 6|7> <rel_tol> <half_exit: 0|1> <out.bin>
 #define VCH_CPU_EMU 1
+#define VCH_CPU_EMU_KERNELS_ONLY 1
 #include "cuda_emu.h"
 #include "../../sparse-optimal-control-of-viscous-chan-hilliard-via-gradient-descent--1d-2d_b200/csrc/vch2d_kernels.cuh"
 
