@@ -31,6 +31,7 @@ struct vch2d_ctx {
     double krylov_first_tol = 1e-6;   // time loop only: relative tolerance of the FIRST linear solve of a Newton solve (0 = krylov_tol)
     int krylov_maxit = 200;
     int floor_aware = 1;         // fp64-resolution-aware Newton stop
+    int bicg6 = 0;               // EXPERIMENTAL (builds with -DVCH_BICG6 only, VCH_BICG6=1): 6-launch BiCGStab iteration, DESIGN.md §7-0
     int pdl = 0;                 // programmatic dependent launch for every kernel of the work stream (vch_common.cuh); VCH_PDL=0|1
     int half_exit = 1;           // forward BiCGStab may stop after the first half of an iteration (VCH_NO_HALF_EXIT=1 disables).
                                  // Not used for the adjoint: its tolerance is on the TRUE residual, whose error is ~1e3 larger;
@@ -118,10 +119,10 @@ void copy_ghosted(vch2d_ctx* c, double* dst, const double* src) {
     dev_copy(c, dst - m, src - m, (size_t)c->g.n + 2 * m);
 }
 // kernels per BiCGStab iteration / per solve prologue (accounting of launches inside solve graphs)
-template <bool ADJ> int iter_launches(const vch2d_ctx* c) { return c->slab ? 7 + 4 : 7; }
+template <bool ADJ> int iter_launches(const vch2d_ctx* c) { return c->slab ? 7 + 4 : (c->bicg6 ? 6 : 7); }
 // FWD: P^-1 b (3 kernels) + init;  ADJ (right-preconditioned): init + the closing x = P^-1 y (3 kernels); slab mode adds the
 // barriers of one preconditioner application (2 + the trailing one)
-template <bool ADJ> int prologue_launches(const vch2d_ctx* c) { return 4 + (c->slab ? 3 : 0); }
+template <bool ADJ> int prologue_launches(const vch2d_ctx* c) { return 4 + (c->slab ? 3 : 0) + (c->bicg6 ? 1 : 0); }
 
 // Orders the library's private stream after the caller's stream on entry and the caller's stream after ours on exit,
 // so callers see ordinary stream semantics (torch.cuda.Event on their stream brackets our kernels).
@@ -153,6 +154,20 @@ void enqueue_bicg_iteration(vch2d_ctx* c, const double* a, const SymbolArgs& sy,
     const int* done = &c->sc->done;
     const double* pro_a = ADJ ? nullptr : a;     // multiply before the transform (forward) ...
     const double* epi_a = ADJ ? a : nullptr;     // ... or after it (adjoint)
+#ifdef VCH_BICG6
+    if (c->bicg6) {   // rows[x/r update of the previous iteration, p] cols rows[v, alpha] rows[s] cols rows[t, omega, rho, (r,r), stop]
+        DotEpilogue e1{1, c->kr0.p, c->sc, c->red.part, c->ticket, c->kp.p, epi_a, (c->half_exit && !ADJ) ? c->kr.p : nullptr};
+        e1.cond = cond; e1.use_cond = use_cond;
+        RowPrologue p3{3, c->kr.p, c->kv.p, pro_a, c->kp.p, c->sc};
+        p3.s = c->ks.p; p3.t = c->kt.p; p3.x = c->kx.p; p3.rw = c->kr.p;
+        c->dct.apply(c->stream, c->kr.p, c->kv.p, sy, done, e1, p3, 1);
+        DotEpilogue e2{4, c->ks.p, c->sc, c->red.part, c->ticket, c->ks.p, epi_a, c->kr0.p};
+        e2.cond = cond; e2.use_cond = use_cond;
+        c->dct.apply(c->stream, c->kr.p, c->kt.p, sy, done, e2, RowPrologue{2, c->kr.p, c->kv.p, pro_a, c->ks.p, c->sc}, 1);
+        (void)n; (void)rb;
+        return;
+    }
+#endif
     c->dct.apply(c->stream, c->kr.p, c->kv.p, sy, done, DotEpilogue{1, c->kr0.p, c->sc, c->red.part, c->ticket, c->kp.p, epi_a, (c->half_exit && !ADJ) ? c->kr.p : nullptr},
                  RowPrologue{1, c->kr.p, c->kq.p, pro_a, c->kp.p, c->sc}, 1);
     c->dct.apply(c->stream, c->kr.p, c->kt.p, sy, done, DotEpilogue{2, c->ks.p, c->sc, c->red.part, c->ticket, c->ks.p, epi_a},
@@ -172,6 +187,9 @@ void enqueue_bicg_prologue(vch2d_ctx* c, const SymbolArgs& sy, cudaGraphConditio
 // End of a solve: ADJ x = P^-1 y.
 template <bool ADJ>
 void enqueue_bicg_epilogue(vch2d_ctx* c, const SymbolArgs& sy) {
+#ifdef VCH_BICG6
+    if (c->bicg6) LAUNCH(c, bicg_close_kernel, c->rb(), kRedThreads, c->kx.p, c->kp.p, c->ks.p, c->g.n, c->sc, c->red.part, c->ticket);
+#endif
     if (ADJ) c->dct.apply(c->stream, c->kx.p, c->kx.p, sy, nullptr);
 }
 
@@ -211,7 +229,7 @@ cudaGraphExec_t solve_graph(vch2d_ctx* c, const double* a) {
     VCH_CUDA(cudaStreamBeginCaptureToGraph(c->stream, body, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal));
     enqueue_bicg_iteration<ADJ>(c, a, sy, cond, iter_launches<ADJ>(c));
     VCH_CUDA(cudaStreamEndCapture(c->stream, &tmp));
-    if (ADJ) {   // closing x = P^-1 y, after the loop
+    if (ADJ || c->bicg6) {   // closing x = P^-1 y (and, 6-launch form, the last x update), after the loop
         VCH_CUDA(cudaStreamBeginCaptureToGraph(c->stream, graph, &wnode, nullptr, 1, cudaStreamCaptureModeThreadLocal));
         enqueue_bicg_epilogue<ADJ>(c, sy);
         VCH_CUDA(cudaStreamEndCapture(c->stream, &tmp));
@@ -626,6 +644,9 @@ static int create_ctx(const vch2d_params* p, int device, int rank, int nranks, v
         c->debug = getenv("VCH_DEBUG") ? atoi(getenv("VCH_DEBUG")) : 0;
         if (getenv("VCH_NEWTON_STRICT")) c->floor_aware = 0;
         if (getenv("VCH_NO_HALF_EXIT")) c->half_exit = 0;
+#ifdef VCH_BICG6
+        c->bicg6 = (getenv("VCH_BICG6") ? atoi(getenv("VCH_BICG6")) : 0) && !slab;
+#endif
         c->pdl = (getenv("VCH_PDL") ? atoi(getenv("VCH_PDL")) : 0) && !slab;   // slab mode: cross-rank waits inside kernels, keep full serialization
         if (getenv("VCH_KRYLOV_FIRST_RTOL")) { const double t = atof(getenv("VCH_KRYLOV_FIRST_RTOL")); if (t >= 0 && t < 1) c->krylov_first_tol = t; }
         if (getenv("VCH_KRYLOV_RTOL")) { const double t = atof(getenv("VCH_KRYLOV_RTOL")); if (t > 0 && t < 1) c->krylov_tol = t; }
@@ -682,6 +703,7 @@ static int create_ctx(const vch2d_params* p, int device, int rank, int nranks, v
         } else {
             c->dct.init(g.no, g.ni, p->hy, p->hx, &c->log);
             c->dct.pdl = c->pdl != 0;
+            if (!(c->dct.inner.fft && c->dct.outer.fft)) c->bicg6 = 0;   // the dense-table path has no fused mode 3 / 4
         }
         c->red.alloc(8 * (size_t)c->dct.max_grid(), c->cm);
         Scal init{}; init.tol2 = c->krylov_tol * c->krylov_tol; init.maxit = c->krylov_maxit;

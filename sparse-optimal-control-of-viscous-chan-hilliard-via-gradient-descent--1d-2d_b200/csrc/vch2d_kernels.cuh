@@ -263,6 +263,28 @@ __global__ void bicg_x_kernel(double* __restrict__ x, double* __restrict__ r, co
     }
 }
 
+#ifdef VCH_BICG6
+// EXPERIMENTAL 6-launch iteration: the iterate lags one update behind (the x/r update lives in the next iteration's first row
+// transform); this kernel applies the last one after the loop:  x += alpha p + omega s, or x += alpha p after a half-step exit.
+// A solve that ended without an iteration (zero right-hand side) leaves x = 0.
+__global__ void bicg_close_kernel(double* __restrict__ x, const double* __restrict__ p, const double* __restrict__ s, long long n,
+                                  Scal* sc, double* part, unsigned int* ticket) {
+    pdl_enter();
+    const int half = sc->half;
+    if (sc->iters == 0 && !half) return;
+    const double al = sc->alpha, om = half ? 0.0 : sc->omega;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (long long)gridDim.x * blockDim.x)
+        x[idx] += half ? al * p[idx] : al * p[idx] + om * s[idx];
+    double one[1] = {0.0};
+    const int op1[1] = {0};
+    double t1[1];
+    if (grid_reduce<1>(one, op1, part, ticket, t1) && threadIdx.x == 0 && half) {   // last block: every block has read sc->half
+        sc->half = 0; sc->iters += 1; sc->iters_total += 1; sc->half_exits += 1;
+        if (sc->iters > sc->iters_max) sc->iters_max = sc->iters;
+    }
+}
+#endif
+
 // ---------------------------------------------------------------------------------- Newton step pieces
 // dmu = 2 (a dphi - kappa/2 L dphi + R_phi) and the step ceiling minima (Forward2_solver.py:377-391).
 __global__ void dmu_ceiling_kernel(const double* __restrict__ dphi, const double* __restrict__ a,

@@ -20,6 +20,9 @@
 #pragma once
 #include "vch_common.cuh"
 #include <algorithm>
+#if defined(VCH_BICG6) && defined(VCH_ROW_PROLOGUE_V2)
+#error "experimental variants: the restrict-qualified epilogue helper (VCH_ROW_PROLOGUE_V2) does not carry the mode-4 dot products of VCH_BICG6 yet"
+#endif
 
 namespace vch {
 
@@ -52,6 +55,13 @@ struct DotEpilogue {
     // mode 1 only: the current residual r.  With (r, out) the kernel also knows ||s||^2 of s = r - alpha*out and can end the
     // solve at the half step (dots_finish)
     const double* rvec = nullptr;
+#ifdef VCH_BICG6
+    // EXPERIMENTAL 6-launch iteration (run only on the CPU emulator so far).  mode 4: second epilogue that also
+    // takes (s,s), (r0,s), (r0,t) — rvec carries r0 — and derives rho_new = (r0,s) - omega (r0,t), (r,r) = (s,s) - 2 omega (t,s)
+    // + omega^2 (t,t), the stop decision and the loop conditional, which the x/r update kernel used to produce.
+    cudaGraphConditionalHandle cond = 0;
+    int use_cond = 0;
+#endif
 };
 
 // Last block of a dot-product epilogue: BiCGStab scalars from the grid-wide sums tot = {(other,out), (out,out), (r,out)}.
@@ -66,17 +76,48 @@ __device__ __forceinline__ void dots_finish(const DotEpilogue& epi, const double
         sc->r0v = tot[0]; sc->alpha = al; sc->rho = sc->rho_new;
         if (epi.rvec) {
             const double ss = sc->rr - 2.0 * al * tot[2] + al * al * tot[1];
-            if (isfinite(ss) && ss <= sc->thr2 && sc->rr <= 1e6 * sc->thr2) { sc->half = 1; sc->done = 1; }
+            if (isfinite(ss) && ss <= sc->thr2 && sc->rr <= 1e6 * sc->thr2) {
+                sc->half = 1; sc->done = 1;
+#ifdef VCH_BICG6   // the rest of the loop body returns on `done`: nobody else would clear the loop conditional
+                if (epi.use_cond) { sc->g_launches += epi.use_cond; cudaGraphSetConditional(epi.cond, 0u); }
+#endif
+            }
         }
     } else {
         sc->ts = tot[0]; sc->tt = tot[1]; sc->omega = (tot[1] > 0.0) ? tot[0] / tot[1] : 0.0;
     }
 }
+#ifdef VCH_BICG6
+// tot = {(s,t), (t,t), (r0,t), (s,s), (r0,s)}: everything bicg_x_kernel's reduction delivered, without forming r.
+// The three-term (r,r) is trusted for the stop test only once (s,s) is within 1e6 of the threshold (see dots_finish).
+__device__ __forceinline__ void dots_finish6(const DotEpilogue& epi, const double (&tot)[5]) {
+    Scal* sc = epi.sc;
+    const double ts = tot[0], tt = tot[1], r0t = tot[2], ss = tot[3], r0s = tot[4];
+    const double om = (tt > 0.0) ? ts / tt : 0.0;
+    double rr = ss - 2.0 * om * ts + om * om * tt;
+    if (rr < 0.0) rr = 0.0;
+    const double rho_new = r0s - om * r0t;
+    sc->ts = ts; sc->tt = tt; sc->omega = om; sc->rr = rr; sc->rho_new = rho_new;
+    sc->iters += 1; sc->iters_total += 1;
+    if (sc->iters > sc->iters_max) sc->iters_max = sc->iters;
+    const bool bad = !isfinite(rr) || !isfinite(rho_new);
+    if (bad) sc->nonfinite = 1;
+    if (bad || (rr <= sc->thr2 && ss <= 1e6 * sc->thr2)) sc->done = 1;
+    if (epi.use_cond) {
+        sc->g_launches += epi.use_cond;
+        const bool stop = sc->done || sc->iters >= sc->maxit;
+        if (stop && !sc->done) sc->stalls += 1;
+        cudaGraphSetConditional(epi.cond, stop ? 0u : 1u);
+    }
+}
+#endif
 
 // Optional prologue of the first row transform (fused BiCGStab vector update + coefficient multiply):
 //   mode 0: x = in
 //   mode 1: p = r + beta*q   (written to w), x = (a - abar) * p        beta = (rho_new/rho)(alpha/omega)
 //   mode 2: s = r - alpha*v  (written to w), x = (a - abar) * s
+//   mode 3 (VCH_BICG6): the deferred update of the previous iteration, then p:  r = s - omega t (written to rw),
+//           x += alpha p + omega s,  p = r + beta (p - omega v) (in place in w),  x_in = (a - abar) p;  first iteration: p = r
 struct RowPrologue {
     int mode = 0;
     const double* r = nullptr;
@@ -84,6 +125,12 @@ struct RowPrologue {
     const double* a = nullptr;      // nullptr: x = w (no coefficient multiply; right-preconditioned form)
     double* w = nullptr;
     const Scal* sc = nullptr;
+#ifdef VCH_BICG6
+    const double* s = nullptr;      // mode 3: s, t of the previous iteration, its v (in qv), the iterate x and the residual buffer
+    const double* t = nullptr;
+    double* x = nullptr;
+    double* rw = nullptr;
+#endif
 };
 
 // Slab mode: the transposes between the row and the column transforms are done by the kernels' own stores, straight
@@ -413,6 +460,48 @@ dct_fft_kernel(const double* in, double* out, int nlines, int n, int in_ls, int 
         }
         __syncthreads();                                          // staging is overwritten by the first-pass store
     } else
+#ifdef VCH_BICG6
+    if (!SOLVE && XM == 0 && pro.mode == 3) {
+        // Deferred x/r update of the previous iteration + the new p.  Every element is touched by exactly one thread (so p and
+        // x can be updated in place); the transform inputs go through shared memory, from where the first pass reads them with
+        // the even extension (as in the slab gather above) — half the global loads of the recomputing prologue.
+        const Scal* sc = pro.sc;
+        const bool first = sc->iters == 0;
+        const double al = sc->alpha, om = sc->omega, abar = sc->abar;
+        const double beta = first ? 0.0 : (sc->rho_new / sc->rho) * (al / om);
+        double* stg = reinterpret_cast<double*>(data);            // line a at [0, N], line b at [N + 2, 2N + 2]
+        for (int k = t; k <= N; k += tpf) {
+#pragma unroll
+            for (int L = 0; L < 2; ++L) {
+                const bool valid = L ? vb : va;
+                double xin = 0.0;
+                if (valid) {
+                    const size_t idx = (size_t)(L ? lb : la) * in_ls + k;
+                    double pn;
+                    if (first) pn = pro.r[idx];
+                    else {
+                        const double sv = pro.s[idx], tv = pro.t[idx], pv = pro.w[idx];
+                        const double rn = sv - om * tv;
+                        pro.x[idx] += al * pv + om * sv;
+                        pro.rw[idx] = rn;
+                        pn = rn + beta * (pv - om * pro.qv[idx]);
+                    }
+                    pro.w[idx] = pn;
+                    xin = pro.a ? (pro.a[idx] - abar) * pn : pn;
+                }
+                stg[(L ? N + 2 : 0) + k] = xin;
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            const int e = t + r * tpf;
+            const int ee = (e <= N) ? e : Lf - e;
+            v[r] = make_double2(stg[ee], stg[N + 2 + ee]);
+        }
+        __syncthreads();
+    } else
+#endif
 #pragma unroll
     for (int r = 0; r < 8; ++r) {
         const int e = t + r * tpf;
@@ -479,6 +568,9 @@ dct_fft_kernel(const double* in, double* out, int nlines, int n, int in_ls, int 
     }
 
     double acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;
+#ifdef VCH_BICG6
+    double acc4 = 0.0, acc5 = 0.0;
+#endif
     const double* ra = epi.rvec + (size_t)la * out_ls;
     const double* rb_ = epi.rvec + (size_t)lb * out_ls;
     double* qa = out + (size_t)la * out_ls;
@@ -508,12 +600,18 @@ dct_fft_kernel(const double* in, double* out, int nlines, int n, int in_ls, int 
                     const double o = epi.addend ? zx + da[off] : zx;
                     qa[off] = o;
                     if (epi.mode) { acc1 += oa[off] * o; acc2 += o * o; if (epi.rvec) acc3 += ra[off] * o; }
+#ifdef VCH_BICG6
+                    if (epi.mode == 4) { const double sv = oa[off]; acc4 += sv * sv; acc5 += ra[off] * sv; }
+#endif
                 }
                 if (vb) {
                     const double zy = epi.mul_a ? (epi.mul_a[(size_t)lb * out_ls + off] - eabar) * z[q].y : z[q].y;
                     const double o = epi.addend ? zy + db[off] : zy;
                     qb[off] = o;
                     if (epi.mode) { acc1 += ob[off] * o; acc2 += o * o; if (epi.rvec) acc3 += rb_[off] * o; }
+#ifdef VCH_BICG6
+                    if (epi.mode == 4) { const double sv = ob[off]; acc4 += sv * sv; acc5 += rb_[off] * sv; }
+#endif
                 }
 #endif
             }
@@ -523,6 +621,14 @@ dct_fft_kernel(const double* in, double* out, int nlines, int n, int in_ls, int 
     if (!SOLVE && XM != 1)
         row_epilogue_store<LOG2L>(z, out, epi.addend, epi.other, epi.rvec, epi.mul_a, eabar, epi.mode, va, vb, (size_t)la * out_ls,
                                   (size_t)lb * out_ls, t, N, out_es, acc1, acc2, acc3);
+#endif
+#ifdef VCH_BICG6
+    if (epi.mode == 4) {
+        double vals[5] = {acc1, acc2, acc3, acc4, acc5};
+        const int op[5] = {0, 0, 0, 0, 0};
+        double tot[5];
+        if (grid_reduce<5>(vals, op, epi.part, epi.ticket, tot) && threadIdx.x == 0) dots_finish6(epi, tot);
+    } else
 #endif
     if (epi.mode) {     // block-uniform: every thread of every CTA takes part in the reduction
         double vals[3] = {acc1, acc2, acc3};

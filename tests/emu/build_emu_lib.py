@@ -61,7 +61,7 @@ def rewrite(src: str) -> str:
     return src
 
 
-def build(out_dir: str) -> str:
+def build(out_dir: str, extra_flags=()) -> str:
     os.makedirs(out_dir, exist_ok=True)
     work = os.path.join(out_dir, "src", "pkg", "csrc")         # keeps the relative include of ../../include/vch_b200.h valid
     os.makedirs(work, exist_ok=True)
@@ -75,7 +75,7 @@ def build(out_dir: str) -> str:
             fh.write(rewrite(text))
     lib = os.path.join(out_dir, "libvch_b200_emu.so")
     cmd = ["g++", "-std=c++17", "-O2", "-fPIC", "-shared", "-DVCH_CPU_EMU", "-I" + os.path.join(CUDA_HOME, "include"),
-           "-include", os.path.join(HERE, "cuda_emu.h"),
+           "-include", os.path.join(HERE, "cuda_emu.h")] + list(extra_flags) + os.environ.get("VCH_EMU_EXTRA_FLAGS", "").split() + [
            "-x", "c++", os.path.join(work, "vch2d.cu"), os.path.join(work, "vch1d.cu"),
            os.path.join(HERE, "cudart_shim.cpp"), "-o", lib]
     subprocess.run(cmd, check=True)
