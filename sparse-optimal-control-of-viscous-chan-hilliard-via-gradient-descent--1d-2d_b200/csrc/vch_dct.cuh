@@ -461,14 +461,15 @@ dct_fft_kernel(const double* in, double* out, int nlines, int n, int in_ls, int 
         __syncthreads();                                          // staging is overwritten by the first-pass store
     } else
 #ifdef VCH_BICG6
-    if (!SOLVE && XM == 0 && pro.mode == 3) {
-        // Deferred x/r update of the previous iteration + the new p.  Every element is touched by exactly one thread (so p and
-        // x can be updated in place); the transform inputs go through shared memory, from where the first pass reads them with
-        // the even extension (as in the slab gather above) — half the global loads of the recomputing prologue.
+    if (!SOLVE && XM == 0 && (pro.mode == 3 || pro.mode == 2)) {
+        // mode 3: deferred x/r update of the previous iteration + the new p; mode 2: s = r - alpha v.  Every element is touched
+        // by exactly one thread (so p and x can be updated in place); the transform inputs go through shared memory, from where
+        // the first pass reads them with the even extension (as in the slab gather above) — half the global loads of the
+        // recomputing prologue.
         const Scal* sc = pro.sc;
-        const bool first = sc->iters == 0;
+        const bool first = sc->iters == 0, m2 = pro.mode == 2;
         const double al = sc->alpha, om = sc->omega, abar = sc->abar;
-        const double beta = first ? 0.0 : (sc->rho_new / sc->rho) * (al / om);
+        const double beta = (first || m2) ? 0.0 : (sc->rho_new / sc->rho) * (al / om);
         double* stg = reinterpret_cast<double*>(data);            // line a at [0, N], line b at [N + 2, 2N + 2]
         for (int k = t; k <= N; k += tpf) {
 #pragma unroll
@@ -478,7 +479,8 @@ dct_fft_kernel(const double* in, double* out, int nlines, int n, int in_ls, int 
                 if (valid) {
                     const size_t idx = (size_t)(L ? lb : la) * in_ls + k;
                     double pn;
-                    if (first) pn = pro.r[idx];
+                    if (m2) pn = pro.r[idx] - al * pro.qv[idx];
+                    else if (first) pn = pro.r[idx];
                     else {
                         const double sv = pro.s[idx], tv = pro.t[idx], pv = pro.w[idx];
                         const double rn = sv - om * tv;
