@@ -68,6 +68,10 @@ typedef struct {
     long long krylov_stalls;           /* solves that stopped above tolerance */
     double    last_newton_residual;
     long long krylov_half_exits;       /* solves that ended after the first half of a BiCGStab iteration (counted as one iteration) */
+    long long krylov_stalls_adjoint;   /* stalled solves of the ADJOINT sweep: vch2d_adjoint / vch2d_pgd_iteration return VCH_E_KRYLOV
+                                          when > 0 (the forward Newton loop checks the true residual itself; the adjoint recurrence,
+                                          backward2_solver.py:226-231, has no outer check, so an inaccurate p_n would silently
+                                          corrupt every earlier level and the gradient) */
 } vch_stats;
 
 const char* vch_last_error(void);

@@ -270,6 +270,8 @@ int krylov_solve(vch2d_ctx* c, const double* b, const double* a, vch_stats* st) 
     if (!c->sc_host->done) {   // mirror the device-side accounting of the graph path
         long long one = c->sc_host->stalls + 1;
         VCH_CUDA(cudaMemcpyAsync(&c->sc->stalls, &one, sizeof(one), cudaMemcpyHostToDevice, c->stream));
+        long long adj1 = c->sc_host->stalls_adj + 1;
+        if (ADJ) VCH_CUDA(cudaMemcpyAsync(&c->sc->stalls_adj, &adj1, sizeof(adj1), cudaMemcpyHostToDevice, c->stream));
         VCH_CUDA(cudaStreamSynchronize(c->stream));
     }
     if (c->sc_host->nonfinite) throw Error(VCH_E_NONFINITE, "non-finite value in Krylov solve");
@@ -278,12 +280,17 @@ int krylov_solve(vch2d_ctx* c, const double* b, const double* a, vch_stats* st) 
 }
 
 // Device-side solver counters -> vch_stats (call after a fetch_scalars).
-struct StatMark { long long its, solves, stalls, launches, glaunches, halves; };
+struct StatMark { long long its, solves, stalls, launches, glaunches, halves, stalls_adj; };
 StatMark stat_mark(vch2d_ctx* c) {
     fetch_scalars(c);
     VCH_CUDA(cudaMemsetAsync(&c->sc->iters_max, 0, sizeof(int), c->stream));   // per-call maximum
+    // Sticky state of an EARLIER call must not leak into this one: a non-finite event (NaN control, overflowing trial step)
+    // raised VCH_E_NONFINITE there; contexts are cached and reused by the Python drop-ins, so the flag is cleared at every
+    // API entry (with the half-step marker a solve aborted mid-iteration could have left behind).
+    VCH_CUDA(cudaMemsetAsync(&c->sc->nonfinite, 0, sizeof(int), c->stream));
+    VCH_CUDA(cudaMemsetAsync(&c->sc->half, 0, sizeof(int), c->stream));
     return {c->sc_host->iters_total, c->sc_host->solves, c->sc_host->stalls, c->log.count, c->sc_host->g_launches,
-            c->sc_host->half_exits};
+            c->sc_host->half_exits, c->sc_host->stalls_adj};
 }
 void stat_collect(vch2d_ctx* c, const StatMark& m0, vch_stats* st) {
     fetch_scalars(c);
@@ -293,6 +300,7 @@ void stat_collect(vch2d_ctx* c, const StatMark& m0, vch_stats* st) {
     st->krylov_iterations += its;
     st->newton_linear_solves += solves;
     st->krylov_stalls += c->sc_host->stalls - m0.stalls;
+    st->krylov_stalls_adjoint += c->sc_host->stalls_adj - m0.stalls_adj;
     st->krylov_half_exits += c->sc_host->half_exits - m0.halves;
     if (c->sc_host->stalls > m0.stalls)    // never silent: the direct solver this replaces cannot stall
         fprintf(stderr, "[vch_b200] warning: %lld linear solve(s) stopped above the Krylov tolerance (max_iter %d); see vch_stats.krylov_stalls\n",
@@ -300,6 +308,17 @@ void stat_collect(vch2d_ctx* c, const StatMark& m0, vch_stats* st) {
     st->krylov_max_iterations = std::max<long long>(st->krylov_max_iterations, c->sc_host->iters_max);
     // kernels inside solve graphs are not seen by the launch log: 4 prologue kernels per solve + 11 per iteration
     st->kernel_launches += (c->log.count - m0.launches) + (c->sc_host->g_launches - m0.glaunches);
+}
+
+// The forward Newton loop re-checks the true residual after every linear solve, so a stalled BiCGStab there only costs an
+// iteration.  The adjoint recurrence has no such outer check: a solve that stopped above tolerance leaves an inaccurate p_n
+// that propagates into every earlier level and into the gradient.  The reference's direct solve cannot fail this way, so it
+// is an error here (VCH_E_KRYLOV -> KrylovStall in Python), raised after the call's outputs have been written.
+void require_adjoint_converged(vch2d_ctx* c, const StatMark& m0) {
+    const long long bad = c->sc_host->stalls_adj - m0.stalls_adj;
+    if (bad > 0)
+        throw Error(VCH_E_KRYLOV, "adjoint sweep: " + std::to_string(bad) + " linear solve(s) stopped above the Krylov tolerance "
+                                  "(raise max_iter with vch2d_set_krylov); the gradient would be inaccurate");
 }
 
 // publish: the kernel's last block also writes the scalars into the pinned mirror (follow with wait_scalars, not fetch_scalars)
@@ -1045,6 +1064,7 @@ int vch2d_adjoint(vch2d_ctx* c, const double* phi_hist, int levels, const double
         adjoint_dev(c, dh, levels, t_hist, b1, b2, dq, dT, po, qo, ro, s);
         st.finish();
         stat_collect(c, mark0, s);
+        require_adjoint_converged(c, mark0);
         return VCH_OK;
     });
 }
@@ -1415,6 +1435,7 @@ int vch2d_pgd_iteration(vch2d_ctx* c, int levels, const double* t_hist, const do
                                             alpha, u_new_out, phi_hist_out, r_out, J_out, red_out, s);
             }
             stat_collect(c, mark0, s);
+            require_adjoint_converged(c, mark0);
             return VCH_OK;
         }
         const double *du = u, *dh = phi_hist, *dq = phiQ, *dT = phiT;
@@ -1437,6 +1458,7 @@ int vch2d_pgd_iteration(vch2d_ctx* c, int levels, const double* t_hist, const do
         }
         VCH_CUDA(cudaStreamSynchronize(c->stream));
         stat_collect(c, mark0, s);
+        require_adjoint_converged(c, mark0);
         return VCH_OK;
     });
 }

@@ -177,7 +177,7 @@ __global__ void jac_diag_kernel(const double* __restrict__ phi, double* __restri
 __global__ void schur_rhs_kernel(const double* __restrict__ Rphi, const double* __restrict__ Rmu, double* __restrict__ b, Geo g,
                                  Scal* sc, double c0, double c2, double tol2) {
     pdl_enter();
-    if (blockIdx.x == 0 && threadIdx.x == 0) { sc->c0 = c0; sc->c2 = c2; sc->tol2 = tol2; }   // coefficients and (squared) relative tolerance of the solve that follows
+    if (blockIdx.x == 0 && threadIdx.x == 0) { sc->c0 = c0; sc->c2 = c2; sc->tol2 = tol2; sc->adj = 0; }   // coefficients and (squared) relative tolerance of the solve that follows
     for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < g.n; idx += (long long)gridDim.x * blockDim.x) {
         const int o = (int)(idx / g.ni), i = (int)(idx - (long long)o * g.ni);
         b[idx] = lap_g(Rphi, o, i, g) - Rmu[idx];
@@ -257,7 +257,7 @@ __global__ void bicg_x_kernel(double* __restrict__ x, double* __restrict__ r, co
         if (use_cond) {
             sc->g_launches += use_cond;
             const bool stop = sc->done || sc->iters >= sc->maxit;
-            if (stop && !sc->done) sc->stalls += 1;
+            if (stop && !sc->done) { sc->stalls += 1; if (sc->adj) sc->stalls_adj += 1; }
             cudaGraphSetConditional(cond, stop ? 0u : 1u);
         }
     }
@@ -395,7 +395,7 @@ __global__ void adj_rhs_kernel(const double* __restrict__ p1, const double* __re
     if (grid_reduce<2>(v, op, part, ticket, tot) && threadIdx.x == 0) {
         sc->amin = tot[0]; sc->amax = tot[1];
         sc->abar = (tot[0] > 0.0) ? sqrt(tot[0] * tot[1]) : 0.5 * (tot[0] + tot[1]);
-        sc->c0 = 1.0; sc->c2 = hdt; sc->tol2 = tol2;                           // coefficients / tolerance of the solve that follows
+        sc->c0 = 1.0; sc->c2 = hdt; sc->tol2 = tol2; sc->adj = 1;              // coefficients / tolerance of the solve that follows
     }
 }
 

@@ -140,7 +140,9 @@ struct Scal {
     long long g_launches;                    // kernels that ran inside solve graphs (not seen by the host launch log)
     long long half_exits;                    // solves that stopped after the first half of a BiCGStab iteration (||s|| <= tol ||b||)
     int iters_max, comm_err;                 // comm_err: a bounded cross-rank wait expired (slab mode)
-    int half, pad_;                          // half = 1: converged at the half step, bicg_x_kernel only applies x += alpha p
+    int half, adj;                           // half = 1: converged at the half step, bicg_x_kernel only applies x += alpha p
+                                             // adj = 1: the current solve belongs to the adjoint sweep (set by adj_rhs_kernel)
+    long long stalls_adj;                    // stalled solves of the adjoint sweep (no outer residual check guards them: an error)
 };
 
 

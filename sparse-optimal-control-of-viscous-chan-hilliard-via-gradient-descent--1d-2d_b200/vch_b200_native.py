@@ -39,7 +39,7 @@ class Stats(C.Structure):
     _fields_ = [("newton_residual_evals", C.c_longlong), ("newton_linear_solves", C.c_longlong),
                 ("krylov_iterations", C.c_longlong), ("krylov_max_iterations", C.c_longlong),
                 ("kernel_launches", C.c_longlong), ("krylov_stalls", C.c_longlong), ("last_newton_residual", C.c_double),
-                ("krylov_half_exits", C.c_longlong)]
+                ("krylov_half_exits", C.c_longlong), ("krylov_stalls_adjoint", C.c_longlong)]
 
     def as_dict(self):
         return {f: getattr(self, f) for f, _ in self._fields_}

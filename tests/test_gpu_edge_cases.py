@@ -82,3 +82,43 @@ def test_1d_edge_cases(native):
     hb, _, _ = big.forward(O.init_phi_1d(512), None, np.full(2, 1e-3))
     fb = O.forward_1d(O.Phys1D(N=512, T=2e-3, dt_initial=1e-3))
     assert rel(hb, fb["phi"]) < 1e-8
+
+
+def test_nonfinite_input_raises_and_context_recovers(native, golden):
+    """the device-side non-finite flag must not stay set.  A NaN initial field raises RuntimeError
+    (VCH_E_NONFINITE); the next valid call on the SAME context succeeds and reproduces the reference golden."""
+    g = golden("g2d_32")
+    P = O.from_json(O.Phys2D, g["cfg_json"])
+    c = native.Ctx2D(P.Nx, P.Ny, P.Lx / P.Nx, P.Ly / P.Ny, P.Lx, P.Ly, P.tau, P.gamma, P.c1, P.c2, P.kappa)
+    dts = np.diff(g["t"])
+    bad = g["phi0"][0].copy()
+    bad[3, 5] = np.nan
+    with pytest.raises(RuntimeError):
+        c.forward(bad, None, dts)
+    with pytest.raises(RuntimeError):                                # NaN control: w -> residual -> non-finite
+        u = np.zeros_like(g["phi0"]); u[1, 2, 2] = np.inf
+        c.forward(g["phi0"][0], u, dts)
+    h, _, _ = c.forward(g["phi0"][0], None, dts)                     # same context, valid input
+    assert rel(h, g["phi0"]) < 1e-8
+    p, q, r = c.adjoint(h, g["t"], 5.0, 10.0, None, None)
+    assert np.isfinite(r).all() and c.last_stats["krylov_stalls"] == 0
+
+
+def test_adjoint_krylov_stall_is_an_error(native, golden):
+    """a BiCGStab solve of the adjoint sweep that stops above tolerance must not return silently (the reference's
+    direct solve cannot fail that way): VCH_E_KRYLOV -> KrylovStall; the forward solve, guarded by Newton's own residual
+    check, keeps returning normally; restoring the iteration cap restores the result."""
+    g = golden("g2d_32")
+    P = O.from_json(O.Phys2D, g["cfg_json"])
+    c = native.Ctx2D(P.Nx, P.Ny, P.Lx / P.Nx, P.Ly / P.Ny, P.Lx, P.Ly, P.tau, P.gamma, P.c1, P.c2, P.kappa)
+    dts = np.diff(g["t"])
+    h, _, _ = c.forward(g["phi0"][0], None, dts)
+    c.set_krylov(1e-17, 1)                                           # below fp64 resolution: cannot be reached
+    with pytest.raises(native.KrylovStall):
+        c.adjoint(h, g["t"], 5.0, 10.0, None, None)
+    c.set_krylov(1e-11, 200)
+    p, q, r = c.adjoint(h, g["t"], 5.0, 10.0, None, None)
+    assert c.last_stats["krylov_stalls_adjoint"] == 0
+    x, y = g["x"], g["y"]
+    po, qo, ro = O.adjoint_2d(P, h, x, y, g["t"], 5.0, 10.0)
+    assert rel(p, po) < 1e-7 and rel(r, ro) < 1e-7
