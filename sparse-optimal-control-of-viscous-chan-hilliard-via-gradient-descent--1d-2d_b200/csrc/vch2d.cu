@@ -31,7 +31,8 @@ struct vch2d_ctx {
     double krylov_first_tol = 1e-6;   // time loop only: relative tolerance of the FIRST linear solve of a Newton solve (0 = krylov_tol)
     int krylov_maxit = 200;
     int floor_aware = 1;         // fp64-resolution-aware Newton stop
-    int bicg6 = 0;               // EXPERIMENTAL (builds with -DVCH_BICG6 only, VCH_BICG6=1): 6-launch BiCGStab iteration, DESIGN.md §7-0
+    int bicg6 = 1;               // 6-launch BiCGStab iteration (x/r update deferred into the next row transform, scalars from the second
+                                 // epilogue; measured +6.6 % it/s).  0 (VCH_BICG6=0, slab mode, dense-table grids): the 7-launch form
     int pdl = 0;                 // programmatic dependent launch for every kernel of the work stream (vch_common.cuh); VCH_PDL=0|1
     int half_exit = 1;           // forward BiCGStab may stop after the first half of an iteration (VCH_NO_HALF_EXIT=1 disables).
                                  // Not used for the adjoint: its tolerance is on the TRUE residual, whose error is ~1e3 larger;
@@ -154,7 +155,6 @@ void enqueue_bicg_iteration(vch2d_ctx* c, const double* a, const SymbolArgs& sy,
     const int* done = &c->sc->done;
     const double* pro_a = ADJ ? nullptr : a;     // multiply before the transform (forward) ...
     const double* epi_a = ADJ ? a : nullptr;     // ... or after it (adjoint)
-#ifdef VCH_BICG6
     if (c->bicg6) {   // rows[x/r update of the previous iteration, p] cols rows[v, alpha] rows[s] cols rows[t, omega, rho, (r,r), stop]
         DotEpilogue e1{1, c->kr0.p, c->sc, c->red.part, c->ticket, c->kp.p, epi_a, (c->half_exit && !ADJ) ? c->kr.p : nullptr};
         e1.cond = cond; e1.use_cond = use_cond;
@@ -167,7 +167,6 @@ void enqueue_bicg_iteration(vch2d_ctx* c, const double* a, const SymbolArgs& sy,
         (void)n; (void)rb;
         return;
     }
-#endif
     c->dct.apply(c->stream, c->kr.p, c->kv.p, sy, done, DotEpilogue{1, c->kr0.p, c->sc, c->red.part, c->ticket, c->kp.p, epi_a, (c->half_exit && !ADJ) ? c->kr.p : nullptr},
                  RowPrologue{1, c->kr.p, c->kq.p, pro_a, c->kp.p, c->sc}, 1);
     c->dct.apply(c->stream, c->kr.p, c->kt.p, sy, done, DotEpilogue{2, c->ks.p, c->sc, c->red.part, c->ticket, c->ks.p, epi_a},
@@ -187,9 +186,7 @@ void enqueue_bicg_prologue(vch2d_ctx* c, const SymbolArgs& sy, cudaGraphConditio
 // End of a solve: ADJ x = P^-1 y.
 template <bool ADJ>
 void enqueue_bicg_epilogue(vch2d_ctx* c, const SymbolArgs& sy) {
-#ifdef VCH_BICG6
     if (c->bicg6) LAUNCH(c, bicg_close_kernel, c->rb(), kRedThreads, c->kx.p, c->kp.p, c->ks.p, c->g.n, c->sc, c->red.part, c->ticket);
-#endif
     if (ADJ) c->dct.apply(c->stream, c->kx.p, c->kx.p, sy, nullptr);
 }
 
@@ -377,7 +374,7 @@ void newton_step(vch2d_ctx* c, const double* phi_old, const double* mu_old, cons
     // would spin to max_iter on rounding noise.  floor_aware stops as soon as ||R|| is at that resolution, or once Newton
     // stalls (fails to halve ||R||) inside 50x of it.
     auto floor_est = [&] { return 2.220446049250313e-16 * (c->g.ihi2 + c->g.iho2) * std::sqrt(c->sc_host->mu2); };
-    double floor_now = floor_est();
+    double floor_now = floor_est(), dbg_prev = 0.0;
     int k_done = 0;
     for (int k = 0; k < max_iter; ++k) {
         k_done = k;
@@ -388,6 +385,7 @@ void newton_step(vch2d_ctx* c, const double* phi_old, const double* mu_old, cons
         if (c->floor_aware && normR <= 1.5 * floor_now) break;   // at the fp64 resolution of the residual (only possible
                                                              // when that resolution exceeds tol, i.e. grids >~ 600^2)
         const double normR_prev = normR;
+        dbg_prev = normR;
         // speculative full step: almost always alpha = 1 is both allowed by the ceiling and accepted by Armijo, so the
         // trial iterate (formed by the dmu kernel) and its residual are enqueued before the host has seen the ceiling
         // -> ONE sync per Newton iteration
@@ -445,7 +443,7 @@ void newton_step(vch2d_ctx* c, const double* phi_old, const double* mu_old, cons
             break;   // stalled at fp64 resolution
         }
     }
-    if (c->debug) fprintf(stderr, "[vch2d] newton: %d its, |R| = %.3e, floor_est = %.3e\n", k_done, normR, floor_now);
+    if (c->debug) fprintf(stderr, "[vch2d] newton: %d its, |R| = %.3e, floor_est = %.3e, before the last solve %.3e\n", k_done, normR, floor_now, dbg_prev);
     if (phi != c->phi.p) {   // leave the result in c->phi / c->mu
         std::swap(c->phi.p, c->phit.p); std::swap(c->mu.p, c->mut.p);
         std::swap(c->phi.n, c->phit.n); std::swap(c->mu.n, c->mut.n);
@@ -663,9 +661,7 @@ static int create_ctx(const vch2d_params* p, int device, int rank, int nranks, v
         c->debug = getenv("VCH_DEBUG") ? atoi(getenv("VCH_DEBUG")) : 0;
         if (getenv("VCH_NEWTON_STRICT")) c->floor_aware = 0;
         if (getenv("VCH_NO_HALF_EXIT")) c->half_exit = 0;
-#ifdef VCH_BICG6
-        c->bicg6 = (getenv("VCH_BICG6") ? atoi(getenv("VCH_BICG6")) : 0) && !slab;
-#endif
+        c->bicg6 = (getenv("VCH_BICG6") ? atoi(getenv("VCH_BICG6")) : 1) && !slab;
         c->pdl = (getenv("VCH_PDL") ? atoi(getenv("VCH_PDL")) : 0) && !slab;   // slab mode: cross-rank waits inside kernels, keep full serialization
         if (getenv("VCH_KRYLOV_FIRST_RTOL")) { const double t = atof(getenv("VCH_KRYLOV_FIRST_RTOL")); if (t >= 0 && t < 1) c->krylov_first_tol = t; }
         if (getenv("VCH_KRYLOV_RTOL")) { const double t = atof(getenv("VCH_KRYLOV_RTOL")); if (t > 0 && t < 1) c->krylov_tol = t; }

@@ -263,8 +263,7 @@ __global__ void bicg_x_kernel(double* __restrict__ x, double* __restrict__ r, co
     }
 }
 
-#ifdef VCH_BICG6
-// EXPERIMENTAL 6-launch iteration: the iterate lags one update behind (the x/r update lives in the next iteration's first row
+// 6-launch iteration: the iterate lags one update behind (the x/r update lives in the next iteration's first row
 // transform); this kernel applies the last one after the loop:  x += alpha p + omega s, or x += alpha p after a half-step exit.
 // A solve that ended without an iteration (zero right-hand side) leaves x = 0.
 __global__ void bicg_close_kernel(double* __restrict__ x, const double* __restrict__ p, const double* __restrict__ s, long long n,
@@ -283,7 +282,6 @@ __global__ void bicg_close_kernel(double* __restrict__ x, const double* __restri
         if (sc->iters > sc->iters_max) sc->iters_max = sc->iters;
     }
 }
-#endif
 
 // ---------------------------------------------------------------------------------- Newton step pieces
 // dmu = 2 (a dphi - kappa/2 L dphi + R_phi) and the step ceiling minima (Forward2_solver.py:377-391).

@@ -20,9 +20,6 @@
 #pragma once
 #include "vch_common.cuh"
 #include <algorithm>
-#if defined(VCH_BICG6) && defined(VCH_ROW_PROLOGUE_V2)
-#error "experimental variants: the restrict-qualified epilogue helper (VCH_ROW_PROLOGUE_V2) does not carry the mode-4 dot products of VCH_BICG6 yet"
-#endif
 
 namespace vch {
 
@@ -45,6 +42,7 @@ struct SymbolArgs {
 // Optional epilogue of the last row transform: add a vector (out = z + addend) and BiCGStab dot products over `out`.
 struct DotEpilogue {
     int mode = 0;                 // 0 none, 1: (other, out) -> alpha = rho_new / dot, rho = rho_new ; 2: (out, other), (out, out) -> omega
+                                  // 4: mode 2 plus (s,s), (r0,s), (r0,t) -> omega, rho_new, (r,r), stop decision (6-launch iteration)
     const double* other = nullptr;
     Scal* sc = nullptr;
     double* part = nullptr;
@@ -55,13 +53,11 @@ struct DotEpilogue {
     // mode 1 only: the current residual r.  With (r, out) the kernel also knows ||s||^2 of s = r - alpha*out and can end the
     // solve at the half step (dots_finish)
     const double* rvec = nullptr;
-#ifdef VCH_BICG6
-    // EXPERIMENTAL 6-launch iteration (run only on the CPU emulator so far).  mode 4: second epilogue that also
-    // takes (s,s), (r0,s), (r0,t) — rvec carries r0 — and derives rho_new = (r0,s) - omega (r0,t), (r,r) = (s,s) - 2 omega (t,s)
-    // + omega^2 (t,t), the stop decision and the loop conditional, which the x/r update kernel used to produce.
+    // 6-launch iteration (measured on B200: -6.6 % per PGD iteration against the 7-launch form).  mode 4: second epilogue that
+    // also takes (s,s), (r0,s), (r0,t) — rvec carries r0 — and derives rho_new = (r0,s) - omega (r0,t), (r,r) = (s,s) - 2 omega (t,s)
+    // + omega^2 (t,t), the stop decision and the loop conditional, which the x/r update kernel produces in the 7-launch form.
     cudaGraphConditionalHandle cond = 0;
     int use_cond = 0;
-#endif
 };
 
 // Last block of a dot-product epilogue: BiCGStab scalars from the grid-wide sums tot = {(other,out), (out,out), (r,out)}.
@@ -78,16 +74,14 @@ __device__ __forceinline__ void dots_finish(const DotEpilogue& epi, const double
             const double ss = sc->rr - 2.0 * al * tot[2] + al * al * tot[1];
             if (isfinite(ss) && ss <= sc->thr2 && sc->rr <= 1e6 * sc->thr2) {
                 sc->half = 1; sc->done = 1;
-#ifdef VCH_BICG6   // the rest of the loop body returns on `done`: nobody else would clear the loop conditional
+                // 6-launch iteration: the rest of the loop body returns on `done`, nobody else would clear the loop conditional
                 if (epi.use_cond) { sc->g_launches += epi.use_cond; cudaGraphSetConditional(epi.cond, 0u); }
-#endif
             }
         }
     } else {
         sc->ts = tot[0]; sc->tt = tot[1]; sc->omega = (tot[1] > 0.0) ? tot[0] / tot[1] : 0.0;
     }
 }
-#ifdef VCH_BICG6
 // tot = {(s,t), (t,t), (r0,t), (s,s), (r0,s)}: everything bicg_x_kernel's reduction delivered, without forming r.
 // The three-term (r,r) is trusted for the stop test only once (s,s) is within 1e6 of the threshold (see dots_finish).
 __device__ __forceinline__ void dots_finish6(const DotEpilogue& epi, const double (&tot)[5]) {
@@ -106,17 +100,16 @@ __device__ __forceinline__ void dots_finish6(const DotEpilogue& epi, const doubl
     if (epi.use_cond) {
         sc->g_launches += epi.use_cond;
         const bool stop = sc->done || sc->iters >= sc->maxit;
-        if (stop && !sc->done) sc->stalls += 1;
+        if (stop && !sc->done) { sc->stalls += 1; if (sc->adj) sc->stalls_adj += 1; }
         cudaGraphSetConditional(epi.cond, stop ? 0u : 1u);
     }
 }
-#endif
 
 // Optional prologue of the first row transform (fused BiCGStab vector update + coefficient multiply):
 //   mode 0: x = in
 //   mode 1: p = r + beta*q   (written to w), x = (a - abar) * p        beta = (rho_new/rho)(alpha/omega)
 //   mode 2: s = r - alpha*v  (written to w), x = (a - abar) * s
-//   mode 3 (VCH_BICG6): the deferred update of the previous iteration, then p:  r = s - omega t (written to rw),
+//   mode 3 (6-launch iteration): the deferred update of the previous iteration, then p:  r = s - omega t (written to rw),
 //           x += alpha p + omega s,  p = r + beta (p - omega v) (in place in w),  x_in = (a - abar) p;  first iteration: p = r
 struct RowPrologue {
     int mode = 0;
@@ -125,12 +118,10 @@ struct RowPrologue {
     const double* a = nullptr;      // nullptr: x = w (no coefficient multiply; right-preconditioned form)
     double* w = nullptr;
     const Scal* sc = nullptr;
-#ifdef VCH_BICG6
     const double* s = nullptr;      // mode 3: s, t of the previous iteration, its v (in qv), the iterate x and the residual buffer
     const double* t = nullptr;
     double* x = nullptr;
     double* rw = nullptr;
-#endif
 };
 
 // Slab mode: the transposes between the row and the column transforms are done by the kernels' own stores, straight
@@ -313,12 +304,12 @@ __device__ __forceinline__ void fft_last_pass(const double2* data, int t, const 
     }
 }
 
-// ---- EXPERIMENTAL, compiled only with -DVCH_ROW_PROLOGUE_V2 (round-2 candidate, NOT yet run on a GPU).
-// SASS of the default build shows the fused prologue as 16 dependent groups of 3 loads + 1 store per thread (the stores to w may
-// alias r/q/a as far as the compiler knows, so the next group's loads wait behind them) and the BiCGStab scalars reloaded and
-// re-divided for every point: rows_pro costs 17.4 us against 14.8 us for the plain transform.  The variant below reads the scalars
-// once and issues the 4-6 loads of a point (both lines) back to back.
-#ifdef VCH_ROW_PROLOGUE_V2
+// ---- Fused BiCGStab vector work around the row transforms.
+// Round-1 SASS showed the in-line prologue as 16 dependent groups of 3 loads + 1 store per thread (the stores to w may alias
+// r/q/a as far as the compiler knows, so the next group's loads waited behind them) and the BiCGStab scalars reloaded and
+// re-divided for every point.  The helpers below take restrict-qualified PARAMETERS (struct members carry no such promise), read
+// the scalars once and issue the 4-8 loads of a point (both lines) back to back.  Measured on B200 (1024^2): fused prologue
+// 17.2 -> 15.1 us (the plain transform takes 14.8), first epilogue 20.5 -> 19.6 us, +4.1 % PGD iterations/s.
 // First-pass inputs of a row pair with the fused BiCGStab vector update (RowPrologue modes 1 and 2):
 //   w = r + coef*q (coef = 0: w = r, q is not read — it may hold anything, bicg_init_kernel does not clear it),
 //   stored once (the mirror images e > N are recomputed, not stored), x = (a - abar)*w or w.
@@ -363,18 +354,19 @@ __device__ __forceinline__ void row_prologue_load(double2 (&v)[8], const double*
 }
 
 
-// Same idea for the fused row epilogue (out = (mul_a - abar) z + addend, BiCGStab dot products): in the default build every
-// store to `out` holds back the loads of the next point (epi1 costs 20.6 us against 14.8 us for the plain transform).  Here
-// the up to 8 loads of a point (both lines: addend, other, r, a) are issued together; out, addend, other, r and a are distinct
-// work vectors (enqueue_bicg_iteration).  Absent lines read line 0 and are discarded.
+// Same idea for the fused row epilogue (out = (mul_a - abar) z + addend, BiCGStab dot products): with in-line code every store
+// to `out` held back the loads of the next point.  Here the up to 8 loads of a point (both lines: addend, other, r, a) are issued
+// together; `out` is distinct from the vectors that are read (enqueue_bicg_iteration).  Absent lines read line 0 and are
+// discarded.  mode 4 also accumulates (other, other) and (rvec, other) — (s,s) and (r0,s) of the 6-launch iteration.
 template <int LOG2L>
 __device__ __forceinline__ void row_epilogue_store(const double2 (&z)[8], double* __restrict__ out, const double* __restrict__ addend,
                                                    const double* __restrict__ other, const double* __restrict__ rvec,
                                                    const double* __restrict__ mul_a, double eabar, int mode, bool va, bool vb,
                                                    size_t base_a, size_t base_b, int t, int N, int out_es,
-                                                   double& acc1, double& acc2, double& acc3) {
+                                                   double& acc1, double& acc2, double& acc3, double& acc4, double& acc5) {
     const size_t ba = va ? base_a : 0, bb = vb ? base_b : 0;
     const bool has_add = addend != nullptr, has_mul = mul_a != nullptr, has_r = rvec != nullptr && mode != 0, has_o = mode != 0;
+    const bool m4 = mode == 4;
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
         const int kk = t + FftOut<LOG2L>::off(q);
@@ -386,12 +378,19 @@ __device__ __forceinline__ void row_epilogue_store(const double2 (&z)[8], double
             const double ra = has_r ? rvec[ba + off] : 0.0, rb = has_r ? rvec[bb + off] : 0.0;
             const double zx = has_mul ? (ma - eabar) * z[q].x : z[q].x, zy = has_mul ? (mb - eabar) * z[q].y : z[q].y;
             const double xo = has_add ? zx + da : zx, yo = has_add ? zy + db : zy;
-            if (va) { out[ba + off] = xo; if (has_o) { acc1 += oa * xo; acc2 += xo * xo; if (has_r) acc3 += ra * xo; } }
-            if (vb) { out[bb + off] = yo; if (has_o) { acc1 += ob * yo; acc2 += yo * yo; if (has_r) acc3 += rb * yo; } }
+            if (va) {
+                out[ba + off] = xo;
+                if (has_o) { acc1 += oa * xo; acc2 += xo * xo; if (has_r) acc3 += ra * xo; }
+                if (m4) { acc4 += oa * oa; acc5 += ra * oa; }
+            }
+            if (vb) {
+                out[bb + off] = yo;
+                if (has_o) { acc1 += ob * yo; acc2 += yo * yo; if (has_r) acc3 += rb * yo; }
+                if (m4) { acc4 += ob * ob; acc5 += rb * ob; }
+            }
         }
     }
 }
-#endif   // VCH_ROW_PROLOGUE_V2
 
 // One CTA = ppb complex FFTs (2*ppb lines).  Line l, element e lives at base[l*line_stride + e*elem_stride].
 //   SOLVE = false: out = DCT-I(in) per line (unnormalised "FFT of the even extension").
@@ -460,12 +459,11 @@ dct_fft_kernel(const double* in, double* out, int nlines, int n, int in_ls, int 
         }
         __syncthreads();                                          // staging is overwritten by the first-pass store
     } else
-#ifdef VCH_BICG6
     if (!SOLVE && XM == 0 && (pro.mode == 3 || pro.mode == 2)) {
-        // mode 3: deferred x/r update of the previous iteration + the new p; mode 2: s = r - alpha v.  Every element is touched
-        // by exactly one thread (so p and x can be updated in place); the transform inputs go through shared memory, from where
-        // the first pass reads them with the even extension (as in the slab gather above) — half the global loads of the
-        // recomputing prologue.
+        // 6-launch iteration.  mode 3: deferred x/r update of the previous iteration + the new p; mode 2: s = r - alpha v.  Every
+        // element is touched by exactly one thread (so p and x can be updated in place); the transform inputs go through shared
+        // memory, from where the first pass reads them with the even extension (as in the slab gather above) — half the global
+        // loads of the recomputing prologue.
         const Scal* sc = pro.sc;
         const bool first = sc->iters == 0, m2 = pro.mode == 2;
         const double al = sc->alpha, om = sc->omega, abar = sc->abar;
@@ -502,39 +500,25 @@ dct_fft_kernel(const double* in, double* out, int nlines, int n, int in_ls, int 
             v[r] = make_double2(stg[ee], stg[N + 2 + ee]);
         }
         __syncthreads();
-    } else
-#endif
-#pragma unroll
-    for (int r = 0; r < 8; ++r) {
-        const int e = t + r * tpf;
-        const int off = (e <= N ? e : Lf - e) * in_es;
-        if (SOLVE) {
-            v[r] = va ? *reinterpret_cast<const double2*>(pa + off) : make_double2(0.0, 0.0);
-        } else if (pro.mode == 0) {
-            v[r].x = va ? pa[off] : 0.0;
-            v[r].y = vb ? pb[off] : 0.0;
-        } else {
-#ifndef VCH_ROW_PROLOGUE_V2
-            // fused vector update: every element is recomputed where its mirror image is needed; it is written once
-            const Scal* sc = pro.sc;
-            const double coef = (pro.mode == 1) ? (sc->rho_new / sc->rho) * (sc->alpha / sc->omega) : -sc->alpha;
-            const double abar = sc->abar;
-            const size_t ia = (size_t)la * in_ls + off, ib = (size_t)lb * in_ls + off;
-            double xa = 0.0, xb = 0.0;
-            // coef == 0 (first iteration: beta = 0): qv is not read — it may hold anything (bicg_init_kernel does not clear it)
-            if (va) { const double w = (coef != 0.0) ? pro.r[ia] + coef * pro.qv[ia] : pro.r[ia]; if (e <= N) pro.w[ia] = w; xa = pro.a ? (pro.a[ia] - abar) * w : w; }
-            if (vb) { const double w = (coef != 0.0) ? pro.r[ib] + coef * pro.qv[ib] : pro.r[ib]; if (e <= N) pro.w[ib] = w; xb = pro.a ? (pro.a[ib] - abar) * w : w; }
-            v[r] = make_double2(xa, xb);
-#endif
-        }
-    }
-#ifdef VCH_ROW_PROLOGUE_V2
-    if (!SOLVE && XM != 3 && pro.mode != 0) {
+    } else if (!SOLVE && pro.mode != 0) {
+        // 7-launch iteration (slab mode, and the reference form the 6-launch one is tested against): p = r + beta q / s = r - alpha v
+        // recomputed where the mirror image is needed, written once
         const Scal* sc = pro.sc;
         const double coef = (pro.mode == 1) ? (sc->rho_new / sc->rho) * (sc->alpha / sc->omega) : -sc->alpha;
         row_prologue_load<LOG2L>(v, pro.r, pro.qv, pro.a, pro.w, coef, sc->abar, va, vb, (size_t)la * in_ls, (size_t)lb * in_ls, t, N, in_es);
+    } else {
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            const int e = t + r * tpf;
+            const int off = (e <= N ? e : Lf - e) * in_es;
+            if (SOLVE) {
+                v[r] = va ? *reinterpret_cast<const double2*>(pa + off) : make_double2(0.0, 0.0);
+            } else {
+                v[r].x = va ? pa[off] : 0.0;
+                v[r].y = vb ? pb[off] : 0.0;
+            }
+        }
     }
-#endif
     fft_first_pass_store(data, v, t);
     fft_middle<LOG2L>(data, t, tw);
     double2 z[8];
@@ -554,12 +538,7 @@ dct_fft_kernel(const double* in, double* out, int nlines, int n, int in_ls, int 
             const int kf = (kk <= N) ? kk : Lf - kk;
             const double le = lam_elem[kf];
             const double s1 = le + lla, s2 = le + llb;
-#ifdef VCH_FAST_SYMBOL   // EXPERIMENTAL (not yet run on a GPU): reciprocal + multiply instead of two IEEE divisions per point — the 16
-                         // divisions per thread are ~30 % of this kernel's FP64 instructions; the factor changes by <= 1 ulp
-            double f1 = norm * __drcp_rn(sc0 + s1 * (abar + sc2 * s1)), f2 = norm * __drcp_rn(sc0 + s2 * (abar + sc2 * s2));
-#else
             double f1 = norm / (sc0 + s1 * (abar + sc2 * s1)), f2 = norm / (sc0 + s2 * (abar + sc2 * s2));
-#endif
             if (scale_mode == 1) { f1 *= s1; f2 *= s2; }
             v[FftOut<LOG2L>::q(i)] = make_double2(z[i].x * f1, z[i].y * f2);   // static permutation into first-pass order
         }
@@ -569,70 +548,35 @@ dct_fft_kernel(const double* in, double* out, int nlines, int n, int in_ls, int 
         fft_last_pass<LOG2L>(data, t, tw, z);
     }
 
-    double acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;
-#ifdef VCH_BICG6
-    double acc4 = 0.0, acc5 = 0.0;
-#endif
-    const double* ra = epi.rvec + (size_t)la * out_ls;
-    const double* rb_ = epi.rvec + (size_t)lb * out_ls;
-    double* qa = out + (size_t)la * out_ls;
-    double* qb = out + (size_t)lb * out_ls;
-    const double* oa = epi.other + (size_t)la * out_ls;
-    const double* ob = epi.other + (size_t)lb * out_ls;
-    const double* da = epi.addend + (size_t)la * out_ls;
-    const double* db = epi.addend + (size_t)lb * out_ls;
+    double acc1 = 0.0, acc2 = 0.0, acc3 = 0.0, acc4 = 0.0, acc5 = 0.0;
     const double eabar = epi.mul_a ? epi.sc->abar : 0.0;
+    if (SOLVE || XM == 1) {
+        double* qa = out + (size_t)la * out_ls;
 #pragma unroll
-    for (int q = 0; q < 8; ++q) {
-        const int kk = t + FftOut<LOG2L>::off(q);
-        if (kk <= N) {
-            const int off = kk * out_es;
-            if (!SOLVE && XM == 1) {   // slab mode: transposing store into the owning peer's buffer
-                int r = kk >> sct.shift; if (r >= sct.nr) r = sct.nr - 1;
-                const int kl = kk - (r << sct.shift);
-                double* dst = sct.peer[r] + sct.off;
-                if (va) dst[(size_t)(sct.base + la) * sct.pitch + kl] = z[q].x;
-                if (vb) dst[(size_t)(sct.base + lb) * sct.pitch + kl] = z[q].y;
-            } else if (SOLVE) {
-                if (va) *reinterpret_cast<double2*>(qa + off) = make_double2(z[q].x, vb ? z[q].y : 0.0);
-            } else {
-#ifndef VCH_ROW_PROLOGUE_V2
-                if (va) {
-                    const double zx = epi.mul_a ? (epi.mul_a[(size_t)la * out_ls + off] - eabar) * z[q].x : z[q].x;
-                    const double o = epi.addend ? zx + da[off] : zx;
-                    qa[off] = o;
-                    if (epi.mode) { acc1 += oa[off] * o; acc2 += o * o; if (epi.rvec) acc3 += ra[off] * o; }
-#ifdef VCH_BICG6
-                    if (epi.mode == 4) { const double sv = oa[off]; acc4 += sv * sv; acc5 += ra[off] * sv; }
-#endif
+        for (int q = 0; q < 8; ++q) {
+            const int kk = t + FftOut<LOG2L>::off(q);
+            if (kk <= N) {
+                if (!SOLVE) {   // slab mode: transposing store into the owning peer's buffer
+                    int r = kk >> sct.shift; if (r >= sct.nr) r = sct.nr - 1;
+                    const int kl = kk - (r << sct.shift);
+                    double* dst = sct.peer[r] + sct.off;
+                    if (va) dst[(size_t)(sct.base + la) * sct.pitch + kl] = z[q].x;
+                    if (vb) dst[(size_t)(sct.base + lb) * sct.pitch + kl] = z[q].y;
+                } else {
+                    if (va) *reinterpret_cast<double2*>(qa + kk * out_es) = make_double2(z[q].x, vb ? z[q].y : 0.0);
                 }
-                if (vb) {
-                    const double zy = epi.mul_a ? (epi.mul_a[(size_t)lb * out_ls + off] - eabar) * z[q].y : z[q].y;
-                    const double o = epi.addend ? zy + db[off] : zy;
-                    qb[off] = o;
-                    if (epi.mode) { acc1 += ob[off] * o; acc2 += o * o; if (epi.rvec) acc3 += rb_[off] * o; }
-#ifdef VCH_BICG6
-                    if (epi.mode == 4) { const double sv = ob[off]; acc4 += sv * sv; acc5 += rb_[off] * sv; }
-#endif
-                }
-#endif
             }
         }
-    }
-#ifdef VCH_ROW_PROLOGUE_V2
-    if (!SOLVE && XM != 1)
+    } else {
         row_epilogue_store<LOG2L>(z, out, epi.addend, epi.other, epi.rvec, epi.mul_a, eabar, epi.mode, va, vb, (size_t)la * out_ls,
-                                  (size_t)lb * out_ls, t, N, out_es, acc1, acc2, acc3);
-#endif
-#ifdef VCH_BICG6
-    if (epi.mode == 4) {
+                                  (size_t)lb * out_ls, t, N, out_es, acc1, acc2, acc3, acc4, acc5);
+    }
+    if (epi.mode == 4) {     // block-uniform: every thread of every CTA takes part in the reduction
         double vals[5] = {acc1, acc2, acc3, acc4, acc5};
         const int op[5] = {0, 0, 0, 0, 0};
         double tot[5];
         if (grid_reduce<5>(vals, op, epi.part, epi.ticket, tot) && threadIdx.x == 0) dots_finish6(epi, tot);
-    } else
-#endif
-    if (epi.mode) {     // block-uniform: every thread of every CTA takes part in the reduction
+    } else if (epi.mode) {
         double vals[3] = {acc1, acc2, acc3};
         const int op[3] = {0, 0, 0};
         double tot[3];

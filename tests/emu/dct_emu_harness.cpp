@@ -1,5 +1,5 @@
 // CPU run of the DCT / BiCGStab-fused transform kernels (csrc/vch_dct.cuh) under tests/emu/cuda_emu.h — TEST INFRASTRUCTURE.
-// Built twice by tests/test_kernel_emulation.py (default and -DVCH_ROW_PROLOGUE_V2 -DVCH_FAST_SYMBOL); each binary runs the same
+// Built by tests/test_kernel_emulation.py; the binary runs the same
 // seeded cases and writes every output array to a file.  The test compares the default build with NumPy/SciPy (so the kernels'
 // logic is pinned on the CPU) and the experimental build with the default build.
 //   usage: dct_emu_harness <log2L: 6|7> <out.bin>
