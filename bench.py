@@ -35,6 +35,11 @@ UNIT = "it/s"
 BYTES_PER_NODE = {
     "op_apply_fwd": 24, "op_apply_adj": 24,            # read x, a; write y
     "dct_rows_fft": 16, "dct_cols_fft_solve": 16,      # read + write the field once
+    "rows16": 16, "cols16_solve": 16,                  # radix-16 kernels (vch_fft16.cuh): same accounting
+    "rows16_pro": 64,                                  # average of mode 2 (read r, v, a; write s, transform = 40) and mode 3
+                                                       # (read s, t, p, v, x, a; write x, r, p, transform = 80): one of each per iteration
+    "rows16_epi1": 40, "rows16_epi4": 40,              # read transform, addend (= other), r0 / r; write v | t
+    "bicg_close_kernel": 32,
     "dct_rows_fft_pro": 40,                            # read r, q|v, a; write p|s and the transform
     "dct_rows_fft_epi1": 40, "dct_rows_fft_epi2": 24,  # read transform input, addend (, r0, r); write v|t
     "residual_kernel": 56,                             # read phi, mu, cphi, cmu; write Rphi, Rmu, a

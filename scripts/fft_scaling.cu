@@ -1,5 +1,6 @@
 // Scratch probe (not part of the product): is the row / column transform latency- or throughput-bound?  Times the kernels
 // in a CUDA graph for 1, 2, 3, 4 CTAs per SM (number of lines varied), N = 1024.
+#define VCH_FFT16_TIMING 1
 #include "../sparse-optimal-control-of-viscous-chan-hilliard-via-gradient-descent--1d-2d_b200/csrc/vch_dct.cuh"
 #include <functional>
 namespace vch { static thread_local std::string g_err; void set_last_error(const std::string& m) { g_err = m; } }
@@ -51,7 +52,51 @@ int main() {
                 sy, norm, 0, RowPrologue(), DotEpilogue(), nullptr, Scatter());
         });
     }
-    bench("full apply", 1025, [&] { plan.apply(s, a, a, sy, nullptr); });
+    bench("full apply (old)", 1025, [&] { plan.lean = false; plan.apply(s, a, a, sy, nullptr); });
+    // ---- radix-16 kernels (vch_fft16.cuh)
+    using G = F16<11>;
+    for (int lines : {2, 148, 296, 592, 888, 1025}) {
+        const int grid = ((lines + 1) / 2 + G::fpb - 1) / G::fpb;
+        bench("rows16 plain", lines, [&] {
+            rows16_kernel<11, 0, 0, false><<<grid, G::rthreads, G::rows_smem_plain, s>>>(a, b, lines, n1, P, plan.inner.tw16, RowPrologue(), DotEpilogue(), nullptr);
+        });
+    }
+    for (int cols : {8, 1025}) {
+        const int grid = (cols + 2 * G::cp - 1) / (2 * G::cp);
+        bench("cols16 solve", cols, [&] {
+            cols16_kernel<11><<<grid, G::cthreads, G::cols_smem_bytes, s>>>(b, P, cols, plan.outer.tw16, plan.inner.lam, plan.outer.lam, sy, norm, 0, nullptr);
+        });
+    }
+    bench("full apply (fft16)", 1025, [&] { plan.lean = true; plan.apply(s, a, a, sy, nullptr); });
+    {   // fused modes, in graph
+        double* w[8]; for (auto& p : w) { cudaMalloc(&p, n * 8); cudaMemcpy(p, h.data(), n * 8, cudaMemcpyHostToDevice); }
+        RedBuf red; red.alloc(8 * 4096, Comm());
+        unsigned int* ticket; cudaMalloc(&ticket, 4); cudaMemset(ticket, 0, 4);
+        Scal* sc; cudaMalloc(&sc, sizeof(Scal)); Scal hs{}; hs.alpha = 0.7; hs.omega = 0.9; hs.rho = 1.0; hs.rho_new = 0.8; hs.abar = 7.0; hs.iters = 1; hs.thr2 = 0.0; hs.rr = 1.0; hs.maxit = 1 << 30;
+        cudaMemcpy(sc, &hs, sizeof(Scal), cudaMemcpyHostToDevice);
+        const int grid = ((n1 + 1) / 2 + G::fpb - 1) / G::fpb;
+        RowPrologue p2{2, w[0], w[1], w[2], w[3], sc};
+        RowPrologue p3{3, w[0], w[1], w[2], w[3], sc}; p3.s = w[4]; p3.t = w[5]; p3.x = w[6]; p3.rw = w[0];
+        bench("rows16 pro2 mul", 1025, [&] { rows16_kernel<11, 2, 0, true><<<grid, G::rthreads, G::rows_smem_staged, s>>>(a, b, n1, n1, P, plan.inner.tw16, p2, DotEpilogue(), nullptr); });
+        bench("rows16 pro3 mul", 1025, [&] { rows16_kernel<11, 3, 0, true><<<grid, G::rthreads, G::rows_smem_staged, s>>>(a, b, n1, n1, P, plan.inner.tw16, p3, DotEpilogue(), nullptr); });
+        DotEpilogue e1{1, w[1], sc, red.part, ticket, w[2], nullptr, w[3]};
+        DotEpilogue e4{4, w[1], sc, red.part, ticket, w[1], nullptr, w[3]};
+        bench("rows16 epi1", 1025, [&] { rows16_kernel<11, 0, 1, false><<<grid, G::rthreads, G::rows_smem_plain, s>>>(b, w[7], n1, P, n1, plan.inner.tw16, RowPrologue(), e1, nullptr); });
+        bench("rows16 epi4", 1025, [&] { rows16_kernel<11, 0, 4, false><<<grid, G::rthreads, G::rows_smem_plain, s>>>(b, w[7], n1, P, n1, plan.inner.tw16, RowPrologue(), e4, nullptr); });
+        DotEpilogue e1n = e1; e1n.rvec = nullptr;
+        bench("rows16 epi1 no r", 1025, [&] { rows16_kernel<11, 0, 1, false><<<grid, G::rthreads, G::rows_smem_plain, s>>>(b, w[7], n1, P, n1, plan.inner.tw16, RowPrologue(), e1n, nullptr); });
+    }
+    {   // phase stamps of the column solve (block 0, thread 0), one launch on an idle GPU and one with the full grid
+        for (int cols : {8, 1025}) {
+            const int grid = (cols + 2 * F16<11>::cp - 1) / (2 * F16<11>::cp);
+            for (int w = 0; w < 10; ++w)
+                cols16_kernel<11><<<grid, F16<11>::cthreads, F16<11>::cols_smem_bytes, s>>>(b, P, cols, plan.outer.tw16, plan.inner.lam, plan.outer.lam, sy, norm, 0, nullptr);
+            cudaStreamSynchronize(s);
+            long long st[32]; cudaMemcpyFromSymbol(st, vch_dbg_clock, sizeof(st));
+            printf("cols16 phases (%d cols), cycles: stage-in %lld | load+first %lld | middle %lld | last %lld | factor+sync %lld | inverse fft %lld | stage-out write %lld | store %lld | total %lld\n",
+                   cols, st[1] - st[0], st[2] - st[1], st[3] - st[2], st[4] - st[3], st[5] - st[4], st[6] - st[5], st[7] - st[6], st[8] - st[7], st[8] - st[0]);
+        }
+    }
     printf("done %s\n", cudaGetErrorString(cudaDeviceSynchronize()));
     return 0;
 }

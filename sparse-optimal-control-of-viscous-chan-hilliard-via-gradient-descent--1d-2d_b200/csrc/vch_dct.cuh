@@ -28,6 +28,7 @@ struct DctAxis {
     bool fft = false;     // N is a power of two, 32 <= N <= 4096
     int Lf = 0, log2L = 0;
     double2* tw = nullptr;    // Lf twiddles exp(-2 pi i m / Lf)
+    double2* tw16 = nullptr;  // per-pass twiddle tables of the radix-16 kernels (vch_fft16.cuh)
     double* denseT = nullptr; // n*n, denseT[j*n + k] = 2 c_j cos(pi j k / N)   (transposed for coalescing)
     double* lam = nullptr;    // n eigenvalues of -L1d (>= 0)
 };
@@ -152,6 +153,7 @@ struct DctPlan {
     DevBuf tmp1, tmp2;
     LaunchLog* log = nullptr;
     bool pdl = false;         // launch the transform kernels with programmatic stream serialization (see launch_pdl)
+    bool lean = true;         // radix-16 kernels of vch_fft16.cuh where they apply (VCH_FFT16=0: the round-1 kernels everywhere)
     DctSlab slab;             // slab mode: no = global rows; the plan transforms the owned rows / columns only
     void init(int no_, int ni_, double h_outer, double h_inner, LaunchLog* launch_log);
     void init_slab(int n_global, double h_outer, double h_inner, LaunchLog* launch_log, const DctSlab& sl);
@@ -584,6 +586,10 @@ dct_fft_kernel(const double* in, double* out, int nlines, int n, int in_ls, int 
     }
 }
 
+}  // namespace vch
+#include "vch_fft16.cuh"
+namespace vch {
+
 // Dense-table fallbacks for N that is not a power of two (small validation grids).
 __global__ void dct_rows_dense_kernel(const double* __restrict__ in, double* __restrict__ out, int lines, int n,
                                       const double* __restrict__ Tt, const int* __restrict__ done) {
@@ -692,6 +698,9 @@ static inline void dct_axis_init(DctAxis& ax, int n, double h) {
         }
         VCH_CUDA(cudaMalloc(&ax.tw, ax.Lf * sizeof(double2)));
         VCH_CUDA(cudaMemcpy(ax.tw, tw.data(), ax.Lf * sizeof(double2), cudaMemcpyHostToDevice));
+        const std::vector<double2> t16 = fft16_twiddles(ax.log2L);
+        VCH_CUDA(cudaMalloc(&ax.tw16, t16.size() * sizeof(double2)));
+        VCH_CUDA(cudaMemcpy(ax.tw16, t16.data(), t16.size() * sizeof(double2), cudaMemcpyHostToDevice));
     } else {
         std::vector<double> T((size_t)n * n);
         for (int j = 0; j < n; ++j)
@@ -733,7 +742,7 @@ inline void DctPlan::init(int no_, int ni_, double h_outer, double h_inner, Laun
     no = no_; ni = ni_; log = launch_log;
     dct_axis_init(inner, ni, h_inner);
     dct_axis_init(outer, no, h_outer);
-    pitch = (ni + 3) & ~3;
+    pitch = (ni + 7) & ~7;        // whole column groups of the column kernels (8 columns per CTA); padding columns stay zero
     tmp1.alloc((size_t)no * pitch);
     VCH_CUDA(cudaMemset(tmp1.p, 0, (size_t)no * pitch * sizeof(double)));
     tmp2.alloc((size_t)no * ni);
@@ -752,6 +761,30 @@ inline void DctPlan::init(int no_, int ni_, double h_outer, double h_inner, Laun
         }
     }
 #undef VCH_FFT_ATTR
+#define VCH_F16_ATTR1(K, BYTES) VCH_CUDA(cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(BYTES)));
+#define VCH_F16_ATTR(LG)                                                                          \
+    VCH_F16_ATTR1((rows16_kernel<LG, 0, 0, false>), F16<LG>::rows_smem_plain)                    \
+    VCH_F16_ATTR1((rows16_kernel<LG, 2, 0, false>), F16<LG>::rows_smem_staged)                     \
+    VCH_F16_ATTR1((rows16_kernel<LG, 2, 0, true>), F16<LG>::rows_smem_staged)                      \
+    VCH_F16_ATTR1((rows16_kernel<LG, 3, 0, false>), F16<LG>::rows_smem_staged)                     \
+    VCH_F16_ATTR1((rows16_kernel<LG, 3, 0, true>), F16<LG>::rows_smem_staged)                      \
+    VCH_F16_ATTR1((rows16_kernel<LG, 0, 1, false>), F16<LG>::rows_smem_plain)                    \
+    VCH_F16_ATTR1((rows16_kernel<LG, 0, 1, true>), F16<LG>::rows_smem_plain)                     \
+    VCH_F16_ATTR1((rows16_kernel<LG, 0, 4, false>), F16<LG>::rows_smem_plain)                    \
+    VCH_F16_ATTR1((rows16_kernel<LG, 0, 4, true>), F16<LG>::rows_smem_plain)                     \
+    VCH_F16_ATTR1((cols16_kernel<LG>), F16<LG>::cols_smem_bytes)
+    if (inner.fft && outer.fft) {
+        if (getenv("VCH_FFT16")) lean = atoi(getenv("VCH_FFT16")) != 0;
+        for (const DctAxis* ax : {&inner, &outer}) {
+            switch (ax->log2L) {
+                case 6: VCH_F16_ATTR(6) break; case 7: VCH_F16_ATTR(7) break; case 8: VCH_F16_ATTR(8) break; case 9: VCH_F16_ATTR(9) break;
+                case 10: VCH_F16_ATTR(10) break; case 11: VCH_F16_ATTR(11) break; case 12: VCH_F16_ATTR(12) break; case 13: VCH_F16_ATTR(13) break;
+                default: break;
+            }
+        }
+    } else lean = false;
+#undef VCH_F16_ATTR
+#undef VCH_F16_ATTR1
 }
 
 // Slab mode: square global grid n_global x n_global (N = n_global - 1 a power of two), T1/T2 carved from the arena by the caller.
@@ -837,6 +870,60 @@ inline void DctPlan::apply(cudaStream_t s, const double* in, double* out, const 
     const int cppb = outer.fft ? dct_cols_ppb(outer, ni) : 0, cthreads = outer.fft ? cppb * (outer.Lf >> 3) : 0;
     const int cgrid = outer.fft ? ((ni + 1) / 2 + cppb - 1) / cppb : 0;
 
+    if (all_fft && lean && (pro.mode == 0 || pro.mode == 2 || pro.mode == 3) && (epi.mode == 0 || epi.mode == 1 || epi.mode == 4)) {
+        // radix-16 kernels (vch_fft16.cuh), one instantiation per fused mode: rows (prologue) -> column solve -> rows (epilogue)
+        const bool pd = pdl;
+        const bool mul_pro = pro.mode != 0 && pro.a != nullptr, mul_epi = epi.mode != 0 && epi.mul_a != nullptr;
+        log->begin(pro.mode ? "rows16_pro" : "rows16", s);
+#define VCH_R16_FWD(LG)                                                                                                                   \
+        case LG: {                                                                                                                        \
+            using G = F16<LG>;                                                                                                            \
+            const int grid = ((no + 1) / 2 + G::fpb - 1) / G::fpb;                                                                        \
+            if (pro.mode == 0) launch_pdl(pd, rows16_kernel<LG, 0, 0, false>, grid, G::rthreads, G::rows_smem_plain, s, in, t1, no, ni, P, inner.tw16, pro, DotEpilogue(), done); \
+            else if (pro.mode == 2 && mul_pro) launch_pdl(pd, rows16_kernel<LG, 2, 0, true>, grid, G::rthreads, G::rows_smem_staged, s, in, t1, no, ni, P, inner.tw16, pro, DotEpilogue(), done); \
+            else if (pro.mode == 2) launch_pdl(pd, rows16_kernel<LG, 2, 0, false>, grid, G::rthreads, G::rows_smem_staged, s, in, t1, no, ni, P, inner.tw16, pro, DotEpilogue(), done); \
+            else if (mul_pro) launch_pdl(pd, rows16_kernel<LG, 3, 0, true>, grid, G::rthreads, G::rows_smem_staged, s, in, t1, no, ni, P, inner.tw16, pro, DotEpilogue(), done); \
+            else launch_pdl(pd, rows16_kernel<LG, 3, 0, false>, grid, G::rthreads, G::rows_smem_staged, s, in, t1, no, ni, P, inner.tw16, pro, DotEpilogue(), done); \
+        } break;
+        switch (inner.log2L) {
+            VCH_R16_FWD(6) VCH_R16_FWD(7) VCH_R16_FWD(8) VCH_R16_FWD(9) VCH_R16_FWD(10) VCH_R16_FWD(11) VCH_R16_FWD(12) VCH_R16_FWD(13)
+            default: throw Error(VCH_E_ARG, "unsupported FFT length");
+        }
+#undef VCH_R16_FWD
+        log->end(s);
+        log->begin("cols16_solve", s);
+#define VCH_C16(LG)                                                                                                                       \
+        case LG: {                                                                                                                        \
+            using G = F16<LG>;                                                                                                            \
+            const int grid = (ni + 2 * G::cp - 1) / (2 * G::cp);                                                                          \
+            launch_pdl(pd, cols16_kernel<LG>, grid, G::cthreads, G::cols_smem_bytes, s, t1, P, ni, outer.tw16, inner.lam, outer.lam, sym, norm, scale_mode, done); \
+        } break;
+        switch (outer.log2L) {
+            VCH_C16(6) VCH_C16(7) VCH_C16(8) VCH_C16(9) VCH_C16(10) VCH_C16(11) VCH_C16(12) VCH_C16(13)
+            default: throw Error(VCH_E_ARG, "unsupported FFT length");
+        }
+#undef VCH_C16
+        log->end(s);
+        log->begin(epi.mode == 1 ? "rows16_epi1" : (epi.mode == 4 ? "rows16_epi4" : "rows16"), s);
+#define VCH_R16_INV(LG)                                                                                                                   \
+        case LG: {                                                                                                                        \
+            using G = F16<LG>;                                                                                                            \
+            const int grid = ((no + 1) / 2 + G::fpb - 1) / G::fpb;                                                                        \
+            if (epi.mode == 0) launch_pdl(pd, rows16_kernel<LG, 0, 0, false>, grid, G::rthreads, G::rows_smem_plain, s, t1, out, no, P, ni, inner.tw16, RowPrologue(), epi, done); \
+            else if (epi.mode == 1 && mul_epi) launch_pdl(pd, rows16_kernel<LG, 0, 1, true>, grid, G::rthreads, G::rows_smem_plain, s, t1, out, no, P, ni, inner.tw16, RowPrologue(), epi, done); \
+            else if (epi.mode == 1) launch_pdl(pd, rows16_kernel<LG, 0, 1, false>, grid, G::rthreads, G::rows_smem_plain, s, t1, out, no, P, ni, inner.tw16, RowPrologue(), epi, done); \
+            else if (mul_epi) launch_pdl(pd, rows16_kernel<LG, 0, 4, true>, grid, G::rthreads, G::rows_smem_plain, s, t1, out, no, P, ni, inner.tw16, RowPrologue(), epi, done); \
+            else launch_pdl(pd, rows16_kernel<LG, 0, 4, false>, grid, G::rthreads, G::rows_smem_plain, s, t1, out, no, P, ni, inner.tw16, RowPrologue(), epi, done); \
+        } break;
+        switch (inner.log2L) {
+            VCH_R16_INV(6) VCH_R16_INV(7) VCH_R16_INV(8) VCH_R16_INV(9) VCH_R16_INV(10) VCH_R16_INV(11) VCH_R16_INV(12) VCH_R16_INV(13)
+            default: throw Error(VCH_E_ARG, "unsupported FFT length");
+        }
+#undef VCH_R16_INV
+        log->end(s);
+        VCH_CUDA(cudaGetLastError());
+        return;
+    }
     if (all_fft) {
         // rows (prologue fused) -> fused column solve in place on the pitched buffer -> rows (addend + dots fused)
         log->begin(pro.mode ? "dct_rows_fft_pro" : "dct_rows_fft", s);
@@ -882,6 +969,8 @@ inline void DctPlan::apply(cudaStream_t s, const double* in, double* out, const 
 inline void DctPlan::destroy() {
     for (DctAxis* ax : {&inner, &outer}) {
         if (ax->tw) cudaFree(ax->tw);
+        if (ax->tw16) cudaFree(ax->tw16);
+        ax->tw16 = nullptr;
         if (ax->denseT) cudaFree(ax->denseT);
         if (ax->lam) cudaFree(ax->lam);
         ax->tw = nullptr; ax->denseT = nullptr; ax->lam = nullptr;

@@ -1,0 +1,445 @@
+// Lean DCT-I transform kernels (round 2): radix-16 Stockham FFT, 16 points per thread, everything a compile-time function of
+// the FFT length, one kernel instantiation per fused mode.
+//
+// Why a second kernel family: measured on B200 (profiles/r02_fft_scaling_before.txt, r02_latency_probe.txt) the round-1 kernel
+// (vch_dct.cuh, dct_fft_kernel) is INSTRUCTION-ISSUE bound, not HBM-, FP64- or launch-bound: 1300-1850 instructions per thread
+// per 2048-point FFT against ~560 of FP64 work (runtime strides and line counts, per-element validity branches, twiddles
+// rebuilt from factored tables, one kernel body carrying every prologue / epilogue mode — with spills under its 64-register
+// cap); a single CTA needs 4.7 us for its load -> 4 passes -> store chain and every further CTA on the same SM adds 1.8 us.
+// Kernel boundaries inside a CUDA graph cost 0.7 us, so nothing is gained by fusing further — the instructions have to go:
+//   * 16 points per thread, passes 16 x 16 x {2,4,8,16}: 2 shared-memory exchanges per 2048-point FFT instead of 3;
+//   * N, the thread count, the pass structure, the padded shared-memory offsets and the even-extension index reflection are
+//     compile-time (the mirrored index of input slot r >= 8 is N - t - (r-8)*tpf: no comparison per element);
+//   * twiddles are read from per-pass tables (w^(k r) stored r-major, so a warp reads consecutive entries), not rebuilt;
+//   * the fused BiCGStab prologues (6-launch iteration: RowPrologue modes 2 and 3) touch every element once and hand the
+//     transform input over through shared memory (even extension applied on the read), the epilogues (DotEpilogue modes 1
+//     and 4) are separate instantiations: no mode branch, no spill, restrict-qualified pointers;
+//   * the column solve stages its strided 32-byte row segments (4 adjacent columns per CTA) through shared memory in and
+//     out, computes the spectral factor for the N+1 distinct spectrum entries only (the mirrored half of the inverse
+//     transform's input is read back from shared memory) with one reciprocal per entry.
+// The round-1 kernel remains for slab mode (transposing stores / gathering loads over NVLink), for the 7-launch iteration
+// (VCH_BICG6=0) and nothing else; grids whose N is not a power of two use the dense-table kernels as before.
+#pragma once
+
+namespace vch {
+
+#ifdef VCH_FFT16_TIMING     // scripts/fft_scaling.cu only: clock64 stamps of block 0 / thread 0 at the phase boundaries
+__device__ long long vch_dbg_clock[32];
+#define VCH_STAMP(i) do { if (blockIdx.x == 0 && threadIdx.x == 0) vch_dbg_clock[i] = clock64(); } while (0)
+#else
+#define VCH_STAMP(i) do { } while (0)
+#endif
+
+__device__ __forceinline__ int padi16(int i) { return i + (i >> 4); }
+
+// L1 is cold at every kernel start, so the first twiddle load of each pass would cost an exposed L2 round trip (measured in
+// the column solve: ~2500 cycles for a middle pass that issues in ~700).  Every thread prefetches the table lines it is going to
+// read while its first global loads are in flight.
+__device__ __forceinline__ void prefetch_l1(const void* p) {
+#ifndef VCH_CPU_EMU
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+#else
+    (void)p;
+#endif
+}
+
+
+template <int LOG2L> struct F16 {
+    static_assert(LOG2L >= 6 && LOG2L <= 13, "FFT length 2N with 32 <= N <= 4096");
+    static constexpr int Lf = 1 << LOG2L, N = Lf / 2, tpf = Lf / 16;        // tpf: threads per FFT (16 points each)
+    static constexpr int rem = LOG2L % 4, n16 = LOG2L / 4;
+    static constexpr int lastR = rem == 0 ? 16 : (1 << rem);                  // radix of the last pass
+    static constexpr int npass = rem == 0 ? n16 : n16 + 1;
+    static constexpr int mids = npass - 2;                                    // radix-16 passes strictly between first and last
+    static constexpr int lastNs = Lf / lastR;
+    static constexpr int NB = 16 / lastR;                                     // butterflies per thread in the last pass
+    static constexpr int ld = Lf + Lf / 16;                                   // padded FFT buffer, double2 entries
+    static constexpr bool fold = (tpf % 16) == 0;                             // padded offsets fold into immediates
+    static constexpr int tw_mid1 = 0, tw_mid2 = 15 * 16;                        // table offsets (double2 entries) of the middle passes
+    static constexpr int tw_last_off = mids == 0 ? 0 : (mids == 1 ? 15 * 16 : 15 * 16 + 15 * 256);
+    static constexpr int tw_total = tw_last_off + (lastR - 1) * lastNs;
+    // row kernels: fpb line pairs per CTA (>= 128 threads);  column kernel: cp column pairs per CTA
+    static constexpr int fpb = tpf >= 128 ? 1 : 128 / tpf;
+    static constexpr int rthreads = fpb * tpf;
+    // cp: as many adjacent columns per CTA as shared memory allows — the strided row segments of the pitched buffer are what
+    // limits the column kernel (measured: one 32-byte request per ~3.2 cycles per SM), and a segment of 2*cp doubles is one request
+    static constexpr int cp = LOG2L <= 11 ? 4 : (LOG2L == 12 ? 2 : 1);
+    static constexpr int cthreads = cp * tpf;
+    static constexpr int sst = N + 2;                                         // stage stride per column pair (N + 2 = 2 mod 8: conflict-free staging stores)
+    static constexpr int rminb = 512 / rthreads > 4 ? 4 : (512 / rthreads > 0 ? 512 / rthreads : 1);
+    static constexpr int cminb = 512 / cthreads > 4 ? 4 : (512 / cthreads > 0 ? 512 / cthreads : 1);
+    static constexpr size_t rows_smem_plain = sizeof(double2) * (size_t)fpb * ld;
+    static constexpr size_t rows_smem_staged = sizeof(double2) * (size_t)fpb * (ld + N + 1);
+    static constexpr size_t cols_smem_bytes = sizeof(double2) * (size_t)cp * (ld + sst);
+};
+
+template <int LOG2L>
+__device__ __forceinline__ void fft16_prefetch_twiddles(const double2* __restrict__ tw, int t) {
+    using G = F16<LOG2L>;
+    // a 128-byte line holds 8 entries: one prefetch per line, spread over the threads of the FFT
+    constexpr int lines = (G::tw_total + 7) / 8;
+    for (int l = t; l < lines; l += G::tpf) prefetch_l1(tw + 8 * l);
+}
+
+// first-pass input slot r of thread t  <->  element t + r*tpf of the even extension  <->  stored element idx16(t, r) <= N
+template <int LOG2L> __device__ __forceinline__ int idx16(int t, int r) {
+    using G = F16<LOG2L>;
+    return r < 8 ? t + r * G::tpf : G::N - t - (r - 8) * G::tpf;
+}
+
+// ---- 16-point DFT (forward sign), 4 x 4:  n = c + 4m, k = r + 4s:  w16^(nk) = w4^(mr) w16^(cr) w4^(cs)
+template <> __device__ __forceinline__ void dft<16>(double2 (&v)[16]) {
+    const double C = 0.92387953251128675613, S = 0.38268343236508977173, h = 0.70710678118654752440;
+    double2 a[4][4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        double2 x[4] = {v[c], v[c + 4], v[c + 8], v[c + 12]};
+        dft<4>(x);
+#pragma unroll
+        for (int r = 0; r < 4; ++r) a[c][r] = x[r];
+    }
+    // multiply a[c][r] by w16^(c r), w16 = exp(-i pi/8)
+    auto w1 = [&](double2 z) { return make_double2(z.x * C + z.y * S, z.y * C - z.x * S); };      // (C, -S)
+    auto w2 = [&](double2 z) { return make_double2(h * (z.x + z.y), h * (z.y - z.x)); };          // (h, -h)
+    auto w3 = [&](double2 z) { return make_double2(z.x * S + z.y * C, z.y * S - z.x * C); };      // (S, -C)
+    auto w6 = [&](double2 z) { return make_double2(h * (z.y - z.x), -h * (z.x + z.y)); };         // (-h, -h)
+    auto w9 = [&](double2 z) { return make_double2(-(z.x * C + z.y * S), z.x * S - z.y * C); };   // (-C, S)
+    a[1][1] = w1(a[1][1]); a[1][2] = w2(a[1][2]); a[1][3] = w3(a[1][3]);
+    a[2][1] = w2(a[2][1]); a[2][2] = mul_mi(a[2][2]); a[2][3] = w6(a[2][3]);
+    a[3][1] = w3(a[3][1]); a[3][2] = w6(a[3][2]); a[3][3] = w9(a[3][3]);
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        double2 y[4] = {a[0][r], a[1][r], a[2][r], a[3][r]};
+        dft<4>(y);
+#pragma unroll
+        for (int s = 0; s < 4; ++s) v[r + 4 * s] = y[s];
+    }
+}
+
+// ---- passes.  Stockham autosort: butterfly j of a radix-R pass with Ns = product of the earlier radices reads
+// j + r*(Lf/R), multiplies by w^(k r Lf/(Ns R)), k = j mod Ns, and writes (j - k) R + k + r Ns.
+template <int LOG2L>
+__device__ __forceinline__ void fft16_first_store(double2* data, double2 (&v)[16], int t) {
+    dft<16>(v);
+    double2* dst = data + 17 * t;                 // padi16(16 t + r) = 17 t + r
+#pragma unroll
+    for (int r = 0; r < 16; ++r) dst[r] = v[r];
+    __syncthreads();
+}
+
+template <int LOG2L, int NS>
+__device__ __forceinline__ void fft16_mid_pass(double2* data, int t, const double2* __restrict__ twp) {
+    using G = F16<LOG2L>;
+    static_assert(G::fold, "a middle pass exists only for Lf >= 512");
+    double2 v[16], w[15];
+    const int k = t & (NS - 1);
+#pragma unroll
+    for (int r = 1; r < 16; ++r) w[r - 1] = __ldg(&twp[(r - 1) * NS + k]);
+    const double2* src = data + padi16(t);
+#pragma unroll
+    for (int r = 0; r < 16; ++r) v[r] = src[r * (G::tpf + G::tpf / 16)];
+#pragma unroll
+    for (int r = 1; r < 16; ++r) v[r] = cmul(v[r], w[r - 1]);
+    dft<16>(v);
+    __syncthreads();
+    double2* dst = data + padi16((t - k) * 16 + k);
+#pragma unroll
+    for (int r = 0; r < 16; ++r) dst[r * (NS + NS / 16)] = v[r];
+    __syncthreads();
+}
+
+template <int LOG2L>
+__device__ __forceinline__ void fft16_middle(double2* data, int t, const double2* __restrict__ tw) {
+    using G = F16<LOG2L>;
+    if constexpr (G::mids >= 1) fft16_mid_pass<LOG2L, 16>(data, t, tw + G::tw_mid1);
+    if constexpr (G::mids >= 2) fft16_mid_pass<LOG2L, 256>(data, t, tw + G::tw_mid2);
+}
+
+// Last pass: output slot q = m + r*NB of thread t is element t + q*tpf in natural order — the same convention as the
+// first-pass input slots, so a following transform (column solve) takes the registers as they are.
+template <int LOG2L>
+__device__ __forceinline__ void fft16_last_pass(const double2* data, int t, const double2* __restrict__ tw, double2 (&z)[16]) {
+    using G = F16<LOG2L>;
+    constexpr int R = G::lastR, NB = G::NB;
+    const double2* twl = tw + G::tw_last_off;
+#pragma unroll
+    for (int m = 0; m < NB; ++m) {
+        const int j = t + m * G::tpf;
+        double2 v[R], w[R - 1];
+#pragma unroll
+        for (int r = 1; r < R; ++r) w[r - 1] = __ldg(&twl[(r - 1) * G::lastNs + j]);
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const int q = m + r * NB;
+            v[r] = G::fold ? data[padi16(t) + q * (G::tpf + G::tpf / 16)] : data[padi16(t + q * G::tpf)];
+        }
+#pragma unroll
+        for (int r = 1; r < R; ++r) v[r] = cmul(v[r], w[r - 1]);
+        dft<R>(v);
+#pragma unroll
+        for (int r = 0; r < R; ++r) z[m + r * NB] = v[r];
+    }
+}
+
+// ---- fused BiCGStab prologues of the 6-launch iteration.  Every element of the two lines is touched by exactly one thread;
+// the transform input goes to stage[e] = (line a, line b).  Pointers are restrict-qualified parameters: each vector that is
+// written is distinct from every vector that is only read (enqueue_bicg_iteration); x and p are updated in place.
+template <int LOG2L, bool MUL>
+__device__ __forceinline__ void pro16_mode2(double2* __restrict__ stage, const double* __restrict__ r, const double* __restrict__ vv,
+                                            const double* __restrict__ a, double* __restrict__ s, double al, double abar,
+                                            size_t ba, size_t bb, bool va, bool vb, int t) {
+    using G = F16<LOG2L>;
+    auto elem = [&](int e) {       // s = r - alpha v;  x_in = (a - abar) s
+        const double ra = r[ba + e], rb = r[bb + e], qa = vv[ba + e], qb = vv[bb + e];
+        const double aa = MUL ? a[ba + e] : 0.0, ab = MUL ? a[bb + e] : 0.0;
+        const double sa = ra - al * qa, sb = rb - al * qb;
+        if (va) s[ba + e] = sa;
+        if (vb) s[bb + e] = sb;
+        stage[e] = make_double2(MUL ? (aa - abar) * sa : sa, MUL ? (ab - abar) * sb : sb);
+    };
+#pragma unroll
+    for (int q = 0; q < 8; ++q) elem(t + q * G::tpf);
+    if (t == 0) elem(G::N);
+}
+template <int LOG2L, bool MUL>
+__device__ __forceinline__ void pro16_mode3_first(double2* __restrict__ stage, const double* __restrict__ r, const double* __restrict__ a,
+                                                  double* __restrict__ p, double abar, size_t ba, size_t bb, bool va, bool vb, int t) {
+    using G = F16<LOG2L>;
+    auto elem = [&](int e) {       // first iteration of a solve: p = r (x = 0 already)
+        const double pa = r[ba + e], pb = r[bb + e];
+        const double aa = MUL ? a[ba + e] : 0.0, ab = MUL ? a[bb + e] : 0.0;
+        if (va) p[ba + e] = pa;
+        if (vb) p[bb + e] = pb;
+        stage[e] = make_double2(MUL ? (aa - abar) * pa : pa, MUL ? (ab - abar) * pb : pb);
+    };
+#pragma unroll
+    for (int q = 0; q < 8; ++q) elem(t + q * G::tpf);
+    if (t == 0) elem(G::N);
+}
+template <int LOG2L, bool MUL>
+__device__ __forceinline__ void pro16_mode3(double2* __restrict__ stage, const double* __restrict__ s, const double* __restrict__ tt,
+                                            const double* __restrict__ vv, const double* __restrict__ a, double* __restrict__ p,
+                                            double* __restrict__ x, double* __restrict__ rw, double al, double om, double beta,
+                                            double abar, size_t ba, size_t bb, bool va, bool vb, int t) {
+    using G = F16<LOG2L>;
+    auto elem = [&](int e) {       // r = s - omega t;  x += alpha p + omega s;  p = r + beta (p - omega v);  x_in = (a - abar) p
+        const double sa = s[ba + e], sb = s[bb + e], ta = tt[ba + e], tb = tt[bb + e];
+        const double pa = p[ba + e], pb = p[bb + e], qa = vv[ba + e], qb = vv[bb + e];
+        const double xa = x[ba + e], xb = x[bb + e];
+        const double aa = MUL ? a[ba + e] : 0.0, ab = MUL ? a[bb + e] : 0.0;
+        const double ra = sa - om * ta, rb = sb - om * tb;
+        const double na = ra + beta * (pa - om * qa), nb = rb + beta * (pb - om * qb);
+        if (va) { x[ba + e] = xa + (al * pa + om * sa); rw[ba + e] = ra; p[ba + e] = na; }
+        if (vb) { x[bb + e] = xb + (al * pb + om * sb); rw[bb + e] = rb; p[bb + e] = nb; }
+        stage[e] = make_double2(MUL ? (aa - abar) * na : na, MUL ? (ab - abar) * nb : nb);
+    };
+#pragma unroll
+    for (int q = 0; q < 8; ++q) elem(t + q * G::tpf);
+    if (t == 0) elem(G::N);
+}
+
+// ---- fused epilogue: out = [(mul_a - abar)] z + addend and the BiCGStab dot products (DotEpilogue modes 1 and 4)
+template <int LOG2L, int EPI, bool MUL>
+__device__ __forceinline__ void epi16_store(const double2 (&z)[16], double* __restrict__ out, const double* __restrict__ addend,
+                                            const double* __restrict__ other, const double* __restrict__ rvec,
+                                            const double* __restrict__ mul_a, double abar, size_t ba, size_t bb, bool va, bool vb,
+                                            int t, double (&acc)[5]) {
+    using G = F16<LOG2L>;
+    const bool has_r = EPI == 4 || rvec != nullptr;
+    auto elem = [&](int e, double2 zz) {
+        if (EPI == 0) {
+            if (va) out[ba + e] = zz.x;
+            if (vb) out[bb + e] = zz.y;
+            return;
+        }
+        const double da = addend[ba + e], db = addend[bb + e], oa = other[ba + e], ob = other[bb + e];
+        const double ma = MUL ? mul_a[ba + e] : 0.0, mb = MUL ? mul_a[bb + e] : 0.0;
+        const double ra = has_r ? rvec[ba + e] : 0.0, rb = has_r ? rvec[bb + e] : 0.0;
+        const double xo = (MUL ? (ma - abar) * zz.x : zz.x) + da, yo = (MUL ? (mb - abar) * zz.y : zz.y) + db;
+        if (va) {
+            out[ba + e] = xo;
+            acc[0] += oa * xo; acc[1] += xo * xo; acc[2] += ra * xo;
+            if (EPI == 4) { acc[3] += oa * oa; acc[4] += ra * oa; }
+        }
+        if (vb) {
+            out[bb + e] = yo;
+            acc[0] += ob * yo; acc[1] += yo * yo; acc[2] += rb * yo;
+            if (EPI == 4) { acc[3] += ob * ob; acc[4] += rb * ob; }
+        }
+    };
+#pragma unroll
+    for (int q = 0; q < 8; ++q) elem(t + q * G::tpf, z[q]);
+    if (t == 0) elem(G::N, z[8]);
+}
+
+// ---- row kernel: one CTA = fpb line pairs; line l at base + l*ls, contiguous elements.
+//   PRO 0: x = in;  2: s = r - alpha v;  3: deferred x/r update + new p  (RowPrologue);   MUL: multiply by (a - abar) on this side
+//   EPI 0: plain store;  1 / 4: addend + dot products (DotEpilogue)
+template <int LOG2L, int PRO, int EPI, bool MUL>
+__global__ void __launch_bounds__(F16<LOG2L>::rthreads, F16<LOG2L>::rminb)
+rows16_kernel(const double* __restrict__ in, double* __restrict__ out, int nlines, int in_ls, int out_ls,
+              const double2* __restrict__ tw, RowPrologue pro, DotEpilogue epi, const int* __restrict__ done) {
+    pdl_enter();
+    using G = F16<LOG2L>;
+    if (done && *done) return;
+#ifdef VCH_CPU_EMU
+    double2* sm = reinterpret_cast<double2*>(vch_emu::dynamic_smem());
+#else
+    extern __shared__ double2 sm[];
+#endif
+    const int f = G::fpb == 1 ? 0 : threadIdx.x / G::tpf, t = threadIdx.x - f * G::tpf;
+    double2* data = sm + (size_t)f * G::ld;
+    const int la = 2 * (blockIdx.x * G::fpb + f), lb = la + 1;
+    const bool va = la < nlines, vb = lb < nlines;
+    // absent lines (odd line count, idle FFT slots of the last CTA) read line 0 and are never written
+    const size_t ia = (size_t)(va ? la : 0) * in_ls, ib = (size_t)(vb ? lb : 0) * in_ls;
+    double2 v[16];
+    if (PRO == 0) {
+#pragma unroll
+        for (int r = 0; r < 16; ++r) { const int e = idx16<LOG2L>(t, r); v[r] = make_double2(in[ia + e], in[ib + e]); }
+    } else {
+        double2* stage = sm + (size_t)G::fpb * G::ld + (size_t)f * (G::N + 1);
+        const Scal* sc = pro.sc;
+        const double al = sc->alpha, om = sc->omega, abar = sc->abar;
+        if (PRO == 2) pro16_mode2<LOG2L, MUL>(stage, pro.r, pro.qv, pro.a, pro.w, al, abar, ia, ib, va, vb, t);
+        else if (sc->iters == 0) pro16_mode3_first<LOG2L, MUL>(stage, pro.r, pro.a, pro.w, abar, ia, ib, va, vb, t);
+        else pro16_mode3<LOG2L, MUL>(stage, pro.s, pro.t, pro.qv, pro.a, pro.w, pro.x, pro.rw, al, om, (sc->rho_new / sc->rho) * (al / om),
+                                      abar, ia, ib, va, vb, t);
+        __syncthreads();
+#pragma unroll
+        for (int r = 0; r < 16; ++r) v[r] = stage[idx16<LOG2L>(t, r)];
+    }
+    fft16_first_store<LOG2L>(data, v, t);
+    fft16_middle<LOG2L>(data, t, tw);
+    double2 z[16];
+    fft16_last_pass<LOG2L>(data, t, tw, z);
+
+    double acc[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+    const size_t oa = (size_t)(va ? la : 0) * out_ls, ob = (size_t)(vb ? lb : 0) * out_ls;
+    epi16_store<LOG2L, EPI, MUL>(z, out, epi.addend, epi.other, epi.rvec, epi.mul_a, MUL && EPI ? epi.sc->abar : 0.0, oa, ob, va, vb, t, acc);
+    if (EPI == 4) {          // every thread of every CTA takes part in the reduction
+        const int op[5] = {0, 0, 0, 0, 0};
+        double tot[5];
+        if (grid_reduce<5>(acc, op, epi.part, epi.ticket, tot) && threadIdx.x == 0) dots_finish6(epi, tot);
+    } else if (EPI == 1) {
+        double vals[3] = {acc[0], acc[1], acc[2]};
+        const int op[3] = {0, 0, 0};
+        double tot[3];
+        if (grid_reduce<3>(vals, op, epi.part, epi.ticket, tot) && threadIdx.x == 0) dots_finish(epi, tot);
+    }
+}
+
+// ---- column solve, in place on the pitched buffer: forward transform -> spectral factor -> inverse transform.
+// One CTA = cp column pairs = 2*cp adjacent columns (64-byte row segments for cp = 4; the buffer's pitch is a multiple of 8 and
+// its padding columns hold zeros, so no column is ever absent).  A pair (c, c+1) is one complex FFT: Re = column c.
+template <int LOG2L>
+__global__ void __launch_bounds__(F16<LOG2L>::cthreads, F16<LOG2L>::cminb)
+cols16_kernel(double* __restrict__ buf, int pitch, int ncols, const double2* __restrict__ tw, const double* __restrict__ lam_col,
+              const double* __restrict__ lam_row, SymbolArgs sy, double norm, int scale_mode, const int* __restrict__ done) {
+    pdl_enter();
+    using G = F16<LOG2L>;
+    constexpr int CP = G::cp, N = G::N;
+    if (done && *done) return;
+#ifdef VCH_CPU_EMU
+    double2* sm = reinterpret_cast<double2*>(vch_emu::dynamic_smem());
+#else
+    extern __shared__ double2 sm[];
+#endif
+    const int f = CP == 1 ? 0 : threadIdx.x / G::tpf, t = threadIdx.x - f * G::tpf;
+    double2* data = sm + (size_t)f * G::ld;
+    double2* stage_all = sm + (size_t)CP * G::ld;                 // [CP][sst]
+    double2* stage = stage_all + (size_t)f * G::sst;
+    const int c0 = 2 * CP * blockIdx.x;                           // first column of this CTA
+    double* base = buf + c0;
+    VCH_STAMP(0);
+    // stage in: CP consecutive threads fetch the CP double2 of one row segment (2*CP doubles, contiguous), every segment once;
+    // the trip count is compile-time so that all loads are in flight together
+    constexpr int NSEG = (N + 1) * CP, NIT = (NSEG + G::cthreads - 1) / G::cthreads;
+    {
+        double2 p[NIT];
+#pragma unroll
+        for (int i = 0; i < NIT; ++i) {
+            const int idx = threadIdx.x + i * G::cthreads;
+            if (idx < NSEG) p[i] = *reinterpret_cast<const double2*>(base + (size_t)(idx / CP) * pitch + 2 * (idx % CP));
+        }
+        fft16_prefetch_twiddles<LOG2L>(tw, t);
+#pragma unroll
+        for (int i = 0; i < NIT; ++i) {
+            const int idx = threadIdx.x + i * G::cthreads;
+            if (idx < NSEG) stage_all[(idx % CP) * G::sst + idx / CP] = p[i];
+        }
+    }
+    // eigenvalues of the 9 spectrum entries this thread scales (slots 0..7, slot 8 for thread 0), fetched early
+    double lrow[9];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) lrow[q] = lam_row[t + q * G::tpf];
+    lrow[8] = lam_row[N];
+    __syncthreads();
+    VCH_STAMP(1);
+    double2 v[16], z[16];
+#pragma unroll
+    for (int r = 0; r < 16; ++r) v[r] = stage[idx16<LOG2L>(t, r)];
+    fft16_first_store<LOG2L>(data, v, t);                        // (its barrier also ends the reads of the stage)
+    VCH_STAMP(2);
+    fft16_middle<LOG2L>(data, t, tw);
+    VCH_STAMP(3);
+    fft16_last_pass<LOG2L>(data, t, tw, z);
+    VCH_STAMP(4);
+    {   // spectral factor on the N+1 distinct entries (slots 0..7, and slot 8 of thread 0); the mirrored half of the next
+        // transform's input is read back from the stage, which also makes the spectrum exactly even
+        const double abar = sy.abar_ptr ? *sy.abar_ptr : sy.abar_const;
+        const double k0 = sy.coef_ptr ? sy.coef_ptr[0] : sy.c0, k2 = sy.coef_ptr ? sy.coef_ptr[1] : sy.c2;
+        const int ca = c0 + 2 * f, cb = ca + 1;
+        const double lca = lam_col[ca < ncols ? ca : ncols - 1], lcb = lam_col[cb < ncols ? cb : ncols - 1];
+        auto elem = [&](int e, double le, double2 zz) {
+            const double s1 = le + lca, s2 = le + lcb;
+            const double d1 = k0 + s1 * (abar + k2 * s1), d2 = k0 + s2 * (abar + k2 * s2);
+            const double inv = norm * __drcp_rn(d1 * d2);        // one reciprocal for both columns
+            double f1 = inv * d2, f2 = inv * d1;
+            if (scale_mode == 1) { f1 *= s1; f2 *= s2; }
+            stage[e] = make_double2(zz.x * f1, zz.y * f2);
+        };
+#pragma unroll
+        for (int q = 0; q < 8; ++q) elem(t + q * G::tpf, lrow[q], z[q]);
+        if (t == 0) elem(N, lrow[8], z[8]);
+    }
+    __syncthreads();
+    VCH_STAMP(5);
+#pragma unroll
+    for (int r = 0; r < 16; ++r) v[r] = stage[idx16<LOG2L>(t, r)];
+    fft16_first_store<LOG2L>(data, v, t);
+    fft16_middle<LOG2L>(data, t, tw);
+    fft16_last_pass<LOG2L>(data, t, tw, z);
+    VCH_STAMP(6);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) stage[t + q * G::tpf] = z[q];
+    if (t == 0) stage[N] = z[8];
+    __syncthreads();
+    VCH_STAMP(7);
+#pragma unroll
+    for (int i = 0; i < NIT; ++i) {
+        const int idx = threadIdx.x + i * G::cthreads;
+        if (idx < NSEG) *reinterpret_cast<double2*>(base + (size_t)(idx / CP) * pitch + 2 * (idx % CP)) = stage_all[(idx % CP) * G::sst + idx / CP];
+    }
+    VCH_STAMP(8);
+}
+
+// host: per-pass twiddle tables for the length Lf = 2^log2L, layout as F16<LOG2L>::tw_* describes
+static inline std::vector<double2> fft16_twiddles(int log2L) {
+    const int Lf = 1 << log2L, rem = log2L % 4, n16 = log2L / 4;
+    const int lastR = rem == 0 ? 16 : (1 << rem), npass = rem == 0 ? n16 : n16 + 1, mids = npass - 2, lastNs = Lf / lastR;
+    std::vector<double2> tab;
+    auto w = [&](long long m) {
+        const long double a = -2.0L * 3.14159265358979323846264338327950288L * (long double)(m % Lf) / Lf;
+        return make_double2((double)cosl(a), (double)sinl(a));
+    };
+    int ns = 16;
+    for (int p = 1; p <= mids; ++p, ns *= 16)
+        for (int r = 1; r < 16; ++r)
+            for (int k = 0; k < ns; ++k) tab.push_back(w((long long)k * r * (Lf / (ns * 16))));
+    for (int r = 1; r < lastR; ++r)
+        for (int k = 0; k < lastNs; ++k) tab.push_back(w((long long)k * r));
+    return tab;
+}
+
+}  // namespace vch

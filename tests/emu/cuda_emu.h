@@ -203,6 +203,7 @@ inline void __threadfence() {}
 inline void __threadfence_block() {}
 inline void __threadfence_system() {}
 template <typename T> inline T __ldcg(const T* p) { return *p; }
+template <typename T> inline T __ldg(const T* p) { return *p; }
 inline unsigned int atomicAdd(unsigned int* p, unsigned int v) { const unsigned int o = *p; *p = o + v; return o; }
 inline double __dmul_rn(double a, double b) { volatile double r = a * b; return r; }
 inline double __dadd_rn(double a, double b) { volatile double r = a + b; return r; }
