@@ -9,8 +9,11 @@ default physics/weights of the reference's 2D config.py, synthetic targets built
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--n 1024] [--horizon 1000]
 
 N > 1 (torchrun, one rank per GPU): every rank owns an independent control problem of the same size (the path shards
-across problems with no data-path collective; slab decomposition of one grid is DESIGN.md's next row) -> "weak" scaling;
-the timed region is bracketed by barriers and the max over ranks is reported.
+across problems with no data-path collective) -> "weak" scaling; the timed region is bracketed by barriers and the max over
+ranks is reported.  The same line also carries `slab_4096`: ONE 4096^2 problem row-slab decomposed over all ranks (BASELINE
+config 5, strong scaling) next to the single-GPU time of the same problem measured by rank 0 on the same box, and, at N = 1,
+`parity_vs_strict` (full-horizon parity of the timed solver settings against the tightest solver) and `cpu_baseline` with a
+measured same-config CPU/GPU pair.
 """
 import argparse
 import json
@@ -101,25 +104,102 @@ def dt_sequence(T, dt):
     return np.array(out)
 
 
-# ------------------------------------------------------------------------------------------------ CPU arm (oracle port)
-def cpu_sample(sizes=(128, 256), target_n=1024, horizon=1000):
-    """Time the reference algorithm (oracle port: SciPy SuperLU solves, same formulas) for one forward CN step and one
-    adjoint step at each grid in `sizes`, fit t ~ nodes^p, extrapolate one PGD iteration at target_n^2 x horizon."""
+# ------------------------------------------------------------------------------------------------ CPU arm
+# The reference's own CPU implementation of the path, timed on the host cores of the box.  SuperLU (scipy.sparse.linalg.spsolve,
+# Forward2_solver.py:370, backward2_solver.py:229) is sequential, so one core does the work whatever the machine has; the BLAS
+# thread count is reported for completeness.  kind = "reference": the UNMODIFIED modules imported from /root/reference (build
+# container only — the tree does not exist on the GPU box); kind = "port": oracle/vch_oracle.py, the restatement pinned to the
+# reference by tests/test_oracle_golden.py.  A full 1024^2 horizon is ~55 h of SuperLU (one factorisation ~10 min), so the
+# number at the metric's config is an extrapolation from measured per-step times at 128^2, 256^2 and 384^2 (power law in the
+# node count, least squares over the three points) and is labelled as one; next to it stands a MEASURED complete PGD iteration
+# at the reference's default grid (config 2, shortened horizon) that the GPU arm repeats on the same config.
+def blas_threads():
+    try:
+        from threadpoolctl import threadpool_info
+        return max([int(d.get("num_threads", 1)) for d in threadpool_info()] or [1])
+    except Exception:
+        return None
+
+
+def _fit_power(points):
+    """Least-squares power law t = c * nodes^p through (nodes, seconds) points."""
+    x = np.log([a for a, _ in points]); y = np.log([b for _, b in points])
+    p, lc = np.polyfit(x, y, 1)
+    return float(p), float(np.exp(lc))
+
+
+def cpu_port_iteration(n=128, M=10):
+    """One COMPLETE optimistic PGD iteration (adjoint + prox + forward + cost) of the oracle port at n^2 x M, from u0 = 0."""
     import vch_oracle as O
-    pts = []
-    for n in sizes:
-        P = O.Phys2D(Nx=n, Ny=n)
-        tf, ta, nsolve = O.time_step_sample_2d(P, n_steps=1)
-        pts.append(((n + 1) ** 2, tf + ta, tf, ta, nsolve))
-    if len(pts) > 1:
-        p = float(np.log(pts[-1][1] / pts[0][1]) / np.log(pts[-1][0] / pts[0][0]))
+    P, Op = O.Phys2D(Nx=n, Ny=n, T=M * 1e-2), O.Opt2D()
+    fw = O.forward_2d(P)                                             # set-up (untimed): the uncontrolled trajectory
+    phiT, phiQ = O.targets_2d(fw["x"], fw["y"], fw["t"], fw["phi"][0], P.Lx, P.Ly, P.T)
+    t0 = time.perf_counter()
+    un, fw1, J, r = O.pgd_iter_2d(P, Op, np.zeros_like(fw["phi"]), fw["phi"], fw["t"], fw["x"], fw["y"], phiQ, phiT, Op.alpha_max)
+    return time.perf_counter() - t0, float(J)
+
+
+def cpu_reference_iteration(n=128, M=20):
+    """The same through the UNMODIFIED reference (GD2_configured.py:299-313), when /root/reference is present."""
+    import contextlib, io
+    ref = "/root/reference/src/2D/Vch_control_2D"
+    sys.path.insert(0, os.path.join(ROOT, "oracle", "_mpl_shim")); sys.path.insert(0, ref)
+    os.environ.setdefault("NUMBA_CACHE_DIR", "/tmp/numba_cache_bench")
+    cwd = os.getcwd(); os.chdir("/tmp")
+    try:
+        import Forward2_solver as F, backward2_solver as B, cost2_and_function as C, GD2_configured as G
+        from config import ForwardSolverConfig, OptimizationConfig
+        cfg, opt = ForwardSolverConfig(Nx=n, Ny=n, T=M * 1e-2), OptimizationConfig()
+        with contextlib.redirect_stdout(io.StringIO()):
+            phi, (x, y), t = F.run_main_simulation(cfg, store_history=True, control_input=None, verbose=False)   # set-up + Numba JIT
+            phiT, phiQ = G.build_targets(x, y, t, phi[0].copy(), cfg.Lx, cfg.Ly, cfg.T, False, 1, 1)
+            u = np.zeros_like(phi)
+            t0 = time.perf_counter()
+            p, q, r = B.run_backward(phi, x, y, t, cfg, opt.b1, opt.b2, phiQ, phiT)
+            u1 = C.proximal_step(u, C.calculate_gradient(r, u, opt), opt.alpha_max, opt)
+            phi1, _, _ = F.run_main_simulation(cfg, store_history=True, control_input=u1, verbose=False)
+            J = C.calculate_cost(phi1, u1, phiQ, phiT, x, y, t, opt)
+            dt = time.perf_counter() - t0
+        return dt, float(J)
+    finally:
+        os.chdir(cwd)
+
+
+def cpu_arm(target_n, horizon, full, prefer_reference):
+    """(it/s at target_n^2 x horizon [extrapolated], cpu_baseline dict).  full: the longer sample of --impl reference."""
+    import vch_oracle as O
+    M0 = 20 if full else 10
+    kind = "port"
+    if prefer_reference and os.path.isdir("/root/reference/src/2D/Vch_control_2D"):
+        try:
+            t_it, J = cpu_reference_iteration(128, M0)
+            kind = "reference"
+        except Exception as exc:   # fall back to the port, say so
+            print(f"[bench] reference import failed ({exc!r}); using the oracle port", file=sys.stderr)
+            t_it, J = cpu_port_iteration(128, M0)
     else:
-        p = 1.5
-    per_step = pts[-1][1] * ((target_n + 1) ** 2 / pts[-1][0]) ** p
-    sec_per_iter = per_step * horizon
-    return 1.0 / sec_per_iter, {"points": [{"grid": f"{int(round(a ** 0.5)) - 1}^2", "fwd_step_s": round(c, 3), "adj_step_s": round(d, 3),
-                                            "newton_solves": e} for a, _, c, d, e in pts],
-                                "exponent": round(p, 3), "sec_per_iteration_extrapolated": sec_per_iter}
+        t_it, J = cpu_port_iteration(128, M0)
+    pts = [(129 ** 2, t_it / M0)]
+    detail = {"config2_iteration": {"grid": "128^2", "steps": M0, "seconds": round(t_it, 3), "J": J,
+                                     "what": "one complete optimistic PGD iteration (adjoint sweep + gradient/prox + forward solve + cost), "
+                                             f"reference default grid and weights, horizon {M0} of the default 100 steps"}}
+    steps = []
+    for n in (256, 384):
+        tf, ta, ns = O.time_step_sample_2d(O.Phys2D(Nx=n, Ny=n), n_steps=1)
+        pts.append(((n + 1) ** 2, tf + ta))
+        steps.append({"grid": f"{n}^2", "fwd_step_s": round(tf, 3), "adj_step_s": round(ta, 3), "newton_solves": ns})
+    p, c = _fit_power(pts)
+    per_step = c * ((target_n + 1) ** 2) ** p
+    sec = per_step * horizon
+    detail.update({"single_step_samples": steps, "exponent": round(p, 3), "points_s_per_time_step": [[a, round(b, 4)] for a, b in pts],
+                   "sec_per_iteration_extrapolated": sec, "extrapolated": True})
+    base = {"value": 1.0 / sec, "unit": UNIT, "cores": 1, "kind": kind, "blas_threads": blas_threads(), "host_cpus": os.cpu_count(),
+            "sample": (f"{'unmodified reference' if kind == 'reference' else 'oracle port of the reference'} (SciPy SuperLU, sequential): one complete "
+                       f"PGD iteration at 128^2 x {M0} steps ({t_it:.1f} s, measured) + one forward and one adjoint time step at 256^2 and 384^2; "
+                       f"power law in nodes (exponent {p:.2f}) extrapolated to {target_n}^2 x {horizon} steps — a full horizon there is "
+                       f"~{sec / 3600:.0f} h of sparse LU"),
+            "detail": detail}
+    return 1.0 / sec, base
 
 
 def run_reference(args):
@@ -127,23 +207,186 @@ def run_reference(args):
     if rank != 0:
         return
     t0 = time.perf_counter()
-    vals, info = [], None
-    steps = max(1, min(args.steps, 2))
-    for _ in range(steps):
-        v, info = cpu_sample(target_n=args.n, horizon=args.horizon)
-        vals.append(v)
-    value = float(np.mean(vals))
-    sample = ("oracle port of the reference algorithm (SciPy SuperLU spsolve, 1 thread): 1 forward CN step (Newton to 1e-6) + "
-              "1 adjoint step at 128^2 and 256^2, power-law fit in nodes, extrapolated to "
-              f"{args.n}^2 x {args.horizon} steps; {steps} samples; exponent {info['exponent']}")
-    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+    value, base = cpu_arm(args.n, args.horizon, full=True, prefer_reference=True)
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": 1,
             "warmup": 0, "ms_per_step": 1e3 / value, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"2D {args.n}^2 grid, M={args.horizon} CN steps, reference 2D defaults, targets (1,1)"},
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample, "detail": info},
+            "config": {"workload": f"2D {args.n}^2 grid ({args.n+1}^2 nodes), M={args.horizon} CN steps (T={args.horizon*1e-2:g}), reference 2D defaults, "
+                                   "targets build_targets(1,1), optimistic PGD iteration from u0=0",
+                       "note": "one bounded CPU sample regardless of --steps/--warmup (see cpu_baseline.sample); the value at this config is extrapolated"},
+            "cpu_baseline": base,
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "wall_s": time.perf_counter() - t0}
     print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ B200 arm: extra legs
+def _targets(torch, hist0, x, t, T, dev, row0=0, rows=None):
+    """GD2_configured.build_targets(choice_t=1, choice_q=1) on the device (rows: slab of the x axis)."""
+    xs = x if rows is None else x[row0:row0 + rows]
+    xx, yy = torch.meshgrid(torch.from_numpy(xs).to(dev), torch.from_numpy(x).to(dev), indexing="ij")
+    phiT = (0.7 * torch.sin(2 * np.pi * xx) * torch.cos(np.pi * yy)).contiguous()
+    s = torch.from_numpy(t / T).to(dev)[:, None, None]
+    return phiT, ((1 - s) * hist0[0] + s * phiT).contiguous()
+
+
+def parity_vs_strict_leg(nat, F2, P, Op, N, M, dev):
+    """Full-horizon parity of the solver settings the timed steps use (forcing term 1e-6 on the first linear solve of each Newton
+    solve, forward half-step exit) against the tightest solver of the same library (every solve to 1e-13, no forcing term, no
+    half-step exit): uncontrolled forward -> adjoint -> prox -> forward under the new control -> cost, same inputs.
+    BASELINE tolerances: phi <= 1e-8, gradient and J <= 1e-7, identical support.  Both keep the fp64-floor Newton stop, without
+    which the reference's rule cannot terminate at >= 1024^2; profiles/r02_parity_study_* holds the wider study."""
+    import torch
+    dts = np.full(M, 1e-2)
+    t = np.concatenate([[0.0], np.minimum(np.cumsum(dts), P.T)])
+    x = np.linspace(0.0, 1.0, N + 1)
+    phi0 = torch.from_numpy(F2.init_phi_random(N, N, 1e-2, amp=0.1, seed=42)).to(dev)
+    keys = ("VCH_KRYLOV_FIRST_RTOL", "VCH_NO_HALF_EXIT", "VCH_KRYLOV_RTOL")
+    saved = {k: os.environ.get(k) for k in keys}
+
+    def run(env):
+        for k in keys:
+            os.environ.pop(k, None)
+        os.environ.update({k: v for k, v in saved.items() if v is not None})
+        os.environ.update(env)
+        c = nat.Ctx2D(N, N, 1.0 / N, 1.0 / N, 1.0, 1.0, P.tau, P.gamma, P.c1, P.c2, P.kappa, device=dev.index or 0)
+        h0, _, _ = c.forward(phi0, None, dts)
+        phiT, phiQ = _targets(torch, h0, x, t, P.T, dev)
+        r = torch.empty_like(h0)
+        u1, h1, J, _, st = c.pgd_iteration(torch.zeros_like(h0), h0, phiQ, phiT, t, dts, x, x, Op.b1, Op.b2, Op.b3, Op.kappa_sparsity,
+                                           Op.u_min, Op.u_max, Op.alpha_max, r_out=r)
+        torch.cuda.synchronize()
+        del c, phiQ
+        return {"phi0": h0, "r": r, "u1": u1, "phi1": h1, "J": float(J[0]), "its": int(st["krylov_iterations"])}
+
+    try:
+        a = run({})
+        b = run({"VCH_KRYLOV_RTOL": "1e-13", "VCH_KRYLOV_FIRST_RTOL": "0", "VCH_NO_HALF_EXIT": "1"})
+    finally:
+        for k in keys:
+            os.environ.pop(k, None)
+        os.environ.update({k: v for k, v in saved.items() if v is not None})
+    out = {"reference_solver": "same library, every linear solve to 1e-13, no forcing term, no half-step exit",
+           "workload": f"{N}^2 x {M} steps: forward(u=0), adjoint, prox(alpha_max), forward(u1), cost"}
+    for k in ("phi0", "r", "u1", "phi1"):
+        d = (a[k] - b[k]).flatten(1).norm(dim=1); nb = b[k].flatten(1).norm(dim=1).clamp_min(1e-300)
+        out[k] = {"rel_l2": float((a[k] - b[k]).norm() / b[k].norm().clamp_min(1e-300)), "worst_level_rel_l2": float((d / nb).max())}
+    out["support_mismatch"] = int(((a["u1"] != 0) != (b["u1"] != 0)).sum())
+    out["support_size"] = int((b["u1"] != 0).sum())
+    out["J_rel"] = abs(a["J"] - b["J"]) / abs(b["J"])
+    out["krylov_iterations"] = {"timed_settings": a["its"], "tightest": b["its"]}
+    out["pass"] = bool(out["phi0"]["rel_l2"] <= 1e-8 and out["phi1"]["rel_l2"] <= 1e-8 and out["r"]["rel_l2"] <= 1e-7
+                       and out["u1"]["rel_l2"] <= 1e-7 and out["J_rel"] <= 1e-7)
+    del a, b
+    torch.cuda.empty_cache()
+    return out
+
+
+def gpu_config2_iteration(nat, F2, Op, n, M, local):
+    """One complete PGD iteration at the reference's default grid (n = 128), M steps, from u0 = 0, through the C ABI with HOST
+    (NumPy) buffers — the same work cpu_port_iteration times on the CPU.  Returns (seconds, J)."""
+    import torch
+    from config import ForwardSolverConfig
+    P = ForwardSolverConfig(Nx=n, Ny=n, T=M * 1e-2)
+    c = nat.Ctx2D(n, n, 1.0 / n, 1.0 / n, 1.0, 1.0, P.tau, P.gamma, P.c1, P.c2, P.kappa, device=local)
+    dts = np.full(M, 1e-2)
+    t = np.concatenate([[0.0], np.cumsum(dts)])
+    x = np.linspace(0.0, 1.0, n + 1)
+    h0, _, _ = c.forward(F2.init_phi_random(n, n, 1e-2, amp=0.1, seed=42), None, dts)
+    X, Y = np.meshgrid(x, x, indexing="ij")
+    phiT = 0.7 * np.sin(2 * np.pi * X) * np.cos(np.pi * Y)
+    s = (t / P.T)[:, None, None]
+    phiQ = (1 - s) * h0[0] + s * phiT
+    u0 = np.zeros_like(h0)
+    best, J = None, None
+    for _ in range(3):
+        t0 = time.perf_counter()
+        _, _, Jv, _, _ = c.pgd_iteration(u0, h0, phiQ, phiT, t, dts, x, x, Op.b1, Op.b2, Op.b3, Op.kappa_sparsity, Op.u_min, Op.u_max, Op.alpha_max)
+        torch.cuda.synchronize()
+        dtw = time.perf_counter() - t0
+        best, J = (dtw if best is None else min(best, dtw)), float(Jv[0])
+    return best, J
+
+
+def slab_leg(nat, F2, P, Op, args, rank, world, local):
+    """BASELINE config 5 next to the headline number: ONE 4096^2 control problem, M = args.slab_horizon CN steps.
+    world > 1: the grid is row-slab decomposed over all ranks (slab mode: halo rows, DCT transposes and reduction partials travel
+    through peer memory over NVLink, no host collective in the step) and rank 0 ALSO runs the same problem alone on its GPU, so
+    the record holds the single-GPU time of the same box.  world == 1: the single-GPU time only."""
+    import torch
+    import torch.distributed as dist
+    Ns, Ms, dt = args.slab_n, args.slab_horizon, 1e-2
+    h = 1.0 / Ns
+    dev = torch.device("cuda", local)
+    dts = np.full(Ms, dt)
+    T = Ms * dt
+    t_hist = np.concatenate([[0.0], np.minimum(np.cumsum(dts), T)])
+    x = np.linspace(0.0, 1.0, Ns + 1)
+    phi_full = F2.init_phi_random(Ns, Ns, 1e-2, amp=0.1, seed=42)
+
+    def timed(ctx, r0, nr, group_barrier):
+        phi0 = torch.from_numpy(np.ascontiguousarray(phi_full[r0:r0 + nr])).to(dev)
+        ha, _, _ = ctx.forward(phi0, None, dts)
+        phiT, phiQ = _targets(torch, ha, x, t_hist, T, dev, r0, nr)
+        st = {"u": torch.zeros_like(ha), "h": ha, "un": torch.empty_like(ha), "hn": torch.empty_like(ha)}
+        rbuf = torch.empty_like(ha)
+        res = {}
+
+        def step():
+            _, _, J, _, s = ctx.pgd_iteration(st["u"], st["h"], phiQ, phiT, t_hist, dts, x, x, Op.b1, Op.b2, Op.b3, Op.kappa_sparsity,
+                                              Op.u_min, Op.u_max, Op.alpha_max, u_out=st["un"], phi_out=st["hn"], r_out=rbuf)
+            st["u"], st["un"] = st["un"], st["u"]; st["h"], st["hn"] = st["hn"], st["h"]
+            res["J"], res["stats"] = float(J[0]), s
+
+        step()                                   # warm-up (graphs, staging)
+        group_barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.slab_steps):
+            step()
+        e1.record()
+        group_barrier()
+        ms = e0.elapsed_time(e1) / args.slab_steps
+        return ms, res
+
+    def bar():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    out = {"workload": f"ONE 2D {Ns}^2 grid ({Ns+1}^2 nodes), M={Ms} CN steps, reference defaults, targets (1,1), chained optimistic PGD iterations",
+           "steps": args.slab_steps, "n_gpus": world}
+    try:
+        ms1 = None
+        if rank == 0:                             # single-GPU time of the same problem on this box
+            c1 = nat.Ctx2D(Ns, Ns, h, h, 1.0, 1.0, P.tau, P.gamma, P.c1, P.c2, P.kappa, device=local)
+            ms1, r1 = timed(c1, 0, Ns + 1, lambda: torch.cuda.synchronize())
+            out["one_gpu"] = {"ms_per_pgd_iteration": ms1, "ms_per_time_step": ms1 / Ms, "J": r1["J"],
+                              "krylov_iterations": int(r1["stats"]["krylov_iterations"]), "linear_solves": int(r1["stats"]["newton_linear_solves"])}
+            del c1
+            torch.cuda.empty_cache()
+        if world > 1:
+            bar()
+            cs = nat.SlabCtx2D.create_distributed(Ns, h, 1.0, P.tau, P.gamma, P.c1, P.c2, P.kappa, 1e-2, device=local)
+            msN, rN = timed(cs, cs.row0, cs.rows, bar)
+            tm = torch.tensor([msN], device=dev, dtype=torch.float64)
+            dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+            if rank == 0:
+                msN = float(tm.item())
+                out["slab"] = {"ms_per_pgd_iteration": msN, "ms_per_time_step": msN / Ms, "it_per_s": 1e3 / msN, "J": rN["J"], "rows_per_gpu": cs.rows,
+                               "krylov_iterations": int(rN["stats"]["krylov_iterations"]), "linear_solves": int(rN["stats"]["newton_linear_solves"]),
+                               "krylov_stalls": int(rN["stats"]["krylov_stalls"])}
+                out["speedup_vs_1gpu"] = ms1 / msN
+                out["efficiency"] = ms1 / msN / world
+                out["J_rel_diff_vs_1gpu"] = abs(rN["J"] - out["one_gpu"]["J"]) / abs(out["one_gpu"]["J"])
+                out["scaling"] = "strong"
+            del cs
+        else:
+            out["note"] = "single-GPU run: slab mode needs >= 2 ranks (its 2- and 4-rank parity tests are skipped on a 1-GPU box)"
+    except Exception as exc:      # report, do not hide
+        out["error"] = repr(exc)
+    torch.cuda.empty_cache()
+    return out if rank == 0 else None
 
 
 # ------------------------------------------------------------------------------------------------ B200 arm
@@ -151,7 +394,10 @@ def run_b200(args):
     import torch
     import torch.distributed as dist
     import vch_b200_native as nat
-    import vch_oracle as O
+    # problem set-up through the product's own drop-in modules (reference names): config defaults and the host-RNG initial field
+    sys.path.insert(0, os.path.join(PKG, "Vch_control_2D"))
+    import Forward2_solver as F2
+    from config import ForwardSolverConfig, OptimizationConfig
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -164,8 +410,9 @@ def run_b200(args):
     dev = torch.device("cuda", local)
 
     N, M, dt = args.n, args.horizon, 1e-2
-    P = O.Phys2D(Nx=N, Ny=N, T=M * dt)
-    Op = O.Opt2D()
+    P = ForwardSolverConfig(Nx=N, Ny=N, T=M * dt)
+    Op = OptimizationConfig()
+    parity = parity_vs_strict_leg(nat, F2, P, Op, N, M, dev) if (rank == 0 and not args.no_parity) else None
     ctx = nat.Ctx2D(N, N, 1.0 / N, 1.0 / N, 1.0, 1.0, P.tau, P.gamma, P.c1, P.c2, P.kappa, device=local)
     dts = np.full(M, dt)
     t_hist = np.concatenate([[0.0], np.minimum(np.cumsum(dts), P.T)])
@@ -175,7 +422,7 @@ def run_b200(args):
 
     # synthetic problem: reference IC (host RNG, Forward2_solver.py:444-486; seed differs per rank = independent problems),
     # uncontrolled forward solve, targets as GD2_configured.build_targets(choice_t=1, choice_q=1)
-    phi0 = torch.from_numpy(O.init_phi_2d(N, N, seed=42 + rank)).to(dev)
+    phi0 = torch.from_numpy(F2.init_phi_random(N, N, 1e-2, amp=0.1, seed=42 + rank)).to(dev)
     hist_a, _, _ = ctx.forward(phi0, None, dts)
     xx, yy = torch.meshgrid(torch.from_numpy(x).to(dev), torch.from_numpy(x).to(dev), indexing="ij")
     phiT = (0.7 * torch.sin(2 * np.pi * xx) * torch.cos(np.pi * yy)).contiguous()
@@ -343,14 +590,29 @@ def run_b200(args):
         except Exception as exc:   # report, do not hide
             e2e = {"value": None, "unit": UNIT, "error": repr(exc)}
 
+    # ---- BASELINE config 5 on the same box: ONE 4096^2 problem over all ranks (slab mode) next to its single-GPU time
+    slab = None
+    if not args.no_slab:
+        try:
+            del hist_a, hist_b, u_a, u_b, r_buf
+        except NameError:
+            pass
+        state.clear()
+        torch.cuda.empty_cache()
+        slab = slab_leg(nat, F2, P, Op, args, rank, world, local)
     if rank == 0:
         cpu = None
         if world == 1 and not args.no_cpu:
-            v, info = cpu_sample(target_n=N, horizon=M)
-            cpu = {"value": v, "unit": UNIT, "cores": 1, "kind": "port",
-                   "sample": "oracle port (SciPy SuperLU, 1 thread): 1 forward CN step + 1 adjoint step at 128^2 and 256^2, "
-                             f"power-law fit in nodes (exponent {info['exponent']}), extrapolated to {N}^2 x {M} steps",
-                   "detail": info}
+            _, cpu = cpu_arm(N, M, full=False, prefer_reference=False)
+            # the SAME config on the GPU, end to end with host buffers: a measured (not extrapolated) ratio
+            try:
+                it = cpu["detail"]["config2_iteration"]
+                gsec, gJ = gpu_config2_iteration(nat, F2, Op, 128, it["steps"], local)
+                cpu["same_config"] = {"workload": f"2D 128^2 (reference default grid), M={it['steps']}, one complete PGD iteration from u0=0, host buffers",
+                                      "cpu_s": it["seconds"], "gpu_s": round(gsec, 5), "ratio": round(it["seconds"] / gsec, 1),
+                                      "J_cpu": it["J"], "J_gpu": gJ, "J_rel_diff": abs(gJ - it["J"]) / abs(it["J"])}
+            except Exception as exc:
+                cpu["same_config"] = {"error": repr(exc)}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
                 "data": "synthetic",
@@ -360,6 +622,7 @@ def run_b200(args):
                            "newton": "reference rule + fp64-floor stop (DESIGN.md)", "krylov_rel_tol": 1e-11,
                            "krylov_first_solve_rel_tol": float(os.environ.get("VCH_KRYLOV_FIRST_RTOL", 1e-6))},
                 "gpu_launches": int(launches), "clocks": clocks, "e2e": e2e, "roofline": roof, "cpu_baseline": cpu,
+                "parity_vs_strict": parity, "slab_4096": slab,
                 "solver": {"linear_solves_per_iteration": agg["newton_linear_solves"] / args.steps,
                            "newton_residual_evals_per_time_step": agg["newton_residual_evals"] / (args.steps * M),
                            "krylov_its_per_solve": agg["krylov_iterations"] / max(1, agg["newton_linear_solves"]),
@@ -438,7 +701,9 @@ def run_slab2d(args):
     import torch
     import torch.distributed as dist
     import vch_b200_native as nat
-    import vch_oracle as O
+    sys.path.insert(0, os.path.join(PKG, "Vch_control_2D"))
+    import Forward2_solver as F2
+    from config import ForwardSolverConfig, OptimizationConfig
     rank, world, local = (int(os.environ.get(k, d)) for k, d in (("RANK", "0"), ("WORLD_SIZE", "1"), ("LOCAL_RANK", "0")))
     torch.cuda.set_device(local)
     if world > 1:
@@ -446,8 +711,8 @@ def run_slab2d(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
     N, M, dt = args.n, args.horizon, 1e-2
-    P = O.Phys2D(Nx=N, Ny=N, T=M * dt)
-    Op = O.Opt2D()
+    P = ForwardSolverConfig(Nx=N, Ny=N, T=M * dt)
+    Op = OptimizationConfig()
     h = 1.0 / N
     if world > 1:
         ctx = nat.SlabCtx2D.create_distributed(N, h, 1.0, P.tau, P.gamma, P.c1, P.c2, P.kappa, 1e-2, device=local)
@@ -458,7 +723,7 @@ def run_slab2d(args):
     dts = np.full(M, dt)
     t_hist = np.concatenate([[0.0], np.minimum(np.cumsum(dts), P.T)])
     x = np.linspace(0.0, 1.0, N + 1)
-    phi0 = torch.from_numpy(np.ascontiguousarray(O.init_phi_2d(N, N, seed=42)[r0:r0 + nr])).to(dev)   # every rank cuts the same global field
+    phi0 = torch.from_numpy(np.ascontiguousarray(F2.init_phi_random(N, N, 1e-2, amp=0.1, seed=42)[r0:r0 + nr])).to(dev)   # every rank cuts the same global field
     hist_a, _, _ = ctx.forward(phi0, None, dts)
     xx, yy = torch.meshgrid(torch.from_numpy(x[r0:r0 + nr]).to(dev), torch.from_numpy(x).to(dev), indexing="ij")
     phiT = (0.7 * torch.sin(2 * np.pi * xx) * torch.cos(np.pi * yy)).contiguous()
@@ -529,6 +794,11 @@ def main():
     ap.add_argument("--stream-budget-gb", type=float, default=0.0,
                     help="e2e leg: cap the device staging (vch2d_set_stream_budget) -> bounded-memory chunk-ring mode; 0 = whole trajectories")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the full-horizon parity_vs_strict leg")
+    ap.add_argument("--no-slab", action="store_true", help="skip the 4096^2 slab_4096 leg")
+    ap.add_argument("--slab-n", type=int, default=4096)
+    ap.add_argument("--slab-horizon", type=int, default=20)
+    ap.add_argument("--slab-steps", type=int, default=2)
     ap.add_argument("--workload", default="pgd2d", choices=["pgd2d", "ensemble1d", "slab2d"],
                     help="pgd2d = BASELINE metric (default); ensemble1d = config 4; slab2d = config 5 (one problem over all ranks)")
     ap.add_argument("--batch", type=int, default=1024, help="ensemble1d: number of problems")

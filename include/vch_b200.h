@@ -185,6 +185,28 @@ int vch2d_pgd_iteration(vch2d_ctx* c, int levels, const double* t_hist, const do
                         double* u_new_out, double* phi_hist_out, double* r_out,
                         double* J_out, double* red_out, vch_stats* stats, int mem);
 
+/* ---- trajectories that do not fit in HBM: checkpoint + recompute (BASELINE north_star (2); the reference keeps the whole
+ * trajectory in RAM, Forward2_solver.py:535-537, :583-585).  The state trajectory exists only as checkpoints (phi, mu, w) at the
+ * levels 0, S, 2S, ..., M (ncp = ceil(M / S) + 1 entries each, S = ckpt_stride, M = levels - 1):
+ *   ck_phi[j] = phi at level min(jS, M);  ck_mu[j] / ck_w[j] = mu / w after that many steps (entry 0: initialize_mu(phi_0, 0) and 0).
+ * vch2d_forward_ckpt      run_main_simulation that keeps only the checkpoints.
+ * vch2d_pgd_iteration_ckpt one optimistic PGD iteration (GD2_configured.py:299-313): the adjoint sweep walks the segments from the last
+ *   to the first, recomputing each from its checkpoint (same kernels, same order, deterministic reductions: the recomputed levels
+ *   are bit-identical to the ones the checkpoints came from) and applying gradient + prox to its levels at once; the forward solve
+ *   under the new control writes the new checkpoints and accumulates the cost per segment.  u, phiQ, u_new_out stay full
+ *   trajectories (levels, ...); r_out may be NULL (then r exists only for S + 1 levels at a time).  Results equal those of
+ *   vch2d_pgd_iteration on the fully stored trajectory bit for bit (u_new, r, checkpoints) resp. to the rounding of the segmented
+ *   cost sums (J).  Cost: one additional forward sweep per iteration; memory: 6 (M/S + 1) + 2 (S + 1) levels instead of 3 (M + 1). */
+int vch2d_forward_ckpt(vch2d_ctx* c, const double* phi0, const double* u, int u_rows, int n_steps, const double* dt_steps,
+                       int ckpt_stride, double* ck_phi_out, double* ck_mu_out, double* ck_w_out, vch_stats* stats, int mem);
+int vch2d_pgd_iteration_ckpt(vch2d_ctx* c, int levels, const double* t_hist, const double* dt_steps,
+                             const double* x, const double* y, const double* u,
+                             const double* ck_phi, const double* ck_mu, const double* ck_w, int ckpt_stride,
+                             const double* phiQ, const double* phiT,
+                             double b1, double b2, double b3, double kappa_sp, double u_min, double u_max, double alpha,
+                             double* u_new_out, double* ck_phi_out, double* ck_mu_out, double* ck_w_out, double* r_out,
+                             double* J_out, double* red_out, vch_stats* stats, int mem);
+
 /* ------------------------------------------------------------------ 1D (batched ensembles; batch = 1 is the reference call) */
 int  vch1d_create(const vch1d_params* p, int device, vch1d_ctx** out);
 void vch1d_destroy(vch1d_ctx* c);

@@ -44,6 +44,7 @@ struct vch2d_ctx {
     DevBuf phi, mu, phit, mut, w0, w1, cphi, cmu, Rphi, Rmu, a, RphiT, RmuT, aT;
     DevBuf kb, kx, kr, kr0, kp, kv, ks, kt, ktmp, kq, dmu;
     DevBuf adj_p[2], adj_q[2], adj_r[2], mu_old;
+    DevBuf ck_seg, ck_r;         // checkpointed sweep: phi levels of the segment being recomputed, ring of r levels
     DevBuf stage[7];             // device staging of the host-buffer PGD iteration, kept across calls (no 50 GB malloc/free per step)
     long long stream_budget = 0; // bytes of device staging the host-buffer path may use; 0 = whatever fits (vch2d_set_stream_budget)
     std::vector<double> r_host;  // host copy of the gradient trajectory for the bounded-memory path when the caller gives no r_out
@@ -468,34 +469,20 @@ struct LevelMap {
     std::function<double*(int)> hist, Q, r, u, hist_new;
 };
 
+// Time steps s0 .. s1-1 of the forward solve (Forward2_solver.py:542-585).  On entry HN(s0) holds phi_{s0}, c->mu_old holds mu_{s0}
+// and c->w0 holds w_{s0}; sc->mass0 has been set from level 0 (forward_begin).  Level s+1 is written to HN(s+1).
 // after_level(k): called once level k of phi_hist has been enqueued (streaming D2H of the trajectory hooks in here).
-void forward_dev(vch2d_ctx* c, const double* phi0, const double* u, int u_rows, int n_steps, const double* dt_steps,
-                 double* phi_hist, double* mu_hist, double* w_hist, vch_stats* st, const LevelHook& after_level = nullptr,
-                 const LevelHook& before_step = nullptr, const LevelMap* lm = nullptr) {
+void forward_steps(vch2d_ctx* c, int s0, int s1, const std::function<double*(int)>& HN, const std::function<const double*(int)>& U,
+                   bool have_u, int u_rows, const double* dt_steps, double* mu_hist, double* w_hist, vch_stats* st,
+                   const LevelHook& after_level, const LevelHook& before_step) {
     const long long n = c->g.n;
-    const size_t bytes = n * sizeof(double);
     const int eb = c->eb();
-    auto HN = [&](int k) -> double* { return (lm && lm->hist_new) ? lm->hist_new(k) : phi_hist + (size_t)k * n; };
-    auto U = [&](int k) -> const double* { return (lm && lm->u) ? lm->u(k) : u + (size_t)k * n; };
-    dev_copy(c, HN(0), phi0, (size_t)n);
-    VCH_CUDA(cudaMemsetAsync(c->w0.p, 0, bytes, c->stream));
-    c->mu_old.alloc(n);
-    double* mu_old = c->mu_old.p;   // mu_0 = initialize_mu(phi_0, w = 0), Forward2_solver.py:520
-    const double* phi_first = HN(0);
-    if (c->slab) {   // the stencil needs ghost rows: work on a ghosted copy of level 0
-        dev_copy(c, c->phi.p, phi0, (size_t)n);
-        halo_push(c, c->phi.p, nullptr, 1);
-        phi_first = c->phi.p;
-    }
-    LAUNCH(c, mu_init_kernel, eb, 256, phi_first, c->w0.p, mu_old, c->g, c->ph);
-    halo_push(c, mu_old, nullptr, 1);
-    LAUNCH(c, clip_mass_kernel, c->rb(), kRedThreads, HN(0), (double*)nullptr, c->g, c->ph, c->prm.hx * c->prm.hy, c->sc, 1,
-           c->red.part, c->ticket);
-    for (int s = 0; s < n_steps; ++s) {
+    double* mu_old = c->mu_old.p;
+    for (int s = s0; s < s1; ++s) {
         const double dt = dt_steps[s];
         if (before_step) before_step(s);     // streaming path: makes sure control rows s and s+1 exist
         const double* un = nullptr; const double* un1 = nullptr;
-        if ((u || (lm && lm->u)) && s < u_rows - 1) { un = U(s); un1 = U(s + 1); }
+        if (have_u && s < u_rows - 1) { un = U(s); un1 = U(s + 1); }
         LAUNCH(c, solve_w_kernel, eb, 256, c->w0.p, un, un1, c->w1.p, n, c->prm.gamma / dt);
         const double* phi_old = HN(s);
         newton_step(c, phi_old, mu_old, c->w0.p, c->w1.p, dt, nullptr, st, true);
@@ -506,13 +493,47 @@ void forward_dev(vch2d_ctx* c, const double* phi0, const double* u, int u_rows, 
         if (w_hist) dev_copy(c, w_hist + (size_t)s * n, c->w0.p, (size_t)n);
         if (after_level) after_level(s + 1);
     }
+}
+
+// Start of a forward solve from level 0 (already stored at lvl0): w_0 = 0, mu_0 = initialize_mu(phi_0, 0) (Forward2_solver.py:520),
+// and the reference mass of the interior mass correction (:565).
+void forward_begin(vch2d_ctx* c, const double* lvl0, bool set_state) {
+    const long long n = c->g.n;
+    const int eb = c->eb();
+    c->mu_old.alloc(n);
+    if (set_state) {
+        VCH_CUDA(cudaMemsetAsync(c->w0.p, 0, n * sizeof(double), c->stream));
+        const double* phi_first = lvl0;
+        if (c->slab) {   // the stencil needs ghost rows: work on a ghosted copy of level 0
+            dev_copy(c, c->phi.p, lvl0, (size_t)n);
+            halo_push(c, c->phi.p, nullptr, 1);
+            phi_first = c->phi.p;
+        }
+        LAUNCH(c, mu_init_kernel, eb, 256, phi_first, c->w0.p, c->mu_old.p, c->g, c->ph);
+        halo_push(c, c->mu_old.p, nullptr, 1);
+    }
+    LAUNCH(c, clip_mass_kernel, c->rb(), kRedThreads, lvl0, (double*)nullptr, c->g, c->ph, c->prm.hx * c->prm.hy, c->sc, 1,
+           c->red.part, c->ticket);
+}
+
+void forward_dev(vch2d_ctx* c, const double* phi0, const double* u, int u_rows, int n_steps, const double* dt_steps,
+                 double* phi_hist, double* mu_hist, double* w_hist, vch_stats* st, const LevelHook& after_level = nullptr,
+                 const LevelHook& before_step = nullptr, const LevelMap* lm = nullptr) {
+    const long long n = c->g.n;
+    auto HN = [&](int k) -> double* { return (lm && lm->hist_new) ? lm->hist_new(k) : phi_hist + (size_t)k * n; };
+    auto U = [&](int k) -> const double* { return (lm && lm->u) ? lm->u(k) : u + (size_t)k * n; };
+    dev_copy(c, HN(0), phi0, (size_t)n);
+    forward_begin(c, HN(0), true);
+    forward_steps(c, 0, n_steps, HN, U, u || (lm && lm->u), u_rows, dt_steps, mu_hist, w_hist, st, after_level, before_step);
     VCH_CUDA(cudaGetLastError());
 }
 
 // need_level(k): called before level k of phi_hist / phiQ is first read (streaming H2D hooks in here; levels descend).
+// k_hi / k_lo: only the levels k_hi (terminal solve, when k_hi is the last level) .. k_lo are processed; the rolling p, q (and r)
+// of level k_hi must then still be in the context's rings from the call that produced them (checkpointed sweep).
 void adjoint_dev(vch2d_ctx* c, const double* phi_hist, int levels, const double* t_hist, double b1, double b2,
                  const double* phiQ, const double* phiT, double* p_out, double* q_out, double* r_out, vch_stats* st,
-                 const LevelHook& need_level = nullptr, const LevelMap* lm = nullptr) {
+                 const LevelHook& need_level = nullptr, const LevelMap* lm = nullptr, int k_hi = -1, int k_lo = 0) {
     const long long n = c->g.n;
     const int eb = c->eb();
     auto H = [&](int k) -> const double* { return (lm && lm->hist) ? lm->hist(k) : phi_hist + (size_t)k * n; };
@@ -528,17 +549,20 @@ void adjoint_dev(vch2d_ctx* c, const double* phi_hist, int levels, const double*
         if (q_user) dev_copy(c, q_user + (size_t)lvl * n, qv, (size_t)n);
     };
     const int M = levels - 1;
+    if (k_hi < 0) k_hi = M;
     auto rslot = [&](int lvl) -> double* { return (lm && lm->r) ? lm->r(lvl) : slot(r_out, c->adj_r, lvl); };
-    if (need_level) need_level(M);
-    double* pM = slot(p_out, c->adj_p, M); double* qM = slot(q_out, c->adj_q, M); double* rM = rslot(M);
-    LAUNCH(c, adj_terminal_rhs_kernel, eb, 256, H(M), phiT, c->kb.p, n, b2);
-    SymbolArgs sy{1.0, 0.0, nullptr, c->ph.tau, nullptr};
-    c->dct.apply(c->stream, c->kb.p, pM, sy, nullptr);          // (I - tau L) p_M = b2 (phi_M - phi_T): exact in the DCT basis
-    halo_push(c, pM, nullptr, 1);
-    LAUNCH(c, adj_qr_kernel, eb, 256, pM, (const double*)nullptr, (const double*)nullptr, qM, rM, c->g, 0.0, 0.0);
-    halo_push(c, qM, nullptr, 1);
-    copy_out(M, pM, qM);
-    for (int k = M - 1; k >= 0; --k) {
+    if (k_hi == M) {
+        if (need_level) need_level(M);
+        double* pM = slot(p_out, c->adj_p, M); double* qM = slot(q_out, c->adj_q, M); double* rM = rslot(M);
+        LAUNCH(c, adj_terminal_rhs_kernel, eb, 256, H(M), phiT, c->kb.p, n, b2);
+        SymbolArgs sy{1.0, 0.0, nullptr, c->ph.tau, nullptr};
+        c->dct.apply(c->stream, c->kb.p, pM, sy, nullptr);          // (I - tau L) p_M = b2 (phi_M - phi_T): exact in the DCT basis
+        halo_push(c, pM, nullptr, 1);
+        LAUNCH(c, adj_qr_kernel, eb, 256, pM, (const double*)nullptr, (const double*)nullptr, qM, rM, c->g, 0.0, 0.0);
+        halo_push(c, qM, nullptr, 1);
+        copy_out(M, pM, qM);
+    }
+    for (int k = k_hi - 1; k >= k_lo; --k) {
         const double dt = t_hist[k + 1] - t_hist[k];
         if (need_level) need_level(k);     // before the level's addresses are taken: ring slots may be recycled in here
         double *p0 = slot(p_out, c->adj_p, k), *q0 = slot(q_out, c->adj_q, k), *r0 = rslot(k);
@@ -1397,6 +1421,161 @@ static void pgd_iteration_host_bounded(vch2d_ctx* c, int levels, const double* t
         VCH_CUDA(cudaStreamSynchronize(c->stream));
     } catch (...) { cleanup(); throw; }
     cleanup();
+}
+
+// ---------------------------------------------------------------------------------------------- checkpointed sweeps
+// The state trajectory exists only as checkpoints (phi, mu, w) every S levels.  The adjoint sweep walks the segments from the
+// last to the first: each is recomputed forward from its checkpoint into a buffer of S+1 levels (the same kernels in the same
+// order as the sweep that produced the checkpoints, deterministic reductions: bit-identical levels), then its adjoint levels
+// follow, then the gradient/prox of those levels — so neither phi_hist nor (unless asked for) r ever exists in full.  The forward
+// sweep under the new control writes the new checkpoints and accumulates the cost integrals segment by segment.  Price: one
+// extra forward sweep per iteration.  Memory: 3 x 2 x (M/S + 1) + 2 (S + 1) levels instead of 3 (M + 1).
+static int ckpt_count(int levels, int S) { return (levels - 1 + S - 1) / S + 1; }
+static int ckpt_level(int j, int levels, int S) { return std::min(j * S, levels - 1); }
+
+static void ckpt_load_state(vch2d_ctx* c, const double* ck_mu_j, const double* ck_w_j) {
+    const size_t n = (size_t)c->g.n;
+    c->mu_old.alloc(n);
+    dev_copy(c, c->mu_old.p, ck_mu_j, n);
+    halo_push(c, c->mu_old.p, nullptr, 1);
+    dev_copy(c, c->w0.p, ck_w_j, n);
+}
+
+// Forward sweep from level 0 that keeps only checkpoints.  seg_done(j, s0, s1, seg): levels s0..s1 of segment j are in seg[0..s1-s0].
+static void forward_ckpt_dev(vch2d_ctx* c, const double* phi0, const double* u, int u_rows, int levels, const double* dt_steps, int S,
+                             double* ck_phi, double* ck_mu, double* ck_w, vch_stats* st,
+                             const std::function<void(int, int, int, const double*)>& seg_done = nullptr) {
+    const size_t n = (size_t)c->g.n;
+    const int M = levels - 1, ncp = ckpt_count(levels, S);
+    c->ck_seg.alloc((size_t)(S + 1) * n);
+    double* seg = c->ck_seg.p;
+    dev_copy(c, seg, phi0, n);
+    forward_begin(c, seg, true);
+    dev_copy(c, ck_phi, seg, n); dev_copy(c, ck_mu, c->mu_old.p, n); dev_copy(c, ck_w, c->w0.p, n);
+    for (int j = 0; j + 1 < ncp; ++j) {
+        const int s0 = j * S, s1 = std::min(s0 + S, M);
+        auto HN = [&](int k) -> double* { return seg + (size_t)(k - s0) * n; };
+        auto U = [&](int k) -> const double* { return u + (size_t)k * n; };
+        forward_steps(c, s0, s1, HN, U, u != nullptr, u_rows, dt_steps, nullptr, nullptr, st, nullptr, nullptr);
+        dev_copy(c, ck_phi + (size_t)(j + 1) * n, HN(s1), n);
+        dev_copy(c, ck_mu + (size_t)(j + 1) * n, c->mu_old.p, n);
+        dev_copy(c, ck_w + (size_t)(j + 1) * n, c->w0.p, n);
+        if (seg_done) seg_done(j, s0, s1, seg);
+        if (j + 2 < ncp) dev_copy(c, seg, HN(s1), n);          // first level of the next segment
+    }
+    if (ncp == 1 && seg_done) seg_done(0, 0, 0, seg);
+    VCH_CUDA(cudaGetLastError());
+}
+
+static void pgd_iteration_ckpt_dev(vch2d_ctx* c, int levels, const double* t_hist, const double* dt_steps, const double* x,
+                                   const double* y, const double* u, const double* ck_phi, const double* ck_mu, const double* ck_w,
+                                   int S, const double* phiQ, const double* phiT, double b1, double b2, double b3, double ksp,
+                                   double umin, double umax, double alpha, double* u_new, double* ck_phi_out, double* ck_mu_out,
+                                   double* ck_w_out, double* r_out, double* J_out, double* red_out, vch_stats* st) {
+    const size_t n = (size_t)c->g.n;
+    const int M = levels - 1, ncp = ckpt_count(levels, S);
+    c->ck_seg.alloc((size_t)(S + 1) * n);
+    if (!r_out) c->ck_r.alloc((size_t)(S + 1) * n);
+    double* seg = c->ck_seg.p;
+    auto R = [&](int k) -> double* { return r_out ? r_out + (size_t)k * n : c->ck_r.p + (size_t)(k % (S + 1)) * n; };
+    forward_begin(c, ck_phi, false);                             // reference mass of the OLD trajectory (its level 0)
+    VCH_CUDA(cudaMemsetAsync(c->out4 + 4, 0, 4 * sizeof(double), c->stream));
+    auto prox_level = [&](int k) {
+        LAUNCH(c, grad_prox_kernel, red_blocks((long long)n), kRedThreads, u + (size_t)k * n, R(k), (double*)nullptr, u_new + (size_t)k * n,
+               (long long)n, b3, alpha, ksp, umin, umax, c->out4 + 4, c->red.part, c->ticket, 1);
+    };
+    if (ncp == 1) {   // a single level: terminal adjoint only
+        LevelMap lm; lm.hist = [&](int) { return const_cast<double*>(ck_phi); }; lm.r = R;
+        if (phiQ) lm.Q = [&](int k) { return const_cast<double*>(phiQ) + (size_t)k * n; };
+        adjoint_dev(c, nullptr, levels, t_hist, b1, b2, nullptr, phiT, nullptr, nullptr, nullptr, st, nullptr, &lm, M, M);
+        prox_level(M);
+    }
+    for (int j = ncp - 2; j >= 0; --j) {
+        const int s0 = j * S, s1 = std::min(s0 + S, M);
+        auto HN = [&](int k) -> double* { return seg + (size_t)(k - s0) * n; };
+        auto U = [&](int k) -> const double* { return u + (size_t)k * n; };
+        // (1a) recompute the segment from its checkpoint
+        dev_copy(c, seg, ck_phi + (size_t)j * n, n);
+        ckpt_load_state(c, ck_mu + (size_t)j * n, ck_w + (size_t)j * n);
+        forward_steps(c, s0, s1, HN, U, true, levels, dt_steps, nullptr, nullptr, st, nullptr, nullptr);
+        // (1b) its adjoint levels (the rolling p, q, r of level s1 are still in the rings / in R(s1))
+        LevelMap lm;
+        lm.hist = [&](int k) { return HN(k); };
+        if (phiQ) lm.Q = [&](int k) { return const_cast<double*>(phiQ) + (size_t)k * n; };
+        lm.r = R;
+        adjoint_dev(c, nullptr, levels, t_hist, b1, b2, nullptr, phiT, nullptr, nullptr, nullptr, st, nullptr, &lm, s1, s0);
+        // (2) gradient + prox of the levels whose r is now final
+        for (int k = (s1 == M ? M : s1 - 1); k >= s0; --k) prox_level(k);
+    }
+    // (3) forward solve under the new control: new checkpoints, cost integrals accumulated per segment       GD2_configured.py:309-312
+    const CostWeights cw = cost_weights(c, levels, x, y, t_hist);
+    VCH_CUDA(cudaMemsetAsync(c->out4, 0, 4 * sizeof(double), c->stream));
+    auto seg_cost = [&](int j, int s0, int s1, const double* sg) {
+        const bool last = (s1 == M);
+        const int cnt = (s1 - s0) + (last ? 1 : 0);              // levels s0 .. s1-1, plus the terminal level in the last segment
+        if (cnt <= 0) return;
+        LAUNCH(c, cost_kernel, red_blocks((long long)cnt * (long long)n), kRedThreads, sg, u_new + (size_t)s0 * n,
+               phiQ ? phiQ + (size_t)s0 * n : (const double*)nullptr, phiT, cnt, c->g.nx1, c->g.ny1, cw.wt + s0, cw.wx, cw.wy, c->out4,
+               c->red.part, c->ticket, last ? cnt - 1 : -1, 1);
+        (void)j;
+    };
+    forward_ckpt_dev(c, ck_phi, u_new, levels, levels, dt_steps, S, ck_phi_out, ck_mu_out, ck_w_out, st, seg_cost);
+    cost_finish(c, b1, b2, b3, ksp, J_out);
+    if (red_out) {
+        VCH_CUDA(cudaMemcpyAsync(c->out4_host + 4, c->out4 + 4, 4 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        VCH_CUDA(cudaStreamSynchronize(c->stream));
+        for (int k = 0; k < 4; ++k) red_out[k] = c->out4_host[4 + k];
+    }
+    VCH_CUDA(cudaStreamSynchronize(c->stream));
+}
+
+int vch2d_forward_ckpt(vch2d_ctx* c, const double* phi0, const double* u, int u_rows, int n_steps, const double* dt_steps,
+                       int ckpt_stride, double* ck_phi_out, double* ck_mu_out, double* ck_w_out, vch_stats* stats, int mem) {
+    return guarded([&] {
+        VCH_REQUIRE(c && phi0 && dt_steps && n_steps >= 0 && ckpt_stride >= 1 && ck_phi_out && ck_mu_out && ck_w_out, VCH_E_SHAPE,
+                    "forward_ckpt: bad arguments");
+        VCH_REQUIRE(!u || u_rows >= 1, VCH_E_SHAPE, "forward_ckpt: control needs at least one row");
+        StreamScope scope(c);
+        const long long n = c->g.n;
+        const StatMark mark0 = stat_mark(c);
+        const int levels = n_steps + 1, ncp = ckpt_count(levels, ckpt_stride);
+        Stager st(c->stream, mem);
+        const double* dphi0 = st.in(phi0, n);
+        const double* du = st.in(u, (size_t)u_rows * n);
+        double *cp = st.out(ck_phi_out, (size_t)ncp * n), *cm = st.out(ck_mu_out, (size_t)ncp * n), *cwv = st.out(ck_w_out, (size_t)ncp * n);
+        vch_stats local{}; vch_stats* s = stats ? stats : &local;
+        forward_ckpt_dev(c, dphi0, du, u_rows, levels, dt_steps, ckpt_stride, cp, cm, cwv, s);
+        st.finish();
+        stat_collect(c, mark0, s);
+        return VCH_OK;
+    });
+}
+
+int vch2d_pgd_iteration_ckpt(vch2d_ctx* c, int levels, const double* t_hist, const double* dt_steps, const double* x, const double* y,
+                             const double* u, const double* ck_phi, const double* ck_mu, const double* ck_w, int ckpt_stride,
+                             const double* phiQ, const double* phiT, double b1, double b2, double b3, double ksp, double umin,
+                             double umax, double alpha, double* u_new_out, double* ck_phi_out, double* ck_mu_out, double* ck_w_out,
+                             double* r_out, double* J_out, double* red_out, vch_stats* stats, int mem) {
+    return guarded([&] {
+        VCH_REQUIRE(c && levels >= 1 && t_hist && dt_steps && x && y && u && ck_phi && ck_mu && ck_w && ckpt_stride >= 1 && u_new_out &&
+                    ck_phi_out && ck_mu_out && ck_w_out && J_out, VCH_E_SHAPE, "pgd_iteration_ckpt: bad arguments");
+        StreamScope scope(c);
+        const long long n = c->g.n;
+        const StatMark mark0 = stat_mark(c);
+        const size_t tot = (size_t)levels * n, ctot = (size_t)ckpt_count(levels, ckpt_stride) * n;
+        vch_stats local{}; vch_stats* s = stats ? stats : &local;
+        Stager st(c->stream, mem);
+        const double *du = st.in(u, tot), *cp = st.in(ck_phi, ctot), *cm = st.in(ck_mu, ctot), *cwv = st.in(ck_w, ctot),
+                     *dq = st.in(phiQ, tot), *dT = st.in(phiT, n);
+        double *dun = st.out(u_new_out, tot), *cpo = st.out(ck_phi_out, ctot), *cmo = st.out(ck_mu_out, ctot), *cwo = st.out(ck_w_out, ctot),
+               *dr = st.out(r_out, tot);
+        pgd_iteration_ckpt_dev(c, levels, t_hist, dt_steps, x, y, du, cp, cm, cwv, ckpt_stride, dq, dT, b1, b2, b3, ksp, umin, umax, alpha,
+                               dun, cpo, cmo, cwo, dr, J_out, red_out, s);
+        st.finish();
+        stat_collect(c, mark0, s);
+        require_adjoint_converged(c, mark0);
+        return VCH_OK;
+    });
 }
 
 int vch2d_pgd_iteration(vch2d_ctx* c, int levels, const double* t_hist, const double* dt_steps, const double* x,

@@ -73,6 +73,19 @@ template <int LOG2L> struct F16 {
     static constexpr size_t cols_smem_bytes = sizeof(double2) * (size_t)cp * (ld + sst);
 };
 
+// Barrier among the tpf threads of ONE FFT (named barrier 1 + f) when they are whole warps, else the CTA barrier.  The FFT
+// groups of a CTA share nothing between the staging steps, so they need not march in lockstep: with their own barriers one group's
+// butterflies overlap another group's shared-memory traffic.  (CPU emulation: every group executes the same barrier sequence,
+// so the CTA barrier is a valid stand-in.)
+template <int LOG2L, bool GROUP>
+__device__ __forceinline__ void fft16_sync(int f) {
+#ifndef VCH_CPU_EMU
+    if (GROUP) { asm volatile("bar.sync %0, %1;" ::"r"(f + 1), "n"(F16<LOG2L>::tpf) : "memory"); return; }
+#endif
+    (void)f;
+    __syncthreads();
+}
+
 template <int LOG2L>
 __device__ __forceinline__ void fft16_prefetch_twiddles(const double2* __restrict__ tw, int t) {
     using G = F16<LOG2L>;
@@ -118,41 +131,55 @@ template <> __device__ __forceinline__ void dft<16>(double2 (&v)[16]) {
 
 // ---- passes.  Stockham autosort: butterfly j of a radix-R pass with Ns = product of the earlier radices reads
 // j + r*(Lf/R), multiplies by w^(k r Lf/(Ns R)), k = j mod Ns, and writes (j - k) R + k + r Ns.
-template <int LOG2L>
-__device__ __forceinline__ void fft16_first_store(double2* data, double2 (&v)[16], int t) {
+template <int LOG2L, bool GROUP = false>
+__device__ __forceinline__ void fft16_first_store(double2* data, double2 (&v)[16], int t, int f = 0) {
     dft<16>(v);
     double2* dst = data + 17 * t;                 // padi16(16 t + r) = 17 t + r
 #pragma unroll
     for (int r = 0; r < 16; ++r) dst[r] = v[r];
-    __syncthreads();
+    fft16_sync<LOG2L, GROUP>(f);
 }
 
-template <int LOG2L, int NS>
-__device__ __forceinline__ void fft16_mid_pass(double2* data, int t, const double2* __restrict__ twp) {
+// Twiddles w^r, r = 1..R-1, of one butterfly: the powers 1, 2, 4, 8 come from the per-pass table (r-major, so a warp reads
+// consecutive entries), the rest are products of at most three of them.  Loading all of them cost more than it saved: the
+// kernels are bound by the load/store pipe (ncu: FP64 pipe ~50 %), and every table entry is a 16-byte L1 access.
+template <int R>
+__device__ __forceinline__ void fft16_twiddles(double2 (&w)[R - 1], const double2* __restrict__ tab, int ns, int k) {
+    w[0] = __ldg(&tab[k]);
+    if (R >= 4) { w[1] = __ldg(&tab[ns + k]); w[2] = cmul(w[0], w[1]); }
+    if (R >= 8) { w[3] = __ldg(&tab[3 * ns + k]); w[4] = cmul(w[0], w[3]); w[5] = cmul(w[1], w[3]); w[6] = cmul(w[2], w[3]); }
+    if (R >= 16) {
+        w[7] = __ldg(&tab[7 * ns + k]);
+#pragma unroll
+        for (int r = 0; r < 7; ++r) w[8 + r] = cmul(w[r], w[7]);
+    }
+}
+
+template <int LOG2L, int NS, bool GROUP>
+__device__ __forceinline__ void fft16_mid_pass(double2* data, int t, const double2* __restrict__ twp, int f) {
     using G = F16<LOG2L>;
     static_assert(G::fold, "a middle pass exists only for Lf >= 512");
     double2 v[16], w[15];
     const int k = t & (NS - 1);
-#pragma unroll
-    for (int r = 1; r < 16; ++r) w[r - 1] = __ldg(&twp[(r - 1) * NS + k]);
+    fft16_twiddles<16>(w, twp, NS, k);
     const double2* src = data + padi16(t);
 #pragma unroll
     for (int r = 0; r < 16; ++r) v[r] = src[r * (G::tpf + G::tpf / 16)];
 #pragma unroll
     for (int r = 1; r < 16; ++r) v[r] = cmul(v[r], w[r - 1]);
     dft<16>(v);
-    __syncthreads();
+    fft16_sync<LOG2L, GROUP>(f);
     double2* dst = data + padi16((t - k) * 16 + k);
 #pragma unroll
     for (int r = 0; r < 16; ++r) dst[r * (NS + NS / 16)] = v[r];
-    __syncthreads();
+    fft16_sync<LOG2L, GROUP>(f);
 }
 
-template <int LOG2L>
-__device__ __forceinline__ void fft16_middle(double2* data, int t, const double2* __restrict__ tw) {
+template <int LOG2L, bool GROUP = false>
+__device__ __forceinline__ void fft16_middle(double2* data, int t, const double2* __restrict__ tw, int f = 0) {
     using G = F16<LOG2L>;
-    if constexpr (G::mids >= 1) fft16_mid_pass<LOG2L, 16>(data, t, tw + G::tw_mid1);
-    if constexpr (G::mids >= 2) fft16_mid_pass<LOG2L, 256>(data, t, tw + G::tw_mid2);
+    if constexpr (G::mids >= 1) fft16_mid_pass<LOG2L, 16, GROUP>(data, t, tw + G::tw_mid1, f);
+    if constexpr (G::mids >= 2) fft16_mid_pass<LOG2L, 256, GROUP>(data, t, tw + G::tw_mid2, f);
 }
 
 // Last pass: output slot q = m + r*NB of thread t is element t + q*tpf in natural order — the same convention as the
@@ -166,8 +193,7 @@ __device__ __forceinline__ void fft16_last_pass(const double2* data, int t, cons
     for (int m = 0; m < NB; ++m) {
         const int j = t + m * G::tpf;
         double2 v[R], w[R - 1];
-#pragma unroll
-        for (int r = 1; r < R; ++r) w[r - 1] = __ldg(&twl[(r - 1) * G::lastNs + j]);
+        fft16_twiddles<R>(w, twl, G::lastNs, j);
 #pragma unroll
         for (int r = 0; r < R; ++r) {
             const int q = m + r * NB;
@@ -379,9 +405,10 @@ cols16_kernel(double* __restrict__ buf, int pitch, int ncols, const double2* __r
     double2 v[16], z[16];
 #pragma unroll
     for (int r = 0; r < 16; ++r) v[r] = stage[idx16<LOG2L>(t, r)];
-    fft16_first_store<LOG2L>(data, v, t);                        // (its barrier also ends the reads of the stage)
+    constexpr bool GS = CP > 1 && (G::tpf % 32) == 0;           // per-FFT barriers between the CTA-wide staging steps
+    fft16_first_store<LOG2L, GS>(data, v, t, f);                 // (its barrier also ends this group's reads of its stage)
     VCH_STAMP(2);
-    fft16_middle<LOG2L>(data, t, tw);
+    fft16_middle<LOG2L, GS>(data, t, tw, f);
     VCH_STAMP(3);
     fft16_last_pass<LOG2L>(data, t, tw, z);
     VCH_STAMP(4);
@@ -403,12 +430,12 @@ cols16_kernel(double* __restrict__ buf, int pitch, int ncols, const double2* __r
         for (int q = 0; q < 8; ++q) elem(t + q * G::tpf, lrow[q], z[q]);
         if (t == 0) elem(N, lrow[8], z[8]);
     }
-    __syncthreads();
+    fft16_sync<LOG2L, GS>(f);          // also: every thread of the group has finished reading `data` in the last pass
     VCH_STAMP(5);
 #pragma unroll
     for (int r = 0; r < 16; ++r) v[r] = stage[idx16<LOG2L>(t, r)];
-    fft16_first_store<LOG2L>(data, v, t);
-    fft16_middle<LOG2L>(data, t, tw);
+    fft16_first_store<LOG2L, GS>(data, v, t, f);
+    fft16_middle<LOG2L, GS>(data, t, tw, f);
     fft16_last_pass<LOG2L>(data, t, tw, z);
     VCH_STAMP(6);
 #pragma unroll

@@ -51,7 +51,7 @@ EXPORTS = [
     "vch2d_create", "vch2d_destroy", "vch2d_set_stream", "vch2d_set_krylov", "vch2d_set_krylov_first", "vch2d_set_newton", "vch2d_set_stream_budget", "vch2d_launch_count", "vch2d_profile", "vch2d_profile_report",
     "vch2d_apply_laplacian", "vch2d_initialize_mu", "vch_solve_w", "vch2d_residual", "vch2d_jacobian_solve",
     "vch2d_newton", "vch2d_forward", "vch2d_adjoint", "vch2d_cost", "vch_grad_prox", "vch_kkt_counts",
-    "vch2d_pgd_iteration",
+    "vch2d_pgd_iteration", "vch2d_forward_ckpt", "vch2d_pgd_iteration_ckpt",
     "vch2d_slab_create", "vch2d_slab_rows", "vch2d_slab_ipc_handle", "vch2d_slab_attach", "vch2d_slab_selftest",
     "vch1d_create", "vch1d_destroy", "vch1d_set_stream", "vch1d_launch_count", "vch1d_residual", "vch1d_initialize_mu", "vch1d_newton",
     "vch1d_forward", "vch1d_adjoint", "vch1d_cost", "vch1d_grad_prox",
@@ -364,6 +364,59 @@ class Ctx2D:
                                          _mem_of(u, phi_hist, phiQ, phiT)))
         self.last_stats = st.as_dict()
         return u_out, phi_out, J, red, self.last_stats
+
+
+def _ckpt_count(levels, stride):
+    return (levels - 1 + stride - 1) // stride + 1
+
+
+def _ctx2d_forward_ckpt(self, phi0, u, dt_steps, stride):
+    """Forward solve that keeps only checkpoints every `stride` levels (include/vch_b200.h).  Returns (ck_phi, ck_mu, ck_w)."""
+    a = _Args(); self._stream()
+    s = self.shape
+    dts = np.ascontiguousarray(dt_steps, dtype=np.float64)
+    M = int(dts.shape[0])
+    ncp = _ckpt_count(M + 1, int(stride))
+    if u is not None and (u.ndim != 3 or tuple(u.shape[1:]) != s):
+        raise ValueError(f"control_input must have shape (M, {s[0]}, {s[1]})")
+    cp, pcp = a.out(phi0, (ncp,) + s); cm, pcm = a.out(phi0, (ncp,) + s); cw, pcw = a.out(phi0, (ncp,) + s)
+    st = Stats()
+    _check(lib().vch2d_forward_ckpt(self.h, a.inp(phi0, s), a.inp(u), int(u.shape[0]) if u is not None else 0, M, a.host(dts),
+                                    int(stride), pcp, pcm, pcw, C.byref(st), _mem_of(phi0, u)))
+    self.last_stats = st.as_dict()
+    return cp, cm, cw
+
+
+def _ctx2d_pgd_iteration_ckpt(self, u, ck, stride, phiQ, phiT, t_hist, dt_steps, x, y, b1, b2, b3, kappa_sp, u_min, u_max, alpha,
+                              u_out=None, r_out=None):
+    """One optimistic PGD iteration on a checkpointed trajectory.  ck = (ck_phi, ck_mu, ck_w).
+    Returns (u_new, (ck_phi, ck_mu, ck_w) of the new trajectory, J[9], red[4], stats)."""
+    a = _Args(); self._stream()
+    s = self.shape
+    lv = int(u.shape[0])
+    full = (lv,) + s
+    ncp = _ckpt_count(lv, int(stride))
+    cshape = (ncp,) + s
+    if u_out is None:
+        u_out, pun = a.out(u, full)
+    else:
+        pun = a.inp(u_out, full)
+    cp, pcp = a.out(u, cshape); cm, pcm = a.out(u, cshape); cw, pcw = a.out(u, cshape)
+    pr = a.inp(r_out, full) if r_out is not None else C.c_void_p(None)
+    J = np.zeros(9); red = np.zeros(4); st = Stats()
+    _check(lib().vch2d_pgd_iteration_ckpt(self.h, lv, a.host(t_hist), a.host(dt_steps), a.host(x), a.host(y), a.inp(u, full),
+                                          a.inp(ck[0], cshape), a.inp(ck[1], cshape), a.inp(ck[2], cshape), int(stride),
+                                          a.inp(phiQ, full if phiQ is not None else None), a.inp(phiT, s if phiT is not None else None),
+                                          C.c_double(b1), C.c_double(b2), C.c_double(b3), C.c_double(kappa_sp), C.c_double(u_min),
+                                          C.c_double(u_max), C.c_double(alpha), pun, pcp, pcm, pcw, pr,
+                                          J.ctypes.data_as(C.c_void_p), red.ctypes.data_as(C.c_void_p), C.byref(st),
+                                          _mem_of(u, ck[0], ck[1], ck[2], phiQ, phiT)))
+    self.last_stats = st.as_dict()
+    return u_out, (cp, cm, cw), J, red, self.last_stats
+
+
+Ctx2D.forward_ckpt = _ctx2d_forward_ckpt
+Ctx2D.pgd_iteration_ckpt = _ctx2d_pgd_iteration_ckpt
 
 
 def slab_partition(N, nranks):

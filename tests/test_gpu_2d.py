@@ -407,3 +407,95 @@ def test_full_size_1024_properties(native):
     assert bool(((un != 0) == (y.abs() - 50.0 * 1e-4 > 0)).all())
     assert abs(red[0] - float(((un - u) ** 2).sum())) <= 1e-9 * red[0] and abs(red[1] - float((u ** 2).sum())) <= 1e-9 * red[1]
     assert red[2] == float((un != 0).sum())
+
+
+def _cmp_sub(field, g, key, stride):
+    """Compare a full trajectory with a fixture stored sub-sampled in space plus per-level l2 norms / sums of the FULL fields
+    (oracle/make_golden_large.py): returns (rel. l2 on the sampled nodes, worst rel. error of the per-level norms)."""
+    a = np.asarray(field)
+    e_sub = rel(a[..., ::stride, ::stride], g[key])
+    nrm = np.array([np.linalg.norm(x.ravel()) for x in a.reshape((-1,) + a.shape[-2:])])
+    ref = g[key + "_norm"]
+    e_nrm = float(np.max(np.abs(nrm - ref) / np.maximum(ref, 1e-300))) if np.any(ref > 0) else float(np.max(np.abs(nrm)))
+    return e_sub, e_nrm
+
+
+@pytest.mark.parametrize("name", ["g2d_512", "g2d_1024_oracle"])
+def test_pgd_iteration_matches_large_grid_golden(native, golden, name):
+    """Parity pinned at the benchmarked scale.
+    g2d_512: the UNMODIFIED reference at 512^2 — 3 CN steps, adjoint, prox, forward + cost under the new control (one optimistic
+      PGD iteration).  The fp64-floor stop never fires there: the Newton evaluation counts must equal the reference's.
+    g2d_1024_oracle: the oracle (pinned to the reference on every grid <= 256^2, tests/test_oracle_golden.py) at 1024^2 with the
+      library's floor-aware Newton stop written into it (the reference's verbatim rule cannot terminate at 1024^2).
+    Tolerances are BASELINE's: phi/mu/w <= 1e-8, gradient and J <= 1e-7, identical support size."""
+    g = golden(name)
+    P = O.from_json(O.Phys2D, g["cfg_json"])
+    Op = O.from_json(O.Opt2D, g["opt_json"])
+    s = int(g["stride"])
+    c = make_ctx(native, P)
+    dts = dt_list(P)
+    phi_init = O.init_phi_2d(P.Nx, P.Ny)
+    hist0, mu0, w0 = c.forward(phi_init, None, dts, want_mu=True, want_w=True)
+    st0 = dict(c.last_stats)
+    assert np.array_equal(hist0[0, ::s, ::s], g["phi0"][0])                      # same initial condition (host RNG)
+    e, en = _cmp_sub(hist0, g, "phi0", s)
+    assert e < TOL_TRAJ and en < TOL_TRAJ, (e, en)
+    e, en = _cmp_sub(mu0, g, "mu0", s)
+    assert e < TOL_TRAJ and en < TOL_TRAJ, (e, en)
+    assert st0["newton_residual_evals"] == int(np.sum(g["nres0"])), (st0, g["nres0"])   # same Newton iteration counts
+    assert st0["krylov_stalls"] == 0
+    phiT, phiQ = O.targets_2d(g["x"], g["y"], g["t"], hist0[0], P.Lx, P.Ly, P.T)
+    r = np.zeros_like(hist0)
+    u1, hist1, J, red, st = c.pgd_iteration(np.zeros_like(hist0), hist0, phiQ, phiT, g["t"], dts, g["x"], g["y"], Op.b1, Op.b2,
+                                            Op.b3, Op.kappa_sparsity, Op.u_min, Op.u_max, Op.alpha_max, r_out=r)
+    e, en = _cmp_sub(r, g, "r0", s)
+    assert e < TOL_GRAD and en < TOL_GRAD, (e, en)
+    e, en = _cmp_sub(u1, g, "u1", s)
+    assert e < TOL_GRAD and en < TOL_GRAD, (e, en)
+    mism = int(np.count_nonzero((u1[..., ::s, ::s] != 0) != (g["u1"] != 0)))
+    assert mism == 0 and int(np.count_nonzero(u1)) == int(g["u1_support"][0]), (mism, np.count_nonzero(u1), g["u1_support"])
+    e, en = _cmp_sub(hist1, g, "phi1", s)
+    assert e < TOL_TRAJ and en < TOL_TRAJ, (e, en)
+    assert abs(J[0] - g["J"][1]) <= TOL_J * abs(g["J"][1])
+    assert st["krylov_stalls"] == 0
+
+
+@pytest.mark.parametrize("stride,with_Q,with_r", [(5, True, True), (4, True, False), (7, False, True), (1, True, True), (40, True, True)])
+def test_checkpointed_pgd_iteration_equals_fully_stored(native, stride, with_Q, with_r):
+    """Checkpoint + recompute (north_star (2), vch2d_pgd_iteration_ckpt): the state trajectory exists only as (phi, mu, w)
+    checkpoints every `stride` levels; the adjoint sweep recomputes each segment from its checkpoint.  Against the fully stored
+    path on the same inputs: identical bits for u_new, r and every checkpoint of the new trajectory (the recomputation runs the
+    same kernels in the same order), J to the rounding of the segmented cost sums.  Strides that divide the horizon, that do
+    not, stride 1, and a stride longer than the horizon."""
+    P = O.Phys2D(Nx=32, Ny=24, Lx=1.0, Ly=0.75, T=0.12)          # 12 steps -> 13 levels
+    Op = O.Opt2D()
+    c = make_ctx(native, P)
+    rng = np.random.default_rng(11)
+    phi0 = O.init_phi_2d(P.Nx, P.Ny)
+    dts = dt_list(P)
+    M = len(dts)
+    t = np.concatenate([[0.0], np.cumsum(dts)])
+    x, y = np.linspace(0, P.Lx, P.Nx + 1), np.linspace(0, P.Ly, P.Ny + 1)
+    u = 0.3 * rng.standard_normal((M + 1, P.Nx + 1, P.Ny + 1))
+    hist, mu, w = c.forward(phi0, u, dts, want_mu=True, want_w=True)
+    phiT = 0.7 * np.sin(2 * np.pi * x)[:, None] * np.cos(np.pi * y)[None, :]
+    phiQ = (1 - t / t[-1])[:, None, None] * hist[0] + (t / t[-1])[:, None, None] * phiT if with_Q else None
+    args = (Op.b1, Op.b2, Op.b3, Op.kappa_sparsity, Op.u_min, Op.u_max, 20.0)
+    r_full = np.zeros_like(hist)
+    u1, h1, J, red, _ = c.pgd_iteration(u, hist, phiQ, phiT, t, dts, x, y, *args, r_out=r_full)
+    _, mu1, w1 = c.forward(phi0, u1, dts, want_mu=True, want_w=True)
+    # checkpoints of the OLD trajectory from the checkpointing forward sweep: they are levels of the stored one
+    ck = c.forward_ckpt(phi0, u, dts, stride)
+    lv = [min(j * stride, M) for j in range((M + stride - 1) // stride + 1)]
+    assert np.array_equal(ck[0], hist[lv])
+    assert np.array_equal(ck[1][1:], mu[[k - 1 for k in lv[1:]]]) and np.array_equal(ck[2][1:], w[[k - 1 for k in lv[1:]]])
+    r_ck = np.zeros_like(hist) if with_r else None
+    u2, ck2, J2, red2, st = c.pgd_iteration_ckpt(u, ck, stride, phiQ, phiT, t, dts, x, y, *args, r_out=r_ck)
+    assert np.array_equal(u2, u1)
+    if with_r:
+        assert np.array_equal(r_ck, r_full)
+    assert np.array_equal(ck2[0], h1[lv])
+    assert np.array_equal(ck2[1][1:], mu1[[k - 1 for k in lv[1:]]]) and np.array_equal(ck2[2][1:], w1[[k - 1 for k in lv[1:]]])
+    np.testing.assert_allclose(J2[:5], J[:5], rtol=1e-13)
+    np.testing.assert_allclose(red2, red, rtol=1e-13)
+    assert st["krylov_stalls"] == 0

@@ -38,6 +38,7 @@ SLOW = [
     "tests/test_gpu_2d.py::test_pgd_iteration_matches_reference_golden[g2d_32]",
     "tests/test_gpu_2d.py::test_inexact_first_newton_solve_keeps_trajectory_and_saves_iterations",
     "tests/test_gpu_1d.py::test_ensemble_equals_single_problem_calls",
+    "tests/test_gpu_2d.py::test_checkpointed_pgd_iteration_equals_fully_stored[5-True-True]",
 ]
 
 
