@@ -288,26 +288,34 @@ __global__ void bicg_close_kernel(double* __restrict__ x, const double* __restri
 __global__ void dmu_ceiling_kernel(const double* __restrict__ dphi, const double* __restrict__ a,
                                    const double* __restrict__ Rphi, const double* __restrict__ phi,
                                    double* __restrict__ dmu, Geo g, Phys p, Scal* sc, double* part, unsigned int* ticket,
-                                   const double* __restrict__ mu, double* __restrict__ phit, double* __restrict__ mut) {
+                                   const double* __restrict__ mu, double* __restrict__ phit, double* __restrict__ mut, double tau_dt) {
     pdl_enter();
     // phit/mut (optional, need phi and mu): the full-step trial iterate phi + dphi, mu + dmu — what trial_kernel(alpha = 1)
     // computes — so the speculative first Armijo trial costs no launch of its own
-    double v[2] = {INFINITY, INFINITY};
+    // v[2]: squared norm of the nonlinear remainder of the FULL step.  The residual is linear in (phi, mu) except for the term
+    // c1 l(phi), l = log((1+s)/(1-s)), so after a full Newton step with an exact linear solve the new residual IS
+    // c1 [l(phi + dphi) - l(phi) - l'(phi) dphi] (first component) — computable without the Laplacians whose rounding noise
+    // (eps / h^2) hides it in the measured residual on fine grids.  newton_step uses it for its stop test there.
+    double v[3] = {INFINITY, INFINITY, 0.0};
     for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < g.n; idx += (long long)gridDim.x * blockDim.x) {
         const int o = (int)(idx / g.ni), i = (int)(idx - (long long)o * g.ni);
         const double d = dphi[idx];
-        const double dm = 2.0 * (a[idx] * d - 0.5 * p.kappa * lap_g(dphi, o, i, g) + Rphi[idx]);
+        const double av = a[idx];
+        const double dm = 2.0 * (av * d - 0.5 * p.kappa * lap_g(dphi, o, i, g) + Rphi[idx]);
         dmu[idx] = dm;
         if (phi) {
             const double f = phi[idx];
             if (phit) { phit[idx] = f + 1.0 * d; mut[idx] = mu[idx] + 1.0 * dm; }
             if (d > 0.0) v[0] = fmin(v[0], (p.lim - f) / d);
             else if (d < 0.0) v[1] = fmin(v[1], (-p.lim - f) / d);
+            // a = tau/dt + c1 l'(phi)  =>  c1 l'(phi) dphi = (a - tau/dt) dphi
+            const double rem = p.c1 * (flory_log(f + d, p.eps_log) - flory_log(f, p.eps_log)) - (av - tau_dt) * d;
+            v[2] += rem * rem;
         }
     }
-    const int op[2] = {1, 1};
-    double tot[2];
-    if (grid_reduce<2>(v, op, part, ticket, tot) && threadIdx.x == 0) { sc->ceil_pos = tot[0]; sc->ceil_neg = tot[1]; }
+    const int op[3] = {1, 1, 0};
+    double tot[3];
+    if (grid_reduce<3>(v, op, part, ticket, tot) && threadIdx.x == 0) { sc->ceil_pos = tot[0]; sc->ceil_neg = tot[1]; sc->rem2 = tot[2]; }
 }
 
 __global__ void trial_kernel(const double* __restrict__ phi, const double* __restrict__ mu, const double* __restrict__ dphi,

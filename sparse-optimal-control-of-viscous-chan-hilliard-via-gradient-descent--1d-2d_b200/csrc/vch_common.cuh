@@ -132,6 +132,7 @@ struct Scal {
     double r0v, ts, tt, rr, thr2, bnorm2;
     double res2, amin, amax, abar, mu2;
     double ceil_pos, ceil_neg;
+    double rem2;              // || c1 [l(phi + dphi) - l(phi) - l'(phi) dphi] ||^2: the nonlinear remainder of a full Newton step (see newton_step)
     double mass, wint, mass0;
     double tol2;
     double c0, c2;            // operator coefficients of the current solve (read by the graph's kernels: one graph serves every dt)

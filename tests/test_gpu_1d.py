@@ -131,3 +131,34 @@ def test_temporal_order_and_symmetry(native):
             errs.append(np.abs(hh[-1] - ref).max())
     slope = np.polyfit(np.log([1e-3, 5e-4, 2.5e-4]), np.log(errs), 1)[0]
     assert 1.2 < slope < 2.3
+
+
+def test_ensemble_members_match_reference_golden(native, golden):
+    """BASELINE config 4: 16 randomly chosen members of the 1024-problem ensemble (varied targets, kappa_sp, b1..b3), each taken
+    through one optimistic PGD iteration by the UNMODIFIED 1D reference (oracle/make_golden_ensemble.py), against ONE batched
+    call per stage of the library — the way the ensemble driver runs it (GD_1D.optimistic_iteration_ensemble).  The members
+    are cut out of the product's own make_ensemble(1024), so the ensemble definition itself is pinned as well."""
+    import sys, os
+    from conftest import load_dropin
+    G = load_dropin("1D")["GD_1D"]
+    g = golden("g1d_ensemble16")
+    ens = G.make_ensemble(1024)
+    mem = g["members"]
+    for k in ("b1", "b2", "b3", "ksp"):
+        np.testing.assert_allclose(ens[k][mem], g[k], rtol=1e-15)
+    assert np.array_equal(ens["choice_t"][mem], g["choice_t"])
+    P = O.Phys1D()
+    c = make_ctx(native, P)
+    sel = lambda a: np.ascontiguousarray(a[mem])
+    phi_init, phiQ, phiT = sel(ens["phi_init"]), sel(ens["phi_Q"]), sel(ens["phi_T"])
+    hist0, _, _ = c.forward(phi_init, None, ens["dts"])
+    assert rel(hist0[0], g["phi0"]) < TOL_TRAJ                                # u = 0: every member has the same trajectory
+    u0 = np.zeros_like(hist0)
+    u1, hist1, J, red, r = G.optimistic_iteration_ensemble(c, c, u0, hist0, phiQ, phiT, ens["x"], ens["t_hist"], ens["dts"],
+                                                           phi_init, g["b1"], g["b2"], g["b3"], g["ksp"], float(g["alpha"]))
+    for k in range(len(mem)):
+        assert rel(r[k], g["r0"][k]) < TOL_GRAD, (k, rel(r[k], g["r0"][k]))
+        assert rel(u1[k], g["u1"][k]) < TOL_GRAD
+        assert np.array_equal(u1[k] != 0, g["u1"][k] != 0), f"member {mem[k]}: control support differs"
+        assert rel(hist1[k], g["phi1"][k]) < TOL_TRAJ, (k, rel(hist1[k], g["phi1"][k]))
+        assert abs(J[k, 0] - g["J1"][k]) <= TOL_J * abs(g["J1"][k])

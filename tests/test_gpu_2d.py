@@ -427,8 +427,14 @@ def test_pgd_iteration_matches_large_grid_golden(native, golden, name):
       PGD iteration).  The fp64-floor stop never fires there: the Newton evaluation counts must equal the reference's.
     g2d_1024_oracle: the oracle (pinned to the reference on every grid <= 256^2, tests/test_oracle_golden.py) at 1024^2 with the
       library's floor-aware Newton stop written into it (the reference's verbatim rule cannot terminate at 1024^2).
-    Tolerances are BASELINE's: phi/mu/w <= 1e-8, gradient and J <= 1e-7, identical support size."""
+    State trajectories: BASELINE's 1e-8 against those fixtures.
+    Gradient: the reference's own fp64 direct solves of the biharmonic adjoint operator (cond ~ dt/2 (8/h^2)^2 = 2e10 / 3.5e11) are
+      off by 6.1e-7 (512^2) / 7.4e-6 (1024^2) from the exact solution of the same recurrence — measured by iterative refinement in
+      extended precision, oracle/make_golden_adjoint_refined.py, recorded in g2d_*_adjoint.npz — i.e. the reference does not
+      define r to BASELINE's 1e-7 there.  The library must (a) match the EXACT recurrence to 1e-7 and (b) match the reference
+      within the reference's own measured error."""
     g = golden(name)
+    ga = golden(name.replace("_oracle", "") + "_adjoint")
     P = O.from_json(O.Phys2D, g["cfg_json"])
     Op = O.from_json(O.Opt2D, g["opt_json"])
     s = int(g["stride"])
@@ -444,16 +450,30 @@ def test_pgd_iteration_matches_large_grid_golden(native, golden, name):
     assert e < TOL_TRAJ and en < TOL_TRAJ, (e, en)
     assert st0["newton_residual_evals"] == int(np.sum(g["nres0"])), (st0, g["nres0"])   # same Newton iteration counts
     assert st0["krylov_stalls"] == 0
+    e, en = _cmp_sub(hist0, ga, "phi", int(ga["stride"]))                        # the adjoint fixture belongs to the same trajectory
+    assert e < TOL_TRAJ and en < TOL_TRAJ, (e, en)
     phiT, phiQ = O.targets_2d(g["x"], g["y"], g["t"], hist0[0], P.Lx, P.Ly, P.T)
-    r = np.zeros_like(hist0)
+    p, _, r = c.adjoint(hist0, g["t"], Op.b1, Op.b2, phiQ, phiT)
+    err_ref = float(ga["err_plain_r"])
+    e, en = _cmp_sub(r, ga, "r", s)                                              # (a) exact recurrence
+    assert e < TOL_GRAD and en < TOL_GRAD, (e, en)
+    e, en = _cmp_sub(p, ga, "p", s)
+    assert e < TOL_GRAD and en < TOL_GRAD, (e, en)
+    e, en = _cmp_sub(r, g, "r0", s)                                              # (b) the reference, within its own error
+    assert e < 1.5 * err_ref + TOL_GRAD, (e, err_ref)
+    r_buf = np.zeros_like(hist0)
     u1, hist1, J, red, st = c.pgd_iteration(np.zeros_like(hist0), hist0, phiQ, phiT, g["t"], dts, g["x"], g["y"], Op.b1, Op.b2,
-                                            Op.b3, Op.kappa_sparsity, Op.u_min, Op.u_max, Op.alpha_max, r_out=r)
-    e, en = _cmp_sub(r, g, "r0", s)
-    assert e < TOL_GRAD and en < TOL_GRAD, (e, en)
-    e, en = _cmp_sub(u1, g, "u1", s)
-    assert e < TOL_GRAD and en < TOL_GRAD, (e, en)
-    mism = int(np.count_nonzero((u1[..., ::s, ::s] != 0) != (g["u1"] != 0)))
-    assert mism == 0 and int(np.count_nonzero(u1)) == int(g["u1_support"][0]), (mism, np.count_nonzero(u1), g["u1_support"])
+                                            Op.b3, Op.kappa_sparsity, Op.u_min, Op.u_max, Op.alpha_max, r_out=r_buf)
+    assert np.array_equal(r_buf, r)
+    e = rel(u1[..., ::s, ::s], ga["u1"])                                         # control from the exact gradient
+    assert e < TOL_GRAD, e
+    mism = int(np.count_nonzero((u1[..., ::s, ::s] != 0) != (ga["u1"] != 0)))
+    assert mism == 0 and int(np.count_nonzero(u1)) == int(ga["u1_support"][0]), (mism, np.count_nonzero(u1), ga["u1_support"])
+    # against the reference's u1 (built from its inexact gradient): agreement to its own error, support differences only
+    # where |alpha r| sits inside that error of the threshold
+    e, _ = _cmp_sub(u1, g, "u1", s)
+    assert e < 1.5 * err_ref + TOL_GRAD, (e, err_ref)
+    assert abs(int(np.count_nonzero(u1)) - int(g["u1_support"][0])) <= int(ga["u1_near_threshold"][0])
     e, en = _cmp_sub(hist1, g, "phi1", s)
     assert e < TOL_TRAJ and en < TOL_TRAJ, (e, en)
     assert abs(J[0] - g["J"][1]) <= TOL_J * abs(g["J"][1])
