@@ -174,6 +174,11 @@ int vch_grad_prox(void* cuda_stream, long long count, const double* u, const dou
  *   counts_out (host, 3) = { #|u|<tol, #|r|<=kappa, #agree } */
 int vch_kkt_counts(void* cuda_stream, long long count, const double* u, const double* r, double kappa_sp,
                    double tol, long long* counts_out, int mem);
+/* free_energy(phi, kappa, c1, c2, hx, hy, w, eps)      Forward2_solver.py:256-319 (monitoring)
+ *   phi (n0, n1) row-major = the reference's (Ny+1, Nx+1): h1 = hx is the spacing of the contiguous axis, h0 = hy of the other;
+ *   w may be NULL; one fused reduction kernel; E_out (host, 1) */
+int vch_free_energy(void* cuda_stream, int n0, int n1, const double* phi, const double* w, double kappa, double c1, double c2,
+                    double h1, double h0, double eps, double* E_out, int mem);
 /* One optimistic PGD iteration                        GD2_configured.py:299-313
  *   adjoint(phi_hist) -> r;  u_new = prox(u - alpha (r + b3 u));  forward(u_new) -> phi_hist_out;  J(u_new).
  *   levels = n_steps+1 = rows of u, phi_hist, phiQ.  phi0 = phi_hist level 0.  r_out may be NULL (device scratch is used).

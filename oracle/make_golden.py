@@ -160,8 +160,31 @@ CASES = {
     "g2d_128": lambda: case_2d("g2d_128", {}, n_iter=1, keep=[0, 1, 50, 99, 100], keep_pq=False),
 }
 
+
+
+def case_soc_2d(name="g2d_32_soc"):
+    """approximate_second_order_condition_2d of the UNMODIFIED reference (second_order_conditions_2d.py:120-235) at the second
+    PGD iterate of g2d_32 (u1, r1, phi1): 3 critical-cone directions, epsilon 1e-3, seed 42."""
+    _load("2D")
+    import second_order_conditions_2d as S
+    from config import ForwardSolverConfig, OptimizationConfig
+    g = np.load(os.path.join(OUT, "g2d_32.npz"))
+    cfg = ForwardSolverConfig(**{k: v for k, v in __import__("json").loads(str(g["cfg_json"])).items() if k in ForwardSolverConfig.model_fields})
+    opt = OptimizationConfig()
+    import GD2_configured as G
+    phiT, phiQ = _quiet(G.build_targets, g["x"], g["y"], g["t"], g["phi0"][0].copy(), cfg.Lx, cfg.Ly, cfg.T, False, 1, 1)
+    d2 = _quiet(S.approximate_second_order_condition_2d, g["u1"], g["r1"], g["phi1"], g["x"], g["y"], g["t"], opt_config=opt,
+                phi_Q_target=phiQ, phi_T_target=phiT, u_min=opt.u_min, u_max=opt.u_max, num_directions=3, epsilon=1e-3, seed=42,
+                fwd_config=cfg)
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), d2=np.array(d2), epsilon=np.float64(1e-3), seed=np.int64(42))
+    print(f"[{name}] d2 = {d2}")
+
+
+CASES["g2d_32_soc"] = case_soc_2d
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
-    names = sys.argv[1:] or [c for c in CASES if c not in ("g2d_128", "g2d_256")]
+    names = sys.argv[1:] or [c for c in CASES if c not in ("g2d_128", "g2d_256", "g2d_32_soc")]
     for n in names:
         CASES[n]()

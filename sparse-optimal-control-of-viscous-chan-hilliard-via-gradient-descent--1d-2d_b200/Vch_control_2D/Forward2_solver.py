@@ -6,7 +6,7 @@ C ABI (include/vch_b200.h).  There is no CPU path: without the library or a CUDA
 What still runs on the host, by design: the RNG of the initial condition (the reference draws it from NumPy's PCG64,
 :455-456, and parity needs the same stream), assembly of the SciPy operator objects that the reference's tests inspect
 (`laplacian_matrix_neumann`, `assemble_jacobian` — the solver itself is matrix-free and never uses them), and the
-scalar diagnostics `free_energy` / `instability_report`.
+scalar diagnostic `instability_report` (`free_energy` is a fused device reduction).
 """
 import os
 import sys
@@ -70,12 +70,32 @@ def laplacian_matrix_neumann(Nx, Ny, hx, hy):
 
 
 def _spacing(L, Nx, Ny):
-    """Recover (hx, hy) from a Laplacian built by laplacian_matrix_neumann (entry (0,1) = 2/hx^2, (0,Nx+1) = 2/hy^2)."""
+    """Recover (hx, hy) from a Laplacian built by laplacian_matrix_neumann (entry (0,1) = 2/hx^2, (0,Nx+1) = 2/hy^2).
+
+    The kernels implement exactly that mirror-ghost 5-point operator, so any OTHER matrix handed in through the reference's
+    `L` argument (scaled, regularised, periodic, built for another grid) cannot be honoured: it is rejected with ValueError
+    instead of being silently replaced (the reference would compute `L @ v` with whatever it is given)."""
     sp = getattr(L, "_vch_spacing", None)
-    if sp is not None:
+    n = (Nx + 1) * (Ny + 1)
+    if sp is not None and L.shape == (n, n):
         return sp
     L = L.tocsr() if sps.issparse(L) else sps.csr_matrix(L)
-    return float(np.sqrt(2.0 / L[0, 1])), float(np.sqrt(2.0 / L[0, Nx + 1]))
+    if L.shape != (n, n):
+        raise ValueError(f"L must be the ({n}, {n}) Neumann Laplacian of the ({Nx+1}, {Ny+1}) grid, got {L.shape}")
+    a, b = float(L[0, 1]), float(L[0, Nx + 1])
+    if not (a > 0.0 and b > 0.0 and np.isfinite(a) and np.isfinite(b)):
+        raise ValueError("L is not the mirror-ghost Neumann Laplacian this library implements (corner row)")
+    ax, ay = 0.5 * a, 0.5 * b                                  # 1/hx^2, 1/hy^2
+    i = (Nx + 1) + 1                                            # an interior node next to the corner (Nx, Ny >= 2)
+    ok = abs(float(L[0, 0]) + 2.0 * (ax + ay)) <= 1e-9 * (ax + ay)
+    if Nx >= 2 and Ny >= 2:
+        ok = ok and abs(float(L[i, i]) + 2.0 * (ax + ay)) <= 1e-9 * (ax + ay) and abs(float(L[i, i + 1]) - ax) <= 1e-9 * ax \
+            and abs(float(L[i, i - 1]) - ax) <= 1e-9 * ax and abs(float(L[i, i + Nx + 1]) - ay) <= 1e-9 * ay
+        ok = ok and L.nnz <= 5 * n
+    if not ok:
+        raise ValueError("L is not the mirror-ghost Neumann 5-point Laplacian this library implements; the CUDA kernels "
+                         "cannot apply an arbitrary operator")
+    return float(np.sqrt(1.0 / ax)), float(np.sqrt(1.0 / ay))
 
 
 def _ctx(Nx, Ny, hx, hy, tau=0.05, gamma=10.0, c1=0.75, c2=1.0, kappa=1e-4, delta_sep=_DELTA_SEP):
@@ -130,17 +150,12 @@ def assemble_jacobian(phi_new, dt, tau, c1, kappa, L, delta_sep):
 
 
 def free_energy(phi, kappa, c1, c2, hx, hy, w=None, eps=None):
-    """Discrete Ginzburg–Landau/Flory–Huggins energy, scalar diagnostic (reference :256-319)."""
-    eps = 1e-8 if eps is None else eps
-    f = np.asarray(phi)
-    wts = np.outer(trapz_weights(f.shape[0]), trapz_weights(f.shape[1]))
-    grad = kappa / (2.0 * hx) * np.sum(np.diff(f, axis=1) ** 2) * hy + kappa / (2.0 * hy) * np.sum(np.diff(f, axis=0) ** 2) * hx
-    s = np.clip(f, -1.0 + eps, 1.0 - eps)
-    bulk = c1 * ((1.0 + s) * np.log(1.0 + s) + (1.0 - s) * np.log(1.0 - s)) - c2 * s ** 2
-    E = grad + hx * hy * np.sum(wts * bulk)
-    if w is not None:
-        E -= hx * hy * np.sum(wts * np.asarray(w) * f)
-    return E
+    """Discrete Ginzburg–Landau/Flory–Huggins energy (reference :256-319): one fused reduction kernel (vch_free_energy)."""
+    f = _f64(phi)
+    if f.ndim != 2:
+        raise ValueError("phi must be a 2D array of shape (Ny+1, Nx+1)")
+    return _nat.free_energy(f, float(kappa), float(c1), float(c2), float(hx), float(hy),
+                            None if w is None else _f64(w), 1e-8 if eps is None else float(eps))
 
 
 def newton_raphson(phi_old, mu_old, w_old, w_new, dt, tau, c1, c2, kappa, delta_sep, L, Nx, Ny, hx, hy,

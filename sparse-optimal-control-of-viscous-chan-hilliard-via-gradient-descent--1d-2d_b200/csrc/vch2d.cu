@@ -1157,6 +1157,28 @@ int vch_kkt_counts(void* stream, long long count, const double* u, const double*
     });
 }
 
+int vch_free_energy(void* stream, int n0, int n1, const double* phi, const double* w, double kappa, double c1, double c2,
+                    double h1, double h0, double eps, double* E_out, int mem) {
+    return guarded([&] {
+        VCH_REQUIRE(n0 >= 1 && n1 >= 1 && phi && E_out, VCH_E_SHAPE, "free_energy: bad arguments");
+        VCH_REQUIRE(vch_device_count() > 0, VCH_E_CUDA, "no CUDA device: vch_b200 has no CPU fallback");
+        cudaStream_t s = (cudaStream_t)stream;
+        g_scratch.ensure();
+        const long long count = (long long)n0 * n1;
+        Stager st(s, mem);
+        const double *dp = st.in(phi, count), *dw = st.in(w, count);
+        energy_kernel<<<red_blocks(count), kRedThreads, 0, s>>>(dp, dw, n0, n1, c1, c2, eps, g_scratch.out, g_scratch.part, g_scratch.ticket);
+        ++g_free_launches;
+        VCH_CUDA(cudaGetLastError());
+        VCH_CUDA(cudaMemcpyAsync(g_scratch.out_host, g_scratch.out, 4 * sizeof(double), cudaMemcpyDeviceToHost, s));
+        st.finish();
+        VCH_CUDA(cudaStreamSynchronize(s));
+        const double* o = g_scratch.out_host;     // h1: spacing along the contiguous axis (x), h0: along the other (y)
+        E_out[0] = kappa / (2.0 * h1) * o[0] * h0 + kappa / (2.0 * h0) * o[1] * h1 + h1 * h0 * o[2] - (w ? h1 * h0 * o[3] : 0.0);
+        return VCH_OK;
+    });
+}
+
 // Host-buffer path of vch2d_pgd_iteration: PCIe traffic is streamed under the compute instead of bracketing it.
 //   H2D on a copy stream: phi_T, then (phi_hist, phi_Q) chunks from the LAST level down — the order in which the adjoint
 //   sweep consumes them — then u; the sweep waits per chunk on events.  D2H: u_new right after the prox, phi_hist_new chunk

@@ -478,6 +478,29 @@ __global__ void grad_prox_kernel(const double* __restrict__ u, const double* __r
     }
 }
 
+// Discrete free energy (Forward2_solver.py:256-319): forward-difference gradient sums along both axes, trapezoid-weighted
+// bulk term c1[(1+s)ln(1+s) + (1-s)ln(1-s)] - c2 s^2 with s = clip(phi, +-(1-eps)), optional coupling sum w phi.
+// phi is (n0, n1) row-major.  out4 = { sum dphi_x^2, sum dphi_y^2, sum wts psi, sum wts w phi }.
+__global__ void energy_kernel(const double* __restrict__ phi, const double* __restrict__ w, int n0, int n1, double c1, double c2,
+                              double eps, double* out4, double* part, unsigned int* ticket) {
+    pdl_enter();
+    double v[4] = {0.0, 0.0, 0.0, 0.0};
+    const long long n = (long long)n0 * n1;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (long long)gridDim.x * blockDim.x) {
+        const int r = (int)(idx / n1), c = (int)(idx - (long long)r * n1);
+        const double f = phi[idx];
+        if (c + 1 < n1) { const double d = phi[idx + 1] - f; v[0] += d * d; }
+        if (r + 1 < n0) { const double d = phi[idx + n1] - f; v[1] += d * d; }
+        const double wt = ((r == 0 || r == n0 - 1) ? 0.5 : 1.0) * ((c == 0 || c == n1 - 1) ? 0.5 : 1.0);
+        const double s = fmin(fmax(f, -1.0 + eps), 1.0 - eps);
+        v[2] += wt * (c1 * ((1.0 + s) * log(1.0 + s) + (1.0 - s) * log(1.0 - s)) - c2 * s * s);
+        if (w) v[3] += wt * w[idx] * f;
+    }
+    const int op[4] = {0, 0, 0, 0};
+    double tot[4];
+    if (grid_reduce<4>(v, op, part, ticket, tot) && threadIdx.x == 0) { out4[0] = tot[0]; out4[1] = tot[1]; out4[2] = tot[2]; out4[3] = tot[3]; }
+}
+
 __global__ void kkt_kernel(const double* __restrict__ u, const double* __restrict__ r, long long n, double ksp, double tol,
                            double* out3, double* part, unsigned int* ticket) {
     pdl_enter();

@@ -9,6 +9,7 @@
 #include <vector>
 #include <stdexcept>
 #include <utility>
+#include <algorithm>
 #include "../../include/vch_b200.h"
 
 namespace vch {
@@ -56,23 +57,70 @@ struct DevBuf {
     DevBuf& operator=(const DevBuf&) = delete;
 };
 
+// Device staging buffers of the host-buffer entry points are recycled through a small per-thread pool instead of a
+// cudaMalloc / cudaFree pair per array per call (every test-level drop-in call pays for them; cudaFree also synchronises
+// the whole device).  At most kStagePoolBytes stay cached; larger requests are freed on return as before.
+constexpr size_t kStagePoolBytes = (size_t)2 << 30;
+struct StagePool {
+    struct Item { double* p; size_t bytes; int dev; };
+    std::vector<Item> free_list;
+    size_t cached = 0;
+    static int cur_dev() { int d = 0; cudaGetDevice(&d); return d; }
+    double* get(size_t bytes) {
+        int best = -1;
+        const int dev = cur_dev();
+        for (int i = 0; i < (int)free_list.size(); ++i)
+            if (free_list[i].dev == dev && free_list[i].bytes >= bytes && free_list[i].bytes <= 2 * bytes + 4096 &&
+                (best < 0 || free_list[i].bytes < free_list[best].bytes)) best = i;
+        if (best >= 0) {
+            double* p = free_list[best].p;
+            cached -= free_list[best].bytes;
+            free_list.erase(free_list.begin() + best);
+            return p;
+        }
+        double* d = nullptr;
+        if (cudaMalloc(&d, bytes) != cudaSuccess) {       // make room and retry once
+            cudaGetLastError();
+            clear();
+            VCH_CUDA(cudaMalloc(&d, bytes));
+        }
+        return d;
+    }
+    void put(double* p, size_t bytes) {
+        if (bytes > kStagePoolBytes / 2 || cached + bytes > kStagePoolBytes || free_list.size() >= 32) { cudaFree(p); return; }
+        free_list.push_back({p, bytes, cur_dev()}); cached += bytes;
+    }
+    void clear() { for (auto& it : free_list) cudaFree(it.p); free_list.clear(); cached = 0; }
+    ~StagePool() { /* process exit: the driver reclaims the memory */ }
+};
+inline StagePool& stage_pool() { static thread_local StagePool pool; return pool; }
+
 // Stages caller arrays when mem == VCH_MEM_HOST; passes device pointers through otherwise.
 struct Stager {
     cudaStream_t s;
     int mem;
-    std::vector<double*> owned;
+    struct Own { double* p; size_t bytes; };
+    std::vector<Own> owned;
     struct Out { double* host; double* dev; size_t n; };
     std::vector<Out> outs;
+    bool drained = true;
     Stager(cudaStream_t st, int m) : s(st), mem(m) {}
+    double* take(size_t n) {
+        const size_t bytes = std::max<size_t>(n, 1) * sizeof(double);
+        double* d = stage_pool().get(bytes);
+        owned.push_back({d, bytes});
+        drained = false;
+        return d;
+    }
     const double* in(const double* a, size_t n) {
         if (!a || mem == VCH_MEM_DEVICE) return a;
-        double* d; VCH_CUDA(cudaMalloc(&d, n * sizeof(double))); owned.push_back(d);
+        double* d = take(n);
         VCH_CUDA(cudaMemcpyAsync(d, a, n * sizeof(double), cudaMemcpyHostToDevice, s));
         return d;
     }
     double* out(double* a, size_t n) {
         if (!a || mem == VCH_MEM_DEVICE) return a;
-        double* d; VCH_CUDA(cudaMalloc(&d, n * sizeof(double))); owned.push_back(d);
+        double* d = take(n);
         outs.push_back({a, d, n});
         return d;
     }
@@ -80,8 +128,12 @@ struct Stager {
         for (auto& o : outs) VCH_CUDA(cudaMemcpyAsync(o.host, o.dev, o.n * sizeof(double), cudaMemcpyDeviceToHost, s));
         VCH_CUDA(cudaStreamSynchronize(s));
         outs.clear();
+        drained = true;
     }
-    ~Stager() { for (auto d : owned) cudaFree(d); }
+    ~Stager() {
+        if (!owned.empty() && !drained) cudaStreamSynchronize(s);     // error path: nothing may still be using the buffers
+        for (auto& o : owned) stage_pool().put(o.p, o.bytes);
+    }
 };
 
 // ---------------------------------------------------------------- launch accounting / per-kernel event timing

@@ -50,7 +50,7 @@ EXPORTS = [
     "vch_last_error", "vch_device_count", "vch_version",
     "vch2d_create", "vch2d_destroy", "vch2d_set_stream", "vch2d_set_krylov", "vch2d_set_krylov_first", "vch2d_set_newton", "vch2d_set_stream_budget", "vch2d_launch_count", "vch2d_profile", "vch2d_profile_report",
     "vch2d_apply_laplacian", "vch2d_initialize_mu", "vch_solve_w", "vch2d_residual", "vch2d_jacobian_solve",
-    "vch2d_newton", "vch2d_forward", "vch2d_adjoint", "vch2d_cost", "vch_grad_prox", "vch_kkt_counts",
+    "vch2d_newton", "vch2d_forward", "vch2d_adjoint", "vch2d_cost", "vch_grad_prox", "vch_kkt_counts", "vch_free_energy",
     "vch2d_pgd_iteration", "vch2d_forward_ckpt", "vch2d_pgd_iteration_ckpt",
     "vch2d_slab_create", "vch2d_slab_rows", "vch2d_slab_ipc_handle", "vch2d_slab_attach", "vch2d_slab_selftest",
     "vch1d_create", "vch1d_destroy", "vch1d_set_stream", "vch1d_launch_count", "vch1d_residual", "vch1d_initialize_mu", "vch1d_newton",
@@ -203,6 +203,18 @@ def kkt_counts(u, r, kappa_sp, tol=1e-6):
     _check(lib().vch_kkt_counts(_current_stream_ptr(), C.c_longlong(int(np.prod(u.shape))), a.inp(u), a.inp(r, tuple(u.shape)),
                                 C.c_double(kappa_sp), C.c_double(tol), cnt.ctypes.data_as(C.c_void_p), mem))
     return int(cnt[0]), int(cnt[1]), int(cnt[2])
+
+
+def free_energy(phi, kappa, c1, c2, hx, hy, w=None, eps=1e-8):
+    """Discrete free energy, one fused reduction kernel (Forward2_solver.py:256-319).  phi: (Ny+1, Nx+1) array or CUDA tensor."""
+    a = _Args()
+    mem = _mem_of(phi, w)
+    n0, n1 = int(phi.shape[0]), int(phi.shape[1])
+    E = np.zeros(1)
+    _check(lib().vch_free_energy(_current_stream_ptr(), n0, n1, a.inp(phi), a.inp(w, (n0, n1) if w is not None else None),
+                                 C.c_double(kappa), C.c_double(c1), C.c_double(c2), C.c_double(hx), C.c_double(hy),
+                                 C.c_double(eps), E.ctypes.data_as(C.c_void_p), mem))
+    return float(E[0])
 
 
 # ------------------------------------------------------------------------------------------------ 2D context
@@ -613,26 +625,44 @@ class Ctx1D:
 
 
 # ------------------------------------------------------------------------------------------------ context cache
-_ctx_cache: dict = {}
+# Contexts handed to the drop-in modules.  They are shared, so a lookup always returns one with the DEFAULT solver settings
+# (a caller that changed tolerances, the stream budget or profiling on a cached context must not leak that into later
+# run_main_simulation / run_backward calls with the same physics), and eviction is least-recently-used, one entry at a time
+# (parameter sweeps such as the reference's convergence-order tests keep their working set instead of rebuilding DCT tables
+# and CUDA graphs after every 16th configuration).
+from collections import OrderedDict
+
+_ctx_cache: "OrderedDict" = OrderedDict()
+_CTX_CACHE_MAX = 16
+
+
+def _cached(key, make, reset):
+    c = _ctx_cache.get(key)
+    if c is None:
+        while len(_ctx_cache) >= _CTX_CACHE_MAX:
+            _ctx_cache.popitem(last=False)
+        c = _ctx_cache[key] = make()
+    else:
+        _ctx_cache.move_to_end(key)
+        reset(c)
+    return c
+
+
+def _reset2d(c):
+    c.set_krylov(1e-11, 200)
+    c.set_krylov_first(float(os.environ.get("VCH_KRYLOV_FIRST_RTOL", 1e-6)))
+    c.set_newton(not os.environ.get("VCH_NEWTON_STRICT"))
+    c.set_stream_budget(0)
+    c.profile(False)
 
 
 def ctx2d(Nx, Ny, hx, hy, Lx, Ly, tau, gamma, c1, c2, kappa, delta_sep=1e-2, device=0) -> Ctx2D:
     key = ("2d", int(Nx), int(Ny), float(hx), float(hy), float(Lx), float(Ly), float(tau), float(gamma), float(c1),
            float(c2), float(kappa), float(delta_sep), int(device))
-    c = _ctx_cache.get(key)
-    if c is None:
-        if len(_ctx_cache) > 16:
-            _ctx_cache.clear()
-        c = _ctx_cache[key] = Ctx2D(*key[1:])
-    return c
+    return _cached(key, lambda: Ctx2D(*key[1:]), _reset2d)
 
 
 def ctx1d(N, h, Lx, tau, gamma, c1, c2, kappa, delta_sep=1e-2, device=0) -> Ctx1D:
     key = ("1d", int(N), float(h), float(Lx), float(tau), float(gamma), float(c1), float(c2), float(kappa),
            float(delta_sep), int(device))
-    c = _ctx_cache.get(key)
-    if c is None:
-        if len(_ctx_cache) > 16:
-            _ctx_cache.clear()
-        c = _ctx_cache[key] = Ctx1D(*key[1:])
-    return c
+    return _cached(key, lambda: Ctx1D(*key[1:]), lambda c: None)

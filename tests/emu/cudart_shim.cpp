@@ -10,6 +10,7 @@ extern "C" {
 
 cudaError_t cudaGetDeviceCount(int* n) { *n = 1; return cudaSuccess; }
 cudaError_t cudaSetDevice(int) { return cudaSuccess; }
+cudaError_t cudaGetDevice(int* d) { *d = 0; return cudaSuccess; }
 cudaError_t cudaGetLastError(void) { return cudaSuccess; }
 const char* cudaGetErrorString(cudaError_t) { return "cuda_emu"; }
 cudaError_t cudaMemGetInfo(size_t* free_b, size_t* total_b) { *free_b = (size_t)8 << 30; *total_b = (size_t)16 << 30; return cudaSuccess; }

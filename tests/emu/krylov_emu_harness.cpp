@@ -122,7 +122,7 @@ static void run(double rel_tol, int half_exit) {
                      (double)(memcmp(x_before.data(), kx.data(), n * sizeof(double)) == 0), (double)sc.nonfinite}; dump("fwd_scal", s, 8); }
     dump("dphi", kx.data(), n);
     std::vector<double> dmu(n), phit(n), mut(n);
-    launch(rb, kRedThreads, [&] { dmu_ceiling_kernel(kx.data(), a.data(), Rphi.data(), phi.data(), dmu.data(), g, ph, &sc, part, &ticket, mu.data(), phit.data(), mut.data()); });
+    launch(rb, kRedThreads, [&] { dmu_ceiling_kernel(kx.data(), a.data(), Rphi.data(), phi.data(), dmu.data(), g, ph, &sc, part, &ticket, mu.data(), phit.data(), mut.data(), ph.tau / dt); });
     dump("dmu", dmu.data(), n); dump("phit", phit.data(), n); dump("mut", mut.data(), n);
     { double s[2] = {sc.ceil_pos, sc.ceil_neg}; dump("ceil", s, 2); }
 

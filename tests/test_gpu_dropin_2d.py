@@ -184,3 +184,33 @@ def test_driver_loop_matches_reference_loop(m, golden):
     assert res["timers"]["ls_attempts"] == int(g["ls_attempts"].sum())
     assert rel(res["u"][[1, 50, 99]][:, ::4, ::4], g["u_final_sub"]) < 1e-6
     assert rel(res["phi_hist"][-1], g["phi_final_T"]) < 1e-7
+
+
+def test_free_energy_and_second_order_condition_match_reference(native, golden):
+    """`free_energy` is a fused device reduction (Forward2_solver.py:256-319) — against the NumPy formula of the
+    reference; `approximate_second_order_condition_2d` (second_order_conditions_2d.py:120-235) — against the values the
+    UNMODIFIED reference produced for the same iterate, directions and epsilon (oracle/make_golden.py g2d_32_soc)."""
+    mods = load_dropin("2D")
+    F, S, G = mods["Forward2_solver"], mods["second_order_conditions_2d"], mods["GD2_configured"]
+    rng = np.random.default_rng(3)
+    phi = 0.9 * np.tanh(rng.standard_normal((21, 13))); w = 0.1 * rng.standard_normal((21, 13))
+    hx, hy, kappa, c1, c2 = 1 / 12, 1.5 / 20, 1e-4, 0.75, 1.0
+    def ref(phi, w, eps=1e-8):
+        tw = lambda n: np.r_[0.5, np.ones(n - 2), 0.5]
+        wts = np.outer(tw(phi.shape[0]), tw(phi.shape[1]))
+        E = kappa / (2 * hx) * np.sum(np.diff(phi, axis=1) ** 2) * hy + kappa / (2 * hy) * np.sum(np.diff(phi, axis=0) ** 2) * hx
+        s = np.clip(phi, -1 + eps, 1 - eps)
+        E += hx * hy * np.sum(wts * (c1 * ((1 + s) * np.log(1 + s) + (1 - s) * np.log(1 - s)) - c2 * s ** 2))
+        return E - (hx * hy * np.sum(wts * w * phi) if w is not None else 0.0)
+    assert abs(F.free_energy(phi, kappa, c1, c2, hx, hy) - ref(phi, None)) <= 1e-12 * abs(ref(phi, None))
+    assert abs(F.free_energy(phi, kappa, c1, c2, hx, hy, w=w, eps=1e-3) - ref(phi, w, 1e-3)) <= 1e-12 * abs(ref(phi, w, 1e-3))
+    g, gs = golden("g2d_32"), golden("g2d_32_soc")
+    import json
+    cfg = mods["config"].ForwardSolverConfig(**{k: v for k, v in json.loads(str(g["cfg_json"])).items()
+                                                if k in mods["config"].ForwardSolverConfig.model_fields})
+    opt = mods["config"].OptimizationConfig()
+    phiT, phiQ = G.build_targets(g["x"], g["y"], g["t"], g["phi0"][0].copy(), cfg.Lx, cfg.Ly, cfg.T, False, 1, 1)
+    d2 = quiet(S.approximate_second_order_condition_2d, g["u1"], g["r1"], g["phi1"], g["x"], g["y"], g["t"], opt_config=opt,
+               phi_Q_target=phiQ, phi_T_target=phiT, u_min=opt.u_min, u_max=opt.u_max,
+               num_directions=3, epsilon=float(gs["epsilon"]), seed=int(gs["seed"]), fwd_config=cfg)
+    np.testing.assert_allclose(d2, gs["d2"], rtol=1e-4)

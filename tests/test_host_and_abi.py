@@ -109,7 +109,16 @@ def test_host_side_helpers_2d():
     oT, oQ = O.targets_2d(x, y, th, p0, 1.0, 1.5, 0.5)
     assert np.array_equal(pT, oT) and np.array_equal(pQ, oQ)
     assert set(np.unique(pT2)) == {-1.0, 1.0} and not pQ2.any()
-    assert F.free_energy(0 * p0, 1e-4, 0.75, 1.0, 1 / 12, 1.5 / 20) == 0.0
+    import vch_b200_native as nat
+    if nat.device_count() == 0:      # free_energy is a device reduction (vch_free_energy): no CPU fallback, fails loudly
+        with pytest.raises(RuntimeError):
+            F.free_energy(0 * p0, 1e-4, 0.75, 1.0, 1 / 12, 1.5 / 20)
+    else:
+        assert F.free_energy(0 * p0, 1e-4, 0.75, 1.0, 1 / 12, 1.5 / 20) == 0.0
+    with pytest.raises(ValueError):  # an operator that is not the Neumann Laplacian of this grid is rejected, not replaced
+        F._spacing((3.0 * L).tocsr() + 1e-3 * __import__("scipy.sparse", fromlist=["eye"]).eye(L.shape[0], format="csr"), 12, 20)
+    with pytest.raises(ValueError):
+        F._spacing(F.laplacian_matrix_neumann(6, 5, 0.1, 0.1), 12, 20)
     assert F.instability_report.__call__ and len(F.regularized_log(np.array([2.0, -2.0, 0.0]), 1e-2)) == 3
 
 
