@@ -672,9 +672,12 @@ def run_ensemble1d(args):
     barrier()
     l0 = ctx.launches()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    per_step = []
     e0.record()
     for _ in range(args.steps):
+        t0 = time.perf_counter()
         step()
+        per_step.append((time.perf_counter() - t0) * 1e3)     # every library call of a step returns synchronised
     e1.record()
     barrier()
     ms = torch.tensor([e0.elapsed_time(e1) / args.steps], device=dev, dtype=torch.float64)
@@ -688,7 +691,9 @@ def run_ensemble1d(args):
                           "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                           "config": {"workload": f"{B} independent 1D problems (N=128, 100 steps), make_ensemble(seed 1234), one optimistic PGD iteration each",
                                      "problems_per_gpu": hi - lo},
-                          "gpu_launches": int(ctx.launches() - l0), "sum_J": float(Jsum.item())}), flush=True)
+                          "gpu_launches": int(ctx.launches() - l0), "sum_J": float(Jsum.item()),
+                          "ms_per_step_median": float(np.median(per_step)), "ms_per_step_min": float(np.min(per_step)),
+                          "ms_per_step_max": float(np.max(per_step))}), flush=True)
     if world > 1:
         dist.destroy_process_group()
 

@@ -121,7 +121,7 @@ void copy_ghosted(vch2d_ctx* c, double* dst, const double* src) {
     dev_copy(c, dst - m, src - m, (size_t)c->g.n + 2 * m);
 }
 // kernels per BiCGStab iteration / per solve prologue (accounting of launches inside solve graphs)
-template <bool ADJ> int iter_launches(const vch2d_ctx* c) { return c->slab ? 7 + 4 : (c->bicg6 ? 6 : 7); }
+template <bool ADJ> int iter_launches(const vch2d_ctx* c) { return (c->bicg6 ? 6 : 7) + (c->slab ? 4 : 0); }
 // FWD: P^-1 b (3 kernels) + init;  ADJ (right-preconditioned): init + the closing x = P^-1 y (3 kernels); slab mode adds the
 // barriers of one preconditioner application (2 + the trailing one)
 template <bool ADJ> int prologue_launches(const vch2d_ctx* c) { return 4 + (c->slab ? 3 : 0) + (c->bicg6 ? 1 : 0); }
@@ -694,7 +694,7 @@ static int create_ctx(const vch2d_params* p, int device, int rank, int nranks, v
         c->debug = getenv("VCH_DEBUG") ? atoi(getenv("VCH_DEBUG")) : 0;
         if (getenv("VCH_NEWTON_STRICT")) c->floor_aware = 0;
         if (getenv("VCH_NO_HALF_EXIT")) c->half_exit = 0;
-        c->bicg6 = (getenv("VCH_BICG6") ? atoi(getenv("VCH_BICG6")) : 1) && !slab;
+        c->bicg6 = (getenv("VCH_BICG6") ? atoi(getenv("VCH_BICG6")) : 1);
         c->pdl = (getenv("VCH_PDL") ? atoi(getenv("VCH_PDL")) : 0) && !slab;   // slab mode: cross-rank waits inside kernels, keep full serialization
         if (getenv("VCH_KRYLOV_FIRST_RTOL")) { const double t = atof(getenv("VCH_KRYLOV_FIRST_RTOL")); if (t >= 0 && t < 1) c->krylov_first_tol = t; }
         if (getenv("VCH_KRYLOV_RTOL")) { const double t = atof(getenv("VCH_KRYLOV_RTOL")); if (t > 0 && t < 1) c->krylov_tol = t; }
@@ -712,7 +712,7 @@ static int create_ctx(const vch2d_params* p, int device, int rank, int nranks, v
             g.glo = rank > 0; g.ghi = rank < nranks - 1;
             sl.nloc = g.no; sl.o0 = g.o0; sl.wloc = g.no; sl.col0 = g.o0;
             sl.shift = 0; while ((1 << sl.shift) < rw) ++sl.shift;
-            sl.p1 = rw + 2;
+            sl.p1 = (rw + 1 + 7) & ~7;      // owned columns (rw or rw + 1) rounded up to whole 8-column groups of the column kernel; padding stays zero
         }
         g.n = (long long)g.ni * g.no;
         c->ph = Phys{p->tau, p->gamma, p->c1, p->c2, p->kappa, 1.0 - p->delta_sep, std::max(1e-8, 0.5 * p->delta_sep),
@@ -748,6 +748,7 @@ static int create_ctx(const vch2d_params* p, int device, int rank, int nranks, v
             c->cm.err = &c->sc->comm_err;
             sl.cm = c->cm;
             c->dct.init_slab(p->Nx + 1, p->hy, p->hx, &c->log, sl);
+            if (!(c->dct.lean && c->dct.inner.log2L >= 8)) c->bicg6 = 0;   // the round-1 kernels carry the 6-launch modes only without transposition
         } else {
             c->dct.init(g.no, g.ni, p->hy, p->hx, &c->log);
             c->dct.pdl = c->pdl != 0;

@@ -761,30 +761,22 @@ inline void DctPlan::init(int no_, int ni_, double h_outer, double h_inner, Laun
         }
     }
 #undef VCH_FFT_ATTR
-#define VCH_F16_ATTR1(K, BYTES) VCH_CUDA(cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(BYTES)));
-#define VCH_F16_ATTR(LG)                                                                          \
-    VCH_F16_ATTR1((rows16_kernel<LG, 0, 0, false>), F16<LG>::rows_smem_plain)                    \
-    VCH_F16_ATTR1((rows16_kernel<LG, 2, 0, false>), F16<LG>::rows_smem_staged)                     \
-    VCH_F16_ATTR1((rows16_kernel<LG, 2, 0, true>), F16<LG>::rows_smem_staged)                      \
-    VCH_F16_ATTR1((rows16_kernel<LG, 3, 0, false>), F16<LG>::rows_smem_staged)                     \
-    VCH_F16_ATTR1((rows16_kernel<LG, 3, 0, true>), F16<LG>::rows_smem_staged)                      \
-    VCH_F16_ATTR1((rows16_kernel<LG, 0, 1, false>), F16<LG>::rows_smem_plain)                    \
-    VCH_F16_ATTR1((rows16_kernel<LG, 0, 1, true>), F16<LG>::rows_smem_plain)                     \
-    VCH_F16_ATTR1((rows16_kernel<LG, 0, 4, false>), F16<LG>::rows_smem_plain)                    \
-    VCH_F16_ATTR1((rows16_kernel<LG, 0, 4, true>), F16<LG>::rows_smem_plain)                     \
-    VCH_F16_ATTR1((cols16_kernel<LG>), F16<LG>::cols_smem_bytes)
+#define VCH_F16_ATTR(LG)                                                                   \
+    case LG:                                                                               \
+        rows16_set_attributes<LG, 0>();                                                    \
+        fft16_attr(cols16_kernel<LG>, F16<LG>::cols_smem_bytes);                           \
+        if (LG >= 8) { rows16_set_attributes<(LG >= 8 ? LG : 8), 1>(); rows16_set_attributes<(LG >= 8 ? LG : 8), 3>(); } \
+        break;
     if (inner.fft && outer.fft) {
         if (getenv("VCH_FFT16")) lean = atoi(getenv("VCH_FFT16")) != 0;
         for (const DctAxis* ax : {&inner, &outer}) {
             switch (ax->log2L) {
-                case 6: VCH_F16_ATTR(6) break; case 7: VCH_F16_ATTR(7) break; case 8: VCH_F16_ATTR(8) break; case 9: VCH_F16_ATTR(9) break;
-                case 10: VCH_F16_ATTR(10) break; case 11: VCH_F16_ATTR(11) break; case 12: VCH_F16_ATTR(12) break; case 13: VCH_F16_ATTR(13) break;
+                VCH_F16_ATTR(6) VCH_F16_ATTR(7) VCH_F16_ATTR(8) VCH_F16_ATTR(9) VCH_F16_ATTR(10) VCH_F16_ATTR(11) VCH_F16_ATTR(12) VCH_F16_ATTR(13)
                 default: break;
             }
         }
     } else lean = false;
 #undef VCH_F16_ATTR
-#undef VCH_F16_ATTR1
 }
 
 // Slab mode: square global grid n_global x n_global (N = n_global - 1 a power of two), T1/T2 carved from the arena by the caller.
@@ -838,6 +830,37 @@ inline void DctPlan::apply(cudaStream_t s, const double* in, double* out, const 
 #undef VCH_FFT_CASE
 #undef VCH_FFT_ARGS
     };
+    if (slab.on && lean && inner.log2L >= 8 && (pro.mode == 0 || pro.mode == 2 || pro.mode == 3) && (epi.mode == 0 || epi.mode == 1 || epi.mode == 4)) {
+        // slab mode with the radix-16 kernels: same protocol as below (rows scattered into the column owners' T1 | barrier | column
+        // solve in place on the owned columns | barrier | rows gathered back), same barriers
+        const DctSlab& sl = slab;
+        Scatter s1; s1.mode = 1; s1.shift = sl.shift; s1.nr = sl.cm.nranks; s1.base = sl.o0; s1.pitch = sl.p1;
+        s1.off = (size_t)(sl.T1 - sl.cm.peer[sl.cm.rank]);
+        for (int r = 0; r < sl.cm.nranks; ++r) s1.peer[r] = sl.cm.peer[r];
+        Scatter s3 = s1; s3.mode = 3;
+#define VCH_F16_SLAB(CALL)                                                                                        \
+        switch (inner.log2L) {                                                                                    \
+            case 8: { constexpr int LG = 8; CALL; } break;   case 9: { constexpr int LG = 9; CALL; } break;       \
+            case 10: { constexpr int LG = 10; CALL; } break; case 11: { constexpr int LG = 11; CALL; } break;     \
+            case 12: { constexpr int LG = 12; CALL; } break; case 13: { constexpr int LG = 13; CALL; } break;     \
+            default: throw Error(VCH_E_ARG, "unsupported FFT length");                                            \
+        }
+        log->begin(pro.mode ? "rows16_pro" : "rows16", s);
+        VCH_F16_SLAB((rows16_forward<LG, 1>(false, s, in, sl.T1, sl.nloc, ni, sl.p1, inner.tw16, pro, done, s1)))
+        log->end(s);
+        barrier(s, done);
+        log->begin("cols16_solve", s);
+        VCH_F16_SLAB((cols16_solve<LG>(false, s, sl.T1, sl.p1, sl.wloc, outer.tw16, inner.lam + sl.col0, outer.lam, sym, norm, scale_mode, done)))
+        log->end(s);
+        barrier(s, done);
+        log->begin(epi.mode == 1 ? "rows16_epi1" : (epi.mode == 4 ? "rows16_epi4" : "rows16"), s);
+        VCH_F16_SLAB((rows16_inverse<LG, 3>(false, s, sl.T1, out, sl.nloc, sl.p1, ni, inner.tw16, epi, done, s3)))
+        log->end(s);
+        if (!epi.mode) barrier(s, done);
+#undef VCH_F16_SLAB
+        VCH_CUDA(cudaGetLastError());
+        return;
+    }
     if (slab.on) {
         // rows of the owned slab, stored transposed into the column owners' T1 | barrier | fused solve in place on the owned
         // columns (all global rows) | barrier | inverse rows, gathered back from the owners' T1.  Re-use of T1 by the next
@@ -872,54 +895,23 @@ inline void DctPlan::apply(cudaStream_t s, const double* in, double* out, const 
 
     if (all_fft && lean && (pro.mode == 0 || pro.mode == 2 || pro.mode == 3) && (epi.mode == 0 || epi.mode == 1 || epi.mode == 4)) {
         // radix-16 kernels (vch_fft16.cuh), one instantiation per fused mode: rows (prologue) -> column solve -> rows (epilogue)
-        const bool pd = pdl;
-        const bool mul_pro = pro.mode != 0 && pro.a != nullptr, mul_epi = epi.mode != 0 && epi.mul_a != nullptr;
-        log->begin(pro.mode ? "rows16_pro" : "rows16", s);
-#define VCH_R16_FWD(LG)                                                                                                                   \
-        case LG: {                                                                                                                        \
-            using G = F16<LG>;                                                                                                            \
-            const int grid = ((no + 1) / 2 + G::fpb - 1) / G::fpb;                                                                        \
-            if (pro.mode == 0) launch_pdl(pd, rows16_kernel<LG, 0, 0, false>, grid, G::rthreads, G::rows_smem_plain, s, in, t1, no, ni, P, inner.tw16, pro, DotEpilogue(), done); \
-            else if (pro.mode == 2 && mul_pro) launch_pdl(pd, rows16_kernel<LG, 2, 0, true>, grid, G::rthreads, G::rows_smem_staged, s, in, t1, no, ni, P, inner.tw16, pro, DotEpilogue(), done); \
-            else if (pro.mode == 2) launch_pdl(pd, rows16_kernel<LG, 2, 0, false>, grid, G::rthreads, G::rows_smem_staged, s, in, t1, no, ni, P, inner.tw16, pro, DotEpilogue(), done); \
-            else if (mul_pro) launch_pdl(pd, rows16_kernel<LG, 3, 0, true>, grid, G::rthreads, G::rows_smem_staged, s, in, t1, no, ni, P, inner.tw16, pro, DotEpilogue(), done); \
-            else launch_pdl(pd, rows16_kernel<LG, 3, 0, false>, grid, G::rthreads, G::rows_smem_staged, s, in, t1, no, ni, P, inner.tw16, pro, DotEpilogue(), done); \
-        } break;
-        switch (inner.log2L) {
-            VCH_R16_FWD(6) VCH_R16_FWD(7) VCH_R16_FWD(8) VCH_R16_FWD(9) VCH_R16_FWD(10) VCH_R16_FWD(11) VCH_R16_FWD(12) VCH_R16_FWD(13)
-            default: throw Error(VCH_E_ARG, "unsupported FFT length");
+        const Scatter nosct;
+#define VCH_F16_SWITCH(AX, CALL)                                                                                  \
+        switch ((AX).log2L) {                                                                                     \
+            case 6: { constexpr int LG = 6; CALL; } break;   case 7: { constexpr int LG = 7; CALL; } break;       \
+            case 8: { constexpr int LG = 8; CALL; } break;   case 9: { constexpr int LG = 9; CALL; } break;       \
+            case 10: { constexpr int LG = 10; CALL; } break; case 11: { constexpr int LG = 11; CALL; } break;     \
+            case 12: { constexpr int LG = 12; CALL; } break; case 13: { constexpr int LG = 13; CALL; } break;     \
+            default: throw Error(VCH_E_ARG, "unsupported FFT length");                                            \
         }
-#undef VCH_R16_FWD
+        log->begin(pro.mode ? "rows16_pro" : "rows16", s);
+        VCH_F16_SWITCH(inner, (rows16_forward<LG, 0>(pdl, s, in, t1, no, ni, P, inner.tw16, pro, done, nosct)))
         log->end(s);
         log->begin("cols16_solve", s);
-#define VCH_C16(LG)                                                                                                                       \
-        case LG: {                                                                                                                        \
-            using G = F16<LG>;                                                                                                            \
-            const int grid = (ni + 2 * G::cp - 1) / (2 * G::cp);                                                                          \
-            launch_pdl(pd, cols16_kernel<LG>, grid, G::cthreads, G::cols_smem_bytes, s, t1, P, ni, outer.tw16, inner.lam, outer.lam, sym, norm, scale_mode, done); \
-        } break;
-        switch (outer.log2L) {
-            VCH_C16(6) VCH_C16(7) VCH_C16(8) VCH_C16(9) VCH_C16(10) VCH_C16(11) VCH_C16(12) VCH_C16(13)
-            default: throw Error(VCH_E_ARG, "unsupported FFT length");
-        }
-#undef VCH_C16
+        VCH_F16_SWITCH(outer, (cols16_solve<LG>(pdl, s, t1, P, ni, outer.tw16, inner.lam, outer.lam, sym, norm, scale_mode, done)))
         log->end(s);
         log->begin(epi.mode == 1 ? "rows16_epi1" : (epi.mode == 4 ? "rows16_epi4" : "rows16"), s);
-#define VCH_R16_INV(LG)                                                                                                                   \
-        case LG: {                                                                                                                        \
-            using G = F16<LG>;                                                                                                            \
-            const int grid = ((no + 1) / 2 + G::fpb - 1) / G::fpb;                                                                        \
-            if (epi.mode == 0) launch_pdl(pd, rows16_kernel<LG, 0, 0, false>, grid, G::rthreads, G::rows_smem_plain, s, t1, out, no, P, ni, inner.tw16, RowPrologue(), epi, done); \
-            else if (epi.mode == 1 && mul_epi) launch_pdl(pd, rows16_kernel<LG, 0, 1, true>, grid, G::rthreads, G::rows_smem_plain, s, t1, out, no, P, ni, inner.tw16, RowPrologue(), epi, done); \
-            else if (epi.mode == 1) launch_pdl(pd, rows16_kernel<LG, 0, 1, false>, grid, G::rthreads, G::rows_smem_plain, s, t1, out, no, P, ni, inner.tw16, RowPrologue(), epi, done); \
-            else if (mul_epi) launch_pdl(pd, rows16_kernel<LG, 0, 4, true>, grid, G::rthreads, G::rows_smem_plain, s, t1, out, no, P, ni, inner.tw16, RowPrologue(), epi, done); \
-            else launch_pdl(pd, rows16_kernel<LG, 0, 4, false>, grid, G::rthreads, G::rows_smem_plain, s, t1, out, no, P, ni, inner.tw16, RowPrologue(), epi, done); \
-        } break;
-        switch (inner.log2L) {
-            VCH_R16_INV(6) VCH_R16_INV(7) VCH_R16_INV(8) VCH_R16_INV(9) VCH_R16_INV(10) VCH_R16_INV(11) VCH_R16_INV(12) VCH_R16_INV(13)
-            default: throw Error(VCH_E_ARG, "unsupported FFT length");
-        }
-#undef VCH_R16_INV
+        VCH_F16_SWITCH(inner, (rows16_inverse<LG, 0>(pdl, s, t1, out, no, P, ni, inner.tw16, epi, done, nosct)))
         log->end(s);
         VCH_CUDA(cudaGetLastError());
         return;

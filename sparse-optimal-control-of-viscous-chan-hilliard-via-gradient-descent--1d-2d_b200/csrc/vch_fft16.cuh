@@ -265,14 +265,21 @@ __device__ __forceinline__ void pro16_mode3(double2* __restrict__ stage, const d
 }
 
 // ---- fused epilogue: out = [(mul_a - abar)] z + addend and the BiCGStab dot products (DotEpilogue modes 1 and 4)
-template <int LOG2L, int EPI, bool MUL>
+template <int LOG2L, int EPI, bool MUL, int XM>
 __device__ __forceinline__ void epi16_store(const double2 (&z)[16], double* __restrict__ out, const double* __restrict__ addend,
                                             const double* __restrict__ other, const double* __restrict__ rvec,
                                             const double* __restrict__ mul_a, double abar, size_t ba, size_t bb, bool va, bool vb,
-                                            int t, double (&acc)[5]) {
+                                            int t, double (&acc)[5], const Scatter& sct, int la) {
     using G = F16<LOG2L>;
     const bool has_r = EPI == 4 || rvec != nullptr;
     auto elem = [&](int e, double2 zz) {
+        if (EPI == 0 && XM == 1) {   // slab mode: transposing store into the buffer of the rank that owns column e
+            int r = e >> sct.shift; if (r >= sct.nr) r = sct.nr - 1;
+            double* dst = sct.peer[r] + sct.off + (size_t)(sct.base + la) * sct.pitch + (e - (r << sct.shift));
+            if (va) dst[0] = zz.x;
+            if (vb) dst[sct.pitch] = zz.y;
+            return;
+        }
         if (EPI == 0) {
             if (va) out[ba + e] = zz.x;
             if (vb) out[bb + e] = zz.y;
@@ -301,10 +308,13 @@ __device__ __forceinline__ void epi16_store(const double2 (&z)[16], double* __re
 // ---- row kernel: one CTA = fpb line pairs; line l at base + l*ls, contiguous elements.
 //   PRO 0: x = in;  2: s = r - alpha v;  3: deferred x/r update + new p  (RowPrologue);   MUL: multiply by (a - abar) on this side
 //   EPI 0: plain store;  1 / 4: addend + dot products (DotEpilogue)
-template <int LOG2L, int PRO, int EPI, bool MUL>
+//   XM (slab mode, Scatter in vch_dct.cuh): 1 = the plain store goes transposed into the column owners' buffers over NVLink;
+//       3 = the input is gathered from the column owners' buffers (every element crosses NVLink once, staged like a prologue)
+template <int LOG2L, int PRO, int EPI, bool MUL, int XM = 0>
 __global__ void __launch_bounds__(F16<LOG2L>::rthreads, F16<LOG2L>::rminb)
 rows16_kernel(const double* __restrict__ in, double* __restrict__ out, int nlines, int in_ls, int out_ls,
-              const double2* __restrict__ tw, RowPrologue pro, DotEpilogue epi, const int* __restrict__ done) {
+              const double2* __restrict__ tw, RowPrologue pro, DotEpilogue epi, const int* __restrict__ done,
+              const __grid_constant__ Scatter sct) {
     pdl_enter();
     using G = F16<LOG2L>;
     if (done && *done) return;
@@ -320,7 +330,20 @@ rows16_kernel(const double* __restrict__ in, double* __restrict__ out, int nline
     // absent lines (odd line count, idle FFT slots of the last CTA) read line 0 and are never written
     const size_t ia = (size_t)(va ? la : 0) * in_ls, ib = (size_t)(vb ? lb : 0) * in_ls;
     double2 v[16];
-    if (PRO == 0) {
+    if (PRO == 0 && XM == 3) {
+        double2* stage = sm + (size_t)G::fpb * G::ld + (size_t)f * (G::N + 1);
+        auto fetch = [&](int e) {
+            int r = e >> sct.shift; if (r >= sct.nr) r = sct.nr - 1;
+            const double* src = sct.peer[r] + sct.off + (size_t)(sct.base + (va ? la : 0)) * sct.pitch + (e - (r << sct.shift));
+            stage[e] = make_double2(src[0], vb ? src[sct.pitch] : 0.0);
+        };
+#pragma unroll
+        for (int q = 0; q < 8; ++q) fetch(t + q * G::tpf);
+        if (t == 0) fetch(G::N);
+        __syncthreads();
+#pragma unroll
+        for (int r = 0; r < 16; ++r) v[r] = stage[idx16<LOG2L>(t, r)];
+    } else if (PRO == 0) {
 #pragma unroll
         for (int r = 0; r < 16; ++r) { const int e = idx16<LOG2L>(t, r); v[r] = make_double2(in[ia + e], in[ib + e]); }
     } else {
@@ -342,7 +365,8 @@ rows16_kernel(const double* __restrict__ in, double* __restrict__ out, int nline
 
     double acc[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
     const size_t oa = (size_t)(va ? la : 0) * out_ls, ob = (size_t)(vb ? lb : 0) * out_ls;
-    epi16_store<LOG2L, EPI, MUL>(z, out, epi.addend, epi.other, epi.rvec, epi.mul_a, MUL && EPI ? epi.sc->abar : 0.0, oa, ob, va, vb, t, acc);
+    epi16_store<LOG2L, EPI, MUL, XM>(z, out, epi.addend, epi.other, epi.rvec, epi.mul_a, MUL && EPI ? epi.sc->abar : 0.0, oa, ob, va, vb, t, acc,
+                                     sct, la);
     if (EPI == 4) {          // every thread of every CTA takes part in the reduction
         const int op[5] = {0, 0, 0, 0, 0};
         double tot[5];
@@ -450,6 +474,69 @@ cols16_kernel(double* __restrict__ buf, int pitch, int ncols, const double2* __r
     }
     VCH_STAMP(8);
 }
+
+// host: launch / attribute helpers.  XM = 0: single GPU; 1 / 3: slab mode (forward rows scatter, inverse rows gather).
+#ifndef VCH_CPU_EMU_KERNELS_ONLY
+template <typename K>
+static inline void fft16_attr(K kern, size_t bytes) {
+    VCH_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+}
+template <int LG, int XM>
+static inline void rows16_set_attributes() {
+    using G = F16<LG>;
+    if (XM != 3) {
+        fft16_attr(rows16_kernel<LG, 0, 0, false, XM>, G::rows_smem_plain);
+        fft16_attr(rows16_kernel<LG, 2, 0, false, XM>, G::rows_smem_staged); fft16_attr(rows16_kernel<LG, 2, 0, true, XM>, G::rows_smem_staged);
+        fft16_attr(rows16_kernel<LG, 3, 0, false, XM>, G::rows_smem_staged); fft16_attr(rows16_kernel<LG, 3, 0, true, XM>, G::rows_smem_staged);
+    }
+    if (XM != 1) {
+        constexpr size_t sm = XM == 3 ? G::rows_smem_staged : G::rows_smem_plain;
+        if (XM == 3) fft16_attr(rows16_kernel<LG, 0, 0, false, XM>, sm);
+        fft16_attr(rows16_kernel<LG, 0, 1, false, XM>, sm); fft16_attr(rows16_kernel<LG, 0, 1, true, XM>, sm);
+        fft16_attr(rows16_kernel<LG, 0, 4, false, XM>, sm); fft16_attr(rows16_kernel<LG, 0, 4, true, XM>, sm);
+    }
+}
+// forward rows: `lines` lines of `in` (prologue fused) -> out (XM = 1: scattered through sct)
+template <int LG, int XM>
+static inline void rows16_forward(bool pd, cudaStream_t s, const double* in, double* out, int lines, int in_ls, int out_ls,
+                                  const double2* tw, const RowPrologue& pro, const int* done, const Scatter& sct) {
+    using G = F16<LG>;
+    const int grid = ((lines + 1) / 2 + G::fpb - 1) / G::fpb;
+    const bool mul = pro.mode != 0 && pro.a != nullptr;
+    const DotEpilogue none;
+#define VCH_R16(PRO, MUL, SM) launch_pdl(pd, rows16_kernel<LG, PRO, 0, MUL, XM>, grid, G::rthreads, SM, s, in, out, lines, in_ls, out_ls, tw, pro, none, done, sct)
+    if (pro.mode == 0) VCH_R16(0, false, G::rows_smem_plain);
+    else if (pro.mode == 2 && mul) VCH_R16(2, true, G::rows_smem_staged);
+    else if (pro.mode == 2) VCH_R16(2, false, G::rows_smem_staged);
+    else if (mul) VCH_R16(3, true, G::rows_smem_staged);
+    else VCH_R16(3, false, G::rows_smem_staged);
+#undef VCH_R16
+}
+// inverse rows: in (XM = 3: gathered through sct) -> out with the fused epilogue
+template <int LG, int XM>
+static inline void rows16_inverse(bool pd, cudaStream_t s, const double* in, double* out, int lines, int in_ls, int out_ls,
+                                  const double2* tw, const DotEpilogue& epi, const int* done, const Scatter& sct) {
+    using G = F16<LG>;
+    const int grid = ((lines + 1) / 2 + G::fpb - 1) / G::fpb;
+    const bool mul = epi.mode != 0 && epi.mul_a != nullptr;
+    constexpr size_t sm = XM == 3 ? G::rows_smem_staged : G::rows_smem_plain;
+    const RowPrologue none;
+#define VCH_R16(EPI, MUL) launch_pdl(pd, rows16_kernel<LG, 0, EPI, MUL, XM>, grid, G::rthreads, sm, s, in, out, lines, in_ls, out_ls, tw, none, epi, done, sct)
+    if (epi.mode == 0) VCH_R16(0, false);
+    else if (epi.mode == 1 && mul) VCH_R16(1, true);
+    else if (epi.mode == 1) VCH_R16(1, false);
+    else if (mul) VCH_R16(4, true);
+    else VCH_R16(4, false);
+#undef VCH_R16
+}
+template <int LG>
+static inline void cols16_solve(bool pd, cudaStream_t s, double* buf, int pitch, int ncols, const double2* tw, const double* lam_col,
+                                const double* lam_row, const SymbolArgs& sym, double norm, int scale_mode, const int* done) {
+    using G = F16<LG>;
+    const int grid = (ncols + 2 * G::cp - 1) / (2 * G::cp);
+    launch_pdl(pd, cols16_kernel<LG>, grid, G::cthreads, G::cols_smem_bytes, s, buf, pitch, ncols, tw, lam_col, lam_row, sym, norm, scale_mode, done);
+}
+#endif
 
 // host: per-pass twiddle tables for the length Lf = 2^log2L, layout as F16<LOG2L>::tw_* describes
 static inline std::vector<double2> fft16_twiddles(int log2L) {
