@@ -53,6 +53,14 @@ BYTES_PER_NODE = {
     "trial_kernel": 48,
     "step_setup_kernel": 56, "solve_w_kernel": 32, "clip_mass_kernel": 16, "mass_shift_kernel": 16,
     "adj_rhs_kernel": 64, "adj_qr_kernel": 40, "adj_terminal_rhs_kernel": 24, "mu_init_kernel": 24,
+    # round-2 tile kernels (vch2d_tiles.cuh) and the fused start of a solve
+    "residual_tile_kernel": 56,                        # read phi, mu, cphi, cmu; write Rphi, Rmu, a
+    "dmu_close_tile_kernel": 88,                       # read x, p, s, a, Rphi, phi, mu; write x, dmu, phi_trial, mu_trial
+    "step_setup_tile_kernel": 72,                      # read phi0, mu0, w0, u_n, u_n+1; write w1, cphi, cmu, mu guess
+    "adj_rhs_tile_kernel": 80,                         # read p1, q1, phi1, phi0, Q1, Q0; write r, r0, x, a
+    "adj_qr_tile_kernel": 48,                          # read p (solution), q1, r1; write p_k, q_k, r_k
+    "rows16_schur": 24,                                # read Rphi, Rmu; write the transform
+    "rows16_init": 32,                                 # read the transform; write r, r0, x
 }
 
 

@@ -1,6 +1,6 @@
 // 2D engine: context, Krylov solver, Newton driver, time loop, adjoint sweep, PGD iteration, C ABI.
-// Host control flow lives here; all arithmetic is in the kernels of vch2d_kernels.cuh / vch_dct.cuh.
-#include "vch2d_kernels.cuh"
+// Host control flow lives here; all arithmetic is in the kernels of vch2d_kernels.cuh / vch2d_tiles.cuh / vch_dct.cuh / vch_fft16.cuh.
+#include "vch2d_tiles.cuh"
 #include <algorithm>
 #include <functional>
 #include <chrono>
@@ -24,7 +24,7 @@ struct vch2d_ctx {
     cudaStream_t user = nullptr;     // caller's stream (vch2d_set_stream); ordered with `stream` by events per call
     cudaEvent_t ev_in = nullptr, ev_out = nullptr;
     int use_graphs = 1;
-    struct SolveGraph { bool adj; const double* a; cudaGraph_t g; cudaGraphExec_t exec; };
+    struct SolveGraph { bool adj; const double* a; const double* rphi; const double* rmu; cudaGraph_t g; cudaGraphExec_t exec; };
     std::vector<SolveGraph> graphs;
     LaunchLog log;
     double krylov_tol = 1e-11;
@@ -39,6 +39,13 @@ struct vch2d_ctx {
                                  // the second half of its last iteration is what keeps the gradient at ~1e-12 of the reference's
                                  // (measured: r moves by 6.6e-9 with the exit, for 6.6 % of the adjoint sweep's time)
     int debug = 0;
+    int tiled = 0;               // shared-memory tile kernels for the stencils (vch2d_tiles.cuh); not in slab mode.  VCH_TILED=0 disables
+    int fused_solve = 0;         // tiled + radix-16 transforms + 6-launch iteration: the Schur right-hand side is formed by the first row
+                                 // transform of the solve, the BiCGStab start by the last one of P^-1 b (forward) / by the adjoint rhs
+                                 // kernel, the closing x update by the dmu kernel — 3 launches fewer per linear solve
+    Tiling tl;
+    const double* cur_rphi = nullptr;   // fused forward solve: R_phi / R_mu the solve's first kernel reads
+    const double* cur_rmu = nullptr;
     DctPlan dct;
     // work vectors (n doubles each)
     DevBuf phi, mu, phit, mut, w0, w1, cphi, cmu, Rphi, Rmu, a, RphiT, RmuT, aT;
@@ -63,6 +70,8 @@ struct vch2d_ctx {
     double* out4 = nullptr;      // device, 8 doubles
     double* out4_host = nullptr; // pinned
 
+    // Newton update dphi after newton_linear_solve: the fused dmu kernel writes the closed iterate into kt (see dmu_close_tile_kernel)
+    double* dphi() const { return fused_solve ? kt.p : kx.p; }
     int eb() const { return (int)((g.n + 255) / 256); }
     int rb() const { return red_blocks(g.n); }
 };
@@ -124,7 +133,10 @@ void copy_ghosted(vch2d_ctx* c, double* dst, const double* src) {
 template <bool ADJ> int iter_launches(const vch2d_ctx* c) { return (c->bicg6 ? 6 : 7) + (c->slab ? 4 : 0); }
 // FWD: P^-1 b (3 kernels) + init;  ADJ (right-preconditioned): init + the closing x = P^-1 y (3 kernels); slab mode adds the
 // barriers of one preconditioner application (2 + the trailing one)
-template <bool ADJ> int prologue_launches(const vch2d_ctx* c) { return 4 + (c->slab ? 3 : 0) + (c->bicg6 ? 1 : 0); }
+template <bool ADJ> int prologue_launches(const vch2d_ctx* c) {
+    if (c->fused_solve) return ADJ ? 4 : 3;      // FWD: P^-1 b with the start fused;  ADJ: closing update + x = P^-1 y (start: adjoint rhs kernel)
+    return 4 + (c->slab ? 3 : 0) + (c->bicg6 ? 1 : 0);
+}
 
 // Orders the library's private stream after the caller's stream on entry and the caller's stream after ours on exit,
 // so callers see ordinary stream semantics (torch.cuda.Event on their stream brackets our kernels).
@@ -180,6 +192,14 @@ void enqueue_bicg_iteration(vch2d_ctx* c, const double* a, const SymbolArgs& sy,
 template <bool ADJ>
 void enqueue_bicg_prologue(vch2d_ctx* c, const SymbolArgs& sy, cudaGraphConditionalHandle cond, int use_cond) {
     const long long n = c->g.n;
+    if (c->fused_solve) {
+        if (ADJ) return;     // adj_rhs_tile_kernel has set r = r0 = b, x = 0 and the scalars
+        RowPrologue p4; p4.mode = 4; p4.r = c->cur_rphi; p4.qv = c->cur_rmu; p4.k_in = c->g.ihi2; p4.k_out = c->g.iho2;
+        DotEpilogue e5; e5.mode = 5; e5.sc = c->sc; e5.part = c->red.part; e5.ticket = c->ticket; e5.out2 = c->kr0.p; e5.zero = c->kx.p;
+        e5.cond = cond; e5.use_cond = use_cond;
+        c->dct.apply(c->stream, c->cur_rphi, c->kr.p, sy, nullptr, e5, p4);     // r = r0 = P^-1 (L R_phi - R_mu), x = 0, ||r||^2
+        return;
+    }
     if (!ADJ) c->dct.apply(c->stream, c->kb.p, c->kr.p, sy, nullptr);
     LAUNCH(c, bicg_init_kernel, c->rb(), kRedThreads, ADJ ? c->kb.p : c->kr.p, c->kr.p, c->kr0.p, c->kx.p, n, c->sc,
            c->red.part, c->ticket, cond, use_cond);
@@ -187,6 +207,7 @@ void enqueue_bicg_prologue(vch2d_ctx* c, const SymbolArgs& sy, cudaGraphConditio
 // End of a solve: ADJ x = P^-1 y.
 template <bool ADJ>
 void enqueue_bicg_epilogue(vch2d_ctx* c, const SymbolArgs& sy) {
+    if (c->fused_solve && !ADJ) return;     // dmu_close_tile_kernel applies the closing update
     if (c->bicg6) LAUNCH(c, bicg_close_kernel, c->rb(), kRedThreads, c->kx.p, c->kp.p, c->ks.p, c->g.n, c->sc, c->red.part, c->ticket);
     if (ADJ) c->dct.apply(c->stream, c->kx.p, c->kx.p, sy, nullptr);
 }
@@ -195,8 +216,10 @@ void enqueue_bicg_epilogue(vch2d_ctx* c, const SymbolArgs& sy) {
 // is set on the device by the last kernel of each iteration (cudaGraphSetConditional), so the host never polls.
 template <bool ADJ>
 cudaGraphExec_t solve_graph(vch2d_ctx* c, const double* a) {
+    const double* key_rp = (c->fused_solve && !ADJ) ? c->cur_rphi : nullptr;
+    const double* key_rm = (c->fused_solve && !ADJ) ? c->cur_rmu : nullptr;
     for (auto& g : c->graphs)
-        if (g.adj == ADJ && g.a == a) return g.exec;
+        if (g.adj == ADJ && g.a == a && g.rphi == key_rp && g.rmu == key_rm) return g.exec;
     if (c->graphs.size() >= 12) {
         for (auto& g : c->graphs) { cudaGraphExecDestroy(g.exec); cudaGraphDestroy(g.g); }
         c->graphs.clear();
@@ -208,13 +231,16 @@ cudaGraphExec_t solve_graph(vch2d_ctx* c, const double* a) {
     cudaGraphConditionalHandle cond;
     VCH_CUDA(cudaGraphConditionalHandleCreate(&cond, graph, 1, cudaGraphCondAssignDefault));
     // prologue nodes
-    VCH_CUDA(cudaStreamBeginCaptureToGraph(c->stream, graph, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal));
-    enqueue_bicg_prologue<ADJ>(c, sy, cond, prologue_launches<ADJ>(c));
-    cudaStreamCaptureStatus st; const cudaGraphNode_t* deps = nullptr; size_t ndeps = 0;
-    VCH_CUDA(cudaStreamGetCaptureInfo(c->stream, &st, nullptr, nullptr, &deps, &ndeps));
-    std::vector<cudaGraphNode_t> leaf(deps, deps + ndeps);
+    std::vector<cudaGraphNode_t> leaf;
     cudaGraph_t tmp;
-    VCH_CUDA(cudaStreamEndCapture(c->stream, &tmp));
+    if (!(c->fused_solve && ADJ)) {   // (fused adjoint solve: no prologue, the graph starts with the WHILE node)
+        VCH_CUDA(cudaStreamBeginCaptureToGraph(c->stream, graph, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal));
+        enqueue_bicg_prologue<ADJ>(c, sy, cond, prologue_launches<ADJ>(c));
+        cudaStreamCaptureStatus st; const cudaGraphNode_t* deps = nullptr; size_t ndeps = 0;
+        VCH_CUDA(cudaStreamGetCaptureInfo(c->stream, &st, nullptr, nullptr, &deps, &ndeps));
+        leaf.assign(deps, deps + ndeps);
+        VCH_CUDA(cudaStreamEndCapture(c->stream, &tmp));
+    }
     // WHILE node
     cudaGraphNodeParams np = {};
     np.type = cudaGraphNodeTypeConditional;
@@ -222,12 +248,12 @@ cudaGraphExec_t solve_graph(vch2d_ctx* c, const double* a) {
     np.conditional.type = cudaGraphCondTypeWhile;
     np.conditional.size = 1;
     cudaGraphNode_t wnode;
-    VCH_CUDA(cudaGraphAddNode(&wnode, graph, leaf.data(), leaf.size(), &np));
+    VCH_CUDA(cudaGraphAddNode(&wnode, graph, leaf.empty() ? nullptr : leaf.data(), leaf.size(), &np));
     cudaGraph_t body = np.conditional.phGraph_out[0];
     VCH_CUDA(cudaStreamBeginCaptureToGraph(c->stream, body, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal));
     enqueue_bicg_iteration<ADJ>(c, a, sy, cond, iter_launches<ADJ>(c));
     VCH_CUDA(cudaStreamEndCapture(c->stream, &tmp));
-    if (ADJ || c->bicg6) {   // closing x = P^-1 y (and, 6-launch form, the last x update), after the loop
+    if (ADJ || (c->bicg6 && !c->fused_solve)) {   // closing x = P^-1 y (and, 6-launch form, the last x update), after the loop
         VCH_CUDA(cudaStreamBeginCaptureToGraph(c->stream, graph, &wnode, nullptr, 1, cudaStreamCaptureModeThreadLocal));
         enqueue_bicg_epilogue<ADJ>(c, sy);
         VCH_CUDA(cudaStreamEndCapture(c->stream, &tmp));
@@ -235,7 +261,7 @@ cudaGraphExec_t solve_graph(vch2d_ctx* c, const double* a) {
     cudaGraphExec_t exec;
     VCH_CUDA(cudaGraphInstantiate(&exec, graph, 0));
     c->log.count = count0;            // capture launches nothing
-    c->graphs.push_back({ADJ, a, graph, exec});
+    c->graphs.push_back({ADJ, a, key_rp, key_rm, graph, exec});
     return exec;
 }
 
@@ -247,7 +273,7 @@ cudaGraphExec_t solve_graph(vch2d_ctx* c, const double* a) {
 template <bool ADJ>
 int krylov_solve(vch2d_ctx* c, const double* b, const double* a, vch_stats* st) {   // coefficients: sc->c0 / sc->c2, set by the rhs kernel
     const long long n = c->g.n;
-    if (b != c->kb.p) dev_copy(c, c->kb.p, b, (size_t)n);
+    if (b && b != c->kb.p) dev_copy(c, c->kb.p, b, (size_t)n);      // b == nullptr (fused solve): the right-hand side is already in place
     if (c->use_graphs && !c->log.profiling) {
         cudaGraphExec_t exec = solve_graph<ADJ>(c, a);
         VCH_CUDA(cudaGraphLaunch(exec, c->stream));
@@ -320,8 +346,19 @@ void require_adjoint_converged(vch2d_ctx* c, const StatMark& m0) {
 }
 
 // publish: the kernel's last block also writes the scalars into the pinned mirror (follow with wait_scalars, not fetch_scalars)
+// next_tol (tiled kernels): relative tolerance of the linear solve that would follow this evaluation; its coefficients and
+// tolerance are then set by the residual kernel itself (the round-1 path sets them in schur_rhs_kernel)
+__global__ void set_solve_kernel(Scal* sc, double c0, double c2, double tol2, int adj) {
+    pdl_enter();
+    sc->c0 = c0; sc->c2 = c2; sc->tol2 = tol2; sc->adj = adj;
+}
 void eval_residual(vch2d_ctx* c, const double* phi, const double* mu, double* Rphi, double* Rmu, double* a, double dt,
-                   bool publish = false) {
+                   bool publish = false, double next_tol = 0.0) {
+    if (c->tiled) {
+        LAUNCH(c, residual_tile_kernel, c->tl.grid(), kTileThreads, phi, mu, c->cphi.p, c->cmu.p, Rphi, Rmu, a, c->g, c->tl, c->ph, dt,
+               c->sc, c->red.part, c->ticket, publish ? c->sc_host : (Scal*)nullptr, 1.0 / dt, 0.5 * c->ph.kappa, next_tol * next_tol);
+        return;
+    }
     LAUNCH(c, residual_kernel, c->rb(), kRedThreads, phi, mu, c->cphi.p, c->cmu.p, Rphi, Rmu, a, c->g, c->ph, dt, c->sc,
            c->red.part, c->ticket, publish ? c->sc_host : (Scal*)nullptr);
 }
@@ -330,11 +367,26 @@ void eval_residual(vch2d_ctx* c, const double* phi, const double* mu, double* Rp
 // dmu = 2 (a dphi - kappa/2 L dphi + Rphi).   dphi -> c->kx, dmu -> c->dmu.  phi may be null (no ceiling minima).
 void newton_linear_solve(vch2d_ctx* c, const double* Rphi, const double* Rmu, const double* a, const double* phi,
                          double dt, vch_stats* st, double rel_tol = 0.0, const double* mu = nullptr, double* phit = nullptr,
-                         double* mut = nullptr) {
+                         double* mut = nullptr, bool scalars_set = false) {
     if (!(rel_tol > 0.0)) rel_tol = c->krylov_tol;
+    if (c->fused_solve) {
+        // rows[b = L R_phi - R_mu] cols rows[r = r0 = P^-1 b, x = 0, ||r||^2] WHILE{6 kernels} | dmu kernel with the closing x update.
+        // scalars_set: the residual kernel in front has already written c0 / c2 / tol2 for this solve
+        if (!scalars_set) LAUNCH(c, set_solve_kernel, 1, 1, c->sc, 1.0 / dt, 0.5 * c->ph.kappa, rel_tol * rel_tol, 0);
+        c->cur_rphi = Rphi; c->cur_rmu = Rmu;
+        krylov_solve<false>(c, nullptr, a, st);
+        LAUNCH(c, dmu_close_tile_kernel, c->tl.grid(), kTileThreads, (const double*)c->kx.p, c->kt.p, c->kp.p, c->ks.p, a, Rphi, phi, c->dmu.p, c->g, c->tl, c->ph,
+               c->sc, c->red.part, c->ticket, mu, (phi && mu) ? phit : nullptr, (phi && mu) ? mut : nullptr, c->ph.tau / dt, 1);
+        return;
+    }
     halo_push(c, Rphi, nullptr, 1);
     LAUNCH(c, schur_rhs_kernel, c->eb(), 256, Rphi, Rmu, c->kb.p, c->g, c->sc, 1.0 / dt, 0.5 * c->ph.kappa, rel_tol * rel_tol);
     krylov_solve<false>(c, c->kb.p, a, st);
+    if (c->tiled) {
+        LAUNCH(c, dmu_close_tile_kernel, c->tl.grid(), kTileThreads, (const double*)c->kx.p, (double*)nullptr, c->kp.p, c->ks.p, a, Rphi, phi, c->dmu.p, c->g, c->tl, c->ph,
+               c->sc, c->red.part, c->ticket, mu, (phi && mu) ? phit : nullptr, (phi && mu) ? mut : nullptr, c->ph.tau / dt, 0);
+        return;
+    }
     halo_push(c, c->kx.p, nullptr, 1);
     LAUNCH(c, dmu_ceiling_kernel, c->rb(), kRedThreads, c->kx.p, a, Rphi, phi, c->dmu.p, c->g, c->ph, c->sc, c->red.part,
            c->ticket, mu, (phi && mu) ? phit : nullptr, (phi && mu) ? mut : nullptr, c->ph.tau / dt);
@@ -348,22 +400,34 @@ void newton_linear_solve(vch2d_ctx* c, const double* Rphi, const double* Rmu, co
 // and that iteration re-solves to krylov_tol from wherever the first one landed: the accepted iterate moves by ~1e-15
 // relative per step (<= 2e-12 over a 1000-step trajectory, measured with the NumPy prototype in scripts/krylov_forcing_study.py)
 // while the BiCGStab iterations of the forward sweep drop by 22 %.  Iteration counts of Newton itself do not change.
+// wstep (time loop, tiled kernels): the set-up kernel first forms w_new = solve_w(w_old, u_n, u_{n+1}) itself (solve_w_kernel fused).
+struct WStep { const double* un; const double* un1; double gdt; double* w_new; };
 void newton_step(vch2d_ctx* c, const double* phi_old, const double* mu_old, const double* w_old, const double* w_new,
-                 double dt, std::vector<double>* hist, vch_stats* st, bool inexact_first = false) {
+                 double dt, std::vector<double>* hist, vch_stats* st, bool inexact_first = false, const WStep* wstep = nullptr) {
     const long long n = c->g.n;
     const int eb = c->eb();
-    dev_copy(c, c->phi.p, phi_old, (size_t)n);
+    // tiled kernels: the first iterate is read where it lies (a trajectory level in the time loop) — no copy into the work vector
+    const bool in_place = c->tiled && phi_old != c->phi.p && phi_old != c->phit.p;
+    if (!in_place) dev_copy(c, c->phi.p, phi_old, (size_t)n);
     if (c->slab && mu_old != c->mu_old.p) {   // test-level entry: bring mu_old into a ghosted work vector
         c->mu_old.alloc(n);
         dev_copy(c, c->mu_old.p, mu_old, (size_t)n);
         mu_old = c->mu_old.p;
         halo_push(c, c->phi.p, c->mu_old.p, 1);
     } else halo_push(c, c->phi.p, nullptr, 1);
-    LAUNCH(c, step_setup_kernel, eb, 256, c->phi.p, mu_old, w_old, w_new, c->cphi.p, c->cmu.p, c->mu.p, c->g, c->ph, dt);
+    if (c->tiled)
+        LAUNCH(c, step_setup_tile_kernel, c->tl.grid(), kTileThreads, in_place ? phi_old : c->phi.p, mu_old, w_old, wstep ? wstep->w_new : const_cast<double*>(w_new),
+               wstep ? wstep->un : (const double*)nullptr, wstep ? wstep->un1 : (const double*)nullptr, wstep ? wstep->gdt : 0.0,
+               c->cphi.p, c->cmu.p, c->mu.p, c->g, c->tl, c->ph, dt);
+    else
+        LAUNCH(c, step_setup_kernel, eb, 256, c->phi.p, mu_old, w_old, w_new, c->cphi.p, c->cmu.p, c->mu.p, c->g, c->ph, dt);
     halo_push(c, c->mu.p, nullptr, 1);
-    double *phi = c->phi.p, *mu = c->mu.p, *phit = c->phit.p, *mut = c->mut.p;
+    const double* phi = in_place ? phi_old : c->phi.p;
+    double *mu = c->mu.p, *phit = c->phit.p, *mut = c->mut.p;
     double *Rp = c->Rphi.p, *Rm = c->Rmu.p, *a = c->a.p, *RpT = c->RphiT.p, *RmT = c->RmuT.p, *aT = c->aT.p;
-    eval_residual(c, phi, mu, Rp, Rm, a, dt, true);
+    // tolerance of the linear solve that follows an evaluation (the tiled residual kernel sets the solver scalars)
+    const double tol_first = (inexact_first && c->krylov_first_tol > c->krylov_tol) ? c->krylov_first_tol : c->krylov_tol;
+    eval_residual(c, phi, mu, Rp, Rm, a, dt, true, tol_first);
     wait_scalars(c);
     if (st) st->newton_residual_evals += 1;
     double normR = std::sqrt(c->sc_host->res2);
@@ -396,9 +460,9 @@ void newton_step(vch2d_ctx* c, const double* phi_old, const double* mu_old, cons
         // speculative full step: almost always alpha = 1 is both allowed by the ceiling and accepted by Armijo, so the
         // trial iterate (formed by the dmu kernel) and its residual are enqueued before the host has seen the ceiling
         // -> ONE sync per Newton iteration
-        newton_linear_solve(c, Rp, Rm, a, phi, dt, st, solve_tol, mu, phit, mut);
+        newton_linear_solve(c, Rp, Rm, a, phi, dt, st, solve_tol, mu, phit, mut, c->tiled != 0);
         halo_push(c, phit, mut, 1);
-        eval_residual(c, phit, mut, RpT, RmT, aT, dt, true);
+        eval_residual(c, phit, mut, RpT, RmT, aT, dt, true, c->krylov_tol);
         wait_scalars(c);
         if (c->sc_host->nonfinite) throw Error(VCH_E_NONFINITE, "non-finite value in Krylov solve");
         if (st) st->newton_residual_evals += 1;
@@ -414,9 +478,9 @@ void newton_step(vch2d_ctx* c, const double* phi_old, const double* mu_old, cons
         bool have_trial = (alpha == 1.0);      // the speculative evaluation is the first trial
         for (int ls = 0; ls < 12; ++ls) {
             if (!have_trial) {
-                LAUNCH(c, trial_kernel, eb, 256, phi, mu, c->kx.p, c->dmu.p, phit, mut, n, alpha);
+                LAUNCH(c, trial_kernel, eb, 256, phi, mu, c->dphi(), c->dmu.p, phit, mut, n, alpha);
                 halo_push(c, phit, mut, 1);
-                eval_residual(c, phit, mut, RpT, RmT, aT, dt, true);
+                eval_residual(c, phit, mut, RpT, RmT, aT, dt, true, c->krylov_tol);
                 wait_scalars(c);
                 if (st) st->newton_residual_evals += 1;
             }
@@ -434,16 +498,19 @@ void newton_step(vch2d_ctx* c, const double* phi_old, const double* mu_old, cons
         true_est = (accepted && full_step && alpha == 1.0) ? std::sqrt(rem_full * rem_full + lin_left * lin_left) : INFINITY;
         if (!accepted) {
             if (best < normR) {   // fall back to the best trial (re-evaluated: same arithmetic, same values)
-                LAUNCH(c, trial_kernel, eb, 256, phi, mu, c->kx.p, c->dmu.p, phit, mut, n, best_alpha);
+                LAUNCH(c, trial_kernel, eb, 256, phi, mu, c->dphi(), c->dmu.p, phit, mut, n, best_alpha);
                 halo_push(c, phit, mut, 1);
-                eval_residual(c, phit, mut, RpT, RmT, aT, dt, true);
+                eval_residual(c, phit, mut, RpT, RmT, aT, dt, true, c->krylov_tol);
                 wait_scalars(c);
                 normR = std::sqrt(c->sc_host->res2);
                 accepted = true;
             }
         }
         if (accepted) {
-            std::swap(phi, phit); std::swap(mu, mut);
+            // the old iterate's buffer becomes the next trial buffer — unless it is the caller's array (in_place, first accept)
+            double* freed = (phi == phi_old && in_place) ? c->phi.p : const_cast<double*>(phi);
+            phi = phit; phit = freed;
+            std::swap(mu, mut);
             std::swap(Rp, RpT); std::swap(Rm, RmT); std::swap(a, aT);
             floor_now = floor_est();
         }
@@ -454,11 +521,10 @@ void newton_step(vch2d_ctx* c, const double* phi_old, const double* mu_old, cons
         }
     }
     if (c->debug) fprintf(stderr, "[vch2d] newton: %d its, |R| = %.3e, floor_est = %.3e, before the last solve %.3e\n", k_done, normR, floor_now, dbg_prev);
-    if (phi != c->phi.p) {   // leave the result in c->phi / c->mu
-        std::swap(c->phi.p, c->phit.p); std::swap(c->mu.p, c->mut.p);
-        std::swap(c->phi.n, c->phit.n); std::swap(c->mu.n, c->mut.n);
-        std::swap(c->phi.view, c->phit.view); std::swap(c->mu.view, c->mut.view);
-    }
+    // leave the result in c->phi / c->mu
+    if (phi == phi_old && in_place) dev_copy(c, c->phi.p, phi_old, (size_t)n);     // no step was taken (already converged)
+    else if (phi != c->phi.p) { std::swap(c->phi.p, c->phit.p); std::swap(c->phi.n, c->phit.n); std::swap(c->phi.view, c->phit.view); }
+    if (mu != c->mu.p) { std::swap(c->mu.p, c->mut.p); std::swap(c->mu.n, c->mut.n); std::swap(c->mu.view, c->mut.view); }
     if (Rp != c->Rphi.p) {
         std::swap(c->Rphi.p, c->RphiT.p); std::swap(c->Rmu.p, c->RmuT.p); std::swap(c->a.p, c->aT.p);
     }
@@ -492,11 +558,19 @@ void forward_steps(vch2d_ctx* c, int s0, int s1, const std::function<double*(int
         if (before_step) before_step(s);     // streaming path: makes sure control rows s and s+1 exist
         const double* un = nullptr; const double* un1 = nullptr;
         if (have_u && s < u_rows - 1) { un = U(s); un1 = U(s + 1); }
-        LAUNCH(c, solve_w_kernel, eb, 256, c->w0.p, un, un1, c->w1.p, n, c->prm.gamma / dt);
         const double* phi_old = HN(s);
-        newton_step(c, phi_old, mu_old, c->w0.p, c->w1.p, dt, nullptr, st, true);
+        if (c->tiled) {
+            const WStep ws{un, un1, c->prm.gamma / dt, c->w1.p};
+            newton_step(c, phi_old, mu_old, c->w0.p, c->w1.p, dt, nullptr, st, true, &ws);
+        } else {
+            LAUNCH(c, solve_w_kernel, eb, 256, c->w0.p, un, un1, c->w1.p, n, c->prm.gamma / dt);
+            newton_step(c, phi_old, mu_old, c->w0.p, c->w1.p, dt, nullptr, st, true);
+        }
         post_step(c, c->phi.p, HN(s + 1));
-        copy_ghosted(c, mu_old, c->mu.p);      // slab mode: the ghost rows of the accepted iterate travel along
+        if (c->tiled) {   // the accepted mu becomes mu_old by exchanging the two work vectors
+            std::swap(c->mu_old.p, c->mu.p); std::swap(c->mu_old.n, c->mu.n); std::swap(c->mu_old.view, c->mu.view);
+            mu_old = c->mu_old.p;
+        } else copy_ghosted(c, mu_old, c->mu.p);      // slab mode: the ghost rows of the accepted iterate travel along
         std::swap(c->w0.p, c->w1.p);
         if (mu_hist) dev_copy(c, mu_hist + (size_t)s * n, mu_old, (size_t)n);
         if (w_hist) dev_copy(c, w_hist + (size_t)s * n, c->w0.p, (size_t)n);
@@ -567,7 +641,8 @@ void adjoint_dev(vch2d_ctx* c, const double* phi_hist, int levels, const double*
         SymbolArgs sy{1.0, 0.0, nullptr, c->ph.tau, nullptr};
         c->dct.apply(c->stream, c->kb.p, pM, sy, nullptr);          // (I - tau L) p_M = b2 (phi_M - phi_T): exact in the DCT basis
         halo_push(c, pM, nullptr, 1);
-        LAUNCH(c, adj_qr_kernel, eb, 256, pM, (const double*)nullptr, (const double*)nullptr, qM, rM, c->g, 0.0, 0.0);
+        if (c->tiled) LAUNCH(c, adj_qr_tile_kernel, c->tl.grid(), kTileThreads, (const double*)pM, pM, (const double*)nullptr, (const double*)nullptr, qM, rM, c->g, c->tl, 0.0, 0.0);
+        else LAUNCH(c, adj_qr_kernel, eb, 256, pM, (const double*)nullptr, (const double*)nullptr, qM, rM, c->g, 0.0, 0.0);
         halo_push(c, qM, nullptr, 1);
         copy_out(M, pM, qM);
     }
@@ -587,11 +662,22 @@ void adjoint_dev(vch2d_ctx* c, const double* phi_hist, int levels, const double*
             continue;
         }
         const double* f1 = H(k + 1); const double* f0 = H(k);
+        const double den = c->ph.gamma + 0.5 * dt;
+        if (c->tiled) {
+            // rhs kernel (+ the BiCGStab start when the solve is fused) | solve graph | q/r recurrence (+ the copy of the solution into p_k)
+            const int fs = c->fused_solve;
+            LAUNCH(c, adj_rhs_tile_kernel, c->tl.grid(), kTileThreads, p1, q1, f1, f0, Q(k + 1), Q(k), fs ? c->kr.p : c->kb.p, c->kr0.p, c->kx.p,
+                   c->a.p, c->g, c->tl, c->ph, dt, b1, c->sc, c->red.part, c->ticket, c->krylov_tol * c->krylov_tol, fs);
+            krylov_solve<true>(c, fs ? (const double*)nullptr : c->kb.p, c->a.p, st);
+            LAUNCH(c, adj_qr_tile_kernel, c->tl.grid(), kTileThreads, (const double*)c->kx.p, p0, q1, r1, q0, r0, c->g, c->tl,
+                   (c->ph.gamma - 0.5 * dt) / den, 0.5 * dt / den);
+            copy_out(k, p0, q0);
+            continue;
+        }
         LAUNCH(c, adj_rhs_kernel, c->rb(), kRedThreads, p1, q1, f1, f0, Q(k + 1), Q(k), c->kb.p, c->a.p, c->g, c->ph, dt, b1, c->sc,
                c->red.part, c->ticket, c->krylov_tol * c->krylov_tol);
         krylov_solve<true>(c, c->kb.p, c->a.p, st);
         dev_copy(c, p0, c->kx.p, (size_t)n);
-        const double den = c->ph.gamma + 0.5 * dt;
         halo_push(c, p0, nullptr, 1);
         LAUNCH(c, adj_qr_kernel, eb, 256, p0, q1, r1, q0, r0, c->g, (c->ph.gamma - 0.5 * dt) / den, 0.5 * dt / den);
         halo_push(c, q0, nullptr, 1);
@@ -754,7 +840,11 @@ static int create_ctx(const vch2d_params* p, int device, int rank, int nranks, v
             c->dct.pdl = c->pdl != 0;
             if (!(c->dct.inner.fft && c->dct.outer.fft)) c->bicg6 = 0;   // the dense-table path has no fused mode 3 / 4
         }
-        c->red.alloc(8 * (size_t)c->dct.max_grid(), c->cm);
+        c->tl = make_tiling(g);
+        c->tiled = !slab && !(getenv("VCH_TILED") && atoi(getenv("VCH_TILED")) == 0);
+        c->fused_solve = c->tiled && c->bicg6 && c->dct.lean && c->dct.inner.fft && c->dct.outer.fft &&
+                         !(getenv("VCH_FUSED_SOLVE") && atoi(getenv("VCH_FUSED_SOLVE")) == 0);
+        c->red.alloc(8 * (size_t)std::max(c->dct.max_grid(), c->tl.grid()), c->cm);
         Scal init{}; init.tol2 = c->krylov_tol * c->krylov_tol; init.maxit = c->krylov_maxit;
         VCH_CUDA(cudaMemcpy(c->sc, &init, sizeof(Scal), cudaMemcpyHostToDevice));
         VCH_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
@@ -1022,7 +1112,7 @@ int vch2d_jacobian_solve(vch2d_ctx* c, const double* phi, double dt, const doubl
             rp = c->Rphi.p;
         }
         newton_linear_solve(c, rp, rm, c->a.p, nullptr, dt, &s);
-        VCH_CUDA(cudaMemcpyAsync(o1, c->kx.p, n * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+        VCH_CUDA(cudaMemcpyAsync(o1, c->dphi(), n * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
         VCH_CUDA(cudaMemcpyAsync(o2, c->dmu.p, n * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
         stat_collect(c, mark0, &s);
         if (its_out) *its_out = (int)s.krylov_iterations;

@@ -59,7 +59,23 @@ struct DotEpilogue {
     // + omega^2 (t,t), the stop decision and the loop conditional, which the x/r update kernel produces in the 7-launch form.
     cudaGraphConditionalHandle cond = 0;
     int use_cond = 0;
+    // mode 5 (start of a forward solve fused into the last row transform of P^-1 b): out = r, out2 = r0 (same values),
+    // zero = x (cleared), (r,r) -> the scalars bicg_init_kernel sets.  Radix-16 kernels only.
+    double* out2 = nullptr;
+    double* zero = nullptr;
 };
+
+// Start-of-solve scalars from ||r||^2 (what bicg_init_kernel's last block does).
+__device__ __forceinline__ void solve_init_scalars(Scal* sc, double rr, cudaGraphConditionalHandle cond, int use_cond) {
+    sc->bnorm2 = rr; sc->rr = rr; sc->rho_new = rr;
+    sc->rho = 1.0; sc->alpha = 0.0; sc->omega = 1.0;
+    sc->thr2 = sc->tol2 * rr;
+    sc->iters = 0; sc->half = 0;
+    sc->done = (rr == 0.0 || !isfinite(rr)) ? 1 : 0;
+    if (!isfinite(rr)) sc->nonfinite = 1;
+    sc->solves += 1;
+    if (use_cond) { sc->g_launches += use_cond; cudaGraphSetConditional(cond, sc->done ? 0u : 1u); }
+}
 
 // Last block of a dot-product epilogue: BiCGStab scalars from the grid-wide sums tot = {(other,out), (out,out), (r,out)}.
 // Half-step exit (mode 1): ||s||^2 = (r,r) - 2 alpha (r,v) + alpha^2 (v,v) for s = r - alpha v.  The three-term formula
@@ -123,6 +139,9 @@ struct RowPrologue {
     const double* t = nullptr;
     double* x = nullptr;
     double* rw = nullptr;
+    // mode 4 (start of a forward Newton solve, radix-16 kernels only): x_in = L r - qv with the 5-point Neumann Laplacian
+    // (r = R_phi, qv = R_mu: the Schur right-hand side, schur_rhs_kernel) evaluated on the fly; k_in / k_out = 1/h^2 along / across the lines
+    double k_in = 0.0, k_out = 0.0;
 };
 
 // Slab mode: the transposes between the row and the column transforms are done by the kernels' own stores, straight
@@ -893,7 +912,8 @@ inline void DctPlan::apply(cudaStream_t s, const double* in, double* out, const 
     const int cppb = outer.fft ? dct_cols_ppb(outer, ni) : 0, cthreads = outer.fft ? cppb * (outer.Lf >> 3) : 0;
     const int cgrid = outer.fft ? ((ni + 1) / 2 + cppb - 1) / cppb : 0;
 
-    if (all_fft && lean && (pro.mode == 0 || pro.mode == 2 || pro.mode == 3) && (epi.mode == 0 || epi.mode == 1 || epi.mode == 4)) {
+    if (all_fft && lean && (pro.mode == 0 || pro.mode == 2 || pro.mode == 3 || pro.mode == 4) &&
+        (epi.mode == 0 || epi.mode == 1 || epi.mode == 4 || epi.mode == 5)) {
         // radix-16 kernels (vch_fft16.cuh), one instantiation per fused mode: rows (prologue) -> column solve -> rows (epilogue)
         const Scatter nosct;
 #define VCH_F16_SWITCH(AX, CALL)                                                                                  \
@@ -904,18 +924,19 @@ inline void DctPlan::apply(cudaStream_t s, const double* in, double* out, const 
             case 12: { constexpr int LG = 12; CALL; } break; case 13: { constexpr int LG = 13; CALL; } break;     \
             default: throw Error(VCH_E_ARG, "unsupported FFT length");                                            \
         }
-        log->begin(pro.mode ? "rows16_pro" : "rows16", s);
+        log->begin(pro.mode == 4 ? "rows16_schur" : (pro.mode ? "rows16_pro" : "rows16"), s);
         VCH_F16_SWITCH(inner, (rows16_forward<LG, 0>(pdl, s, in, t1, no, ni, P, inner.tw16, pro, done, nosct)))
         log->end(s);
         log->begin("cols16_solve", s);
         VCH_F16_SWITCH(outer, (cols16_solve<LG>(pdl, s, t1, P, ni, outer.tw16, inner.lam, outer.lam, sym, norm, scale_mode, done)))
         log->end(s);
-        log->begin(epi.mode == 1 ? "rows16_epi1" : (epi.mode == 4 ? "rows16_epi4" : "rows16"), s);
+        log->begin(epi.mode == 1 ? "rows16_epi1" : (epi.mode == 4 ? "rows16_epi4" : (epi.mode == 5 ? "rows16_init" : "rows16")), s);
         VCH_F16_SWITCH(inner, (rows16_inverse<LG, 0>(pdl, s, t1, out, no, P, ni, inner.tw16, epi, done, nosct)))
         log->end(s);
         VCH_CUDA(cudaGetLastError());
         return;
     }
+    if (pro.mode == 4 || epi.mode == 5) throw Error(VCH_E_ARG, "DctPlan::apply: prologue mode 4 / epilogue mode 5 need the radix-16 kernels");
     if (all_fft) {
         // rows (prologue fused) -> fused column solve in place on the pitched buffer -> rows (addend + dots fused)
         log->begin(pro.mode ? "dct_rows_fft_pro" : "dct_rows_fft", s);

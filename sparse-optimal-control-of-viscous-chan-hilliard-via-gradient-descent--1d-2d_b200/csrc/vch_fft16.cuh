@@ -264,12 +264,38 @@ __device__ __forceinline__ void pro16_mode3(double2* __restrict__ stage, const d
     if (t == 0) elem(G::N);
 }
 
+// Start of a forward Newton solve: the Schur right-hand side b = L R_phi - R_mu (schur_rhs_kernel's formula, same operation
+// order as lap_g) formed while loading, so that kernel and the round trip of b through memory disappear.  Lines la, lb of an
+// nlines x (N+1) field; the line neighbours of la / lb are lb / la themselves plus one more line each.
+template <int LOG2L>
+__device__ __forceinline__ void pro16_mode4(double2* __restrict__ stage, const double* __restrict__ rp, const double* __restrict__ rm,
+                                            double k_in, double k_out, int la, int lb, int nlines, int ls, bool vb, int t) {
+    using G = F16<LOG2L>;
+    const int lbb = vb ? lb : la;                                                   // absent second line: results unused
+    const size_t ba = (size_t)la * ls, bb = (size_t)lbb * ls;
+    const size_t bam = (size_t)(la > 0 ? la - 1 : 1) * ls;                          // line below la
+    const size_t bap = (size_t)(la < nlines - 1 ? la + 1 : nlines - 2) * ls;        // line above la (= lb when present)
+    const size_t bbm = (size_t)(lbb > 0 ? lbb - 1 : 1) * ls;
+    const size_t bbp = (size_t)(lbb < nlines - 1 ? lbb + 1 : nlines - 2) * ls;
+    auto elem = [&](int e) {
+        const int em = e > 0 ? e - 1 : 1, ep = e < G::N ? e + 1 : G::N - 1;
+        const double ca = rp[ba + e], cb = rp[bb + e];
+        const double a_in = (rp[ba + ep] - ca) + (rp[ba + em] - ca), a_out = (rp[bap + e] - ca) + (rp[bam + e] - ca);
+        const double b_in = (rp[bb + ep] - cb) + (rp[bb + em] - cb), b_out = (rp[bbp + e] - cb) + (rp[bbm + e] - cb);
+        stage[e] = make_double2((a_in * k_in + a_out * k_out) - rm[ba + e], (b_in * k_in + b_out * k_out) - rm[bb + e]);
+    };
+#pragma unroll
+    for (int q = 0; q < 8; ++q) elem(t + q * G::tpf);
+    if (t == 0) elem(G::N);
+}
+
 // ---- fused epilogue: out = [(mul_a - abar)] z + addend and the BiCGStab dot products (DotEpilogue modes 1 and 4)
 template <int LOG2L, int EPI, bool MUL, int XM>
 __device__ __forceinline__ void epi16_store(const double2 (&z)[16], double* __restrict__ out, const double* __restrict__ addend,
                                             const double* __restrict__ other, const double* __restrict__ rvec,
                                             const double* __restrict__ mul_a, double abar, size_t ba, size_t bb, bool va, bool vb,
-                                            int t, double (&acc)[5], const Scatter& sct, int la) {
+                                            int t, double (&acc)[5], const Scatter& sct, int la, double* __restrict__ out2 = nullptr,
+                                            double* __restrict__ zero = nullptr) {
     using G = F16<LOG2L>;
     const bool has_r = EPI == 4 || rvec != nullptr;
     auto elem = [&](int e, double2 zz) {
@@ -283,6 +309,11 @@ __device__ __forceinline__ void epi16_store(const double2 (&z)[16], double* __re
         if (EPI == 0) {
             if (va) out[ba + e] = zz.x;
             if (vb) out[bb + e] = zz.y;
+            return;
+        }
+        if (EPI == 5) {   // start of a solve: r = r0 = z, x = 0, (r,r)
+            if (va) { out[ba + e] = zz.x; out2[ba + e] = zz.x; zero[ba + e] = 0.0; acc[0] += zz.x * zz.x; }
+            if (vb) { out[bb + e] = zz.y; out2[bb + e] = zz.y; zero[bb + e] = 0.0; acc[0] += zz.y * zz.y; }
             return;
         }
         const double da = addend[ba + e], db = addend[bb + e], oa = other[ba + e], ob = other[bb + e];
@@ -306,8 +337,9 @@ __device__ __forceinline__ void epi16_store(const double2 (&z)[16], double* __re
 }
 
 // ---- row kernel: one CTA = fpb line pairs; line l at base + l*ls, contiguous elements.
-//   PRO 0: x = in;  2: s = r - alpha v;  3: deferred x/r update + new p  (RowPrologue);   MUL: multiply by (a - abar) on this side
-//   EPI 0: plain store;  1 / 4: addend + dot products (DotEpilogue)
+//   PRO 0: x = in;  2: s = r - alpha v;  3: deferred x/r update + new p;  4: x = L R_phi - R_mu (Schur right-hand side)  (RowPrologue);
+//       MUL: multiply by (a - abar) on this side
+//   EPI 0: plain store;  1 / 4: addend + dot products;  5: start of a solve (r = r0 = out, x = 0, (r,r))  (DotEpilogue)
 //   XM (slab mode, Scatter in vch_dct.cuh): 1 = the plain store goes transposed into the column owners' buffers over NVLink;
 //       3 = the input is gathered from the column owners' buffers (every element crosses NVLink once, staged like a prologue)
 template <int LOG2L, int PRO, int EPI, bool MUL, int XM = 0>
@@ -317,7 +349,12 @@ rows16_kernel(const double* __restrict__ in, double* __restrict__ out, int nline
               const __grid_constant__ Scatter sct) {
     pdl_enter();
     using G = F16<LOG2L>;
-    if (done && *done) return;
+    if (done && *done) {
+        // A solve that is already finished when its loop body starts (zero right-hand side with the start fused into the kernel
+        // in front of the graph): the body's last kernel must still clear the WHILE condition, nobody else will.
+        if (EPI == 4 && epi.use_cond && blockIdx.x == 0 && threadIdx.x == 0) cudaGraphSetConditional(epi.cond, 0u);
+        return;
+    }
 #ifdef VCH_CPU_EMU
     double2* sm = reinterpret_cast<double2*>(vch_emu::dynamic_smem());
 #else
@@ -349,8 +386,9 @@ rows16_kernel(const double* __restrict__ in, double* __restrict__ out, int nline
     } else {
         double2* stage = sm + (size_t)G::fpb * G::ld + (size_t)f * (G::N + 1);
         const Scal* sc = pro.sc;
-        const double al = sc->alpha, om = sc->omega, abar = sc->abar;
-        if (PRO == 2) pro16_mode2<LOG2L, MUL>(stage, pro.r, pro.qv, pro.a, pro.w, al, abar, ia, ib, va, vb, t);
+        const double al = PRO == 4 ? 0.0 : sc->alpha, om = PRO == 4 ? 0.0 : sc->omega, abar = PRO == 4 ? 0.0 : sc->abar;
+        if (PRO == 4) pro16_mode4<LOG2L>(stage, pro.r, pro.qv, pro.k_in, pro.k_out, va ? la : 0, lb, nlines, in_ls, vb, t);
+        else if (PRO == 2) pro16_mode2<LOG2L, MUL>(stage, pro.r, pro.qv, pro.a, pro.w, al, abar, ia, ib, va, vb, t);
         else if (sc->iters == 0) pro16_mode3_first<LOG2L, MUL>(stage, pro.r, pro.a, pro.w, abar, ia, ib, va, vb, t);
         else pro16_mode3<LOG2L, MUL>(stage, pro.s, pro.t, pro.qv, pro.a, pro.w, pro.x, pro.rw, al, om, (sc->rho_new / sc->rho) * (al / om),
                                       abar, ia, ib, va, vb, t);
@@ -366,8 +404,13 @@ rows16_kernel(const double* __restrict__ in, double* __restrict__ out, int nline
     double acc[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
     const size_t oa = (size_t)(va ? la : 0) * out_ls, ob = (size_t)(vb ? lb : 0) * out_ls;
     epi16_store<LOG2L, EPI, MUL, XM>(z, out, epi.addend, epi.other, epi.rvec, epi.mul_a, MUL && EPI ? epi.sc->abar : 0.0, oa, ob, va, vb, t, acc,
-                                     sct, la);
-    if (EPI == 4) {          // every thread of every CTA takes part in the reduction
+                                     sct, la, epi.out2, epi.zero);
+    if (EPI == 5) {
+        double vals[1] = {acc[0]};
+        const int op[1] = {0};
+        double tot[1];
+        if (grid_reduce<1>(vals, op, epi.part, epi.ticket, tot) && threadIdx.x == 0) solve_init_scalars(epi.sc, tot[0], epi.cond, epi.use_cond);
+    } else if (EPI == 4) {          // every thread of every CTA takes part in the reduction
         const int op[5] = {0, 0, 0, 0, 0};
         double tot[5];
         if (grid_reduce<5>(acc, op, epi.part, epi.ticket, tot) && threadIdx.x == 0) dots_finish6(epi, tot);
@@ -488,12 +531,14 @@ static inline void rows16_set_attributes() {
         fft16_attr(rows16_kernel<LG, 0, 0, false, XM>, G::rows_smem_plain);
         fft16_attr(rows16_kernel<LG, 2, 0, false, XM>, G::rows_smem_staged); fft16_attr(rows16_kernel<LG, 2, 0, true, XM>, G::rows_smem_staged);
         fft16_attr(rows16_kernel<LG, 3, 0, false, XM>, G::rows_smem_staged); fft16_attr(rows16_kernel<LG, 3, 0, true, XM>, G::rows_smem_staged);
+        if (XM == 0) fft16_attr(rows16_kernel<LG, 4, 0, false, 0>, G::rows_smem_staged);
     }
     if (XM != 1) {
         constexpr size_t sm = XM == 3 ? G::rows_smem_staged : G::rows_smem_plain;
         if (XM == 3) fft16_attr(rows16_kernel<LG, 0, 0, false, XM>, sm);
         fft16_attr(rows16_kernel<LG, 0, 1, false, XM>, sm); fft16_attr(rows16_kernel<LG, 0, 1, true, XM>, sm);
         fft16_attr(rows16_kernel<LG, 0, 4, false, XM>, sm); fft16_attr(rows16_kernel<LG, 0, 4, true, XM>, sm);
+        if (XM == 0) fft16_attr(rows16_kernel<LG, 0, 5, false, 0>, sm);
     }
 }
 // forward rows: `lines` lines of `in` (prologue fused) -> out (XM = 1: scattered through sct)
@@ -502,10 +547,14 @@ static inline void rows16_forward(bool pd, cudaStream_t s, const double* in, dou
                                   const double2* tw, const RowPrologue& pro, const int* done, const Scatter& sct) {
     using G = F16<LG>;
     const int grid = ((lines + 1) / 2 + G::fpb - 1) / G::fpb;
-    const bool mul = pro.mode != 0 && pro.a != nullptr;
+    const bool mul = pro.mode != 0 && pro.mode != 4 && pro.a != nullptr;
     const DotEpilogue none;
 #define VCH_R16(PRO, MUL, SM) launch_pdl(pd, rows16_kernel<LG, PRO, 0, MUL, XM>, grid, G::rthreads, SM, s, in, out, lines, in_ls, out_ls, tw, pro, none, done, sct)
     if (pro.mode == 0) VCH_R16(0, false, G::rows_smem_plain);
+    else if (pro.mode == 4) {
+        if constexpr (XM == 0) launch_pdl(pd, rows16_kernel<LG, 4, 0, false, 0>, grid, G::rthreads, G::rows_smem_staged, s, in, out, lines, in_ls, out_ls, tw, pro, none, done, sct);
+        else throw Error(VCH_E_ARG, "prologue mode 4 is not available in slab mode");
+    }
     else if (pro.mode == 2 && mul) VCH_R16(2, true, G::rows_smem_staged);
     else if (pro.mode == 2) VCH_R16(2, false, G::rows_smem_staged);
     else if (mul) VCH_R16(3, true, G::rows_smem_staged);
@@ -523,6 +572,10 @@ static inline void rows16_inverse(bool pd, cudaStream_t s, const double* in, dou
     const RowPrologue none;
 #define VCH_R16(EPI, MUL) launch_pdl(pd, rows16_kernel<LG, 0, EPI, MUL, XM>, grid, G::rthreads, sm, s, in, out, lines, in_ls, out_ls, tw, none, epi, done, sct)
     if (epi.mode == 0) VCH_R16(0, false);
+    else if (epi.mode == 5) {
+        if constexpr (XM == 0) launch_pdl(pd, rows16_kernel<LG, 0, 5, false, 0>, grid, G::rthreads, sm, s, in, out, lines, in_ls, out_ls, tw, none, epi, done, sct);
+        else throw Error(VCH_E_ARG, "epilogue mode 5 is not available in slab mode");
+    }
     else if (epi.mode == 1 && mul) VCH_R16(1, true);
     else if (epi.mode == 1) VCH_R16(1, false);
     else if (mul) VCH_R16(4, true);
