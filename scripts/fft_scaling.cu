@@ -58,7 +58,7 @@ int main() {
     for (int lines : {2, 148, 296, 592, 888, 1025}) {
         const int grid = ((lines + 1) / 2 + G::fpb - 1) / G::fpb;
         bench("rows16 plain", lines, [&] {
-            rows16_kernel<11, 0, 0, false><<<grid, G::rthreads, G::rows_smem_plain, s>>>(a, b, lines, n1, P, plan.inner.tw16, RowPrologue(), DotEpilogue(), nullptr);
+            rows16_kernel<11, 0, 0, false><<<grid, G::rthreads, G::rows_smem_plain, s>>>(a, b, lines, n1, P, plan.inner.tw16, RowPrologue(), DotEpilogue(), nullptr, Scatter());
         });
     }
     for (int cols : {8, 1025}) {
@@ -66,6 +66,17 @@ int main() {
         bench("cols16 solve", cols, [&] {
             cols16_kernel<11><<<grid, G::cthreads, G::cols_smem_bytes, s>>>(b, P, cols, plan.outer.tw16, plan.inner.lam, plan.outer.lam, sy, norm, 0, nullptr);
         });
+    }
+    {
+        CUtensorMap tm;
+        const bool ok = cols16_tensor_map(&tm, 11, b, P, n1);
+        cudaFuncSetAttribute(cols16_tma_kernel<11>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)F16T<11>::smem_bytes);
+        for (int cols : {8, 1025}) {
+            const int grid = (cols + 2 * G::cp - 1) / (2 * G::cp);
+            if (ok) bench("cols16 tma solve", cols, [&] {
+                cols16_tma_kernel<11><<<grid, G::cthreads, F16T<11>::smem_bytes, s>>>(tm, cols, plan.outer.tw16, plan.inner.lam, plan.outer.lam, sy, norm, 0, nullptr);
+            });
+        }
     }
     bench("full apply (fft16)", 1025, [&] { plan.lean = true; plan.apply(s, a, a, sy, nullptr); });
     {   // fused modes, in graph
@@ -77,14 +88,14 @@ int main() {
         const int grid = ((n1 + 1) / 2 + G::fpb - 1) / G::fpb;
         RowPrologue p2{2, w[0], w[1], w[2], w[3], sc};
         RowPrologue p3{3, w[0], w[1], w[2], w[3], sc}; p3.s = w[4]; p3.t = w[5]; p3.x = w[6]; p3.rw = w[0];
-        bench("rows16 pro2 mul", 1025, [&] { rows16_kernel<11, 2, 0, true><<<grid, G::rthreads, G::rows_smem_staged, s>>>(a, b, n1, n1, P, plan.inner.tw16, p2, DotEpilogue(), nullptr); });
-        bench("rows16 pro3 mul", 1025, [&] { rows16_kernel<11, 3, 0, true><<<grid, G::rthreads, G::rows_smem_staged, s>>>(a, b, n1, n1, P, plan.inner.tw16, p3, DotEpilogue(), nullptr); });
+        bench("rows16 pro2 mul", 1025, [&] { rows16_kernel<11, 2, 0, true><<<grid, G::rthreads, G::rows_smem_staged, s>>>(a, b, n1, n1, P, plan.inner.tw16, p2, DotEpilogue(), nullptr, Scatter()); });
+        bench("rows16 pro3 mul", 1025, [&] { rows16_kernel<11, 3, 0, true><<<grid, G::rthreads, G::rows_smem_staged, s>>>(a, b, n1, n1, P, plan.inner.tw16, p3, DotEpilogue(), nullptr, Scatter()); });
         DotEpilogue e1{1, w[1], sc, red.part, ticket, w[2], nullptr, w[3]};
         DotEpilogue e4{4, w[1], sc, red.part, ticket, w[1], nullptr, w[3]};
-        bench("rows16 epi1", 1025, [&] { rows16_kernel<11, 0, 1, false><<<grid, G::rthreads, G::rows_smem_plain, s>>>(b, w[7], n1, P, n1, plan.inner.tw16, RowPrologue(), e1, nullptr); });
-        bench("rows16 epi4", 1025, [&] { rows16_kernel<11, 0, 4, false><<<grid, G::rthreads, G::rows_smem_plain, s>>>(b, w[7], n1, P, n1, plan.inner.tw16, RowPrologue(), e4, nullptr); });
+        bench("rows16 epi1", 1025, [&] { rows16_kernel<11, 0, 1, false><<<grid, G::rthreads, G::rows_smem_plain, s>>>(b, w[7], n1, P, n1, plan.inner.tw16, RowPrologue(), e1, nullptr, Scatter()); });
+        bench("rows16 epi4", 1025, [&] { rows16_kernel<11, 0, 4, false><<<grid, G::rthreads, G::rows_smem_plain, s>>>(b, w[7], n1, P, n1, plan.inner.tw16, RowPrologue(), e4, nullptr, Scatter()); });
         DotEpilogue e1n = e1; e1n.rvec = nullptr;
-        bench("rows16 epi1 no r", 1025, [&] { rows16_kernel<11, 0, 1, false><<<grid, G::rthreads, G::rows_smem_plain, s>>>(b, w[7], n1, P, n1, plan.inner.tw16, RowPrologue(), e1n, nullptr); });
+        bench("rows16 epi1 no r", 1025, [&] { rows16_kernel<11, 0, 1, false><<<grid, G::rthreads, G::rows_smem_plain, s>>>(b, w[7], n1, P, n1, plan.inner.tw16, RowPrologue(), e1n, nullptr, Scatter()); });
     }
     {   // phase stamps of the column solve (block 0, thread 0), one launch on an idle GPU and one with the full grid
         for (int cols : {8, 1025}) {

@@ -19,6 +19,7 @@
 // dense-table kernels at the bottom (small validation grids).
 #pragma once
 #include "vch_common.cuh"
+#include <cuda.h>          // CUtensorMap (types only: the encoder is fetched through cudaGetDriverEntryPoint)
 #include <algorithm>
 
 namespace vch {
@@ -174,6 +175,8 @@ struct DctPlan {
     bool pdl = false;         // launch the transform kernels with programmatic stream serialization (see launch_pdl)
     bool lean = true;         // radix-16 kernels of vch_fft16.cuh where they apply (VCH_FFT16=0: the round-1 kernels everywhere)
     DctSlab slab;             // slab mode: no = global rows; the plan transforms the owned rows / columns only
+    CUtensorMap tmap;         // tensor map of tmp1 (slab mode: T1) for the TMA column kernel (vch_fft16.cuh)
+    bool have_tmap = false;
     void init(int no_, int ni_, double h_outer, double h_inner, LaunchLog* launch_log);
     void init_slab(int n_global, double h_outer, double h_inner, LaunchLog* launch_log, const DctSlab& sl);
     void barrier(cudaStream_t s, const int* done);
@@ -796,6 +799,14 @@ inline void DctPlan::init(int no_, int ni_, double h_outer, double h_inner, Laun
         }
     } else lean = false;
 #undef VCH_F16_ATTR
+    if (lean) {
+        have_tmap = cols16_tensor_map(&tmap, outer.log2L, tmp1.p, pitch, no);
+#ifndef VCH_CPU_EMU
+#define VCH_F16T_ATTR(LG) case LG: if (F16T<LG>::use) fft16_attr(cols16_tma_kernel<LG>, F16T<LG>::smem_bytes); break;
+        switch (outer.log2L) { VCH_F16T_ATTR(9) VCH_F16T_ATTR(10) VCH_F16T_ATTR(11) VCH_F16T_ATTR(12) VCH_F16T_ATTR(13) default: break; }
+#undef VCH_F16T_ATTR
+#endif
+    }
 }
 
 // Slab mode: square global grid n_global x n_global (N = n_global - 1 a power of two), T1/T2 carved from the arena by the caller.
@@ -804,6 +815,7 @@ inline void DctPlan::init_slab(int n_global, double h_outer, double h_inner, Lau
     if (!(inner.fft && outer.fft)) throw Error(VCH_E_SHAPE, "slab mode needs N = 2^k, 32 <= N <= 4096");
     tmp1.release(); tmp2.release();
     slab = sl; slab.on = true;
+    have_tmap = lean && cols16_tensor_map(&tmap, outer.log2L, slab.T1, slab.p1, no);
 }
 inline void DctPlan::barrier(cudaStream_t s, const int* done) {
     log->begin("xbar", s);
@@ -869,7 +881,7 @@ inline void DctPlan::apply(cudaStream_t s, const double* in, double* out, const 
         log->end(s);
         barrier(s, done);
         log->begin("cols16_solve", s);
-        VCH_F16_SLAB((cols16_solve<LG>(false, s, sl.T1, sl.p1, sl.wloc, outer.tw16, inner.lam + sl.col0, outer.lam, sym, norm, scale_mode, done)))
+        VCH_F16_SLAB((cols16_solve<LG>(false, s, sl.T1, sl.p1, sl.wloc, outer.tw16, inner.lam + sl.col0, outer.lam, sym, norm, scale_mode, done, have_tmap ? &tmap : nullptr)))
         log->end(s);
         barrier(s, done);
         log->begin(epi.mode == 1 ? "rows16_epi1" : (epi.mode == 4 ? "rows16_epi4" : "rows16"), s);
@@ -928,7 +940,7 @@ inline void DctPlan::apply(cudaStream_t s, const double* in, double* out, const 
         VCH_F16_SWITCH(inner, (rows16_forward<LG, 0>(pdl, s, in, t1, no, ni, P, inner.tw16, pro, done, nosct)))
         log->end(s);
         log->begin("cols16_solve", s);
-        VCH_F16_SWITCH(outer, (cols16_solve<LG>(pdl, s, t1, P, ni, outer.tw16, inner.lam, outer.lam, sym, norm, scale_mode, done)))
+        VCH_F16_SWITCH(outer, (cols16_solve<LG>(pdl, s, t1, P, ni, outer.tw16, inner.lam, outer.lam, sym, norm, scale_mode, done, have_tmap ? &tmap : nullptr)))
         log->end(s);
         log->begin(epi.mode == 1 ? "rows16_epi1" : (epi.mode == 4 ? "rows16_epi4" : (epi.mode == 5 ? "rows16_init" : "rows16")), s);
         VCH_F16_SWITCH(inner, (rows16_inverse<LG, 0>(pdl, s, t1, out, no, P, ni, inner.tw16, epi, done, nosct)))

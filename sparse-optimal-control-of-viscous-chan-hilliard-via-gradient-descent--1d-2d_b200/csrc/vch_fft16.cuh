@@ -448,18 +448,26 @@ cols16_kernel(double* __restrict__ buf, int pitch, int ncols, const double2* __r
     // stage in: CP consecutive threads fetch the CP double2 of one row segment (2*CP doubles, contiguous), every segment once;
     // the trip count is compile-time so that all loads are in flight together
     constexpr int NSEG = (N + 1) * CP, NIT = (NSEG + G::cthreads - 1) / G::cthreads;
+    // Every CTA walks its strip in a different row order (rotation by blockIdx): with all CTAs starting at row 0 the whole grid
+    // requests pieces of the SAME few rows at the same time, i.e. a handful of L2 slices serve all SMs.
+#ifndef VCH_COLS_NO_ROT
+    const int rot = (int)(((long long)blockIdx.x * (N + 1)) / gridDim.x);
+#else
+    const int rot = 0;
+#endif
+    auto seg_row = [&](int idx) { int r = idx / CP + rot; return r > N ? r - (N + 1) : r; };
     {
         double2 p[NIT];
 #pragma unroll
         for (int i = 0; i < NIT; ++i) {
             const int idx = threadIdx.x + i * G::cthreads;
-            if (idx < NSEG) p[i] = *reinterpret_cast<const double2*>(base + (size_t)(idx / CP) * pitch + 2 * (idx % CP));
+            if (idx < NSEG) p[i] = *reinterpret_cast<const double2*>(base + (size_t)seg_row(idx) * pitch + 2 * (idx % CP));
         }
         fft16_prefetch_twiddles<LOG2L>(tw, t);
 #pragma unroll
         for (int i = 0; i < NIT; ++i) {
             const int idx = threadIdx.x + i * G::cthreads;
-            if (idx < NSEG) stage_all[(idx % CP) * G::sst + idx / CP] = p[i];
+            if (idx < NSEG) stage_all[(idx % CP) * G::sst + seg_row(idx)] = p[i];
         }
     }
     // eigenvalues of the 9 spectrum entries this thread scales (slots 0..7, slot 8 for thread 0), fetched early
@@ -513,10 +521,127 @@ cols16_kernel(double* __restrict__ buf, int pitch, int ncols, const double2* __r
 #pragma unroll
     for (int i = 0; i < NIT; ++i) {
         const int idx = threadIdx.x + i * G::cthreads;
-        if (idx < NSEG) *reinterpret_cast<double2*>(base + (size_t)(idx / CP) * pitch + 2 * (idx % CP)) = stage_all[(idx % CP) * G::sst + idx / CP];
+        if (idx < NSEG) *reinterpret_cast<double2*>(base + (size_t)seg_row(idx) * pitch + 2 * (idx % CP)) = stage_all[(idx % CP) * G::sst + seg_row(idx)];
     }
     VCH_STAMP(8);
 }
+
+// ---- column solve with TMA staging (sm_100a; not compiled for the CPU emulation).
+// Same transform chain as cols16_kernel; what changes is how the strip of 2*cp columns travels between the pitched buffer and shared
+// memory.  Measured (profiles/r02_fft_scaling_*.txt): the per-thread 16-byte loads of 16*cp-byte row segments cost 9050 of the
+// kernel's 28200 cycles at 1024^2 with the full grid (3700 alone) — half-line requests exhaust the SM's outstanding-load slots long
+// before its bandwidth — and the stores another 2400.  Here one thread issues nb bulk tensor copies (boxes of BR rows x 2*cp
+// columns, cp.async.bulk.tensor.2d) that land on an mbarrier, and the result leaves the same way; the hardware swizzle of the
+// tensor map (16-byte chunk index XOR row bits: SWIZZLE_64B for 64-byte rows, SWIZZLE_32B for 32-byte rows) makes the
+// column-pair reads and writes of the stage conflict-free without padding.  Rows beyond N (the last box) are zero-filled on
+// load and clipped on store.
+#ifndef VCH_CPU_EMU
+template <int LOG2L> struct F16T {
+    using G = F16<LOG2L>;
+    static constexpr int CP = G::cp, CPB = CP == 4 ? 2 : (CP == 2 ? 1 : 0);
+    static constexpr int rows = G::N + 1;
+    static constexpr int nb = (rows + 255) / 256;                              // boxes per strip (box height <= 256)
+    static constexpr int BR = (((rows + nb - 1) / nb) + 7) & ~7;               // box height: multiple of 8 rows -> box bases stay swizzle-aligned
+    static constexpr int row_bytes = 16 * CP;
+    static constexpr unsigned box_bytes = (unsigned)BR * row_bytes;
+    static constexpr size_t stage_bytes = (size_t)nb * box_bytes;              // multiple of 128
+    static constexpr size_t data_off = (stage_bytes + 1023) & ~size_t(1023);
+    static constexpr size_t bar_off = data_off + sizeof(double2) * (size_t)CP * G::ld;
+    static constexpr size_t smem_bytes = bar_off + 16;
+    static constexpr bool use = LOG2L >= 9;                                    // N >= 256; smaller strips keep the plain kernel
+    // byte offset of entry e of column pair f in the swizzled stage
+    __device__ static __forceinline__ unsigned off(int e, int f) {
+        return (unsigned)e * row_bytes + (unsigned)((f ^ ((e >> (3 - CPB)) & (CP - 1))) << 4);
+    }
+};
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+template <int LOG2L>
+__global__ void __launch_bounds__(F16<LOG2L>::cthreads, 1)
+cols16_tma_kernel(const __grid_constant__ CUtensorMap tmap, int ncols, const double2* __restrict__ tw, const double* __restrict__ lam_col,
+                  const double* __restrict__ lam_row, SymbolArgs sy, double norm, int scale_mode, const int* __restrict__ done) {
+    pdl_enter();
+    using G = F16<LOG2L>;
+    using T = F16T<LOG2L>;
+    constexpr int CP = G::cp, N = G::N;
+    if (done && *done) return;
+    extern __shared__ __align__(1024) unsigned char smraw[];
+    unsigned char* stage = smraw;
+    double2* data_all = reinterpret_cast<double2*>(smraw + T::data_off);
+    unsigned long long* bar = reinterpret_cast<unsigned long long*>(smraw + T::bar_off);
+    const int f = CP == 1 ? 0 : threadIdx.x / G::tpf, t = threadIdx.x - f * G::tpf;
+    double2* data = data_all + (size_t)f * G::ld;
+    const int c0 = 2 * CP * blockIdx.x;
+    const unsigned bar_a = smem_u32(bar), stage_a = smem_u32(stage);
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_a));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a), "r"((unsigned)T::stage_bytes) : "memory");
+#pragma unroll
+        for (int k = 0; k < T::nb; ++k) {
+            const int b = (k + (int)blockIdx.x) % T::nb;          // CTAs start on different boxes: fewer CTAs on the same rows at once
+            asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                         ::"r"(stage_a + b * T::box_bytes), "l"(&tmap), "r"(c0), "r"(b * T::BR), "r"(bar_a) : "memory");
+        }
+    }
+    fft16_prefetch_twiddles<LOG2L>(tw, t);
+    double lrow[9];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) lrow[q] = lam_row[t + q * G::tpf];
+    lrow[8] = lam_row[N];
+    __syncthreads();                                    // the barrier is initialised before anybody polls it
+    {
+        unsigned ok = 0;
+        while (!ok)
+            asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }"
+                         : "=r"(ok) : "r"(bar_a) : "memory");
+    }
+    auto st = [&](int e) -> double2& { return *reinterpret_cast<double2*>(stage + T::off(e, f)); };
+    double2 v[16], z[16];
+#pragma unroll
+    for (int r = 0; r < 16; ++r) v[r] = st(idx16<LOG2L>(t, r));
+    constexpr bool GS = CP > 1 && (G::tpf % 32) == 0;
+    fft16_first_store<LOG2L, GS>(data, v, t, f);
+    fft16_middle<LOG2L, GS>(data, t, tw, f);
+    fft16_last_pass<LOG2L>(data, t, tw, z);
+    {
+        const double abar = sy.abar_ptr ? *sy.abar_ptr : sy.abar_const;
+        const double k0 = sy.coef_ptr ? sy.coef_ptr[0] : sy.c0, k2 = sy.coef_ptr ? sy.coef_ptr[1] : sy.c2;
+        const int ca = c0 + 2 * f, cb = ca + 1;
+        const double lca = lam_col[ca < ncols ? ca : ncols - 1], lcb = lam_col[cb < ncols ? cb : ncols - 1];
+        auto elem = [&](int e, double le, double2 zz) {
+            const double s1 = le + lca, s2 = le + lcb;
+            const double d1 = k0 + s1 * (abar + k2 * s1), d2 = k0 + s2 * (abar + k2 * s2);
+            const double inv = norm * __drcp_rn(d1 * d2);
+            double f1 = inv * d2, f2 = inv * d1;
+            if (scale_mode == 1) { f1 *= s1; f2 *= s2; }
+            st(e) = make_double2(zz.x * f1, zz.y * f2);
+        };
+#pragma unroll
+        for (int q = 0; q < 8; ++q) elem(t + q * G::tpf, lrow[q], z[q]);
+        if (t == 0) elem(N, lrow[8], z[8]);
+    }
+    fft16_sync<LOG2L, GS>(f);
+#pragma unroll
+    for (int r = 0; r < 16; ++r) v[r] = st(idx16<LOG2L>(t, r));
+    fft16_first_store<LOG2L, GS>(data, v, t, f);
+    fft16_middle<LOG2L, GS>(data, t, tw, f);
+    fft16_last_pass<LOG2L>(data, t, tw, z);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) st(t + q * G::tpf) = z[q];
+    if (t == 0) st(N) = z[8];
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy writes of the stage -> visible to the bulk copies
+    __syncthreads();
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int b = 0; b < T::nb; ++b)
+            asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];"
+                         ::"l"(&tmap), "r"(c0), "r"(b * T::BR), "r"(stage_a + b * T::box_bytes) : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    }
+}
+#endif   // !VCH_CPU_EMU
 
 // host: launch / attribute helpers.  XM = 0: single GPU; 1 / 3: slab mode (forward rows scatter, inverse rows gather).
 #ifndef VCH_CPU_EMU_KERNELS_ONLY
@@ -582,12 +707,57 @@ static inline void rows16_inverse(bool pd, cudaStream_t s, const double* in, dou
     else VCH_R16(4, false);
 #undef VCH_R16
 }
+// tmap: tensor map of the pitched buffer (cols16_tensor_map) or nullptr -> the plain kernel
 template <int LG>
 static inline void cols16_solve(bool pd, cudaStream_t s, double* buf, int pitch, int ncols, const double2* tw, const double* lam_col,
-                                const double* lam_row, const SymbolArgs& sym, double norm, int scale_mode, const int* done) {
+                                const double* lam_row, const SymbolArgs& sym, double norm, int scale_mode, const int* done,
+                                const CUtensorMap* tmap = nullptr) {
     using G = F16<LG>;
     const int grid = (ncols + 2 * G::cp - 1) / (2 * G::cp);
+#ifndef VCH_CPU_EMU
+    if constexpr (F16T<LG>::use) {
+        if (tmap) {
+            launch_pdl(pd, cols16_tma_kernel<LG>, grid, G::cthreads, F16T<LG>::smem_bytes, s, *tmap, ncols, tw, lam_col, lam_row, sym, norm, scale_mode, done);
+            return;
+        }
+    }
+#endif
     launch_pdl(pd, cols16_kernel<LG>, grid, G::cthreads, G::cols_smem_bytes, s, buf, pitch, ncols, tw, lam_col, lam_row, sym, norm, scale_mode, done);
+}
+
+// Tensor map of a pitched buffer of `rows` rows (row stride pitch doubles, pitch a multiple of 2*cp) for the strips of the TMA column
+// kernel: boxes of BR rows x 2*cp columns, swizzle matched to the row width.  Returns false when TMA staging does not apply (short
+// columns, CPU emulation, driver entry point missing): the caller then passes nullptr to cols16_solve.
+static inline bool cols16_tensor_map(CUtensorMap* out, int log2L, double* buf, int pitch, int rows) {
+#ifdef VCH_CPU_EMU
+    (void)out; (void)log2L; (void)buf; (void)pitch; (void)rows;
+    return false;
+#else
+    if (log2L < 9 || log2L > 13) return false;
+    if (getenv("VCH_COLS_TMA") && atoi(getenv("VCH_COLS_TMA")) == 0) return false;
+    int cp = 4, br = 0;
+    switch (log2L) {
+        case 9: cp = F16<9>::cp; br = F16T<9>::BR; break;    case 10: cp = F16<10>::cp; br = F16T<10>::BR; break;
+        case 11: cp = F16<11>::cp; br = F16T<11>::BR; break; case 12: cp = F16<12>::cp; br = F16T<12>::BR; break;
+        default: cp = F16<13>::cp; br = F16T<13>::BR; break;
+    }
+    typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                 const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || !fn || q != cudaDriverEntryPointSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    const cuuint64_t gdim[2] = {(cuuint64_t)pitch, (cuuint64_t)rows};
+    const cuuint64_t gstr[1] = {(cuuint64_t)pitch * sizeof(double)};
+    const cuuint32_t box[2] = {(cuuint32_t)(2 * cp), (cuuint32_t)br};
+    const cuuint32_t est[2] = {1, 1};
+    const CUtensorMapSwizzle sw = cp == 4 ? CU_TENSOR_MAP_SWIZZLE_64B : (cp == 2 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_NONE);
+    const CUresult r = reinterpret_cast<EncodeFn>(fn)(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, buf, gdim, gstr, box, est, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                                      sw, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS;
+#endif
 }
 #endif
 
