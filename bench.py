@@ -524,8 +524,8 @@ def run_b200(args):
         ach = bpn * n / (rep[top][0] / rep[top][1] * 1e-3) / 1e9
         traffic = None
         try:    # DRAM bytes per launch of that kernel from the committed ncu --set full capture (profiles/)
-            with open(os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")) as fh:
-                traffic = json.load(fh)["kernels"].get("dct_rows_fft" if top.startswith("dct_rows_fft") else top) if N == 1024 else None
+            with open(os.path.join(ROOT, "profiles", "r02_ncu_traffic.json")) as fh:
+                traffic = json.load(fh)["kernels"].get(top) if N == 1024 else None
         except Exception:
             traffic = None
         # whole iteration: sum of algorithmic bytes of every profiled launch over the summed kernel time

@@ -26,7 +26,7 @@ def num(x):
     except Exception: return float("nan")
 best = {}
 for r in rows:
-    name = re.sub(r"^void |\(.*$", "", r[kn]).replace("vch::", "")
+    name = re.sub(r"^void |\(.*$", "", r[kn].replace("(anonymous namespace)::", "").replace("<unnamed>::", "")).replace("vch::", "")
     d = num(r[col["gpu__time_duration.sum"]])
     if name not in best or d > best[name][0]:
         best[name] = (d, r)

@@ -16,11 +16,11 @@ for r in rd:
     unit = r.get("Metric Unit", "ns")
     us = val / 1e3 if unit in ("ns", "nsecond") else (val if unit in ("us", "usecond") else val * 1e3)
     name = r["Kernel Name"]
-    name = re.sub(r"^void |\(.*$", "", name)
+    name = re.sub(r"^void |\(.*$", "", name.replace("(anonymous namespace)::", "").replace("<unnamed>::", ""))
     name = name.replace("vch::", "")
-    if not re.match(r"(dct_|bicg_|residual|dmu_|schur|trial|step_setup|adj_|clip_mass|mass_shift|solve_w|cost_|grad_prox|mu_init|xbar|halo|lap_|jac_|kkt|publish_scalars|copy_kernel)", name):
+    if not re.match(r"(dct_|rows16|cols16|bicg_|residual|dmu_|schur|trial|step_setup|adj_|clip_mass|mass_shift|solve_w|set_solve|cost_|grad_prox|mu_init|xbar|halo|lap_|jac_|kkt|energy|publish_scalars|copy_kernel)", name):
         name = "torch (setup: targets, zeros)"
-    elif us < 4.5 and re.match(r"(dct_fft_kernel|bicg_x_kernel)", name):
+    elif us < 4.5 and re.match(r"(dct_fft_kernel|bicg_x_kernel|rows16_kernel|cols16)", name):
         name += " [exits on done flag]"
     rows.append((name, us))
 tot = sum(u for _, u in rows)

@@ -139,6 +139,24 @@ def _time_grid(T, dt):
     return np.array(steps), np.array(stamps)
 
 
+def run_main_simulation_batch(fwd_config, controls, initial_phi=None):
+    """B forward solves with B different controls in ONE multi-problem launch (one CTA per problem: line-search trials,
+    finite-difference directions, ensembles).  controls: (B, rows, N+1).  Returns (phi_hists (B, M+2, N+1), x, t_hist);
+    member b equals run_main_simulation(fwd_config, True, controls[b])[0] bit for bit."""
+    cfg = ForwardSolverConfig() if fwd_config is None else fwd_config
+    N, Lx = int(cfg.N), float(cfg.Lx)
+    controls = _f64(controls)
+    B = int(controls.shape[0])
+    if initial_phi is not None and initial_phi.shape == (N + 1,):
+        phi0 = _f64(initial_phi).copy()
+    else:
+        phi0 = init_phi_random(N, delta_sep, amp=0.01, seed=42, enforce_zero_mean=True)
+    dts, t_hist = _time_grid(float(cfg.T), float(cfg.dt_initial))
+    ctx = _nat.ctx1d(N, Lx / N, Lx, float(cfg.tau), float(cfg.gamma), float(cfg.c1), float(cfg.c2), float(cfg.kappa), delta_sep)
+    phi_hists, _, _ = ctx.forward(np.ascontiguousarray(np.broadcast_to(phi0, (B, N + 1))), controls, dts)
+    return phi_hists, np.linspace(0, Lx, N + 1), t_hist
+
+
 def run_main_simulation(fwd_config=None, store_history=False, control_input=None, verbose=True, initial_phi=None):
     """Reference :286-397.  Returns (phi_hist (M+2, N+1), x, t_hist (M+2,)) when store_history (level 0 twice, t_hist =
     [0, 0, dt, ...]); otherwise (phi_final, x, t_hist) after an optional plot."""

@@ -16,9 +16,9 @@ _PKG = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if _PKG not in sys.path:
     sys.path.insert(0, _PKG)
 import vch_b200_native as _nat                                                        # noqa: E402
-from Forward_solver import run_main_simulation, init_phi_random, _time_grid, delta_sep  # noqa: E402
+from Forward_solver import run_main_simulation, run_main_simulation_batch, init_phi_random, _time_grid, delta_sep  # noqa: E402
 from backward_solver import run_backward                                              # noqa: E402
-from cost_and_function import calculate_cost, calculate_gradient, perform_gradient_step   # noqa: E402
+from cost_and_function import calculate_cost, calculate_cost_batch, calculate_gradient, perform_gradient_step   # noqa: E402
 from second_order_conditions import approximate_second_order_condition               # noqa: E402
 from config import (ForwardSolverConfig, OptimizationConfig, get_user_input_for_config, get_yes_no_input,   # noqa: E402
                     save_params, load_params)
@@ -39,8 +39,36 @@ def perform_proximal_and_projection(u_temp, alpha, kappa, u_min, u_max):
 
 
 def perform_backtracking_line_search(u_k, cost_k, grad_smooth, phi_Q_target, phi_T_target, x, t_hist, b1, b2, b3, kappa,
-                                     u_min, u_max, fwd_config, alpha_init=10.0, beta=0.8, max_ls_iter=5):
-    """Returns (alpha, u_next, cost_next, phi_next, rejected_seconds, accepted_seconds, trials) — reference :73-113."""
+                                     u_min, u_max, fwd_config, alpha_init=10.0, beta=0.8, max_ls_iter=5, batch=None):
+    """Returns (alpha, u_next, cost_next, phi_next, rejected_seconds, accepted_seconds, trials) — reference :73-113.
+
+    batch > 1 (argument, or VCH_LS_BATCH): the trial step sizes alpha_init * beta^j are evaluated `batch` at a time as ONE
+    multi-problem launch (forward solves and costs carry a batch axis; one CTA per trial), and the first trial in the
+    reference's order that lowers the cost is returned — the same (alpha, u, cost, phi, trials) as the sequential search."""
+    if batch is None:
+        batch = int(os.environ.get("VCH_LS_BATCH", "1"))
+    if batch > 1:
+        alphas = [float(alpha_init)]
+        for _ in range(1, max_ls_iter):
+            alphas.append(alphas[-1] * beta)            # the reference's running product, not a power
+        rejected, done = 0.0, 0
+        u_next = phi_next = cost_next = None
+        while done < max_ls_iter:
+            chunk = alphas[done:done + batch]
+            t0 = time.perf_counter()
+            us = np.stack([perform_proximal_and_projection(perform_gradient_step(u_k, grad_smooth, a), a, kappa, u_min, u_max)
+                           for a in chunk])
+            phis, _, _ = run_main_simulation_batch(fwd_config, us)
+            J = calculate_cost_batch(phis, us, phi_Q_target, phi_T_target, x, t_hist, b1, b2, b3, kappa)
+            dt = (time.perf_counter() - t0) / len(chunk)
+            for j, a in enumerate(chunk):
+                u_next, phi_next, cost_next = us[j], phis[j], float(J[j, 0])
+                if cost_next < cost_k:
+                    return a, u_next, cost_next, phi_next, rejected, dt, done + j + 1
+                rejected += dt
+            done += len(chunk)
+        print("[Warning] Line search could not find a step that reduces cost.")
+        return alphas[-1] * beta, u_next, cost_next, phi_next, rejected, 0.0, max_ls_iter
     alpha, rejected, trials = alpha_init, 0.0, 0
     u_next = phi_next = cost_next = None
     for _ in range(max_ls_iter):

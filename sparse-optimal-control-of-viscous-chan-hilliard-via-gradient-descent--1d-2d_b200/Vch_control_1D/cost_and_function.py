@@ -30,6 +30,18 @@ def calculate_cost(phi_hist, u, phi_Q_target, phi_T_target, x, t_hist, b1, b2, b
     return total
 
 
+def calculate_cost_batch(phi_hists, us, phi_Q_target, phi_T_target, x, t_hist, b1, b2, b3, kappa) -> np.ndarray:
+    """Total cost of B trajectories (B, levels, N+1) against the same targets, one multi-problem launch; quiet.
+    Returns J (B, 5) = (total, J1, J2, J3, J4) per member, each row equal to calculate_cost's values."""
+    phi_hists = _f64(phi_hists)
+    B, lv, n = phi_hists.shape
+    h = float(x[1] - x[0])
+    ctx = _nat.ctx1d(n - 1, h, (n - 1) * h, 0.05, 10.0, 0.75, 1.0, 0.03 ** 2, 1e-2)
+    Q = np.ascontiguousarray(np.broadcast_to(_f64(phi_Q_target), (B, lv, n)))
+    T = np.ascontiguousarray(np.broadcast_to(_f64(phi_T_target), (B, n)))
+    return ctx.cost(phi_hists, _f64(us), Q, T, _f64(x), _f64(t_hist), b1, b2, b3, kappa)
+
+
 def calculate_gradient(r, u, b3):
     """r + b3 u (reference :99)."""
     _, g, _ = _nat.grad_prox(_f64(u), _f64(r), float(b3), 0.0, 0.0, -np.inf, np.inf, want_grad=True)

@@ -34,11 +34,40 @@ DEFAULT_TRACKING_CHOICE = 1    # 1: ramp initial -> target, 2: zeros
 
 
 def perform_backtracking_line_search_2D(u_k, cost_k, grad_smooth, phi_Q_target, phi_T_target, x, y, fwd_config,
-                                        opt_config, alpha_init: float = 1.0, beta: float = 0.8, max_ls_iter: int = 10
+                                        opt_config, alpha_init: float = 1.0, beta: float = 0.8, max_ls_iter: int = 10,
+                                        batch: int = None
                                         ) -> Tuple[float, np.ndarray, float, np.ndarray, np.ndarray, float, int]:
     """Shrink alpha by beta until J(prox(u_k - alpha g)) < J(u_k) (reference :71-146).
-    Returns (alpha, u_next, cost_next, phi_next, t_hist_next, seconds, attempts); the last trial if none succeeds."""
+    Returns (alpha, u_next, cost_next, phi_next, t_hist_next, seconds, attempts); the last trial if none succeeds.
+
+    batch > 1 (argument, or VCH_LS_BATCH): `batch` trial step sizes are evaluated concurrently — one worker thread per trial,
+    each on its own library context (own stream and work vectors, vch_b200_native.run_concurrent), so the independent forward
+    solves overlap on the GPU; the first trial in the reference's order that lowers the cost is returned, i.e. the result
+    equals the sequential search's.  Every concurrent trial holds its own trajectory: size `batch` for the host memory."""
     t0 = time.perf_counter()
+    if batch is None:
+        batch = int(os.environ.get("VCH_LS_BATCH", "1"))
+    if batch > 1:
+        alphas = [float(alpha_init)]
+        for _ in range(1, max_ls_iter):
+            alphas.append(alphas[-1] * beta)            # the reference's running product
+
+        def trial(a):
+            u = proximal_step(u_k, grad_smooth, a, opt_config)
+            phi, _, t = run_main_simulation(config=fwd_config, store_history=True, control_input=u, verbose=False)
+            return u, phi, t, calculate_cost(phi, u, phi_Q_target, phi_T_target, x, y, t, opt_config)
+        done, last = 0, None
+        while done < max_ls_iter:
+            chunk = alphas[done:done + batch]
+            res = _nat.run_concurrent(lambda j: trial(chunk[j]), len(chunk), batch)
+            for j, (u, phi, t, c) in enumerate(res):
+                last = (chunk[j], u, c, phi, t)
+                if c < cost_k:
+                    print(f"   ✓ Backtracking found a good step (α = {chunk[j]:.4f}) after {done + j + 1} attempts.")
+                    return chunk[j], u, c, phi, t, time.perf_counter() - t0, done + j + 1
+            done += len(chunk)
+        print("[Warning] Line search could not find a step that reduces cost. Returning last try.")
+        return last[0] * beta, last[1], last[2], last[3], last[4], time.perf_counter() - t0, max_ls_iter
     alpha, u_next, phi_next, t_next, cost_next = alpha_init, u_k, None, None, cost_k
     for attempt in range(1, max_ls_iter + 1):
         u_next = proximal_step(u_k, grad_smooth, alpha, opt_config)

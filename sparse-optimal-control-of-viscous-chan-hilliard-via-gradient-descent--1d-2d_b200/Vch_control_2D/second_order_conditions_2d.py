@@ -1,9 +1,8 @@
 """KKT / second-order diagnostics of the 2D problem — drop-in for 2D/Vch_control_2D/second_order_conditions_2d.py.
 
 `verify_sparsity_condition` (reference :238-297) is the KKT reduction on the hot path: its three counts come from one
-fused device kernel (vch_kkt_counts).  `approximate_second_order_condition_2d` (reference :120-235) is a diagnostic that
-only re-runs the forward solve and the cost for perturbed controls; it is kept as a thin host loop over those two
-device calls.
+fused device kernel (vch_kkt_counts).  `approximate_second_order_condition_2d` (reference :120-235) re-runs the forward solve and the
+cost for perturbed controls; the directions are independent problems and can run concurrently (batch / VCH_FD_BATCH).
 """
 import os
 import sys
@@ -37,8 +36,10 @@ def approximate_second_order_condition_2d(u_star, r_star, phi_star, x, y, t_hist
                                           opt_config: Optional[OptimizationConfig] = None, b1=None, b2=None, b3=None,
                                           kappa=None, phi_Q_target=None, phi_T_target=None, u_min=-np.inf, u_max=np.inf,
                                           num_directions: int = 10, epsilon: float = 1e-4, seed: Optional[int] = None,
-                                          fwd_config: Optional[ForwardSolverConfig] = None) -> List[float]:
-    """(J(u*+eps h) - J(u*) - eps <r*+b3 u*, h>) / (eps^2/2) along random critical-cone directions h."""
+                                          fwd_config: Optional[ForwardSolverConfig] = None, batch: Optional[int] = None) -> List[float]:
+    """(J(u*+eps h) - J(u*) - eps <r*+b3 u*, h>) / (eps^2/2) along random critical-cone directions h.
+    batch > 1 (argument, or VCH_FD_BATCH): that many perturbed forward solves + costs run concurrently, one worker thread and
+    one library context each (vch_b200_native.run_concurrent); directions and results are those of the sequential loop."""
     if opt_config is None:
         if any(v is None for v in (b1, b2, b3, kappa)):
             raise ValueError("Either provide opt_config or all of (b1, b2, b3, kappa_sparsity).")
@@ -50,13 +51,17 @@ def approximate_second_order_condition_2d(u_star, r_star, phi_star, x, y, t_hist
     g = r_star + opt_config.b3 * u_star
     out: List[float] = []
     print(f"Testing {num_directions} random directions in the critical cone...")
-    for i in range(num_directions):
-        h = _cone_direction(u_star, u_min, u_max, rng)
-        u_eps = u_star + epsilon * h
+    if batch is None:
+        batch = int(os.environ.get("VCH_FD_BATCH", "1"))
+    hs = [_cone_direction(u_star, u_min, u_max, rng) for _ in range(num_directions)]   # drawn in the reference's order
+
+    def one(i):
+        u_eps = u_star + epsilon * hs[i]
         phi_eps, _, _ = run_main_simulation(config=fwd_config, store_history=True, control_input=u_eps, verbose=False)
         J1 = calculate_cost(phi_eps, u_eps, Q, T, x, y, t_hist, opt_config)
-        d2 = (J1 - J0 - epsilon * float(np.sum(g * h))) / (0.5 * epsilon ** 2)
-        out.append(float(d2))
+        return float((J1 - J0 - epsilon * float(np.sum(g * hs[i]))) / (0.5 * epsilon ** 2))
+    out = _nat.run_concurrent(one, num_directions, max(1, batch))
+    for i, d2 in enumerate(out):
         print(f"  Direction {i+1}/{num_directions}: estimated d²J/dh² ≈ {d2:.6e}")
     return out
 

@@ -631,19 +631,59 @@ class Ctx1D:
 # (parameter sweeps such as the reference's convergence-order tests keep their working set instead of rebuilding DCT tables
 # and CUDA graphs after every 16th configuration).
 from collections import OrderedDict
+import threading
 
 _ctx_cache: "OrderedDict" = OrderedDict()
 _CTX_CACHE_MAX = 16
+_ctx_lock = threading.Lock()
+_tls = threading.local()
+
+
+def set_ctx_slot(slot: int = 0) -> None:
+    """Context slot of the calling thread.  The drop-in modules look their contexts up per (parameters, slot), so worker
+    threads with different slots drive DIFFERENT contexts (own stream, own work vectors) and their kernels overlap on the
+    GPU — how independent 2D problems (line-search trials, finite-difference directions) are run concurrently."""
+    _tls.slot = int(slot)
+
+
+def ctx_slot() -> int:
+    return int(getattr(_tls, "slot", 0))
+
+
+def run_concurrent(fn, n_jobs: int, workers: int):
+    """[fn(j) for j in range(n_jobs)], `workers` at a time, worker w on context slot w (ctypes releases the GIL inside
+    the library calls).  workers <= 1: a plain loop on the caller's slot."""
+    if workers <= 1 or n_jobs <= 1:
+        return [fn(j) for j in range(n_jobs)]
+    from concurrent.futures import ThreadPoolExecutor
+    import queue
+    free = queue.SimpleQueue()
+    for w in range(min(workers, n_jobs)):
+        free.put(w)
+
+    def job(j):
+        w = free.get()
+        try:
+            set_ctx_slot(w)
+            return fn(j)
+        finally:
+            set_ctx_slot(0)
+            free.put(w)
+    with ThreadPoolExecutor(min(workers, n_jobs)) as pool:
+        return list(pool.map(job, range(n_jobs)))
 
 
 def _cached(key, make, reset):
-    c = _ctx_cache.get(key)
-    if c is None:
-        while len(_ctx_cache) >= _CTX_CACHE_MAX:
-            _ctx_cache.popitem(last=False)
-        c = _ctx_cache[key] = make()
-    else:
-        _ctx_cache.move_to_end(key)
+    with _ctx_lock:
+        c = _ctx_cache.get(key)
+        fresh = c is None
+        if fresh:
+            while len(_ctx_cache) >= _CTX_CACHE_MAX:
+                _ctx_cache.popitem(last=False)
+            c = _ctx_cache[key] = make()
+        else:
+            _ctx_cache.move_to_end(key)
+    if not fresh:
         reset(c)
     return c
 
@@ -659,10 +699,10 @@ def _reset2d(c):
 def ctx2d(Nx, Ny, hx, hy, Lx, Ly, tau, gamma, c1, c2, kappa, delta_sep=1e-2, device=0) -> Ctx2D:
     key = ("2d", int(Nx), int(Ny), float(hx), float(hy), float(Lx), float(Ly), float(tau), float(gamma), float(c1),
            float(c2), float(kappa), float(delta_sep), int(device))
-    return _cached(key, lambda: Ctx2D(*key[1:]), _reset2d)
+    return _cached(key + (ctx_slot(),), lambda: Ctx2D(*key[1:]), _reset2d)
 
 
 def ctx1d(N, h, Lx, tau, gamma, c1, c2, kappa, delta_sep=1e-2, device=0) -> Ctx1D:
     key = ("1d", int(N), float(h), float(Lx), float(tau), float(gamma), float(c1), float(c2), float(kappa),
            float(delta_sep), int(device))
-    return _cached(key, lambda: Ctx1D(*key[1:]), lambda c: None)
+    return _cached(key + (ctx_slot(),), lambda: Ctx1D(*key[1:]), lambda c: None)

@@ -116,3 +116,35 @@ def test_driver_and_ensemble(m, golden):
         assert rel(r[b], ro) < 1e-7 and rel(u1[b], un) < 1e-7 and np.array_equal(u1[b] != 0, un != 0)
         assert rel(hist1[b], fw["phi"]) < 1e-8 and abs(J[b, 0] - Jo) < 1e-7 * abs(Jo)
     assert G.shard_range(1024, 3, 8) == (384, 512) and G.shard_range(10, 0, 4) == (0, 3) and G.shard_range(10, 3, 4) == (8, 10)
+
+
+def test_batched_line_search_and_fd_directions_equal_sequential(m, golden):
+    """line-search trials and finite-difference directions as ONE multi-problem launch (batch axis of the 1D
+    kernels) return exactly what the reference's sequential loops return (GD_1D.py:73-113, second_order_conditions.py:58-110)."""
+    G, C, S, F, Cst, B = (m[k] for k in ("GD_1D", "config", "second_order_conditions", "Forward_solver", "cost_and_function", "backward_solver"))
+    cfg, opt = C.ForwardSolverConfig(), C.OptimizationConfig()
+    phi, x, t = quiet(F.run_main_simulation, cfg, True, None, False)
+    phi_T, phi_Q = quiet(G.build_targets_1d, x, t, phi[0].copy(), cfg.Lx, cfg.T, False, 1, 1)
+    u = np.zeros_like(phi)
+    J0 = quiet(Cst.calculate_cost, phi, u, phi_Q, phi_T, x, t, opt.b1, opt.b2, opt.b3, opt.kappa_sparsity)
+    _, _, r = quiet(B.run_backward, phi, x, t, opt.b1, opt.b2, phi_Q, phi_T)
+    g = Cst.calculate_gradient(r, u, opt.b3)
+    # costs of the six trial step sizes, then a reference cost that the first trials do NOT beat: the search has to shrink alpha
+    alphas = [4.0e4 * 0.5 ** j for j in range(6)]
+    us = np.stack([G.perform_proximal_and_projection(Cst.perform_gradient_step(u, g, a), a, opt.kappa_sparsity, opt.u_min, opt.u_max)
+                   for a in alphas])
+    Js = Cst.calculate_cost_batch(F.run_main_simulation_batch(cfg, us)[0], us, phi_Q, phi_T, x, t, opt.b1, opt.b2, opt.b3,
+                                  opt.kappa_sparsity)[:, 0]
+    first = next((j for j in range(1, 6) if Js[j] < Js[:j].min()), None)
+    cost_k = 0.5 * (Js[first] + Js[:first].min()) if first is not None else Js.min() - 1.0     # (else: every trial fails)
+    args = (u, cost_k, g, phi_Q, phi_T, x, t, opt.b1, opt.b2, opt.b3, opt.kappa_sparsity, opt.u_min, opt.u_max, cfg)
+    seq = quiet(G.perform_backtracking_line_search, *args, alpha_init=4.0e4, beta=0.5, max_ls_iter=6, batch=1)
+    bat = quiet(G.perform_backtracking_line_search, *args, alpha_init=4.0e4, beta=0.5, max_ls_iter=6, batch=4)
+    assert seq[6] == bat[6] and seq[6] >= 2, (seq[6], bat[6])                 # same number of trials, more than one
+    assert seq[0] == bat[0] and seq[2] == bat[2]                                # alpha and cost bit for bit
+    assert np.array_equal(seq[1], bat[1]) and np.array_equal(seq[3], bat[3])    # control and trajectory bit for bit
+    kw = dict(num_directions=4, epsilon=1e-4, seed=5)
+    sargs = (cfg, seq[1], r, seq[3], x, t, opt.b1, opt.b2, opt.b3, opt.kappa_sparsity, phi_Q, phi_T, opt.u_min, opt.u_max)
+    d_seq = quiet(S.approximate_second_order_condition, *sargs, batch=1, **kw)
+    d_bat = quiet(S.approximate_second_order_condition, *sargs, **kw)           # default: all directions in one launch
+    assert d_seq == d_bat and len(d_bat) == 4

@@ -214,3 +214,30 @@ def test_free_energy_and_second_order_condition_match_reference(native, golden):
                phi_Q_target=phiQ, phi_T_target=phiT, u_min=opt.u_min, u_max=opt.u_max,
                num_directions=3, epsilon=float(gs["epsilon"]), seed=int(gs["seed"]), fwd_config=cfg)
     np.testing.assert_allclose(d2, gs["d2"], rtol=1e-4)
+
+
+def test_concurrent_line_search_and_fd_directions_equal_sequential(native, golden):
+    """trial step sizes / finite-difference directions evaluated concurrently (one worker thread and one
+    library context per trial: independent streams and work vectors) return exactly what the sequential loops of the
+    reference return (GD2_configured.py:71-146, second_order_conditions_2d.py:120-235)."""
+    import json
+    mods = load_dropin("2D")
+    G, S, Cst, B = mods["GD2_configured"], mods["second_order_conditions_2d"], mods["cost2_and_function"], mods["backward2_solver"]
+    g = golden("g2d_32")
+    cfg = mods["config"].ForwardSolverConfig(**{k: v for k, v in json.loads(str(g["cfg_json"])).items()
+                                                if k in mods["config"].ForwardSolverConfig.model_fields})
+    opt = mods["config"].OptimizationConfig()
+    phiT, phiQ = quiet(G.build_targets, g["x"], g["y"], g["t"], g["phi0"][0].copy(), cfg.Lx, cfg.Ly, cfg.T, False, 1, 1)
+    u0 = np.zeros_like(g["phi0"])
+    J0 = quiet(Cst.calculate_cost, g["phi0"], u0, phiQ, phiT, g["x"], g["y"], g["t"], opt)
+    grad = Cst.calculate_gradient(g["r0"], u0, opt)
+    args = (u0, J0, grad, phiQ, phiT, g["x"], g["y"], cfg, opt)
+    seq = quiet(G.perform_backtracking_line_search_2D, *args, alpha_init=3.0e5, beta=0.25, max_ls_iter=6, batch=1)
+    con = quiet(G.perform_backtracking_line_search_2D, *args, alpha_init=3.0e5, beta=0.25, max_ls_iter=6, batch=3)
+    assert seq[6] == con[6], (seq[6], con[6])
+    assert seq[0] == con[0] and seq[2] == con[2] and np.array_equal(seq[1], con[1]) and np.array_equal(seq[3], con[3])
+    kw = dict(opt_config=opt, phi_Q_target=phiQ, phi_T_target=phiT, u_min=opt.u_min, u_max=opt.u_max, num_directions=4,
+              epsilon=1e-4, seed=11, fwd_config=cfg)
+    d_seq = quiet(S.approximate_second_order_condition_2d, g["u1"], g["r1"], g["phi1"], g["x"], g["y"], g["t"], batch=1, **kw)
+    d_con = quiet(S.approximate_second_order_condition_2d, g["u1"], g["r1"], g["phi1"], g["x"], g["y"], g["t"], batch=4, **kw)
+    assert d_seq == d_con and len(d_con) == 4
