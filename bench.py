@@ -608,6 +608,12 @@ def run_b200(args):
         state.clear()
         torch.cuda.empty_cache()
         slab = slab_leg(nat, F2, P, Op, args, rank, world, local)
+    ens1d = None
+    if not args.no_ensemble:
+        try:
+            ens1d = ensemble_leg(nat, args, rank, world, local)
+        except Exception as exc:   # report, do not hide
+            ens1d = {"error": repr(exc)}
     if rank == 0:
         cpu = None
         if world == 1 and not args.no_cpu:
@@ -630,7 +636,7 @@ def run_b200(args):
                            "newton": "reference rule + fp64-floor stop (DESIGN.md)", "krylov_rel_tol": 1e-11,
                            "krylov_first_solve_rel_tol": float(os.environ.get("VCH_KRYLOV_FIRST_RTOL", 1e-6))},
                 "gpu_launches": int(launches), "clocks": clocks, "e2e": e2e, "roofline": roof, "cpu_baseline": cpu,
-                "parity_vs_strict": parity, "slab_4096": slab,
+                "parity_vs_strict": parity, "slab_4096": slab, "ensemble1d": ens1d,
                 "solver": {"linear_solves_per_iteration": agg["newton_linear_solves"] / args.steps,
                            "newton_residual_evals_per_time_step": agg["newton_residual_evals"] / (args.steps * M),
                            "krylov_its_per_solve": agg["krylov_iterations"] / max(1, agg["newton_linear_solves"]),
@@ -638,6 +644,69 @@ def run_b200(args):
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def _load_gd1d():
+    """GD_1D beside the already imported 2D drop-ins: both packages have a module called `config`."""
+    saved = sys.modules.pop("config", None)
+    path = os.path.join(PKG, "Vch_control_1D")
+    sys.path.insert(0, path)
+    try:
+        import GD_1D as G
+    finally:
+        sys.path.remove(path)
+        if saved is not None:
+            sys.modules["config"] = saved
+    return G
+
+
+def ensemble_leg(nat, args, rank, world, local, B=1024, warmup=2, steps=5):
+    """BASELINE config 4 inside the default run, so that the driver's records carry it: B independent 1D control problems (default
+    1D grid, varied targets / weights), one optimistic PGD iteration for the whole ensemble per step (4 launches), the batch split
+    across the ranks without communication.  First iterates from u0 = 0 (later chained iterates of this synthetic ensemble drive
+    single members into many-Newton-iteration regimes; `--workload ensemble1d` reports those with the per-step median)."""
+    import torch
+    import torch.distributed as dist
+    G = _load_gd1d()
+    dev = torch.device("cuda", local)
+    cfg = G.ForwardSolverConfig()
+    ens = G.make_ensemble(B)
+    lo, hi = G.shard_range(B, rank, world)
+    ctx = nat.Ctx1D(cfg.N, cfg.Lx / cfg.N, cfg.Lx, cfg.tau, cfg.gamma, cfg.c1, cfg.c2, cfg.kappa, device=local)
+    up = lambda a: torch.from_numpy(np.ascontiguousarray(a[lo:hi])).to(dev)
+    phi_init, phiQ, phiT = up(ens["phi_init"]), up(ens["phi_Q"]), up(ens["phi_T"])
+    w = {k: np.ascontiguousarray(ens[k][lo:hi]) for k in ("b1", "b2", "b3", "ksp")}
+    hist, _, _ = ctx.forward(phi_init, None, ens["dts"])
+    u0 = torch.zeros_like(hist)
+    run = lambda: G.optimistic_iteration_ensemble(ctx, ctx, u0, hist, phiQ, phiT, ens["x"], ens["t_hist"], ens["dts"], phi_init,
+                                                  w["b1"], w["b2"], w["b3"], w["ksp"], 100.0)
+    for _ in range(warmup):
+        run()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    l0 = ctx.launches()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        J = run()[2]
+    e1.record()
+    torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1) / steps], device=dev, dtype=torch.float64)
+    Jsum = torch.tensor([float(J[:, 0].sum())], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(Jsum, op=dist.ReduceOp.SUM)
+    n1, lv = cfg.N + 1, len(ens["t_hist"])
+    # algorithmic bytes of one iteration per problem: adjoint reads phi, Q, writes r (3 trajectories); prox reads u, r, writes u_new;
+    # forward reads u_new, writes phi_new; cost reads phi_new, u_new, Q  ->  11 trajectory passes (the state lives in shared memory)
+    gb = 11 * 8.0 * n1 * lv * B / 1e9
+    return {"workload": f"{B} independent 1D problems (N = {cfg.N}, {lv - 2} steps), make_ensemble(seed 1234), one optimistic PGD iteration each from u0 = 0",
+            "n_gpus": world, "problems_per_gpu": hi - lo, "ms_per_ensemble_iteration": float(ms.item()),
+            "problem_it_per_s": B * 1e3 / float(ms.item()), "launches_per_iteration": int((ctx.launches() - l0) // steps),
+            "sum_J": float(Jsum.item()), "scaling": "strong",
+            "hbm_GBps_algorithmic": round(gb / (float(ms.item()) * 1e-3), 1),
+            "bound": "latency of one CTA per problem (22 state vectors in shared memory, sequential time loop); HBM traffic is negligible"}
 
 
 def run_ensemble1d(args):
@@ -809,6 +878,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-parity", action="store_true", help="skip the full-horizon parity_vs_strict leg")
     ap.add_argument("--no-slab", action="store_true", help="skip the 4096^2 slab_4096 leg")
+    ap.add_argument("--no-ensemble", action="store_true", help="skip the 1D ensemble leg (BASELINE config 4)")
     ap.add_argument("--slab-n", type=int, default=4096)
     ap.add_argument("--slab-horizon", type=int, default=20)
     ap.add_argument("--slab-steps", type=int, default=2)
