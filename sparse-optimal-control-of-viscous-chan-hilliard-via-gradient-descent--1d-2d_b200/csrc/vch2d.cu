@@ -1289,7 +1289,10 @@ static void pgd_iteration_host_streamed(vch2d_ctx* c, int levels, const double* 
     if (phiT) dT.alloc(n);
     cudaStream_t cp;
     VCH_CUDA(cudaStreamCreateWithFlags(&cp, cudaStreamNonBlocking));
-    const int CH = 32;                                   // levels per chunk (269 MB at 1024^2)
+    // levels per chunk (269 MB at 1024^2).  Measured with 8 / 32 / 128: no difference (e2e 0.4935 / 0.4942 / 0.4863 it/s); what the
+    // host-buffer path loses against the device-resident one (~0.11 s of 1.9 s) is the kernels slowing down while the copy engines
+    // move the trajectories through the memory system (48 ms of it vanish when the D2H copies are left out), not waiting.
+    const int CH = getenv("VCH_STREAM_CHUNK") ? std::max(1, atoi(getenv("VCH_STREAM_CHUNK"))) : 32;
     const int nch = (levels + CH - 1) / CH;
     std::vector<cudaEvent_t> ev_in(nch), ev_out(nch);
     cudaEvent_t ev_u, ev_prox, ev_adj;
