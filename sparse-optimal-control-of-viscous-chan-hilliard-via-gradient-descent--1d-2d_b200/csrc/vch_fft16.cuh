@@ -513,6 +513,14 @@ cols16_kernel(double* __restrict__ buf, int pitch, int ncols, const double2* __r
     fft16_middle<LOG2L, GS>(data, t, tw, f);
     fft16_last_pass<LOG2L>(data, t, tw, z);
     VCH_STAMP(6);
+    {   // Padding columns (>= ncols) are written back as exact zeros.  A padding column shares its complex FFT with the last real
+        // column; the split of the two real transforms is exact only up to rounding, so it would otherwise collect ~1e-16 of its
+        // neighbour, keep it (no row kernel writes there) and feed ~1e-32 of it back on the next application: harmless, but
+        // results would depend on the context's history and a zero right-hand side would not give an exactly zero solution.
+        const bool za = c0 + 2 * f >= ncols, zb = c0 + 2 * f + 1 >= ncols;
+#pragma unroll
+        for (int q = 0; q < 9; ++q) { if (za) z[q].x = 0.0; if (zb) z[q].y = 0.0; }
+    }
 #pragma unroll
     for (int q = 0; q < 8; ++q) stage[t + q * G::tpf] = z[q];
     if (t == 0) stage[N] = z[8];
@@ -627,6 +635,11 @@ cols16_tma_kernel(const __grid_constant__ CUtensorMap tmap, int ncols, const dou
     fft16_first_store<LOG2L, GS>(data, v, t, f);
     fft16_middle<LOG2L, GS>(data, t, tw, f);
     fft16_last_pass<LOG2L>(data, t, tw, z);
+    {   // padding columns leave as exact zeros (see cols16_kernel)
+        const bool za = c0 + 2 * f >= ncols, zb = c0 + 2 * f + 1 >= ncols;
+#pragma unroll
+        for (int q = 0; q < 9; ++q) { if (za) z[q].x = 0.0; if (zb) z[q].y = 0.0; }
+    }
 #pragma unroll
     for (int q = 0; q < 8; ++q) st(t + q * G::tpf) = z[q];
     if (t == 0) st(N) = z[8];

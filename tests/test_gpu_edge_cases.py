@@ -122,3 +122,26 @@ def test_adjoint_krylov_stall_is_an_error(native, golden):
     x, y = g["x"], g["y"]
     po, qo, ro = O.adjoint_2d(P, h, x, y, g["t"], 5.0, 10.0)
     assert rel(p, po) < 1e-7 and rel(r, ro) < 1e-7
+
+
+@pytest.mark.timeout(120)
+def test_zero_right_hand_side_ends_the_solve_graph(native):
+    """A linear solve whose right-hand side is exactly zero is finished before its first iteration.  In the fused adjoint solve
+    the start (||b||^2 -> done) lives in the kernel IN FRONT of the graph, so the WHILE body is entered once with `done` set
+    and its last kernel has to clear the loop condition on its early return — otherwise the graph would spin.  b1 = b2 = 0 makes
+    every adjoint right-hand side zero; the power-of-two grid takes the graph path with the radix-16 kernels."""
+    P = O.Phys2D(Nx=32, Ny=32, T=0.04)
+    c = native.Ctx2D(32, 32, 1 / 32, 1 / 32, 1.0, 1.0, P.tau, P.gamma, P.c1, P.c2, P.kappa)
+    dts = np.full(4, 1e-2)
+    hist, _, _ = c.forward(O.init_phi_2d(32, 32), None, dts)
+    t = np.concatenate([[0.0], np.cumsum(dts)])
+    p, q, r = c.adjoint(hist, t, 0.0, 0.0, np.zeros_like(hist), np.zeros_like(hist[0]))
+    assert not p.any() and not q.any() and not r.any()
+    assert c.last_stats["krylov_iterations"] == 0 and c.last_stats["krylov_stalls"] == 0
+    # and the context is fine afterwards: an ordinary adjoint sweep equals the oracle's
+    fw = O.forward_2d(P)
+    phiT, phiQ = O.targets_2d(fw["x"], fw["y"], fw["t"], fw["phi"][0], P.Lx, P.Ly, P.T)
+    Op = O.Opt2D()
+    p2, q2, r2 = c.adjoint(hist, t, Op.b1, Op.b2, phiQ, phiT)
+    ro = O.adjoint_2d(P, fw["phi"], fw["x"], fw["y"], fw["t"], Op.b1, Op.b2, phiQ, phiT)
+    assert rel(r2, ro[2]) < 1e-7 and rel(hist, fw["phi"]) < 1e-8
