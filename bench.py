@@ -663,8 +663,8 @@ def _load_gd1d():
 def ensemble_leg(nat, args, rank, world, local, B=1024, warmup=2, steps=5):
     """BASELINE config 4 inside the default run, so that the driver's records carry it: B independent 1D control problems (default
     1D grid, varied targets / weights), one optimistic PGD iteration for the whole ensemble per step (4 launches), the batch split
-    across the ranks without communication.  First iterates from u0 = 0 (later chained iterates of this synthetic ensemble drive
-    single members into many-Newton-iteration regimes; `--workload ensemble1d` reports those with the per-step median)."""
+    across the ranks without communication.  The iterate from u0 = 0 is repeated (`--workload ensemble1d` chains the iterates:
+    same time per step)."""
     import torch
     import torch.distributed as dist
     G = _load_gd1d()
