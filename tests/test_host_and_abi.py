@@ -142,3 +142,31 @@ def test_host_side_helpers_1d():
     assert parts[0][0] == 0 and parts[-1][1] == 1024 and all(a[1] == b[0] for a, b in zip(parts, parts[1:]))
     sizes = [b - a for a, b in (G.shard_range(10, r, 4) for r in range(4))]
     assert sizes == [3, 3, 2, 2]
+
+
+def test_context_slots_and_concurrent_runner():
+    """Worker threads of vch_b200_native.run_concurrent drive distinct context slots (so that batched 2D trials use distinct library
+    contexts), results come back in job order, and the caller's slot is untouched."""
+    import threading
+    import vch_b200_native as nat
+    seen = []
+    lock = threading.Lock()
+
+    def job(j):
+        with lock:
+            seen.append((j, nat.ctx_slot(), threading.get_ident()))
+        return j * j
+    assert nat.run_concurrent(job, 7, 3) == [j * j for j in range(7)]
+    assert nat.ctx_slot() == 0
+    slots = {s for _, s, _ in seen}
+    assert slots <= {0, 1, 2} and len(seen) == 7
+    # two jobs that overlap in time never share a slot: with as many workers as jobs every job has its own
+    seen.clear()
+    barrier = threading.Barrier(3)
+
+    def job2(j):
+        barrier.wait(timeout=10)
+        return nat.ctx_slot()
+    assert sorted(nat.run_concurrent(job2, 3, 3)) == [0, 1, 2]
+    # workers <= 1: a plain loop on the caller's slot
+    assert nat.run_concurrent(lambda j: nat.ctx_slot(), 3, 1) == [0, 0, 0]

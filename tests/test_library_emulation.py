@@ -39,6 +39,8 @@ SLOW = [
     "tests/test_gpu_2d.py::test_inexact_first_newton_solve_keeps_trajectory_and_saves_iterations",
     "tests/test_gpu_1d.py::test_ensemble_equals_single_problem_calls",
     "tests/test_gpu_2d.py::test_checkpointed_pgd_iteration_equals_fully_stored[5-True-True]",
+    "tests/test_gpu_dropin_1d.py::test_batched_line_search_and_fd_directions_equal_sequential",
+    "tests/test_gpu_edge_cases.py::test_zero_right_hand_side_ends_the_solve_graph",
 ]
 
 
