@@ -221,7 +221,7 @@ __device__ __forceinline__ void pro16_mode2(double2* __restrict__ stage, const d
         const double sa = ra - al * qa, sb = rb - al * qb;
         if (va) s[ba + e] = sa;
         if (vb) s[bb + e] = sb;
-        stage[e] = make_double2(MUL ? (aa - abar) * sa : sa, MUL ? (ab - abar) * sb : sb);
+        stage[e] = make_double2(va ? (MUL ? (aa - abar) * sa : sa) : 0.0, vb ? (MUL ? (ab - abar) * sb : sb) : 0.0);
     };
 #pragma unroll
     for (int q = 0; q < 8; ++q) elem(t + q * G::tpf);
@@ -236,7 +236,7 @@ __device__ __forceinline__ void pro16_mode3_first(double2* __restrict__ stage, c
         const double aa = MUL ? a[ba + e] : 0.0, ab = MUL ? a[bb + e] : 0.0;
         if (va) p[ba + e] = pa;
         if (vb) p[bb + e] = pb;
-        stage[e] = make_double2(MUL ? (aa - abar) * pa : pa, MUL ? (ab - abar) * pb : pb);
+        stage[e] = make_double2(va ? (MUL ? (aa - abar) * pa : pa) : 0.0, vb ? (MUL ? (ab - abar) * pb : pb) : 0.0);
     };
 #pragma unroll
     for (int q = 0; q < 8; ++q) elem(t + q * G::tpf);
@@ -257,7 +257,7 @@ __device__ __forceinline__ void pro16_mode3(double2* __restrict__ stage, const d
         const double na = ra + beta * (pa - om * qa), nb = rb + beta * (pb - om * qb);
         if (va) { x[ba + e] = xa + (al * pa + om * sa); rw[ba + e] = ra; p[ba + e] = na; }
         if (vb) { x[bb + e] = xb + (al * pb + om * sb); rw[bb + e] = rb; p[bb + e] = nb; }
-        stage[e] = make_double2(MUL ? (aa - abar) * na : na, MUL ? (ab - abar) * nb : nb);
+        stage[e] = make_double2(va ? (MUL ? (aa - abar) * na : na) : 0.0, vb ? (MUL ? (ab - abar) * nb : nb) : 0.0);
     };
 #pragma unroll
     for (int q = 0; q < 8; ++q) elem(t + q * G::tpf);
@@ -271,7 +271,7 @@ template <int LOG2L>
 __device__ __forceinline__ void pro16_mode4(double2* __restrict__ stage, const double* __restrict__ rp, const double* __restrict__ rm,
                                             double k_in, double k_out, int la, int lb, int nlines, int ls, bool vb, int t) {
     using G = F16<LOG2L>;
-    const int lbb = vb ? lb : la;                                                   // absent second line: results unused
+    const int lbb = vb ? lb : la;                                                   // absent second line: staged as zero
     const size_t ba = (size_t)la * ls, bb = (size_t)lbb * ls;
     const size_t bam = (size_t)(la > 0 ? la - 1 : 1) * ls;                          // line below la
     const size_t bap = (size_t)(la < nlines - 1 ? la + 1 : nlines - 2) * ls;        // line above la (= lb when present)
@@ -282,7 +282,7 @@ __device__ __forceinline__ void pro16_mode4(double2* __restrict__ stage, const d
         const double ca = rp[ba + e], cb = rp[bb + e];
         const double a_in = (rp[ba + ep] - ca) + (rp[ba + em] - ca), a_out = (rp[bap + e] - ca) + (rp[bam + e] - ca);
         const double b_in = (rp[bb + ep] - cb) + (rp[bb + em] - cb), b_out = (rp[bbp + e] - cb) + (rp[bbm + e] - cb);
-        stage[e] = make_double2((a_in * k_in + a_out * k_out) - rm[ba + e], (b_in * k_in + b_out * k_out) - rm[bb + e]);
+        stage[e] = make_double2((a_in * k_in + a_out * k_out) - rm[ba + e], vb ? (b_in * k_in + b_out * k_out) - rm[bb + e] : 0.0);
     };
 #pragma unroll
     for (int q = 0; q < 8; ++q) elem(t + q * G::tpf);
@@ -364,7 +364,11 @@ rows16_kernel(const double* __restrict__ in, double* __restrict__ out, int nline
     double2* data = sm + (size_t)f * G::ld;
     const int la = 2 * (blockIdx.x * G::fpb + f), lb = la + 1;
     const bool va = la < nlines, vb = lb < nlines;
-    // absent lines (odd line count, idle FFT slots of the last CTA) read line 0 and are never written
+    // Absent lines (the odd line out — N + 1 lines is always odd — and idle FFT slots of the last CTA) load line 0 so that no branch
+    // separates the loads, are never written, and enter the transform as ZEROS.  Not as what was loaded: the deferred update of
+    // mode 3 rewrites x and p of line 0 in place in another CTA at the same time, the value read here depends on which CTA runs
+    // first, and the imaginary input of the shared complex FFT leaks into the real line at rounding level — results were
+    // reproducible only to ~1e-16 per application (measured: scripts/determinism_probe.py; 1e-11 after a few time steps at 1024^2).
     const size_t ia = (size_t)(va ? la : 0) * in_ls, ib = (size_t)(vb ? lb : 0) * in_ls;
     double2 v[16];
     if (PRO == 0 && XM == 3) {
@@ -382,7 +386,7 @@ rows16_kernel(const double* __restrict__ in, double* __restrict__ out, int nline
         for (int r = 0; r < 16; ++r) v[r] = stage[idx16<LOG2L>(t, r)];
     } else if (PRO == 0) {
 #pragma unroll
-        for (int r = 0; r < 16; ++r) { const int e = idx16<LOG2L>(t, r); v[r] = make_double2(in[ia + e], in[ib + e]); }
+        for (int r = 0; r < 16; ++r) { const int e = idx16<LOG2L>(t, r); v[r] = make_double2(va ? in[ia + e] : 0.0, vb ? in[ib + e] : 0.0); }
     } else {
         double2* stage = sm + (size_t)G::fpb * G::ld + (size_t)f * (G::N + 1);
         const Scal* sc = pro.sc;
