@@ -314,8 +314,17 @@ __device__ int newton1(Sm& s, const P1& p, double dt, double* hist, int hist_cap
     return status;
 }
 
+// Occupancy of the two time-loop kernels (one CTA per problem).  Uncapped they take 106 / 112 registers and ran with 160 threads
+// (one per node): 3 CTAs per SM, 444 at a time, THREE waves for the 1024-problem ensemble.  They are barrier-bound (block cyclic
+// reduction over (n + 1) / 2 block rows), not register-hungry: with one thread per BLOCK ROW (96 threads at N = 128, threads_for) and
+// 80 registers (12 - 64 bytes of spills) 7 CTAs fit an SM — 1036 at a time, the ensemble is ONE wave.  Measured on B200, ms per
+// ensemble iteration (profiles/r02_1d_occupancy.txt): 8.79 uncapped / 160 threads, 7.21 with 96 registers, 7.97 with 96 threads alone,
+// 6.06 with both at 80 registers (169 000 problem-iterations/s instead of 116 000).
+#ifndef VCH_1D_REGS
+#define VCH_1D_REGS __maxnreg__(80)
+#endif
 // Whole forward solve of one problem per CTA (Forward_solver.py:286-386).
-__global__ void forward1d_kernel(P1 p, const double* __restrict__ phi_init, const double* __restrict__ u, int u_rows,
+__global__ void VCH_1D_REGS forward1d_kernel(P1 p, const double* __restrict__ phi_init, const double* __restrict__ u, int u_rows,
                                  int n_steps, const double* __restrict__ dts, double* __restrict__ phi_hist,
                                  double* __restrict__ mu_hist, double* __restrict__ w_hist, int* __restrict__ status_out) {
     extern __shared__ double smem[];
@@ -410,7 +419,7 @@ __global__ void mu_init1d_kernel(P1 p, const double* __restrict__ phi, const dou
 }
 
 // Whole adjoint sweep of one problem per CTA (backward_solver.py:72-125).
-__global__ void adjoint1d_kernel(P1 p, const double* __restrict__ phi_hist, int levels, const double* __restrict__ t,
+__global__ void VCH_1D_REGS adjoint1d_kernel(P1 p, const double* __restrict__ phi_hist, int levels, const double* __restrict__ t,
                                  const double* __restrict__ b1v, const double* __restrict__ b2v,
                                  const double* __restrict__ phiQ, const double* __restrict__ phiT,
                                  double* __restrict__ pO, double* __restrict__ qO, double* __restrict__ rO) {
@@ -541,7 +550,8 @@ P1 make_p1(const vch1d_params& q) {
     p.kappa = q.kappa; p.lim = 1.0 - q.delta_sep; p.eps_log = std::max(1e-8, 0.5 * q.delta_sep);
     return p;
 }
-int threads_for(int n) { int t = ((n + 31) / 32) * 32; return std::min(std::max(t, 64), 256); }
+// one thread per block row of the cyclic reduction (the node loops take two trips), whole warps, 64 .. 256
+int threads_for(int n) { int t = (((n + 1) / 2 + 31) / 32) * 32; return std::min(std::max(t, 64), 256); }
 size_t smem_for(int n) {          // 22 state arrays + the solver's scratch buffer Y (and X for tiny grids, see Sm)
     const size_t nb = (size_t)(n + 1) / 2;
     return ((size_t)kSmArrays * n + (n >= 8 ? 14 : 28) * nb) * sizeof(double);

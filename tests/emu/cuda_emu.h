@@ -31,6 +31,9 @@
 #ifndef __launch_bounds__
 #define __launch_bounds__(...)
 #endif
+#ifndef __maxnreg__
+#define __maxnreg__(...)
+#endif
 
 namespace vch_emu {
 
