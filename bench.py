@@ -614,6 +614,12 @@ def run_b200(args):
             ens1d = ensemble_leg(nat, args, rank, world, local)
         except Exception as exc:   # report, do not hide
             ens1d = {"error": repr(exc)}
+    conc = None
+    if rank == 0 and world == 1 and not args.no_concurrent:
+        try:
+            conc = concurrent_leg(nat, F2, Op, N, dev)
+        except Exception as exc:   # report, do not hide
+            conc = {"error": repr(exc)}
     if rank == 0:
         cpu = None
         if world == 1 and not args.no_cpu:
@@ -636,7 +642,7 @@ def run_b200(args):
                            "newton": "reference rule + fp64-floor stop (DESIGN.md)", "krylov_rel_tol": 1e-11,
                            "krylov_first_solve_rel_tol": float(os.environ.get("VCH_KRYLOV_FIRST_RTOL", 1e-6))},
                 "gpu_launches": int(launches), "clocks": clocks, "e2e": e2e, "roofline": roof, "cpu_baseline": cpu,
-                "parity_vs_strict": parity, "slab_4096": slab, "ensemble1d": ens1d,
+                "parity_vs_strict": parity, "slab_4096": slab, "ensemble1d": ens1d, "concurrent_problems": conc,
                 "solver": {"linear_solves_per_iteration": agg["newton_linear_solves"] / args.steps,
                            "newton_residual_evals_per_time_step": agg["newton_residual_evals"] / (args.steps * M),
                            "krylov_its_per_solve": agg["krylov_iterations"] / max(1, agg["newton_linear_solves"]),
@@ -658,6 +664,69 @@ def _load_gd1d():
         if saved is not None:
             sys.modules["config"] = saved
     return G
+
+
+def concurrent_leg(nat, F2, Op, N, dev, M=100, iters=2, kmax=3):
+    """K independent problems of the metric's grid on ONE GPU at the same time (one library context, one stream and one host thread
+    per problem) against the same problems one after the other: aggregate PGD iterations/s.  The kernels of the Krylov loop are
+    single-wave latency chains, so further problems fill what one leaves idle.  NOT the headline (that stays one problem per GPU, the
+    latency a user of the reference waits for); shortened horizon (M steps) so that the leg takes seconds."""
+    import threading
+    import torch
+    from config import ForwardSolverConfig
+    dt = 1e-2
+    P = ForwardSolverConfig(Nx=N, Ny=N, T=M * dt)
+    dts = np.full(M, dt)
+    t_hist = np.concatenate([[0.0], np.minimum(np.cumsum(dts), P.T)])
+    x = np.linspace(0.0, 1.0, N + 1)
+
+    class Problem:
+        def __init__(self, seed):
+            self.stream = torch.cuda.Stream()
+            with torch.cuda.stream(self.stream):
+                self.ctx = nat.Ctx2D(N, N, 1.0 / N, 1.0 / N, 1.0, 1.0, P.tau, P.gamma, P.c1, P.c2, P.kappa, device=dev.index or 0)
+                phi0 = torch.from_numpy(F2.init_phi_random(N, N, 1e-2, amp=0.1, seed=seed)).to(dev)
+                self.h0, _, _ = self.ctx.forward(phi0, None, dts)
+                self.phiT, self.phiQ = _targets(torch, self.h0, x, t_hist, P.T, dev)
+                self.u0 = torch.zeros_like(self.h0)
+                self.buf = [torch.empty_like(self.h0) for _ in range(5)]
+            self.stream.synchronize()
+            self.J = None
+
+        def run(self, n_it):        # always from (u0, h0): iteration i reads the pair written by iteration i - 1
+            u, h = self.u0, self.h0
+            pairs = [(self.buf[0], self.buf[1]), (self.buf[2], self.buf[3])]
+            with torch.cuda.stream(self.stream):
+                for i in range(n_it):
+                    un, hn = pairs[i & 1]
+                    _, _, J, _, _ = self.ctx.pgd_iteration(u, h, self.phiQ, self.phiT, t_hist, dts, x, x, Op.b1, Op.b2, Op.b3, Op.kappa_sparsity,
+                                                           Op.u_min, Op.u_max, Op.alpha_max, u_out=un, phi_out=hn, r_out=self.buf[4])
+                    u, h = un, hn
+                    self.J = float(J[0])
+                self.stream.synchronize()
+
+    probs = [Problem(42 + k) for k in range(kmax)]
+    for pr in probs:
+        pr.run(1)
+    torch.cuda.synchronize()
+    out = {"workload": f"{N}^2 x {M} steps, {iters} chained optimistic PGD iterations per problem from u0 = 0, K problems on one GPU", "K": {}}
+    for K in range(1, kmax + 1):
+        t0 = time.perf_counter()
+        for pr in probs[:K]:
+            pr.run(iters)
+        torch.cuda.synchronize()
+        seq = time.perf_counter() - t0
+        Js = [pr.J for pr in probs[:K]]
+        t0 = time.perf_counter()
+        th = [threading.Thread(target=pr.run, args=(iters,)) for pr in probs[:K]]
+        [t.start() for t in th]; [t.join() for t in th]
+        torch.cuda.synchronize()
+        con = time.perf_counter() - t0
+        out["K"][str(K)] = {"one_after_the_other_it_per_s": round(K * iters / seq, 3), "concurrent_it_per_s": round(K * iters / con, 3),
+                            "gain": round(seq / con, 3), "J_bit_identical": Js == [pr.J for pr in probs[:K]]}
+    del probs
+    torch.cuda.empty_cache()
+    return out
 
 
 def ensemble_leg(nat, args, rank, world, local, B=1024, warmup=2, steps=5):
@@ -879,6 +948,7 @@ def main():
     ap.add_argument("--no-parity", action="store_true", help="skip the full-horizon parity_vs_strict leg")
     ap.add_argument("--no-slab", action="store_true", help="skip the 4096^2 slab_4096 leg")
     ap.add_argument("--no-ensemble", action="store_true", help="skip the 1D ensemble leg (BASELINE config 4)")
+    ap.add_argument("--no-concurrent", action="store_true", help="skip the concurrent-problems leg (K problems on one GPU, N = 1 only)")
     ap.add_argument("--slab-n", type=int, default=4096)
     ap.add_argument("--slab-horizon", type=int, default=20)
     ap.add_argument("--slab-steps", type=int, default=2)
