@@ -428,9 +428,9 @@ def run_b200(args):
     n = (N + 1) ** 2
     field_bytes = 8 * n
 
-    # synthetic problem: reference IC (host RNG, Forward2_solver.py:444-486; seed differs per rank = independent problems),
+    # synthetic problem: reference IC (host RNG, Forward2_solver.py:444-486; --rank-seeds: the same problem on every rank or one per rank),
     # uncontrolled forward solve, targets as GD2_configured.build_targets(choice_t=1, choice_q=1)
-    phi0 = torch.from_numpy(F2.init_phi_random(N, N, 1e-2, amp=0.1, seed=42 + rank)).to(dev)
+    phi0 = torch.from_numpy(F2.init_phi_random(N, N, 1e-2, amp=0.1, seed=42 + (rank if args.rank_seeds == "distinct" else 0))).to(dev)
     hist_a, _, _ = ctx.forward(phi0, None, dts)
     xx, yy = torch.meshgrid(torch.from_numpy(x).to(dev), torch.from_numpy(x).to(dev), indexing="ij")
     phiT = (0.7 * torch.sin(2 * np.pi * xx) * torch.cos(np.pi * yy)).contiguous()
@@ -491,7 +491,15 @@ def run_b200(args):
     barrier()
     clocks = sampler.stop() if rank == 0 else None
     ms = torch.tensor([e0.elapsed_time(e1) / args.steps], device=dev, dtype=torch.float64)
+    per_rank = None
     if world > 1:
+        # every rank's own time and work next to the maximum that the metric uses
+        mine = torch.tensor([float(ms.item()), float(agg["krylov_iterations"]) / args.steps, float(agg["newton_linear_solves"]) / args.steps],
+                            device=dev, dtype=torch.float64)
+        allr = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        per_rank = {"ms_per_step": [round(float(a[0]), 2) for a in allr], "krylov_iterations_per_step": [float(a[1]) for a in allr],
+                    "linear_solves_per_step": [float(a[2]) for a in allr]}
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms_per_step = float(ms.item())
     launches = ctx.launches() - l0
@@ -638,10 +646,13 @@ def run_b200(args):
                 "data": "synthetic",
                 "config": {"workload": f"2D {N}^2 grid ({N+1}^2 nodes), M={M} CN steps (T={M*dt:g}), reference 2D defaults, "
                                        "targets build_targets(1,1), optimistic PGD iteration from u0=0",
-                           "problems_per_gpu": 1, "l2": "inputs (8.4 GB trajectories) exceed the 126 MB L2; no flush needed",
+                           "problems_per_gpu": 1, "rank_problems": ("one GPU" if world == 1 else (
+                               "every rank solves its own copy of the same synthetic problem, no communication (per-GPU work fixed)" if args.rank_seeds == "same"
+                               else "every rank solves a problem of its own (initial noise seeded by rank), no communication")),
+                           "l2": "inputs (8.4 GB trajectories) exceed the 126 MB L2; no flush needed",
                            "newton": "reference rule + fp64-floor stop (DESIGN.md)", "krylov_rel_tol": 1e-11,
                            "krylov_first_solve_rel_tol": float(os.environ.get("VCH_KRYLOV_FIRST_RTOL", 1e-6))},
-                "gpu_launches": int(launches), "clocks": clocks, "e2e": e2e, "roofline": roof, "cpu_baseline": cpu,
+                "gpu_launches": int(launches), "per_rank": per_rank, "clocks": clocks, "e2e": e2e, "roofline": roof, "cpu_baseline": cpu,
                 "parity_vs_strict": parity, "slab_4096": slab, "ensemble1d": ens1d, "concurrent_problems": conc,
                 "solver": {"linear_solves_per_iteration": agg["newton_linear_solves"] / args.steps,
                            "newton_residual_evals_per_time_step": agg["newton_residual_evals"] / (args.steps * M),
@@ -948,6 +959,9 @@ def main():
     ap.add_argument("--no-parity", action="store_true", help="skip the full-horizon parity_vs_strict leg")
     ap.add_argument("--no-slab", action="store_true", help="skip the 4096^2 slab_4096 leg")
     ap.add_argument("--no-ensemble", action="store_true", help="skip the 1D ensemble leg (BASELINE config 4)")
+    ap.add_argument("--rank-seeds", default="same", choices=["same", "distinct"],
+                    help="N > 1: every rank solves its own copy of the SAME synthetic problem (per-GPU work fixed as N grows: weak scaling) or a "
+                         "problem of its own (different initial noise: the iteration counts, hence the work, differ from rank to rank)")
     ap.add_argument("--no-concurrent", action="store_true", help="skip the concurrent-problems leg (K problems on one GPU, N = 1 only)")
     ap.add_argument("--slab-n", type=int, default=4096)
     ap.add_argument("--slab-horizon", type=int, default=20)
