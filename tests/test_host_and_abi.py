@@ -170,3 +170,30 @@ def test_context_slots_and_concurrent_runner():
     assert sorted(nat.run_concurrent(job2, 3, 3)) == [0, 1, 2]
     # workers <= 1: a plain loop on the caller's slot
     assert nat.run_concurrent(lambda j: nat.ctx_slot(), 3, 1) == [0, 0, 0]
+
+
+def test_bench_and_entry_scripts_parse_and_expose_the_contract():
+    """bench.py and __graft_entry__.py only ever run on the GPU box; a typo there would cost the round's measurement.  Here: both
+    compile, bench.py's command line has the driver's flags (--gpus / --steps / --warmup / --impl) and the workload switches the docs
+    name, the B200 arm refuses to run without a device instead of falling back, and the fit used by the CPU arm recovers a power law."""
+    import importlib.util
+    import subprocess
+    for name in ("bench.py", "__graft_entry__.py"):
+        with open(os.path.join(ROOT, name)) as fh:
+            compile(fh.read(), name, "exec")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--help"], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stderr[-2000:]
+    for flag in ("--gpus", "--steps", "--warmup", "--impl", "--workload", "--horizon", "--rank-seeds", "--no-e2e", "--no-slab",
+                 "--no-ensemble", "--no-concurrent", "--no-parity", "--no-cpu", "--profile-steps"):
+        assert flag in out.stdout, flag
+    spec = importlib.util.spec_from_file_location("bench_under_test", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    p, c = bench._fit_power([(1e4, 2.0 * 1e4 ** 1.5), (4e4, 2.0 * 4e4 ** 1.5), (9e4, 2.0 * 9e4 ** 1.5)])
+    assert abs(p - 1.5) < 1e-9 and abs(c - 2.0) < 1e-6
+    assert bench.METRIC.startswith("PGD iters/s") and bench.UNIT == "it/s"
+    import torch
+    if not torch.cuda.is_available():      # no CPU fallback: the B200 arm must fail loudly without a device
+        run = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1", "--warmup", "0", "--horizon", "2", "--n", "32"],
+                             capture_output=True, text=True, timeout=300)
+        assert run.returncode != 0 and not any(l.startswith('{"metric"') for l in run.stdout.splitlines())
